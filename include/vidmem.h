@@ -1,0 +1,222 @@
+/*
+ * vidmem.h -- C ABI of libvidmem.so, the B200 (sm_100a) embedding-similarity engine.
+ *
+ * The reference (RaphaelHaddad/Real-Time-Brain-Inspired-Video-Memory, "VidGraph") is pure
+ * Python and has NO FFI/plugin interface for this path: the seams it exposes
+ * are Python methods.  Each entry point below therefore cites the reference method whose
+ * arithmetic it replaces; the Python adapters that keep those method signatures live in
+ * real-time-brain-inspired-video-memory_b200/adapters.py and the binding a maintainer would
+ * add to the reference is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - C linkage, plain pointers and sizes, no torch / C++ types.
+ *  - Every function returns int: VM_OK (0) or a negative vm_status; vm_last_error() returns a
+ *    thread-local message for the last failure on the calling thread.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Work is
+ *    enqueued on it.  Calls whose outputs live in HOST memory synchronise the stream before
+ *    returning; calls whose inputs and outputs are all DEVICE memory and that pass
+ *    VM_FLAG_ASYNC return as soon as the work is enqueued (outputs valid after the stream
+ *    reaches that point).
+ *  - The library owns only opaque handles (vm_store, vm_comm) and its workspaces; every
+ *    input/output buffer is owned by the caller.
+ *  - One caller thread per store (the reference calls this path from a single asyncio
+ *    thread); handles are not re-entrant.
+ *  - There is no CPU fallback: without a CUDA device of compute capability 10.x every compute
+ *    entry point fails with VM_ERR_CUDA / VM_ERR_UNSUPPORTED.
+ *
+ * Row identity: the engine works on dense row indices (append order == store order of the
+ * reference's dict); the adapters keep the row <-> chunk-id table on the host.
+ */
+#ifndef VIDMEM_H_
+#define VIDMEM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VM_ABI_VERSION 1
+
+typedef enum vm_status {
+    VM_OK = 0,
+    VM_ERR_BADARG = -1,
+    VM_ERR_OOM = -2,
+    VM_ERR_CUDA = -3,
+    VM_ERR_NCCL = -4,
+    VM_ERR_OVERFLOW = -5,    /* a caller-provided output capacity was exceeded (count is still returned) */
+    VM_ERR_UNSUPPORTED = -6, /* wrong GPU architecture / shape outside the supported envelope */
+    VM_ERR_STATE = -7
+} vm_status;
+
+typedef enum vm_dtype { VM_F32 = 0, VM_BF16 = 1, VM_F64 = 2 } vm_dtype;
+typedef enum vm_mem { VM_MEM_HOST = 0, VM_MEM_DEVICE = 1 } vm_mem;
+
+/* Score convention of the returned `score` field.
+ *   VM_SCORE_RAW   : cosine, as PreLLMInjector._cosine_similarity returns it
+ *                    (src/components/pre_llm_injector.py:374-388).
+ *   VM_SCORE_NEO4J : (1 + cosine) / 2, the normalised value Neo4j's vector.similarity.cosine
+ *                    yields in the Cypher of _vector_search_chunks
+ *                    (src/pipeline/retriever_hybrid.py:295-301; SURVEY.md 9.3, parity unpinned).
+ * `min_score` (strict `>`) is applied to the value in the selected convention. */
+typedef enum vm_score_mode { VM_SCORE_RAW = 0, VM_SCORE_NEO4J = 1 } vm_score_mode;
+
+/* Summation order of the reference's Python `sum()` over binary64 products:
+ * plain left-to-right on CPython < 3.12, Neumaier-compensated on CPython >= 3.12. */
+typedef enum vm_sum_mode { VM_SUM_NAIVE = 0, VM_SUM_NEUMAIER = 1 } vm_sum_mode;
+
+enum {
+    VM_FLAG_ASYNC = 1,       /* do not synchronise (device outputs only) */
+    VM_FLAG_FORCE_EXACT = 2, /* skip the fast scan: binary64 scan of every row (slow, always exact) */
+    VM_FLAG_FORCE_SIMT = 4,  /* use the CUDA-core scan kernel even where the tcgen05 kernel applies */
+    VM_FLAG_FORCE_TC = 8     /* use the tcgen05/TMA scan kernel even for small query batches */
+};
+
+typedef struct vm_store vm_store; /* a row-major embedding store resident in HBM (one shard) */
+typedef struct vm_comm vm_comm;   /* an NCCL communicator wrapper (one rank) */
+
+/* Filled by vm_topk* when `stats` is non-NULL (all values for the last call). */
+typedef struct vm_topk_stats {
+    int32_t scan_kernel;      /* 0 = exact only, 1 = SIMT scan, 2 = tcgen05 scan */
+    int32_t scan_launches;    /* kernels launched by the call (all kinds) */
+    int32_t uncertified;      /* queries the fast scan could not certify and the exact scan re-did */
+    int32_t candidates;       /* candidate list length per query (KP) */
+    int32_t scan_ctas;
+    int32_t reserved[3];
+} vm_topk_stats;
+
+/* ---- library ----------------------------------------------------------------------- */
+int vm_version(void);                  /* VM_ABI_VERSION */
+const char *vm_last_error(void);       /* thread-local, never NULL */
+/* sm count / compute capability / HBM bytes of `device`; any out pointer may be NULL */
+int vm_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem);
+
+/* ---- embedding store (one shard = rows resident on one GPU) --------------------------
+ * Replaces the per-call store fetch of PreLLMInjector._get_chunk_embeddings
+ * (src/components/pre_llm_injector.py:390-412: the whole store crosses Bolt every batch) with
+ * rows that stay resident in HBM.  dtype is VM_F32 or VM_BF16; `dim` is the logical embedding
+ * length; rows are stored with a leading dimension of vm_store_ld() elements (dim rounded up
+ * to 8, zero padded). */
+int vm_store_create(vm_store **out, int device, int dim, int dtype, int64_t capacity);
+/* Same, over caller-owned device buffers (e.g. torch tensors): rows_dev holds
+ * capacity * vm_ld(dim) elements of `dtype`, inv_norms_dev holds capacity floats. */
+int vm_store_attach(vm_store **out, int device, int dim, int dtype, int64_t capacity, void *rows_dev,
+                    float *inv_norms_dev);
+int vm_store_destroy(vm_store *s);
+int64_t vm_store_size(const vm_store *s);
+int64_t vm_store_capacity(const vm_store *s);
+int vm_store_dim(const vm_store *s);
+int vm_store_ld(const vm_store *s);
+int vm_ld(int dim); /* leading dimension used for a given dim */
+
+/* Append n rows ([n][dim], row-major, src_dtype VM_F32/VM_BF16/VM_F64, host or device).
+ * Replaces the per-row `SET c.embedding = $embedding` round trip of
+ * Neo4jHandler._create_chunks_with_embeddings (src/components/neo4j_handler.py:221-253) as the
+ * insert hook; values are rounded to the store dtype once, and 1/||row|| of the STORED values
+ * is cached (binary64 accumulate) -- this is the "fused normalisation" the scan kernels use.
+ * first_row (may be NULL) receives the index of the first appended row.  A later vm_topk on
+ * the same stream sees every row appended before it. */
+int vm_store_append(vm_store *s, const void *rows, int src_dtype, int src_mem, int64_t n, int64_t *first_row,
+                    void *stream);
+/* Overwrite rows [row0, row0+n) in place (idempotent upsert by id, neo4j_handler.py:229 MERGE). */
+int vm_store_update(vm_store *s, int64_t row0, const void *rows, int src_dtype, int src_mem, int64_t n,
+                    void *stream);
+/* Mark rows as skipped: they are never returned, like a falsy `existing_emb`
+ * (src/components/pre_llm_injector.py:363) or `c.embedding IS NULL` (retriever_hybrid.py:296). */
+int vm_store_invalidate(vm_store *s, const int64_t *rows_host, int64_t n, void *stream);
+/* Tell an attached store that rows [0, n) are already filled (e.g. generated on device);
+ * recomputes the cached inverse norms for [row0, n). */
+int vm_store_set_size(vm_store *s, int64_t n, int64_t recompute_from_row, void *stream);
+int vm_store_clear(vm_store *s);
+
+/* ---- top-k scorer ---------------------------------------------------------------------
+ * Replaces the hot loop of PreLLMInjector._calculate_batch_similarities
+ * (src/components/pre_llm_injector.py:356-370: every query x every stored row through
+ * _cosine_similarity, stable sort descending, slice [:k]) and the exhaustive Cypher scan of
+ * HybridRetriever._vector_search_chunks (src/pipeline/retriever_hybrid.py:293-306).
+ *
+ *  queries    [nq][dim] row-major, q_dtype VM_F32/VM_BF16/VM_F64, q_mem host or device
+ *  k          entries wanted per query, 1 <= k <= 64
+ *  min_score  strict lower bound on the returned score (use -INFINITY for none)
+ *  out_idx    [nq][k] int64 row indices, best first; ties -> lowest row
+ *  out_score  [nq][k] binary64 scores, BIT-IDENTICAL to the reference formula evaluated on the
+ *             stored (dtype-rounded) row values and the given query values
+ *  out_count  [nq] number of valid entries (rows may be fewer than k: no padding, :370)
+ *  out_mem    where the three outputs live
+ *
+ * How: a fast scan (tcgen05/TMA tensor-core kernel, or the CUDA-core kernel for small query
+ * batches) streams the store once and keeps, per query, a candidate list by approximate fp32
+ * score; an exact binary64 pass rescores the candidates in the reference's summation order,
+ * sorts them and CERTIFIES that no other row can reach the k-th score (approximation error
+ * bound); uncertified queries (rare: more near-ties than the candidate list holds) are redone
+ * by a binary64 scan of all rows.  Results are therefore exact, not approximate. */
+int vm_topk(vm_store *s, const void *queries, int q_dtype, int q_mem, int nq, int k, double min_score,
+            int score_mode, int sum_mode, int flags, int64_t *out_idx, double *out_score, int32_t *out_count,
+            int out_mem, vm_topk_stats *stats, void *stream);
+
+/* Row-sharded variant: every rank holds one shard whose first row has global index
+ * row_offset.  Local scan + exact rescoring, then ONE ncclAllGather of the per-rank
+ * (score, global row)[nq][k] lists over NVLink and a device-side merge (ties -> lowest global
+ * row); every rank receives identical outputs (global row indices). */
+int vm_topk_sharded(vm_store *s, vm_comm *comm, int64_t row_offset, const void *queries, int q_dtype, int q_mem,
+                    int nq, int k, double min_score, int score_mode, int sum_mode, int flags, int64_t *out_idx,
+                    double *out_score, int32_t *out_count, int out_mem, vm_topk_stats *stats, void *stream);
+
+/* The device-side merge alone (exposed for tests and for callers that gather themselves):
+ * lists [nlists][nq][k] (idx, score, count per list) -> best k per query. */
+int vm_merge_topk_lists(int device, const int64_t *idx_dev, const double *score_dev, const int32_t *count_dev,
+                        int nlists, int nq, int k, int64_t *out_idx_dev, double *out_score_dev,
+                        int32_t *out_count_dev, void *stream);
+
+/* Cross-query merge of _parallel_chunk_extraction_with_similarity
+ * (src/components/pre_llm_injector.py:235-249): max score per row id over all queries' lists
+ * (strict `>` replace), stable sort descending (first-seen order on ties), first k2.
+ * Device buffers in, device buffers out; out_count is a single int32. */
+int vm_merge_max_by_id(int device, const int64_t *idx_dev, const double *score_dev, const int32_t *count_dev,
+                       int nq, int k, int k2, int64_t *out_idx_dev, double *out_score_dev,
+                       int32_t *out_count_dev, void *stream);
+
+/* ---- scalar cosine seams ---------------------------------------------------------------
+ * n independent pairs a[i], b[i] of length dim (row-major [n][dim], VM_F32/VM_F64, host or
+ * device) -> out[i] binary64, bit-identical to PreLLMInjector._cosine_similarity
+ * (pre_llm_injector.py:374-388) / HybridRetriever._cosine_similarity
+ * (retriever_hybrid.py:655-664; used by _post_compress_chunks :492-504).
+ * zero_rule 0: norm1 == 0 or norm2 == 0 -> 0.0 ; zero_rule 1: mag1 * mag2 == 0 -> 0.0. */
+int vm_cosine_pairs(int device, const void *a, const void *b, int dtype, int mem, int64_t n, int dim, int zero_rule,
+                    int sum_mode, double *out, int out_mem, void *stream);
+
+/* ---- all-pairs threshold scorer (entity / relation dedup) ------------------------------
+ * Replaces Graph._are_same_context (src/pipeline/prune.py:67-79): S = cosine_similarity(E);
+ * fill_diagonal(S, 0); S > threshold -- generalised from `any()` to the pair set.
+ * x_dev [n][ld] bf16 or fp32 device rows (ld = vm_ld(dim)); emits every (i, j, S_ij) with
+ * i < j and S_ij > threshold (strict) into out_* (device, capacity cap, unordered);
+ * *out_count_dev (int64, device) receives the TOTAL number of hits, which may exceed cap, in
+ * which case the call reports VM_ERR_OVERFLOW on sync paths and only the first cap hits are
+ * written.  part/nparts split the upper-triangular tile grid across ranks (0/1 = all).
+ * Scores are fp32 (bf16 x bf16 products accumulated in fp32 on the tensor cores), rows
+ * normalised by cached fp32 inverse norms; pairs whose score lies within tie_eps of the
+ * threshold are re-decided in binary64 so the pair SET is exact for the stored values. */
+int vm_pairs_above(int device, const void *x_dev, int dtype, int64_t n, int dim, float threshold, int64_t cap,
+                   int64_t *out_i_dev, int64_t *out_j_dev, float *out_score_dev, int64_t *out_count_dev, int part,
+                   int nparts, int flags, void *stream);
+
+/* ---- multi-GPU plumbing -----------------------------------------------------------------
+ * One process per GPU; the 128-byte NCCL unique id is created on rank 0 and shipped to the
+ * other ranks by the host (torch.distributed / any out-of-band channel). */
+int vm_comm_unique_id(void *out128);
+int vm_comm_init_rank(vm_comm **out, int device, int nranks, int rank, const void *id128);
+int vm_comm_destroy(vm_comm *c);
+int vm_comm_nranks(const vm_comm *c);
+int vm_comm_rank(const vm_comm *c);
+
+/* ---- synthetic data (bench / tests) ------------------------------------------------------
+ * Fills rows [row0, row0+n) of a device buffer ([n][ld]) with the counter-based generator of
+ * SURVEY.md 8d (same definition as oracle/synth.py). */
+int vm_synth_fill(int device, void *rows_dev, int dtype, uint64_t seed, int64_t row0, int64_t n, int dim,
+                  uint64_t dup_period, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIDMEM_H_ */

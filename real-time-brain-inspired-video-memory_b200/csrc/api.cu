@@ -1,0 +1,692 @@
+// api.cu -- the C ABI of libvidmem.so (include/vidmem.h): handles, workspaces, orchestration of
+// scan -> merge -> exact rescoring -> (rare) exact re-scan, NCCL gather + merge for shards.
+#include "common.cuh"
+
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <string.h>
+#include <new>
+
+namespace vm {
+
+// ---- thread-local error message -----------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---- kernels implemented in the other translation units -----------------------------------
+int k_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype, int64_t n, int dim, int ld, cudaStream_t st);
+int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, cudaStream_t st);
+int k_invalidate_rows(float *inv_norms, const int64_t *rows_dev, int64_t n, int64_t size, cudaStream_t st);
+int k_normalize_queries(const void *q, int q_dtype, int nq, int nq_pad, int dim, int ld, float *out_f32, void *out_bf16,
+                        cudaStream_t st);
+int k_synth_fill(void *rows, int dtype, uint64_t seed, int64_t row0, int64_t n, int dim, int ld, uint64_t dup_period,
+                 cudaStream_t st);
+int k_merge_candidates(const uint64_t *cand, int lists, int nq, int kp, uint64_t *merged, cudaStream_t st);
+
+int k_rescore(const RescoreArgs &a, cudaStream_t st);
+int k_exact(const ExactArgs &a, cudaStream_t st);
+int k_merge_topk_lists(const void *idx, const void *score, const void *count, size_t stride_bytes, int lists, int nq, int k,
+                       int64_t *out_idx, double *out_score, int32_t *out_count, cudaStream_t st);
+int k_merge_max_by_id(const int64_t *idx, const double *score, const int32_t *count, int nq, int k, int k2,
+                      int64_t *out_idx, double *out_score, int32_t *out_count, cudaStream_t st);
+int k_cosine_pairs(const void *a, const void *b, int dtype, int64_t n, int dim, int zero_rule, int sum_mode, double *out,
+                   cudaStream_t st);
+int k_pairs_above(int device, const void *x, int dtype, int64_t n, int dim, int ld, float threshold, int64_t cap,
+                  int64_t *out_i, int64_t *out_j, float *out_score, int64_t *out_count, int part, int nparts, int flags,
+                  cudaStream_t st);
+
+static constexpr int MAXQ = 64;   // queries per scan pass
+static constexpr int MAXK = 64;   // k and candidate-list bound
+static constexpr int XCTAS = 148; // exact-scan grid
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+struct Buf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes) return VM_OK;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e)); return VM_ERR_OOM; }
+        bytes = need;
+        return VM_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct Workspace {
+    bool ready = false;
+    int lists_max = 0;
+    Buf q_raw, q_f32, q_bf16, cand, merged, o_idx, o_score, o_count, flags, xs, xr, xc, taken, gather_send, gather_recv, misc;
+    int32_t *h_uncert = nullptr;  // pinned
+    void release()
+    {
+        Buf *all[] = {&q_raw, &q_f32, &q_bf16, &cand, &merged, &o_idx, &o_score, &o_count, &flags, &xs, &xr, &xc, &taken,
+                      &gather_send, &gather_recv, &misc};
+        for (Buf *b : all) b->release();
+        if (h_uncert) cudaFreeHost(h_uncert);
+        h_uncert = nullptr;
+        ready = false;
+    }
+};
+
+}  // namespace vm
+
+using namespace vm;
+
+struct vm_store {
+    int device = 0, dim = 0, ld = 0, dtype = VM_F32, sm_count = 148;
+    int64_t capacity = 0, size = 0;
+    void *rows = nullptr;
+    float *inv_norms = nullptr;
+    bool owns = false;
+    Buf stage, stage_idx;
+    Workspace ws;
+};
+
+struct vm_comm {
+    void *nccl = nullptr;  // ncclComm_t
+    int nranks = 1, rank = 0, device = 0;
+};
+
+// ---- NCCL, resolved at run time so the library loads on hosts without it --------------------
+struct Id128 { char b[128]; };
+namespace {
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, /*ncclUniqueId by value*/ Id128, int) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi g_nccl;
+
+static int nccl_load()
+{
+    if (g_nccl.h) return VM_OK;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    VM_REQUIRE(h, VM_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(void *))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void **, int, Id128, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(h, "ncclAllGather");
+    g_nccl.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    VM_REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllGather && g_nccl.CommDestroy, VM_ERR_NCCL,
+               "libnccl lacks a required symbol");
+    g_nccl.h = h;
+    return VM_OK;
+}
+#define VM_NCCL_CHECK(expr)                                                                            \
+    do {                                                                                               \
+        int _r = (expr);                                                                               \
+        if (_r != 0) {                                                                                 \
+            set_error("%s failed: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?"); \
+            return VM_ERR_NCCL;                                                                        \
+        }                                                                                              \
+    } while (0)
+
+// ---- small helpers ----------------------------------------------------------------------------
+static int check_arch(int device, int *sm_count)
+{
+    cudaDeviceProp p;
+    VM_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
+    VM_REQUIRE(p.major == 10, VM_ERR_UNSUPPORTED, "device %d is sm_%d%d; libvidmem is built for sm_100a only", device,
+               p.major, p.minor);
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    return VM_OK;
+}
+
+static int ws_prepare(vm_store *s)
+{
+    Workspace &w = s->ws;
+    if (w.ready) return VM_OK;
+    int lists = 2 * s->sm_count;
+    w.lists_max = lists;
+    int rc;
+#define ENS(b, bytes) if ((rc = (b).ensure(bytes)) != VM_OK) return rc
+    ENS(w.q_raw, (size_t)MAXQ * s->dim * 8);
+    ENS(w.q_f32, (size_t)MAXQ * s->ld * 4);
+    ENS(w.q_bf16, (size_t)MAXQ * s->ld * 2);
+    ENS(w.cand, (size_t)lists * MAXQ * MAXK * 8);
+    ENS(w.merged, (size_t)MAXQ * MAXK * 8);
+    ENS(w.o_idx, (size_t)MAXQ * MAXK * 8);
+    ENS(w.o_score, (size_t)MAXQ * MAXK * 8);
+    ENS(w.o_count, (size_t)MAXQ * 4);
+    ENS(w.flags, (size_t)(MAXQ + 1) * 4);
+    ENS(w.xs, (size_t)XCTAS * MAXQ * MAXK * 8);
+    ENS(w.xr, (size_t)XCTAS * MAXQ * MAXK * 4);
+    ENS(w.xc, (size_t)XCTAS * MAXQ * 4);
+    ENS(w.taken, (size_t)MAXQ * XCTAS * MAXK);
+#undef ENS
+    VM_CUDA_CHECK(cudaMallocHost((void **)&w.h_uncert, 64));
+    w.ready = true;
+    return VM_OK;
+}
+
+static double scan_eps(int kernel, int store_dtype, int dim)
+{
+    // Bound on |approximate cosine - exact cosine| (DESIGN.md "certification").
+    double fp32_acc = (double)(dim + 16) * 1.1920928955078125e-07;  // (D+16) * 2^-23
+    if (kernel == 1) return fp32_acc;                                  // CUDA-core fp32 scan
+    if (store_dtype == VM_F32) return 1.953125e-3 + fp32_acc;          // tf32: both operands truncated, 2 * 2^-10
+    return 3.90625e-3 + fp32_acc;                                      // bf16 store, query rounded to bf16: 2^-8
+}
+
+// ---- library --------------------------------------------------------------------------------
+extern "C" int vm_version(void) { return VM_ABI_VERSION; }
+extern "C" const char *vm_last_error(void) { return g_err; }
+
+extern "C" int vm_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem)
+{
+    cudaDeviceProp p;
+    VM_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (total_mem) *total_mem = p.totalGlobalMem;
+    return VM_OK;
+}
+
+extern "C" int vm_ld(int dim) { return ld_for_dim(dim); }
+
+// ---- store -----------------------------------------------------------------------------------
+static int store_new(vm_store **out, int device, int dim, int dtype, int64_t capacity)
+{
+    VM_REQUIRE(out, VM_ERR_BADARG, "out is NULL");
+    VM_REQUIRE(dim >= 1 && dim <= 4096, VM_ERR_BADARG, "dim %d outside [1, 4096]", dim);
+    VM_REQUIRE(dtype == VM_F32 || dtype == VM_BF16, VM_ERR_BADARG, "store dtype must be VM_F32 or VM_BF16");
+    VM_REQUIRE(capacity >= 1 && capacity < 0xFFFFFFFFLL, VM_ERR_BADARG, "capacity %lld outside [1, 2^32-2]", (long long)capacity);
+    int sms = 0;
+    int rc = check_arch(device, &sms);
+    if (rc != VM_OK) return rc;
+    vm_store *s = new (std::nothrow) vm_store();
+    VM_REQUIRE(s, VM_ERR_OOM, "host allocation failed");
+    s->device = device; s->dim = dim; s->ld = ld_for_dim(dim); s->dtype = dtype; s->capacity = capacity; s->sm_count = sms;
+    *out = s;
+    return VM_OK;
+}
+
+extern "C" int vm_store_create(vm_store **out, int device, int dim, int dtype, int64_t capacity)
+{
+    int rc = store_new(out, device, dim, dtype, capacity);
+    if (rc != VM_OK) return rc;
+    vm_store *s = *out;
+    DeviceGuard g(device);
+    size_t bytes = (size_t)capacity * s->ld * dtype_size(dtype);
+    cudaError_t e = cudaMalloc(&s->rows, bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->inv_norms, (size_t)capacity * 4);
+    if (e != cudaSuccess) {
+        set_error("store allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        if (s->rows) cudaFree(s->rows);
+        delete s;
+        *out = nullptr;
+        return VM_ERR_OOM;
+    }
+    s->owns = true;
+    return VM_OK;
+}
+
+extern "C" int vm_store_attach(vm_store **out, int device, int dim, int dtype, int64_t capacity, void *rows_dev,
+                               float *inv_norms_dev)
+{
+    VM_REQUIRE(rows_dev && inv_norms_dev, VM_ERR_BADARG, "attach needs device buffers");
+    VM_REQUIRE(((uintptr_t)rows_dev & 127) == 0, VM_ERR_BADARG, "rows buffer must be 128-byte aligned");
+    int rc = store_new(out, device, dim, dtype, capacity);
+    if (rc != VM_OK) return rc;
+    (*out)->rows = rows_dev;
+    (*out)->inv_norms = inv_norms_dev;
+    (*out)->owns = false;
+    return VM_OK;
+}
+
+extern "C" int vm_store_destroy(vm_store *s)
+{
+    if (!s) return VM_OK;
+    DeviceGuard g(s->device);
+    cudaDeviceSynchronize();
+    if (s->owns) { cudaFree(s->rows); cudaFree(s->inv_norms); }
+    s->stage.release(); s->stage_idx.release();
+    s->ws.release();
+    delete s;
+    return VM_OK;
+}
+
+extern "C" int64_t vm_store_size(const vm_store *s) { return s ? s->size : -1; }
+extern "C" int64_t vm_store_capacity(const vm_store *s) { return s ? s->capacity : -1; }
+extern "C" int vm_store_dim(const vm_store *s) { return s ? s->dim : -1; }
+extern "C" int vm_store_ld(const vm_store *s) { return s ? s->ld : -1; }
+
+static int store_write(vm_store *s, int64_t row0, const void *rows, int src_dtype, int src_mem, int64_t n, cudaStream_t st)
+{
+    VM_REQUIRE(src_dtype == VM_F32 || src_dtype == VM_BF16 || src_dtype == VM_F64, VM_ERR_BADARG, "bad source dtype");
+    if (n == 0) return VM_OK;
+    VM_REQUIRE(rows, VM_ERR_BADARG, "rows is NULL");
+    DeviceGuard g(s->device);
+    const void *src = rows;
+    if (src_mem == VM_MEM_HOST) {
+        size_t bytes = (size_t)n * s->dim * dtype_size(src_dtype);
+        int rc = s->stage.ensure(bytes);
+        if (rc != VM_OK) return rc;
+        VM_CUDA_CHECK(cudaMemcpyAsync(s->stage.p, rows, bytes, cudaMemcpyHostToDevice, st));
+        src = s->stage.p;
+    }
+    char *dst = (char *)s->rows + (size_t)row0 * s->ld * dtype_size(s->dtype);
+    int rc = k_convert_rows(src, src_dtype, dst, s->dtype, n, s->dim, s->ld, st);
+    if (rc != VM_OK) return rc;
+    return k_row_inv_norms(s->rows, s->dtype, s->inv_norms, row0, row0 + n, s->ld, st);
+}
+
+extern "C" int vm_store_append(vm_store *s, const void *rows, int src_dtype, int src_mem, int64_t n, int64_t *first_row,
+                               void *stream)
+{
+    VM_REQUIRE(s, VM_ERR_BADARG, "store is NULL");
+    VM_REQUIRE(n >= 0, VM_ERR_BADARG, "n < 0");
+    VM_REQUIRE(s->size + n <= s->capacity, VM_ERR_OVERFLOW, "append of %lld rows exceeds capacity %lld (size %lld)",
+               (long long)n, (long long)s->capacity, (long long)s->size);
+    int rc = store_write(s, s->size, rows, src_dtype, src_mem, n, (cudaStream_t)stream);
+    if (rc != VM_OK) return rc;
+    if (first_row) *first_row = s->size;
+    s->size += n;
+    return VM_OK;
+}
+
+extern "C" int vm_store_update(vm_store *s, int64_t row0, const void *rows, int src_dtype, int src_mem, int64_t n, void *stream)
+{
+    VM_REQUIRE(s, VM_ERR_BADARG, "store is NULL");
+    VM_REQUIRE(row0 >= 0 && n >= 0 && row0 + n <= s->size, VM_ERR_BADARG, "update range [%lld, %lld) outside [0, %lld)",
+               (long long)row0, (long long)(row0 + n), (long long)s->size);
+    return store_write(s, row0, rows, src_dtype, src_mem, n, (cudaStream_t)stream);
+}
+
+extern "C" int vm_store_invalidate(vm_store *s, const int64_t *rows_host, int64_t n, void *stream)
+{
+    VM_REQUIRE(s, VM_ERR_BADARG, "store is NULL");
+    if (n <= 0) return VM_OK;
+    VM_REQUIRE(rows_host, VM_ERR_BADARG, "rows is NULL");
+    DeviceGuard g(s->device);
+    int rc = s->stage_idx.ensure((size_t)n * 8);
+    if (rc != VM_OK) return rc;
+    VM_CUDA_CHECK(cudaMemcpyAsync(s->stage_idx.p, rows_host, (size_t)n * 8, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return k_invalidate_rows(s->inv_norms, (const int64_t *)s->stage_idx.p, n, s->size, (cudaStream_t)stream);
+}
+
+extern "C" int vm_store_set_size(vm_store *s, int64_t n, int64_t recompute_from_row, void *stream)
+{
+    VM_REQUIRE(s, VM_ERR_BADARG, "store is NULL");
+    VM_REQUIRE(n >= 0 && n <= s->capacity, VM_ERR_BADARG, "size %lld outside [0, capacity]", (long long)n);
+    DeviceGuard g(s->device);
+    s->size = n;
+    if (recompute_from_row >= 0 && recompute_from_row < n)
+        return k_row_inv_norms(s->rows, s->dtype, s->inv_norms, recompute_from_row, n, s->ld, (cudaStream_t)stream);
+    return VM_OK;
+}
+
+extern "C" int vm_store_clear(vm_store *s)
+{
+    VM_REQUIRE(s, VM_ERR_BADARG, "store is NULL");
+    s->size = 0;
+    return VM_OK;
+}
+
+// ---- top-k ------------------------------------------------------------------------------------
+namespace {
+struct TopkCall {
+    vm_store *s;
+    const void *queries;  // host or device, [nq][dim]
+    int q_dtype, q_mem, nq, k;
+    double min_score;
+    int score_mode, sum_mode, flags;
+    int64_t row_offset;
+    // device destinations for this batch
+    int64_t *d_idx;
+    double *d_score;
+    int32_t *d_count;
+    cudaStream_t st;
+    vm_topk_stats *stats;
+};
+}  // namespace
+
+// One batch of <= MAXQ queries; results land in c.d_* (device).  May synchronise the stream
+// (unless VM_FLAG_ASYNC) to learn whether any query needs the exact re-scan.
+static int topk_batch(const TopkCall &c)
+{
+    vm_store *s = c.s;
+    Workspace &w = s->ws;
+    cudaStream_t st = c.st;
+    const void *q_dev = c.queries;
+    if (c.q_mem == VM_MEM_HOST) {
+        VM_CUDA_CHECK(cudaMemcpyAsync(w.q_raw.p, c.queries, (size_t)c.nq * s->dim * dtype_size(c.q_dtype),
+                                      cudaMemcpyHostToDevice, st));
+        q_dev = w.q_raw.p;
+    }
+    FinalizeArgs fin{c.k, c.min_score, c.score_mode, c.row_offset, c.d_idx, c.d_score, c.d_count};
+    ExactArgs ex{s->rows, s->inv_norms, s->dtype, s->ld, s->dim, s->size, q_dev, c.q_dtype, c.nq, c.k, c.sum_mode,
+                 nullptr, (double *)w.xs.p, (uint32_t *)w.xr.p, (int32_t *)w.xc.p, (uint8_t *)w.taken.p, XCTAS, fin};
+    int launches = 0;
+    if (c.stats) { c.stats->uncertified = 0; c.stats->candidates = 0; c.stats->scan_ctas = 0; }
+
+    // choose the scan kernel
+    int kernel = 0, kp = 0;
+    if (!(c.flags & VM_FLAG_FORCE_EXACT) && s->size > 0) {
+        int kp_tc = c.k <= 16 ? 32 : (c.k <= 48 ? 64 : 0);
+        int kp_simt = c.k <= 24 ? (c.k + 8 > 16 ? ((c.k + 8 + 7) & ~7) : 16) : 0;
+        bool tc_ok = kp_tc > 0 && scan_tc_supported(s->dtype, s->dim, c.nq, kp_tc);
+        bool want_tc = (c.flags & VM_FLAG_FORCE_TC) || (c.nq > scan_simt_max_queries() && !(c.flags & VM_FLAG_FORCE_SIMT));
+        if (want_tc && tc_ok) { kernel = 2; kp = kp_tc; }
+        else if (kp_simt > 0) { kernel = 1; kp = kp_simt; }
+        else if (tc_ok) { kernel = 2; kp = kp_tc; }
+    }
+    if (kernel == 0) {
+        int rc = k_exact(ex, st);
+        if (rc != VM_OK) return rc;
+        launches += 2;
+        if (c.stats) { c.stats->scan_kernel = 0; c.stats->scan_launches += launches; }
+        return VM_OK;
+    }
+
+    int nq_pad = kernel == 2 ? ((c.nq + 15) & ~15) : c.nq;
+    int rc = k_normalize_queries(q_dev, c.q_dtype, c.nq, nq_pad, s->dim, s->ld, (float *)w.q_f32.p,
+                                 (kernel == 2 && s->dtype == VM_BF16) ? w.q_bf16.p : nullptr, st);
+    if (rc != VM_OK) return rc;
+    ++launches;
+
+    ScanArgs a;
+    a.rows = s->rows; a.inv_norms = s->inv_norms; a.dtype = s->dtype; a.n = s->size; a.dim = s->dim; a.ld = s->ld;
+    a.queries = (const float *)w.q_f32.p; a.nq = c.nq; a.kp = kp; a.cand = (uint64_t *)w.cand.p; a.stream = st;
+    if (kernel == 1) {
+        int64_t need = (s->size + 31) / 32;
+        a.ctas = (int)imin64(need, 2 * s->sm_count);
+        rc = launch_scan_simt(a);
+        launches += (c.nq + 7) / 8;
+    } else {
+        int64_t tiles = (s->size + 127) / 128;
+        a.ctas = (int)imin64(tiles, s->sm_count);
+        rc = launch_scan_tc(a, s->dtype == VM_BF16 ? w.q_bf16.p : w.q_f32.p);
+        launches += 1;
+    }
+    if (rc != VM_OK) return rc;
+
+    rc = k_merge_candidates(a.cand, a.ctas, c.nq, kp, (uint64_t *)w.merged.p, st);
+    if (rc != VM_OK) return rc;
+    int32_t *flags = (int32_t *)w.flags.p;
+    int32_t *uncert = flags + MAXQ;
+    VM_CUDA_CHECK(cudaMemsetAsync(uncert, 0, 4, st));
+    RescoreArgs rs{(const uint64_t *)w.merged.p, kp, s->rows, s->inv_norms, s->dtype, s->ld, s->dim, s->size, q_dev,
+                   c.q_dtype, c.nq, scan_eps(kernel, s->dtype, s->dim), c.sum_mode, fin, flags, uncert};
+    rc = k_rescore(rs, st);
+    if (rc != VM_OK) return rc;
+    launches += 2;
+
+    ex.flags = flags;
+    int n_uncert = 0;
+    if (c.flags & VM_FLAG_ASYNC) {
+        rc = k_exact(ex, st);  // device-side conditional: returns immediately when nothing is flagged
+        if (rc != VM_OK) return rc;
+        launches += 2;
+        n_uncert = -1;
+    } else {
+        VM_CUDA_CHECK(cudaMemcpyAsync(w.h_uncert, uncert, 4, cudaMemcpyDeviceToHost, st));
+        VM_CUDA_CHECK(cudaStreamSynchronize(st));
+        n_uncert = *w.h_uncert;
+        if (n_uncert > 0) {
+            rc = k_exact(ex, st);
+            if (rc != VM_OK) return rc;
+            launches += 2;
+        }
+    }
+    if (c.stats) {
+        c.stats->scan_kernel = kernel;
+        c.stats->scan_launches += launches;
+        c.stats->uncertified += n_uncert > 0 ? n_uncert : 0;
+        c.stats->candidates = kp;
+        c.stats->scan_ctas = a.ctas;
+    }
+    return VM_OK;
+}
+
+static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const void *queries, int q_dtype, int q_mem, int nq,
+                       int k, double min_score, int score_mode, int sum_mode, int flags, int64_t *out_idx,
+                       double *out_score, int32_t *out_count, int out_mem, vm_topk_stats *stats, void *stream)
+{
+    VM_REQUIRE(s, VM_ERR_BADARG, "store is NULL");
+    VM_REQUIRE(nq >= 0, VM_ERR_BADARG, "nq < 0");
+    VM_REQUIRE(k >= 1 && k <= MAXK, VM_ERR_BADARG, "k %d outside [1, %d]", k, MAXK);
+    VM_REQUIRE(q_dtype == VM_F32 || q_dtype == VM_BF16 || q_dtype == VM_F64, VM_ERR_BADARG, "bad query dtype");
+    VM_REQUIRE(score_mode == VM_SCORE_RAW || score_mode == VM_SCORE_NEO4J, VM_ERR_BADARG, "bad score_mode");
+    VM_REQUIRE(sum_mode == VM_SUM_NAIVE || sum_mode == VM_SUM_NEUMAIER, VM_ERR_BADARG, "bad sum_mode");
+    VM_REQUIRE(!(flags & VM_FLAG_ASYNC) || (out_mem == VM_MEM_DEVICE && q_mem == VM_MEM_DEVICE), VM_ERR_BADARG,
+               "VM_FLAG_ASYNC needs device queries and device outputs");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (nq == 0) return VM_OK;
+    VM_REQUIRE(queries && out_idx && out_score && out_count, VM_ERR_BADARG, "NULL buffer");
+    DeviceGuard g(s->device);
+    VM_REQUIRE(g.ok, VM_ERR_CUDA, "cannot select device %d", s->device);
+    int rc = ws_prepare(s);
+    if (rc != VM_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace &w = s->ws;
+    const size_t qrow = (size_t)s->dim * dtype_size(q_dtype);
+    const bool sharded = comm && comm->nranks > 1;
+
+    for (int q0 = 0; q0 < nq; q0 += MAXQ) {
+        int nb = nq - q0 < MAXQ ? nq - q0 : MAXQ;
+        // where this batch's local results go
+        bool direct = out_mem == VM_MEM_DEVICE && !sharded;
+        int64_t *d_idx = direct ? out_idx + (size_t)q0 * k : (int64_t *)w.o_idx.p;
+        double *d_score = direct ? out_score + (size_t)q0 * k : (double *)w.o_score.p;
+        int32_t *d_count = direct ? out_count + q0 : (int32_t *)w.o_count.p;
+        if (sharded) {
+            // pack [idx | score | count] contiguously so ONE all-gather moves the batch
+            size_t seg = (size_t)nb * k * 8;
+            size_t per_rank = 2 * seg + (((size_t)nb * 4 + 7) & ~(size_t)7);
+            rc = w.gather_send.ensure(per_rank);
+            if (rc == VM_OK) rc = w.gather_recv.ensure(per_rank * comm->nranks);
+            if (rc != VM_OK) return rc;
+            d_idx = (int64_t *)w.gather_send.p;
+            d_score = (double *)((char *)w.gather_send.p + seg);
+            d_count = (int32_t *)((char *)w.gather_send.p + 2 * seg);
+        }
+        TopkCall c{s, (const char *)queries + (size_t)q0 * qrow, q_dtype, q_mem, nb, k, min_score, score_mode, sum_mode,
+                   flags, row_offset, d_idx, d_score,
+                   d_count, st, stats};
+        rc = topk_batch(c);
+        if (rc != VM_OK) return rc;
+        if (sharded) {
+            size_t seg = (size_t)nb * k * 8;
+            size_t per_rank = 2 * seg + (((size_t)nb * 4 + 7) & ~(size_t)7);
+            VM_NCCL_CHECK(g_nccl.AllGather(w.gather_send.p, w.gather_recv.p, per_rank, /*ncclInt8*/ 0, comm->nccl, st));
+            bool dd = out_mem == VM_MEM_DEVICE;
+            int64_t *m_idx = dd ? out_idx + (size_t)q0 * k : (int64_t *)w.o_idx.p;
+            double *m_score = dd ? out_score + (size_t)q0 * k : (double *)w.o_score.p;
+            int32_t *m_count = dd ? out_count + q0 : (int32_t *)w.o_count.p;
+            const char *rb = (const char *)w.gather_recv.p;
+            rc = k_merge_topk_lists(rb, rb + seg, rb + 2 * seg, per_rank, comm->nranks, nb, k, m_idx, m_score, m_count, st);
+            if (rc != VM_OK) return rc;
+            if (stats) stats->scan_launches += 2;
+            d_idx = m_idx; d_score = m_score; d_count = m_count;
+        }
+        if (out_mem == VM_MEM_HOST) {
+            VM_CUDA_CHECK(cudaMemcpyAsync(out_idx + (size_t)q0 * k, d_idx, (size_t)nb * k * 8, cudaMemcpyDeviceToHost, st));
+            VM_CUDA_CHECK(cudaMemcpyAsync(out_score + (size_t)q0 * k, d_score, (size_t)nb * k * 8, cudaMemcpyDeviceToHost, st));
+            VM_CUDA_CHECK(cudaMemcpyAsync(out_count + q0, d_count, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+            VM_CUDA_CHECK(cudaStreamSynchronize(st));
+        }
+    }
+    return VM_OK;
+}
+
+extern "C" int vm_topk(vm_store *s, const void *queries, int q_dtype, int q_mem, int nq, int k, double min_score,
+                       int score_mode, int sum_mode, int flags, int64_t *out_idx, double *out_score, int32_t *out_count,
+                       int out_mem, vm_topk_stats *stats, void *stream)
+{
+    return topk_common(s, nullptr, 0, queries, q_dtype, q_mem, nq, k, min_score, score_mode, sum_mode, flags, out_idx,
+                       out_score, out_count, out_mem, stats, stream);
+}
+
+extern "C" int vm_topk_sharded(vm_store *s, vm_comm *comm, int64_t row_offset, const void *queries, int q_dtype, int q_mem,
+                               int nq, int k, double min_score, int score_mode, int sum_mode, int flags, int64_t *out_idx,
+                               double *out_score, int32_t *out_count, int out_mem, vm_topk_stats *stats, void *stream)
+{
+    VM_REQUIRE(comm, VM_ERR_BADARG, "comm is NULL");
+    return topk_common(s, comm, row_offset, queries, q_dtype, q_mem, nq, k, min_score, score_mode, sum_mode, flags, out_idx,
+                       out_score, out_count, out_mem, stats, stream);
+}
+
+extern "C" int vm_merge_topk_lists(int device, const int64_t *idx_dev, const double *score_dev, const int32_t *count_dev,
+                                   int nlists, int nq, int k, int64_t *out_idx_dev, double *out_score_dev,
+                                   int32_t *out_count_dev, void *stream)
+{
+    VM_REQUIRE(idx_dev && score_dev && count_dev && out_idx_dev && out_score_dev && out_count_dev, VM_ERR_BADARG, "NULL buffer");
+    VM_REQUIRE(nlists >= 1 && nq >= 1 && k >= 1, VM_ERR_BADARG, "bad shape");
+    DeviceGuard g(device);
+    // three separate arrays: each has its own per-list stride, so run with stride == idx stride
+    // only when they coincide (nq*k*8 for idx/score, nq*4 for count) -> use a packed copy-free
+    // trick: launch with per-array strides equalised by passing count through a widened view.
+    // Simplest correct path: the kernel takes ONE stride, so gather the counts to that stride.
+    size_t stride = (size_t)nq * k * 8;
+    static thread_local Buf cnt_wide;
+    int rc = cnt_wide.ensure(stride * nlists);
+    if (rc != VM_OK) return rc;
+    VM_CUDA_CHECK(cudaMemcpy2DAsync(cnt_wide.p, stride, count_dev, (size_t)nq * 4, (size_t)nq * 4, nlists,
+                                    cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return k_merge_topk_lists(idx_dev, score_dev, cnt_wide.p, stride, nlists, nq, k, out_idx_dev, out_score_dev,
+                              out_count_dev, (cudaStream_t)stream);
+}
+
+extern "C" int vm_merge_max_by_id(int device, const int64_t *idx_dev, const double *score_dev, const int32_t *count_dev,
+                                  int nq, int k, int k2, int64_t *out_idx_dev, double *out_score_dev, int32_t *out_count_dev,
+                                  void *stream)
+{
+    VM_REQUIRE(idx_dev && score_dev && count_dev && out_idx_dev && out_score_dev && out_count_dev, VM_ERR_BADARG, "NULL buffer");
+    VM_REQUIRE(nq >= 1 && k >= 1 && k2 >= 1, VM_ERR_BADARG, "bad shape");
+    DeviceGuard g(device);
+    return k_merge_max_by_id(idx_dev, score_dev, count_dev, nq, k, k2, out_idx_dev, out_score_dev, out_count_dev,
+                             (cudaStream_t)stream);
+}
+
+// ---- scalar cosine seams ----------------------------------------------------------------------
+extern "C" int vm_cosine_pairs(int device, const void *a, const void *b, int dtype, int mem, int64_t n, int dim, int zero_rule,
+                               int sum_mode, double *out, int out_mem, void *stream)
+{
+    VM_REQUIRE(n >= 0 && dim >= 0, VM_ERR_BADARG, "bad shape");
+    VM_REQUIRE(dtype == VM_F32 || dtype == VM_F64, VM_ERR_BADARG, "dtype must be VM_F32 or VM_F64");
+    if (n == 0) return VM_OK;
+    VM_REQUIRE(a && b && out, VM_ERR_BADARG, "NULL buffer");
+    int rc = check_arch(device, nullptr);
+    if (rc != VM_OK) return rc;
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    static thread_local Buf da, db, dout;
+    size_t bytes = (size_t)n * dim * dtype_size(dtype);
+    const void *pa = a, *pb = b;
+    if (mem == VM_MEM_HOST) {
+        if ((rc = da.ensure(bytes ? bytes : 8)) != VM_OK || (rc = db.ensure(bytes ? bytes : 8)) != VM_OK) return rc;
+        VM_CUDA_CHECK(cudaMemcpyAsync(da.p, a, bytes, cudaMemcpyHostToDevice, st));
+        VM_CUDA_CHECK(cudaMemcpyAsync(db.p, b, bytes, cudaMemcpyHostToDevice, st));
+        pa = da.p; pb = db.p;
+    }
+    double *po = out;
+    if (out_mem == VM_MEM_HOST) {
+        if ((rc = dout.ensure((size_t)n * 8)) != VM_OK) return rc;
+        po = (double *)dout.p;
+    }
+    rc = k_cosine_pairs(pa, pb, dtype, n, dim, zero_rule, sum_mode, po, st);
+    if (rc != VM_OK) return rc;
+    if (out_mem == VM_MEM_HOST) {
+        VM_CUDA_CHECK(cudaMemcpyAsync(out, po, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        VM_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    return VM_OK;
+}
+
+// ---- all-pairs --------------------------------------------------------------------------------
+extern "C" int vm_pairs_above(int device, const void *x_dev, int dtype, int64_t n, int dim, float threshold, int64_t cap,
+                              int64_t *out_i_dev, int64_t *out_j_dev, float *out_score_dev, int64_t *out_count_dev, int part,
+                              int nparts, int flags, void *stream)
+{
+    VM_REQUIRE(x_dev && out_count_dev, VM_ERR_BADARG, "NULL buffer");
+    VM_REQUIRE(cap == 0 || (out_i_dev && out_j_dev && out_score_dev), VM_ERR_BADARG, "NULL output with cap > 0");
+    VM_REQUIRE(dtype == VM_F32 || dtype == VM_BF16, VM_ERR_BADARG, "dtype must be VM_F32 or VM_BF16");
+    VM_REQUIRE(n >= 0 && n < (1LL << 31), VM_ERR_BADARG, "n outside [0, 2^31)");
+    VM_REQUIRE(dim >= 1 && dim <= 4096, VM_ERR_BADARG, "dim outside [1, 4096]");
+    VM_REQUIRE(nparts >= 1 && part >= 0 && part < nparts, VM_ERR_BADARG, "bad part/nparts");
+    int rc = check_arch(device, nullptr);
+    if (rc != VM_OK) return rc;
+    DeviceGuard g(device);
+    return k_pairs_above(device, x_dev, dtype, n, dim, ld_for_dim(dim), threshold, cap, out_i_dev, out_j_dev, out_score_dev,
+                         out_count_dev, part, nparts, flags, (cudaStream_t)stream);
+}
+
+// ---- communicator -----------------------------------------------------------------------------
+extern "C" int vm_comm_unique_id(void *out128)
+{
+    VM_REQUIRE(out128, VM_ERR_BADARG, "out is NULL");
+    int rc = nccl_load();
+    if (rc != VM_OK) return rc;
+    VM_NCCL_CHECK(g_nccl.GetUniqueId(out128));
+    return VM_OK;
+}
+
+extern "C" int vm_comm_init_rank(vm_comm **out, int device, int nranks, int rank, const void *id128)
+{
+    VM_REQUIRE(out && id128, VM_ERR_BADARG, "NULL argument");
+    VM_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, VM_ERR_BADARG, "bad rank %d / nranks %d", rank, nranks);
+    int rc = nccl_load();
+    if (rc != VM_OK) return rc;
+    DeviceGuard g(device);
+    VM_CUDA_CHECK(cudaSetDevice(device));
+    vm_comm *c = new (std::nothrow) vm_comm();
+    VM_REQUIRE(c, VM_ERR_OOM, "host allocation failed");
+    Id128 id;
+    memcpy(id.b, id128, 128);
+    int r = g_nccl.CommInitRank(&c->nccl, nranks, id, rank);
+    if (r != 0) {
+        set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+        delete c;
+        return VM_ERR_NCCL;
+    }
+    c->nranks = nranks; c->rank = rank; c->device = device;
+    *out = c;
+    return VM_OK;
+}
+
+extern "C" int vm_comm_destroy(vm_comm *c)
+{
+    if (!c) return VM_OK;
+    if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
+    delete c;
+    return VM_OK;
+}
+extern "C" int vm_comm_nranks(const vm_comm *c) { return c ? c->nranks : -1; }
+extern "C" int vm_comm_rank(const vm_comm *c) { return c ? c->rank : -1; }
+
+// ---- synthetic data ---------------------------------------------------------------------------
+extern "C" int vm_synth_fill(int device, void *rows_dev, int dtype, uint64_t seed, int64_t row0, int64_t n, int dim,
+                             uint64_t dup_period, void *stream)
+{
+    VM_REQUIRE(rows_dev, VM_ERR_BADARG, "rows is NULL");
+    VM_REQUIRE(dtype == VM_F32 || dtype == VM_BF16, VM_ERR_BADARG, "dtype must be VM_F32 or VM_BF16");
+    DeviceGuard g(device);
+    return k_synth_fill(rows_dev, dtype, seed, row0, n, dim, ld_for_dim(dim), dup_period, (cudaStream_t)stream);
+}

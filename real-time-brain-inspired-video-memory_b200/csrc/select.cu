@@ -1,0 +1,520 @@
+// select.cu -- everything after the streaming scan: candidate merge, binary64 rescoring in the
+// reference's summation order + certification, the always-exact binary64 scan used for
+// uncertified queries, the cross-shard merge and the cross-query max-by-id merge.
+#include "common.cuh"
+
+namespace vm {
+
+// =========================================================================================
+// 1. merge per-CTA candidate lists -> one descending list of kp keys per query
+// =========================================================================================
+// cand [lists][nq][kp] -> merged [nq][kp] (descending, 0 = empty).  One CTA per query.
+// Each thread owns a strided slice of the lists*kp keys and keeps its local maximum; every
+// round a block-wide max picks the winner (keys are unique), the owner clears it and rescans.
+__global__ void __launch_bounds__(256) merge_candidates_kernel(const uint64_t *__restrict__ cand, int lists, int nq,
+                                                              int kp, uint64_t *__restrict__ merged)
+{
+    extern __shared__ uint64_t skeys[];  // [lists*kp]
+    __shared__ uint64_t wmax[8];
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total = lists * kp;
+    for (int e = tid; e < total; e += 256) {
+        int l = e / kp, j = e - l * kp;
+        skeys[e] = cand[((int64_t)l * nq + q) * kp + j];
+    }
+    __syncthreads();
+    uint64_t best = 0;
+    int bpos = -1;
+    for (int e = tid; e < total; e += 256)
+        if (skeys[e] > best) { best = skeys[e]; bpos = e; }
+    for (int r = 0; r < kp; ++r) {
+        uint64_t m = best;
+        for (int o = 16; o > 0; o >>= 1) {
+            uint64_t t = __shfl_xor_sync(0xffffffffu, m, o);
+            m = t > m ? t : m;
+        }
+        if (lane == 0) wmax[warp] = m;
+        __syncthreads();
+        uint64_t g = wmax[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) g = wmax[w] > g ? wmax[w] : g;
+        if (tid == 0) merged[(int64_t)q * kp + r] = g;
+        if (g != 0 && g == best) {  // unique keys: exactly one thread wins
+            skeys[bpos] = 0;
+            best = 0;
+            bpos = -1;
+            for (int e = tid; e < total; e += 256)
+                if (skeys[e] > best) { best = skeys[e]; bpos = e; }
+        }
+        __syncthreads();
+    }
+}
+
+// =========================================================================================
+// 2. exact binary64 rescoring + sort + certification
+// =========================================================================================
+
+__device__ __forceinline__ double convert_score(double c, int score_mode)
+{
+    return score_mode == VM_SCORE_NEO4J ? __ddiv_rn(__dadd_rn(1.0, c), 2.0) : c;
+}
+
+// Reference cosine on (query, row): pre_llm_injector.py:374-388 in binary64, products and sums
+// in index order.  Rows are read with their stored dtype; `dim` real columns only.
+template <bool NEUMAIER, typename T>
+__device__ double exact_cosine(const void *q, int q_dtype, int64_t qoff, const T *row, int dim)
+{
+    RefSum dot, qq, rr;
+    dot.init(); qq.init(); rr.init();
+    for (int i = 0; i < dim; ++i) {
+        double x = load_as_double(q, q_dtype, qoff + i);
+        double y = (double)load_as_float(row, i);
+        dot.add<NEUMAIER>(__dmul_rn(x, y));
+        qq.add<NEUMAIER>(__dmul_rn(x, x));
+        rr.add<NEUMAIER>(__dmul_rn(y, y));
+    }
+    double n1 = __dsqrt_rn(qq.result<NEUMAIER>());
+    double n2 = __dsqrt_rn(rr.result<NEUMAIER>());
+    if (n1 == 0.0 || n2 == 0.0) return 0.0;
+    return __ddiv_rn(dot.result<NEUMAIER>(), __dmul_rn(n1, n2));
+}
+
+// Same, with the query already staged as doubles in shared memory.
+template <bool NEUMAIER, typename T>
+__device__ double exact_cosine_sq(const double *sq, double n1, const T *row, int dim)
+{
+    RefSum dot, rr;
+    dot.init(); rr.init();
+    for (int i = 0; i < dim; ++i) {
+        double x = sq[i];
+        double y = (double)load_as_float(row, i);
+        dot.add<NEUMAIER>(__dmul_rn(x, y));
+        rr.add<NEUMAIER>(__dmul_rn(y, y));
+    }
+    double n2 = __dsqrt_rn(rr.result<NEUMAIER>());
+    if (n1 == 0.0 || n2 == 0.0) return 0.0;
+    return __ddiv_rn(dot.result<NEUMAIER>(), __dmul_rn(n1, n2));
+}
+
+// (score desc, row asc) strict order
+__device__ __forceinline__ bool better(double sa, uint32_t ra, double sb, uint32_t rb)
+{
+    return sa > sb || (sa == sb && ra < rb);
+}
+
+// One CTA (64 threads) per query.  Thread j rescoring candidate j of merged[q][0..kp).
+// eps: bound on |approximate cosine - exact cosine| of the scan that produced the candidates.
+template <bool NEUMAIER, typename T>
+__global__ void __launch_bounds__(64) rescore_kernel(const uint64_t *__restrict__ merged, int kp, const T *__restrict__ rows,
+                                                    const float *__restrict__ inv_norms, int ld, int dim, int64_t n_rows,
+                                                    const void *__restrict__ queries, int q_dtype, double eps,
+                                                    FinalizeArgs f, int32_t *__restrict__ flags,
+                                                    int32_t *__restrict__ uncertified_count)
+{
+    __shared__ double s_score[64];
+    __shared__ uint32_t s_row[64];
+    __shared__ int s_valid[64];
+    __shared__ int s_cnt;
+    const int q = blockIdx.x, j = threadIdx.x;
+    if (j == 0) s_cnt = 0;
+    uint64_t key = j < kp ? merged[(int64_t)q * kp + j] : 0;
+    bool valid = key != 0;
+    double sc = 0.0;
+    uint32_t row = 0;
+    if (valid) {
+        row = key_row(key);
+        sc = exact_cosine<NEUMAIER, T>(queries, q_dtype, (int64_t)q * dim, rows + (int64_t)row * ld, dim);
+    }
+    s_score[j] = sc;
+    s_row[j] = row;
+    s_valid[j] = valid ? 1 : 0;
+    __syncthreads();
+    int ncand = 0;
+    for (int i = 0; i < 64; ++i) ncand += s_valid[i];
+    // rank among valid candidates
+    int rank = 0;
+    if (valid)
+        for (int i = 0; i < 64; ++i)
+            if (s_valid[i] && i != j && better(s_score[i], s_row[i], sc, row)) ++rank;
+    double outv = convert_score(sc, f.score_mode);
+    bool emit = valid && rank < f.k && outv > f.min_score;
+    if (emit) {
+        f.out_idx[(int64_t)q * f.k + rank] = (int64_t)row + f.row_offset;
+        f.out_score[(int64_t)q * f.k + rank] = outv;
+        atomicAdd(&s_cnt, 1);
+    }
+    __syncthreads();
+    // certification: every non-candidate row r has approx(r) <= approx(worst candidate), hence
+    // exact(r) <= approx_worst + eps; certified iff that is strictly below the k-th exact score.
+    // Fewer than kp candidates means every scorable row of the shard is already a candidate.
+    if (valid && rank == min(f.k, ncand) - 1) {
+        bool cert = true;
+        if (ncand >= kp && (int64_t)ncand < n_rows) {
+            float worst = key_score(merged[(int64_t)q * kp + kp - 1]);
+            cert = ((double)worst + eps) < sc;
+        }
+        flags[q] = cert ? 0 : 1;
+        if (!cert) atomicAdd(uncertified_count, 1);
+    }
+    if (ncand == 0 && j == 0) flags[q] = 0;
+    if (j == 0) f.out_count[q] = s_cnt;
+    int cnt = s_cnt;
+    for (int t = cnt + j; t < f.k; t += 64) {
+        f.out_idx[(int64_t)q * f.k + t] = -1;
+        f.out_score[(int64_t)q * f.k + t] = 0.0;
+    }
+}
+
+// =========================================================================================
+// 3. always-exact binary64 scan (uncertified queries / VM_FLAG_FORCE_EXACT)
+// =========================================================================================
+// Grid-stride over 128-row tiles; thread t scores row tile*128+t against one flagged query at a
+// time.  Per-CTA exact top-k list in shared memory, updated by parallel rank-merge whenever a
+// tile produced a row that beats the current k-th entry.  Lists go to
+// xlist_*[cta][q][k]; exact_merge_kernel reduces them.
+#define XK 64
+template <bool NEUMAIER, typename T>
+__global__ void __launch_bounds__(128) exact_scan_kernel(const T *__restrict__ rows, const float *__restrict__ inv_norms,
+                                                        int64_t n, int ld, int dim, const void *__restrict__ queries,
+                                                        int q_dtype, int nq, const int32_t *__restrict__ flags, int k,
+                                                        double *__restrict__ xlist_score, uint32_t *__restrict__ xlist_row,
+                                                        int32_t *__restrict__ xlist_cnt)
+{
+    extern __shared__ double sq[];  // [dim] query as doubles
+    __shared__ double l_score[XK], n_score[XK];
+    __shared__ uint32_t l_row[XK], n_row[XK];
+    __shared__ double c_score[128];
+    __shared__ uint32_t c_row[128];
+    __shared__ int l_cnt, c_cnt;
+    __shared__ double s_n1;
+    const int tid = threadIdx.x;
+    for (int q = 0; q < nq; ++q) {
+        if (flags && flags[q] == 0) continue;  // uniform across the grid
+        __syncthreads();
+        for (int i = tid; i < dim; i += 128) sq[i] = load_as_double(queries, q_dtype, (int64_t)q * dim + i);
+        if (tid == 0) { l_cnt = 0; c_cnt = 0; }
+        __syncthreads();
+        if (tid == 0) {
+            RefSum qq; qq.init();
+            for (int i = 0; i < dim; ++i) qq.add<NEUMAIER>(__dmul_rn(sq[i], sq[i]));
+            s_n1 = __dsqrt_rn(qq.result<NEUMAIER>());
+        }
+        __syncthreads();
+        const double n1 = s_n1;
+        for (int64_t tile = blockIdx.x; tile * 128 < n; tile += gridDim.x) {
+            int64_t r = tile * 128 + tid;
+            bool live = r < n && inv_norms[r] >= 0.0f;
+            double sc = 0.0;
+            if (live) sc = exact_cosine_sq<NEUMAIER, T>(sq, n1, rows + r * (int64_t)ld, dim);
+            // candidate iff list not full or beats the current worst (k-th) entry
+            bool hit = false;
+            if (live) {
+                int lc = l_cnt;
+                hit = lc < k || better(sc, (uint32_t)r, l_score[lc - 1], l_row[lc - 1]);
+            }
+            if (hit) {
+                int p = atomicAdd(&c_cnt, 1);
+                c_score[p] = sc;
+                c_row[p] = (uint32_t)r;
+            }
+            // barrier + block-wide hit count in one step: every thread sees the same cc, so the
+            // merge branch below is taken uniformly (a plain read of c_cnt could race with the
+            // next tile's atomicAdd)
+            int cc = __syncthreads_count(hit ? 1 : 0);
+            int lc = l_cnt;
+            if (cc > 0) {
+                // rank-merge list (lc) and candidates (cc): entry e in [0, lc+cc)
+                for (int e = tid; e < lc + cc; e += 128) {
+                    double se = e < lc ? l_score[e] : c_score[e - lc];
+                    uint32_t re = e < lc ? l_row[e] : c_row[e - lc];
+                    int rank = 0;
+                    for (int i = 0; i < lc; ++i) rank += better(l_score[i], l_row[i], se, re) ? 1 : 0;
+                    for (int i = 0; i < cc; ++i) rank += better(c_score[i], c_row[i], se, re) ? 1 : 0;
+                    if (rank < k) { n_score[rank] = se; n_row[rank] = re; }
+                }
+                __syncthreads();
+                int nl = min(k, lc + cc);
+                for (int e = tid; e < nl; e += 128) { l_score[e] = n_score[e]; l_row[e] = n_row[e]; }
+                if (tid == 0) { l_cnt = nl; c_cnt = 0; }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+        int lc = l_cnt;
+        int64_t base = ((int64_t)blockIdx.x * nq + q) * k;
+        for (int e = tid; e < lc; e += 128) { xlist_score[base + e] = l_score[e]; xlist_row[base + e] = l_row[e]; }
+        if (tid == 0) xlist_cnt[(int64_t)blockIdx.x * nq + q] = lc;
+    }
+}
+
+// One CTA (256 threads) per query: k rounds of block arg-best over lists*k (score,row) pairs
+// that stay in global/L2.  Skips queries whose flag is 0.
+__global__ void __launch_bounds__(256) exact_merge_kernel(const double *__restrict__ xlist_score, const uint32_t *__restrict__ xlist_row,
+                                                         const int32_t *__restrict__ xlist_cnt, int lists, int nq, int k,
+                                                         const int32_t *__restrict__ flags, FinalizeArgs f, uint8_t *__restrict__ taken)
+{
+    __shared__ double w_s[8];
+    __shared__ uint32_t w_r[8];
+    __shared__ int w_p[8];
+    __shared__ int s_out;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (flags && flags[q] == 0) return;
+    const int total = lists * k;
+    uint8_t *tk = taken + (int64_t)q * total;
+    for (int e = tid; e < total; e += 256) tk[e] = 0;
+    if (tid == 0) s_out = 0;
+    __syncthreads();
+    auto scan_local = [&](double &bs, uint32_t &br, int &bp) {
+        bp = -1; bs = 0.0; br = 0;
+        for (int e = tid; e < total; e += 256) {
+            int l = e / k, j = e - l * k;
+            if (tk[e] || j >= xlist_cnt[(int64_t)l * nq + q]) continue;
+            int64_t g = ((int64_t)l * nq + q) * k + j;
+            double s = xlist_score[g];
+            uint32_t r = xlist_row[g];
+            if (bp < 0 || better(s, r, bs, br)) { bs = s; br = r; bp = e; }
+        }
+    };
+    double bs; uint32_t br; int bp;
+    scan_local(bs, br, bp);
+    for (int r = 0; r < f.k; ++r) {
+        double ms = bs; uint32_t mr = br; int mp = bp;
+        for (int o = 16; o > 0; o >>= 1) {
+            double ts = __shfl_xor_sync(0xffffffffu, ms, o);
+            uint32_t tr = __shfl_xor_sync(0xffffffffu, mr, o);
+            int tp = __shfl_xor_sync(0xffffffffu, mp, o);
+            if (tp >= 0 && (mp < 0 || better(ts, tr, ms, mr))) { ms = ts; mr = tr; mp = tp; }
+        }
+        if (lane == 0) { w_s[warp] = ms; w_r[warp] = mr; w_p[warp] = mp; }
+        __syncthreads();
+        ms = w_s[0]; mr = w_r[0]; mp = w_p[0];
+        for (int w = 1; w < 8; ++w)
+            if (w_p[w] >= 0 && (mp < 0 || better(w_s[w], w_r[w], ms, mr))) { ms = w_s[w]; mr = w_r[w]; mp = w_p[w]; }
+        if (mp < 0) break;  // uniform
+        double outv = convert_score(ms, f.score_mode);
+        if (tid == 0 && outv > f.min_score) {
+            f.out_idx[(int64_t)q * f.k + r] = (int64_t)mr + f.row_offset;
+            f.out_score[(int64_t)q * f.k + r] = outv;
+            s_out = r + 1;
+        }
+        if (mp == bp) {
+            tk[bp] = 1;
+            scan_local(bs, br, bp);
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    int cnt = s_out;
+    if (tid == 0) f.out_count[q] = cnt;
+    for (int t = cnt + tid; t < f.k; t += 256) {
+        f.out_idx[(int64_t)q * f.k + t] = -1;
+        f.out_score[(int64_t)q * f.k + t] = 0.0;
+    }
+}
+
+// =========================================================================================
+// 4. cross-shard merge: lists [L][nq][k] of (idx i64, score f64) + count [L][nq] -> best k
+// =========================================================================================
+// List l lives at base + l*stride (bytes) for each of the three arrays, so both the public
+// [L][nq][k] layout and the packed all-gather receive buffer are accepted.
+__global__ void __launch_bounds__(256) merge_topk_lists_kernel(const char *__restrict__ idx_b, const char *__restrict__ score_b,
+                                                              const char *__restrict__ count_b, size_t stride, int lists, int nq, int k,
+                                                              int64_t *__restrict__ out_idx, double *__restrict__ out_score,
+                                                              int32_t *__restrict__ out_count)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int total = lists * k;
+    double *s_s = (double *)smem_raw;
+    int64_t *s_i = (int64_t *)(s_s + total);
+    int *s_v = (int *)(s_i + total);
+    for (int e = tid; e < total; e += 256) {
+        int l = e / k, j = e - l * k;
+        const int64_t *idx = (const int64_t *)(idx_b + (size_t)l * stride);
+        const double *score = (const double *)(score_b + (size_t)l * stride);
+        const int32_t *count = (const int32_t *)(count_b + (size_t)l * stride);
+        int64_t g = (int64_t)q * k + j;
+        bool v = j < count[q];
+        s_s[e] = v ? score[g] : 0.0;
+        s_i[e] = v ? idx[g] : -1;
+        s_v[e] = v ? 1 : 0;
+    }
+    __syncthreads();
+    int nvalid = 0;
+    for (int e = 0; e < total; ++e) nvalid += s_v[e];
+    for (int e = tid; e < total; e += 256) {
+        if (!s_v[e]) continue;
+        int rank = 0;
+        for (int i = 0; i < total; ++i)
+            if (s_v[i] && (s_s[i] > s_s[e] || (s_s[i] == s_s[e] && s_i[i] < s_i[e]))) ++rank;
+        if (rank < k) { out_idx[(int64_t)q * k + rank] = s_i[e]; out_score[(int64_t)q * k + rank] = s_s[e]; }
+    }
+    int cnt = min(nvalid, k);
+    if (tid == 0) out_count[q] = cnt;
+    for (int t = cnt + tid; t < k; t += 256) { out_idx[(int64_t)q * k + t] = -1; out_score[(int64_t)q * k + t] = 0.0; }
+}
+
+// =========================================================================================
+// 5. cross-query merge (pre_llm_injector.py:235-249): max score per id, stable sort desc, [:k2]
+// =========================================================================================
+__global__ void __launch_bounds__(256) merge_max_by_id_kernel(const int64_t *__restrict__ idx, const double *__restrict__ score,
+                                                             const int32_t *__restrict__ count, int nq, int k, int k2,
+                                                             int64_t *__restrict__ out_idx, double *__restrict__ out_score,
+                                                             int32_t *__restrict__ out_count)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const int tid = threadIdx.x, total = nq * k;
+    double *s_s = (double *)smem_raw;       // per entry: max score of its id (valid on representatives)
+    int64_t *s_i = (int64_t *)(s_s + total);
+    int *s_rep = (int *)(s_i + total);      // 1 = first occurrence of its id (dict insertion order)
+    __shared__ int s_n;
+    if (tid == 0) s_n = 0;
+    for (int e = tid; e < total; e += 256) {
+        int qi = e / k, j = e - qi * k;
+        bool v = j < count[qi];
+        s_i[e] = v ? idx[e] : -1;
+        s_s[e] = v ? score[e] : 0.0;
+        s_rep[e] = 0;
+    }
+    __syncthreads();
+    for (int e = tid; e < total; e += 256) {
+        if (s_i[e] < 0) continue;
+        bool first = true;
+        for (int i = 0; i < e; ++i)
+            if (s_i[i] == s_i[e]) { first = false; break; }
+        if (!first) continue;
+        double m = s_s[e];
+        for (int i = e + 1; i < total; ++i)
+            if (s_i[i] == s_i[e] && score[i] > m) m = score[i];  // strict `>` replace == running max
+        s_rep[e] = 1;
+        // safe: only the representative writes its own slot, later entries read score[] (global)
+        s_s[e] = m;
+        atomicAdd(&s_n, 1);
+    }
+    __syncthreads();
+    for (int e = tid; e < total; e += 256) {
+        if (!s_rep[e]) continue;
+        int rank = 0;
+        for (int i = 0; i < total; ++i)
+            if (s_rep[i] && (s_s[i] > s_s[e] || (s_s[i] == s_s[e] && i < e))) ++rank;  // stable: first seen wins ties
+        if (rank < k2) { out_idx[rank] = s_i[e]; out_score[rank] = s_s[e]; }
+    }
+    if (tid == 0) *out_count = min(s_n, k2);
+}
+
+// =========================================================================================
+// 6. scalar cosine seams (S2 / S4), one thread per pair
+// =========================================================================================
+template <bool NEUMAIER>
+__global__ void cosine_pairs_kernel(const void *__restrict__ a, const void *__restrict__ b, int dtype, int64_t n, int dim,
+                                    int zero_rule, double *__restrict__ out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RefSum dot, aa, bb;
+    dot.init(); aa.init(); bb.init();
+    for (int c = 0; c < dim; ++c) {
+        double x = load_as_double(a, dtype, i * dim + c), y = load_as_double(b, dtype, i * dim + c);
+        dot.add<NEUMAIER>(__dmul_rn(x, y));
+        aa.add<NEUMAIER>(__dmul_rn(x, x));
+        bb.add<NEUMAIER>(__dmul_rn(y, y));
+    }
+    double n1 = __dsqrt_rn(aa.result<NEUMAIER>()), n2 = __dsqrt_rn(bb.result<NEUMAIER>());
+    double den = __dmul_rn(n1, n2);
+    bool zero = zero_rule == 0 ? (n1 == 0.0 || n2 == 0.0) : (den == 0.0);
+    out[i] = zero ? 0.0 : __ddiv_rn(dot.result<NEUMAIER>(), den);
+}
+
+// ---- host wrappers ---------------------------------------------------------------------
+int k_merge_candidates(const uint64_t *cand, int lists, int nq, int kp, uint64_t *merged, cudaStream_t st)
+{
+    size_t smem = (size_t)lists * kp * sizeof(uint64_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        VM_CUDA_CHECK(cudaFuncSetAttribute(merge_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    VM_REQUIRE(smem <= 200 * 1024, VM_ERR_UNSUPPORTED, "candidate merge: %d lists x %d exceeds shared memory", lists, kp);
+    merge_candidates_kernel<<<nq, 256, smem, st>>>(cand, lists, nq, kp, merged);
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
+
+int k_rescore(const RescoreArgs &a, cudaStream_t st)
+{
+#define LAUNCH_RS(NEU, T)                                                                                              \
+    rescore_kernel<NEU, T><<<a.nq, 64, 0, st>>>(a.merged, a.kp, (const T *)a.rows, a.inv_norms, a.ld, a.dim, a.n_rows, \
+                                                a.queries, a.q_dtype, a.eps, a.fin, a.flags, a.uncertified_count)
+    bool neu = a.sum_mode == VM_SUM_NEUMAIER;
+    if (a.dtype == VM_F32) { if (neu) LAUNCH_RS(true, float); else LAUNCH_RS(false, float); }
+    else { if (neu) LAUNCH_RS(true, __nv_bfloat16); else LAUNCH_RS(false, __nv_bfloat16); }
+#undef LAUNCH_RS
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
+
+int k_exact(const ExactArgs &a, cudaStream_t st)
+{
+    size_t smem = (size_t)a.dim * sizeof(double);
+    VM_REQUIRE(smem <= 40 * 1024, VM_ERR_UNSUPPORTED, "exact scan: dim %d too large", a.dim);
+#define LAUNCH_EX(NEU, T)                                                                                               \
+    exact_scan_kernel<NEU, T><<<a.ctas, 128, smem, st>>>((const T *)a.rows, a.inv_norms, a.n, a.ld, a.dim, a.queries, \
+                                                         a.q_dtype, a.nq, a.flags, a.k, a.xlist_score, a.xlist_row,  \
+                                                         a.xlist_cnt)
+    bool neu = a.sum_mode == VM_SUM_NEUMAIER;
+    if (a.dtype == VM_F32) { if (neu) LAUNCH_EX(true, float); else LAUNCH_EX(false, float); }
+    else { if (neu) LAUNCH_EX(true, __nv_bfloat16); else LAUNCH_EX(false, __nv_bfloat16); }
+#undef LAUNCH_EX
+    VM_CUDA_CHECK(cudaGetLastError());
+    exact_merge_kernel<<<a.nq, 256, 0, st>>>(a.xlist_score, a.xlist_row, a.xlist_cnt, a.ctas, a.nq, a.k, a.flags, a.fin, a.taken);
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
+int k_merge_topk_lists(const void *idx, const void *score, const void *count, size_t stride_bytes, int lists, int nq, int k,
+                       int64_t *out_idx, double *out_score, int32_t *out_count, cudaStream_t st)
+{
+    int total = lists * k;
+    VM_REQUIRE(total <= 4096, VM_ERR_UNSUPPORTED, "merge_topk_lists: lists*k = %d > 4096", total);
+    size_t smem = (size_t)total * (8 + 8 + 4);
+    static bool attr_set = false;
+    if (!attr_set) {
+        VM_CUDA_CHECK(cudaFuncSetAttribute(merge_topk_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    merge_topk_lists_kernel<<<nq, 256, smem, st>>>((const char *)idx, (const char *)score, (const char *)count, stride_bytes, lists, nq, k,
+                                                  out_idx, out_score, out_count);
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
+int k_merge_max_by_id(const int64_t *idx, const double *score, const int32_t *count, int nq, int k, int k2,
+                      int64_t *out_idx, double *out_score, int32_t *out_count, cudaStream_t st)
+{
+    int total = nq * k;
+    VM_REQUIRE(total <= 4096, VM_ERR_UNSUPPORTED, "merge_max_by_id: nq*k = %d > 4096", total);
+    size_t smem = (size_t)total * (8 + 8 + 4);
+    static bool attr_set = false;
+    if (!attr_set) {
+        VM_CUDA_CHECK(cudaFuncSetAttribute(merge_max_by_id_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    merge_max_by_id_kernel<<<1, 256, smem, st>>>(idx, score, count, nq, k, k2, out_idx, out_score, out_count);
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
+int k_cosine_pairs(const void *a, const void *b, int dtype, int64_t n, int dim, int zero_rule, int sum_mode, double *out,
+                   cudaStream_t st)
+{
+    if (n <= 0) return VM_OK;
+    int grid = (int)((n + 127) / 128);
+    if (sum_mode == VM_SUM_NEUMAIER) cosine_pairs_kernel<true><<<grid, 128, 0, st>>>(a, b, dtype, n, dim, zero_rule, out);
+    else cosine_pairs_kernel<false><<<grid, 128, 0, st>>>(a, b, dtype, n, dim, zero_rule, out);
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
+}  // namespace vm

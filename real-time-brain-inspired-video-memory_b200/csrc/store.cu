@@ -1,0 +1,173 @@
+// store.cu -- store-side kernels: dtype conversion on append, cached inverse norms,
+// query normalisation, synthetic fill.  None of these is on the per-query critical path.
+#include "common.cuh"
+#include "synth.cuh"
+
+namespace vm {
+
+// src [n][dim] (f32/bf16/f64) -> dst [n][ld] (f32/bf16), zero padded columns [dim, ld).
+template <typename DST>
+__global__ void convert_rows_kernel(const void *__restrict__ src, int src_dtype, DST *__restrict__ dst, int64_t n,
+                                    int dim, int ld)
+{
+    int64_t total = n * (int64_t)ld;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = e / ld;
+        int c = (int)(e - r * ld);
+        float v = 0.0f;
+        if (c < dim) {
+            int64_t si = r * dim + c;
+            if (src_dtype == VM_F32) v = ((const float *)src)[si];
+            else if (src_dtype == VM_BF16) v = __bfloat162float(((const __nv_bfloat16 *)src)[si]);
+            else v = (float)((const double *)src)[si];  // binary64 -> binary32, round to nearest
+        }
+        if constexpr (sizeof(DST) == 4) dst[e] = v;
+        else dst[e] = __float2bfloat16_rn(v);
+    }
+}
+
+// One warp per row: 1/||row|| of the STORED values, accumulated in binary64.
+// 0 for a zero-norm row (its score is 0.0: pre_llm_injector.py:385-386).
+template <typename T>
+__global__ void row_inv_norms_kernel(const T *__restrict__ rows, float *__restrict__ inv_norms, int64_t row0,
+                                     int64_t n, int ld)
+{
+    int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = row0 + warp; r < n; r += nwarps) {
+        const T *p = rows + r * (int64_t)ld;
+        double ss = 0.0;
+        for (int c = lane; c < ld; c += 32) {
+            double v = (double)load_as_float(p, c);
+            ss += v * v;
+        }
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) {
+            // keep an earlier "skipped" mark (negative) only when the caller re-marks it; fresh rows get the norm
+            inv_norms[r] = ss > 0.0 ? (float)(1.0 / sqrt(ss)) : 0.0f;
+        }
+    }
+}
+
+__global__ void invalidate_rows_kernel(float *inv_norms, const int64_t *rows, int64_t n, int64_t size)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n && rows[i] >= 0 && rows[i] < size) inv_norms[rows[i]] = -1.0f;
+}
+
+// Queries (any dtype) -> fp32 [nq_pad][ld], each scaled by 1/||q|| (binary64 norm, zero query
+// stays zero), plus an optional bf16 copy for the tcgen05 bf16 path.  One warp per query.
+__global__ void normalize_queries_kernel(const void *__restrict__ q, int q_dtype, int nq, int nq_pad, int dim, int ld,
+                                         float *__restrict__ out_f32, __nv_bfloat16 *__restrict__ out_bf16)
+{
+    int lane = threadIdx.x & 31;
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= nq_pad) return;
+    double ss = 0.0;
+    if (w < nq)
+        for (int c = lane; c < dim; c += 32) {
+            double v = load_as_double(q, q_dtype, (int64_t)w * dim + c);
+            ss += v * v;
+        }
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    double inv = (ss > 0.0 && isfinite(ss)) ? 1.0 / sqrt(ss) : 0.0;
+    for (int c = lane; c < ld; c += 32) {
+        float v = 0.0f;
+        if (w < nq && c < dim) v = (float)(load_as_double(q, q_dtype, (int64_t)w * dim + c) * inv);
+        out_f32[(int64_t)w * ld + c] = v;
+        if (out_bf16) out_bf16[(int64_t)w * ld + c] = __float2bfloat16_rn(v);
+    }
+}
+
+template <typename T>
+__global__ void synth_fill_kernel(T *__restrict__ rows, uint64_t seed, int64_t row0, int64_t n, int dim, int ld,
+                                  uint64_t dup_period)
+{
+    // one thread per 8-column group: one splitmix64 word yields 8 values
+    int groups = ld >> 3;
+    int64_t total = n * (int64_t)groups;
+    uint64_t hk = splitmix64(seed ^ 0xD6E8FEB86659FD93ULL);
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = e / groups;
+        int g = (int)(e - i * groups);
+        uint64_t row = (uint64_t)(row0 + i);
+        uint64_t own = splitmix64(splitmix64(seed * 0x9E3779B97F4A7C15ULL + row) + (uint64_t)g);
+        uint64_t par = 0, sel = 0;
+        bool planted = false;
+        if (dup_period > 0 && row > 0) {
+            uint64_t hr = splitmix64(hk + row);
+            if (hr % dup_period == 0) {
+                planted = true;
+                uint64_t parent = splitmix64(hr) % row;
+                par = splitmix64(splitmix64(seed * 0x9E3779B97F4A7C15ULL + parent) + (uint64_t)g);
+                sel = splitmix64(hr + 0x632BE59BD9B4E019ULL + (uint64_t)g);
+            }
+        }
+        T *dst = rows + i * (int64_t)ld + g * 8;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            int col = g * 8 + b;
+            int v = synth_int(own, b);
+            if (planted && (((sel >> (8 * b)) & 15ULL) != 0ULL)) v = synth_int(par, b);
+            float f = col < dim ? (float)v * (1.0f / 128.0f) : 0.0f;
+            if constexpr (sizeof(T) == 4) dst[b] = f;
+            else dst[b] = __float2bfloat16_rn(f);
+        }
+    }
+}
+
+// ---- host wrappers ---------------------------------------------------------------------
+int k_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype, int64_t n, int dim, int ld, cudaStream_t st)
+{
+    if (n <= 0) return VM_OK;
+    int64_t total = n * (int64_t)ld;
+    int grid = (int)vm::imin64((total + 255) / 256, 148 * 16);
+    if (dst_dtype == VM_F32) convert_rows_kernel<float><<<grid, 256, 0, st>>>(src, src_dtype, (float *)dst, n, dim, ld);
+    else convert_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, src_dtype, (__nv_bfloat16 *)dst, n, dim, ld);
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
+int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, cudaStream_t st)
+{
+    if (n <= row0) return VM_OK;
+    int64_t warps = n - row0;
+    int grid = (int)vm::imin64((warps * 32 + 255) / 256, 148 * 16);
+    if (dtype == VM_F32) row_inv_norms_kernel<float><<<grid, 256, 0, st>>>((const float *)rows, inv_norms, row0, n, ld);
+    else row_inv_norms_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)rows, inv_norms, row0, n, ld);
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
+int k_invalidate_rows(float *inv_norms, const int64_t *rows_dev, int64_t n, int64_t size, cudaStream_t st)
+{
+    if (n <= 0) return VM_OK;
+    invalidate_rows_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(inv_norms, rows_dev, n, size);
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
+int k_normalize_queries(const void *q, int q_dtype, int nq, int nq_pad, int dim, int ld, float *out_f32,
+                        void *out_bf16, cudaStream_t st)
+{
+    int threads = 128;
+    int grid = (nq_pad * 32 + threads - 1) / threads;
+    normalize_queries_kernel<<<grid, threads, 0, st>>>(q, q_dtype, nq, nq_pad, dim, ld, out_f32, (__nv_bfloat16 *)out_bf16);
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
+int k_synth_fill(void *rows, int dtype, uint64_t seed, int64_t row0, int64_t n, int dim, int ld, uint64_t dup_period,
+                 cudaStream_t st)
+{
+    if (n <= 0) return VM_OK;
+    int64_t total = n * (int64_t)(ld >> 3);
+    int grid = (int)vm::imin64((total + 255) / 256, 148 * 32);
+    if (dtype == VM_F32) synth_fill_kernel<float><<<grid, 256, 0, st>>>((float *)rows, seed, row0, n, dim, ld, dup_period);
+    else synth_fill_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16 *)rows, seed, row0, n, dim, ld, dup_period);
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
+}  // namespace vm

@@ -1,0 +1,211 @@
+"""EmbeddingStore: one HBM-resident shard of chunk embeddings + the exact top-k scorer.
+
+Host-side mirror of the reference's store for this path: where the reference re-fetches
+`{chunk_id: embedding}` from Neo4j on every batch (src/components/pre_llm_injector.py:390-412)
+and loops over it in Python (:356-370), this class keeps the rows resident on the GPU
+(PyTorch owns the device memory and the stream; libvidmem.so does the arithmetic).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+_DT = {"f32": L.VM_F32, "fp32": L.VM_F32, "float32": L.VM_F32, "bf16": L.VM_BF16, "bfloat16": L.VM_BF16}
+_TORCH_DT = {L.VM_F32: torch.float32, L.VM_BF16: torch.bfloat16}
+
+
+def _np_dtype_code(a: np.ndarray) -> int:
+    if a.dtype == np.float32:
+        return L.VM_F32
+    if a.dtype == np.float64:
+        return L.VM_F64
+    raise TypeError(f"unsupported host dtype {a.dtype}")
+
+
+def _torch_dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return L.VM_F32
+    if t.dtype == torch.bfloat16:
+        return L.VM_BF16
+    if t.dtype == torch.float64:
+        return L.VM_F64
+    raise TypeError(f"unsupported tensor dtype {t.dtype}")
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class EmbeddingStore:
+    """Row-major embedding shard on one GPU.  Row index == append order (the reference's dict
+    insertion order)."""
+
+    def __init__(self, dim: int, capacity: int, dtype: str = "f32", device: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("EmbeddingStore needs a CUDA device (sm_100); there is no CPU fallback")
+        self.lib = L.load()
+        self.dim, self.capacity = int(dim), int(capacity)
+        self.dtype_code = _DT[dtype]
+        self.device = torch.device("cuda", device)
+        self.ld = self.lib.vm_ld(self.dim)
+        # PyTorch owns the HBM; the library attaches to it
+        self.rows = torch.empty((self.capacity, self.ld), dtype=_TORCH_DT[self.dtype_code], device=self.device)
+        self.inv_norms = torch.empty((self.capacity,), dtype=torch.float32, device=self.device)
+        h = C.c_void_p()
+        L.check(self.lib.vm_store_attach(C.byref(h), device, self.dim, self.dtype_code, self.capacity,
+                                         self.rows.data_ptr(), self.inv_norms.data_ptr()))
+        self._h = h
+        self.last_stats = L.TopkStats()
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.vm_store_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return int(self.lib.vm_store_size(self._h))
+
+    # -- writes -----------------------------------------------------------------------------
+    def _src(self, rows) -> Tuple[int, int, int, int, object]:
+        """-> (ptr, dtype_code, mem, n, keepalive)"""
+        if isinstance(rows, torch.Tensor):
+            t = rows.contiguous()
+            if t.dim() != 2 or t.shape[1] != self.dim:
+                raise ValueError(f"expected [n, {self.dim}] rows, got {tuple(t.shape)}")
+            if t.is_cuda:
+                return t.data_ptr(), _torch_dtype_code(t), L.VM_MEM_DEVICE, t.shape[0], t
+            if t.dtype == torch.bfloat16:
+                return t.data_ptr(), L.VM_BF16, L.VM_MEM_HOST, t.shape[0], t
+            rows = t.numpy()
+        a = np.asarray(rows)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)
+        a = np.ascontiguousarray(a)
+        if a.ndim != 2 or a.shape[1] != self.dim:
+            raise ValueError(f"expected [n, {self.dim}] rows, got {a.shape}")
+        return a.ctypes.data, _np_dtype_code(a), L.VM_MEM_HOST, a.shape[0], a
+
+    def append(self, rows) -> int:
+        """Appends rows, returns the index of the first one (insert hook of
+        src/components/neo4j_handler.py:221-253)."""
+        ptr, dt, mem, n, keep = self._src(rows)
+        first = C.c_int64(-1)
+        L.check(self.lib.vm_store_append(self._h, ptr, dt, mem, n, C.byref(first), _stream_ptr(self.device)))
+        if mem == L.VM_MEM_HOST:
+            torch.cuda.current_stream(self.device).synchronize()  # host buffer may be released after return
+        return int(first.value)
+
+    def update(self, row0: int, rows) -> None:
+        ptr, dt, mem, n, keep = self._src(rows)
+        L.check(self.lib.vm_store_update(self._h, int(row0), ptr, dt, mem, n, _stream_ptr(self.device)))
+        if mem == L.VM_MEM_HOST:
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def invalidate(self, rows: Sequence[int]) -> None:
+        a = np.ascontiguousarray(np.asarray(list(rows), dtype=np.int64))
+        L.check(self.lib.vm_store_invalidate(self._h, a.ctypes.data, a.size, _stream_ptr(self.device)))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def set_size(self, n: int, recompute_from_row: int = 0) -> None:
+        """Declare rows [0, n) of `self.rows` filled in place (e.g. by synth_fill)."""
+        L.check(self.lib.vm_store_set_size(self._h, int(n), int(recompute_from_row), _stream_ptr(self.device)))
+
+    def clear(self) -> None:
+        L.check(self.lib.vm_store_clear(self._h))
+
+    def synth_fill(self, seed: int, n: int, row0: int = 0, dup_period: int = 0, first_buffer_row: int = 0) -> None:
+        """Generates synthetic rows [row0, row0+n) of the SURVEY.md 8d generator directly in HBM at
+        buffer rows [first_buffer_row, ...)."""
+        dst = self.rows[first_buffer_row:first_buffer_row + n]
+        L.check(self.lib.vm_synth_fill(self.device.index, dst.data_ptr(), self.dtype_code, seed, row0, n, self.dim,
+                                       dup_period, _stream_ptr(self.device)))
+
+    # -- reads ------------------------------------------------------------------------------
+    def topk(self, queries, k: int, min_score: float = -math.inf, score_mode: int = L.VM_SCORE_RAW,
+             sum_mode: Optional[int] = None, flags: int = 0, comm=None, row_offset: int = 0):
+        """Host in / host out.  -> (idx [nq,k] int64, score [nq,k] float64, count [nq] int32).
+        Scores are bit-identical to the reference formula; ties -> lowest row."""
+        if isinstance(queries, torch.Tensor) and queries.is_cuda:
+            raise TypeError("use topk_device for CUDA tensors")
+        q = np.asarray(queries.numpy() if isinstance(queries, torch.Tensor) else queries)
+        if q.dtype not in (np.float32, np.float64):
+            q = q.astype(np.float64)
+        q = np.ascontiguousarray(q)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"expected [nq, {self.dim}] queries, got {q.shape}")
+        nq = q.shape[0]
+        idx = np.full((nq, k), -1, np.int64)
+        score = np.zeros((nq, k), np.float64)
+        count = np.zeros((nq,), np.int32)
+        sm = L.DEFAULT_SUM_MODE if sum_mode is None else sum_mode
+        st = _stream_ptr(self.device)
+        if comm is None:
+            rc = self.lib.vm_topk(self._h, q.ctypes.data, _np_dtype_code(q), L.VM_MEM_HOST, nq, k, float(min_score),
+                                  score_mode, sm, flags, idx.ctypes.data, score.ctypes.data, count.ctypes.data,
+                                  L.VM_MEM_HOST, C.byref(self.last_stats), st)
+        else:
+            rc = self.lib.vm_topk_sharded(self._h, comm.handle, int(row_offset), q.ctypes.data, _np_dtype_code(q),
+                                          L.VM_MEM_HOST, nq, k, float(min_score), score_mode, sm, flags,
+                                          idx.ctypes.data, score.ctypes.data, count.ctypes.data, L.VM_MEM_HOST,
+                                          C.byref(self.last_stats), st)
+        L.check(rc)
+        return idx, score, count
+
+    def topk_device(self, queries: torch.Tensor, k: int, out=None, min_score: float = -math.inf,
+                    score_mode: int = L.VM_SCORE_RAW, sum_mode: Optional[int] = None, flags: int = 0, comm=None,
+                    row_offset: int = 0):
+        """Device in / device out on the current stream.  -> (idx, score, count) CUDA tensors."""
+        if not queries.is_cuda:
+            raise TypeError("queries must be a CUDA tensor")
+        q = queries.contiguous()
+        nq = q.shape[0]
+        if out is None:
+            out = (torch.empty((nq, k), dtype=torch.int64, device=self.device),
+                   torch.empty((nq, k), dtype=torch.float64, device=self.device),
+                   torch.empty((nq,), dtype=torch.int32, device=self.device))
+        idx, score, count = out
+        sm = L.DEFAULT_SUM_MODE if sum_mode is None else sum_mode
+        st = _stream_ptr(self.device)
+        if comm is None:
+            rc = self.lib.vm_topk(self._h, q.data_ptr(), _torch_dtype_code(q), L.VM_MEM_DEVICE, nq, k, float(min_score),
+                                  score_mode, sm, flags, idx.data_ptr(), score.data_ptr(), count.data_ptr(),
+                                  L.VM_MEM_DEVICE, C.byref(self.last_stats), st)
+        else:
+            rc = self.lib.vm_topk_sharded(self._h, comm.handle, int(row_offset), q.data_ptr(), _torch_dtype_code(q),
+                                          L.VM_MEM_DEVICE, nq, k, float(min_score), score_mode, sm, flags,
+                                          idx.data_ptr(), score.data_ptr(), count.data_ptr(), L.VM_MEM_DEVICE,
+                                          C.byref(self.last_stats), st)
+        L.check(rc)
+        return idx, score, count
+
+
+def cosine_pairs(a, b, zero_rule: int = 0, sum_mode: Optional[int] = None, device: int = 0) -> np.ndarray:
+    """n independent cosines, bit-identical to PreLLMInjector._cosine_similarity (zero_rule 0,
+    pre_llm_injector.py:374-388) or HybridRetriever._cosine_similarity (zero_rule 1,
+    retriever_hybrid.py:655-664) on equal-length vectors."""
+    lib = L.load()
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    b = np.ascontiguousarray(np.asarray(b, dtype=np.float64))
+    if a.ndim == 1:
+        a, b = a[None, :], b[None, :]
+    if a.shape != b.shape:
+        raise ValueError("shape mismatch")
+    out = np.zeros(a.shape[0], np.float64)
+    sm = L.DEFAULT_SUM_MODE if sum_mode is None else sum_mode
+    dev = torch.device("cuda", device)
+    L.check(lib.vm_cosine_pairs(device, a.ctypes.data, b.ctypes.data, L.VM_F64, L.VM_MEM_HOST, a.shape[0], a.shape[1],
+                                zero_rule, sm, out.ctypes.data, L.VM_MEM_HOST, _stream_ptr(dev)))
+    return out

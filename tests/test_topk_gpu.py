@@ -1,0 +1,199 @@
+"""GPU parity tests of the top-k scorer, through the C ABI (libvidmem.so), against the CPU
+oracle and the committed golden fixtures.  Bar: index lists identical, binary64 scores
+bit-identical (the engine rescoring runs the reference's own summation order)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vm():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import vidmem_b200
+    vidmem_b200._lib.load()
+    return vidmem_b200
+
+
+def _check(idx, score, count, ref, k):
+    for qi, lst in enumerate(ref):
+        assert count[qi] == len(lst), (qi, count[qi], len(lst))
+        assert list(idx[qi, :len(lst)]) == [r for r, _ in lst], (qi, idx[qi], lst)
+        assert list(score[qi, :len(lst)]) == [s for _, s in lst], qi  # bit-exact binary64
+        assert (idx[qi, len(lst):] == -1).all()
+
+
+def _quantise(x, dtype):
+    if dtype == "bf16":
+        import torch
+        return torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
+    return x
+
+
+@pytest.mark.parametrize("flags_name", ["default", "exact", "simt"])
+@pytest.mark.parametrize("k", [3, 10])
+def test_golden_batch_small(vm, golden_dir, k, flags_name):
+    g = np.load(os.path.join(golden_dir, "batch_small.npz"))
+    X, Q = g["X"], g["Q"]
+    flags = {"default": 0, "exact": vm.VM_FLAG_FORCE_EXACT, "simt": vm.VM_FLAG_FORCE_SIMT}[flags_name]
+    st = vm.EmbeddingStore(X.shape[1], 1024, "f32")
+    st.append(X.astype(np.float64))
+    st.invalidate(np.nonzero(g["row_ok"] == 0)[0])
+    ok = np.nonzero(g["query_ok"])[0]          # Exception-valued queries never reach the engine (adapter -> [])
+    idx, score, count = st.topk(Q[ok].astype(np.float64), k, sum_mode=vm.VM_SUM_NEUMAIER, flags=flags)
+    for out_i, qi in enumerate(ok):
+        c = int(g[f"count_k{k}"][qi])
+        assert count[out_i] == c
+        assert np.array_equal(idx[out_i, :c], g[f"idx_k{k}"][qi, :c])
+        assert np.array_equal(score[out_i, :c], g[f"score_k{k}"][qi, :c])
+    st.close()
+
+
+def test_golden_c1(vm, golden_dir):
+    g = np.load(os.path.join(golden_dir, "batch_c1.npz"))
+    n, d, q, k = int(g["n"]), int(g["d"]), int(g["q"]), int(g["k"])
+    X = synth.synth_rows(int(g["store_seed"]), 0, n, d)
+    Q = synth.synth_queries(int(g["query_seed"]), q, d, int(g["store_seed"]), n)
+    st = vm.EmbeddingStore(d, n, "f32")
+    st.append(X)
+    for flags in (0, vm.VM_FLAG_FORCE_SIMT, vm.VM_FLAG_FORCE_EXACT):
+        idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER, flags=flags)
+        assert (count == k).all()
+        assert np.array_equal(idx, g["idx"]), flags
+        assert np.array_equal(score, g["score"]), flags
+    # device-side generator must reproduce the host generator bit for bit
+    st2 = vm.EmbeddingStore(d, n, "f32")
+    st2.synth_fill(int(g["store_seed"]), n)
+    st2.set_size(n)
+    idx2, score2, _ = st2.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)
+    assert np.array_equal(idx2, g["idx"]) and np.array_equal(score2, g["score"])
+    st.close(); st2.close()
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("n,d,nq,k", [(1, 8, 1, 1), (7, 24, 3, 10), (1000, 384, 5, 10), (4097, 768, 8, 3),
+                                      (20000, 100, 2, 24), (3000, 384, 17, 10)])
+def test_simt_vs_oracle(vm, dtype, n, d, nq, k):
+    rng = np.random.default_rng(n * 31 + d)
+    X = _quantise(rng.standard_normal((n, d)).astype(np.float32), dtype)
+    Q = rng.standard_normal((nq, d)).astype(np.float32)
+    if n > 10:
+        X[3] = X[1]; X[n - 1] = X[1]; X[5] = 0.0
+        Q[0] = X[1]
+    st = vm.EmbeddingStore(d, n + 5, dtype)
+    st.append(X)
+    for sm, osm in ((vm.VM_SUM_NEUMAIER, oracle.SUM_NEUMAIER), (vm.VM_SUM_NAIVE, oracle.SUM_NAIVE)):
+        ref = oracle.batch_similarities(Q, X, k, sum_mode=osm)
+        for flags in (vm.VM_FLAG_FORCE_SIMT, vm.VM_FLAG_FORCE_EXACT):
+            if flags == vm.VM_FLAG_FORCE_SIMT and k > 24:
+                continue
+            idx, score, count = st.topk(Q, k, sum_mode=sm, flags=flags)
+            _check(idx, score, count, ref, k)
+    st.close()
+
+
+def test_many_duplicates_fall_back_to_exact(vm):
+    # more exact ties at the top than the candidate list holds -> uncertified -> exact re-scan
+    d, n, k = 64, 5000, 10
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    X[100:400] = X[100]
+    Q = np.stack([X[100], rng.standard_normal(d).astype(np.float32), np.zeros(d, np.float32)])
+    st = vm.EmbeddingStore(d, n, "f32")
+    st.append(X)
+    idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)
+    assert st.last_stats.uncertified >= 1
+    _check(idx, score, count, oracle.batch_similarities(Q, X, k), k)
+    assert list(idx[0]) == list(range(100, 110))
+    assert list(idx[2]) == list(range(10)) and (score[2] == 0.0).all()   # zero query: store order
+    st.close()
+
+
+def test_min_score_and_neo4j_mode(vm):
+    d, n = 32, 300
+    X = synth.synth_rows(9, 0, n, d)
+    q = X[7:8].copy()
+    st = vm.EmbeddingStore(d, n, "f32")
+    st.append(X)
+    idx, score, count = st.topk(q, 5, min_score=0.3, score_mode=vm.VM_SCORE_NEO4J, sum_mode=vm.VM_SUM_NEUMAIER)
+    ref = oracle.vector_search(q[0], X, 5, 0.3)
+    assert count[0] == len(ref) and [(int(i), float(s)) for i, s in zip(idx[0, :count[0]], score[0, :count[0]])] == ref
+    idx, score, count = st.topk(q, 5, min_score=0.999, sum_mode=vm.VM_SUM_NEUMAIER)
+    assert count[0] == 1 and idx[0, 0] == 7 and idx[0, 1] == -1
+    st.close()
+
+
+def test_update_invalidate_append_visibility(vm):
+    d = 48
+    X = synth.synth_rows(21, 0, 200, d)
+    st = vm.EmbeddingStore(d, 400, "f32")
+    assert st.append(X[:100]) == 0
+    assert st.append(X[100:]) == 100 and len(st) == 200
+    q = X[150:151]
+    idx, score, _ = st.topk(q, 1, sum_mode=vm.VM_SUM_NEUMAIER)
+    assert idx[0, 0] == 150 and score[0, 0] == oracle.cosine(q[0], X[150])
+    st.update(150, X[0:1])                  # upsert overwrites the row
+    X2 = X.copy(); X2[150] = X[0]
+    _check(*st.topk(q, 3, sum_mode=vm.VM_SUM_NEUMAIER), oracle.batch_similarities(q, X2, 3), 3)
+    st.invalidate([int(idx[0, 0])])
+    ok = np.ones(200, np.uint8); ok[150] = 0
+    _check(*st.topk(q, 3, sum_mode=vm.VM_SUM_NEUMAIER), oracle.batch_similarities(q, X2, 3, row_ok=ok), 3)
+    with pytest.raises(vm.VidmemError):
+        st.append(np.zeros((500, d), np.float32))   # capacity overflow is loud
+    st.close()
+
+
+def test_device_api_async(vm):
+    import torch
+    d, n, nq, k = 384, 6000, 6, 10
+    X = synth.synth_rows(31, 0, n, d)
+    Q = synth.synth_queries(32, nq, d, 31, n)
+    st = vm.EmbeddingStore(d, n, "bf16")
+    st.append(torch.from_numpy(X).cuda())
+    qd = torch.from_numpy(Q).cuda()
+    idx, score, count = st.topk_device(qd, k, sum_mode=vm.VM_SUM_NEUMAIER, flags=vm.VM_FLAG_ASYNC)
+    torch.cuda.synchronize()
+    _check(idx.cpu().numpy(), score.cpu().numpy(), count.cpu().numpy(), oracle.batch_similarities(Q, X, k), k)
+    st.close()
+
+
+def test_cosine_pairs_golden(vm, golden_dir):
+    from vidmem_b200.store import cosine_pairs
+    g = np.load(os.path.join(golden_dir, "cosine_kat.npz"))
+    for i in range(len(g["out"])):
+        la, lb = int(g["len_a"][i]), int(g["len_b"][i])
+        if la != lb:
+            continue  # length mismatch is decided in the adapter, not on the device
+        a, b = g["a"][i, :la], g["b"][i, :lb]
+        assert cosine_pairs(a, b, zero_rule=0, sum_mode=vm.VM_SUM_NEUMAIER)[0] == g["out"][i, 0]
+        assert cosine_pairs(a, b, zero_rule=1, sum_mode=vm.VM_SUM_NEUMAIER)[0] == g["out"][i, 1]
+
+
+def test_merge_max_by_id_golden(vm, golden_dir):
+    import ctypes as C
+    import torch
+    g = np.load(os.path.join(golden_dir, "merge.npz"))
+    X, Q = g["X"], g["Q"]
+    st = vm.EmbeddingStore(X.shape[1], len(X), "f32")
+    st.append(X)
+    lib = vm._lib.load()
+    for k, k2 in ((3, 2), (10, 4), (10, 25)):
+        idx, score, count = st.topk_device(torch.from_numpy(Q).cuda(), k, sum_mode=vm.VM_SUM_NEUMAIER)
+        oi = torch.full((k2,), -1, dtype=torch.int64, device="cuda")
+        os_ = torch.zeros((k2,), dtype=torch.float64, device="cuda")
+        oc = torch.zeros((1,), dtype=torch.int32, device="cuda")
+        vm._lib.check(lib.vm_merge_max_by_id(0, idx.data_ptr(), score.data_ptr(), count.data_ptr(), len(Q), k, k2,
+                                             oi.data_ptr(), os_.data_ptr(), oc.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        m = int(oc.item())
+        assert m == len(g[f"idx_{k}_{k2}"])
+        assert np.array_equal(oi.cpu().numpy()[:m], g[f"idx_{k}_{k2}"])
+        assert np.array_equal(os_.cpu().numpy()[:m], g[f"score_{k}_{k2}"])
+    st.close()
