@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the embedding-similarity hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c5]
+
+A "step" is one pass of the hot path over one batch: 64 queries, top-10, scored against every
+row of the HBM-resident synthetic store (SURVEY.md 8d generator).
+  N = 1 : config C2 -- 1 000 000 x 384 fp32 store on one B200 (BASELINE.json configs[1]).
+  N > 1 : config C3 -- 100 000 000 x 384 bf16 store row-sharded over N GPUs (100M/N rows each),
+          local scan + exact rescoring, ONE ncclAllGather of the per-rank lists, device merge
+          (strong scaling: the store is fixed, rows per GPU shrink with N).
+One JSON line on stdout (rank 0).  `value` = queries/s with queries and outputs resident in
+HBM; `e2e` = the same metric through the public host-buffer API (pinned host queries in, host
+results out, copies inside the timed region).  `--impl reference` times the reference's CPU
+algorithm (oracle port, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "queries_per_sec_top10_384d"
+UNIT = "queries/s"
+CONFIGS = {
+    # name: (rows_total, dim, store dtype, queries, k, store seed, query seed)
+    "c2": (1_000_000, 384, "f32", 64, 10, 2, 2002),
+    "c3": (100_000_000, 384, "bf16", 64, 10, 3, 3003),
+    "c5": (10_000_000, 384, "f32", 1, 10, 5, 5005),
+}
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port (C restatement of the reference's Python loop)
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_leg(cfg_name: str, steps: int, warmup: int, sample_rows: int):
+    """Times the reference algorithm (pre_llm_injector.py:346-388 restated in C, OpenMP over
+    queries) on `sample_rows` rows of the same synthetic store; returns (queries/s at the FULL
+    store size by linear extrapolation in rows -- the algorithm is a flat loop over rows --,
+    ms per sampled step, description)."""
+    import numpy as np
+    from oracle import oracle, synth
+    rows_total, dim, _dt, nq, k, sseed, qseed = CONFIGS[cfg_name]
+    X = synth.synth_rows(sseed, 0, sample_rows, dim).astype(np.float64)
+    Q = synth.synth_queries(qseed, nq, dim, sseed, rows_total).astype(np.float64)
+    oracle.lib()
+    for _ in range(warmup):
+        oracle.batch_similarities(Q[:8], X[:2000], k)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        oracle.batch_similarities(Q, X, k)
+        times.append(time.perf_counter() - t0)
+    per_step = sum(times) / len(times)
+    full = per_step * (rows_total / sample_rows)
+    return nq / full, per_step * 1e3, (f"{nq} queries x {sample_rows} rows x {dim} (of {rows_total} rows), "
+                                       f"time scaled linearly in rows to the full store")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = args.config or ("c2" if args.gpus == 1 else "c3")
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample_rows or 100000
+    steps = max(1, min(args.steps, 5))
+    qps, ms, desc = cpu_reference_leg(cfg, steps, min(args.warmup, 1), sample)
+    rows_total, dim, dt, nq, k, _, _ = CONFIGS[cfg]
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{cfg}: {rows_total}x{dim} {dt} store, {nq}-query batch, top-{k} cosine",
+                       "timed_sample": desc},
+            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import vidmem_b200 as vm
+    from vidmem_b200.store import EmbeddingStore
+    from oracle import synth  # synthetic query generator only (numpy); nothing from the oracle is timed here
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        from vidmem_b200.sharded import Communicator
+        comm = Communicator.from_torch_distributed(local_rank)
+
+    cfg = args.config or ("c2" if world == 1 else "c3")
+    rows_total, dim, dt, nq, k, sseed, qseed = CONFIGS[cfg]
+    if args.rows:
+        rows_total = args.rows
+    row_lo = rows_total * rank // world
+    row_hi = rows_total * (rank + 1) // world
+    n_local = row_hi - row_lo
+    es = 4 if dt == "f32" else 2
+
+    store = EmbeddingStore(dim, n_local, dt, device=local_rank)
+    store.synth_fill(sseed, n_local, row0=row_lo)
+    store.set_size(n_local)
+    torch.cuda.synchronize()
+    Q = synth.synth_queries(qseed, nq, dim, sseed, rows_total)
+    q_pinned = torch.from_numpy(Q).pin_memory()
+    q_dev = q_pinned.to(dev)
+    out = (torch.empty((nq, k), dtype=torch.int64, device=dev), torch.empty((nq, k), dtype=torch.float64, device=dev),
+           torch.empty((nq,), dtype=torch.int32, device=dev))
+    flags_dev = vm.VM_FLAG_ASYNC | vm.VM_FLAG_TIMING | args.flags
+
+    def step_device():
+        store.topk_device(q_dev, k, out=out, flags=flags_dev, comm=comm, row_offset=row_lo)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- leg 1: inputs resident in HBM ------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    scan_ms = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = int(store.last_stats.scan_launches) * args.steps
+    stats = store.last_stats
+    # scan-kernel time: CUDA events recorded by the library on the launching stream (VM_FLAG_TIMING),
+    # read per step in a second short loop so the read-back does not perturb the timed region above
+    for _ in range(min(args.steps, 20)):
+        step_device()
+        scan_ms.append(store.last_scan_ms())
+    barrier()
+
+    # ---- leg 2: end to end through the host-buffer API ----------------------------------------
+    def step_host():
+        return store.topk(q_pinned.numpy(), k, comm=comm, row_offset=row_lo, flags=args.flags)
+
+    for _ in range(3):
+        res = step_host()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = step_host()
+    e1.record()
+    barrier()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), e2e_wall_ms)  # host-synchronous API: wall clock is the honest number
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([dev_ms, e2e_ms, float(sum(scan_ms) / max(len(scan_ms), 1))], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms, scan_avg = [float(x) for x in t.tolist()]
+    else:
+        scan_avg = sum(scan_ms) / max(len(scan_ms), 1)
+
+    if rank == 0:
+        ms_per_step = dev_ms / args.steps
+        value = nq / (ms_per_step * 1e-3)
+        e2e_value = nq / (e2e_ms / args.steps * 1e-3)
+        peak, peak_src = _peaks()
+        alg_bytes = n_local * dim * es + n_local * 4          # store rows once + cached inverse norms
+        achieved = alg_bytes / (scan_avg * 1e-3) / 1e9 if scan_avg > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+            "dtype": "tf32" if (dt == "f32" and stats.scan_kernel == 2) else ("f32" if dt == "f32" else "bf16"),
+            "data": "synthetic",
+            "config": {"workload": f"{cfg}: {rows_total}x{dim} {dt} store, {nq}-query batch, top-{k} cosine, "
+                                   f"{'row-sharded over %d GPUs + NCCL all-gather merge' % world if world > 1 else '1 GPU'}",
+                       "rows_per_gpu": n_local, "l2_policy": "inputs larger than L2 (%.0f MB store per GPU vs 126 MB L2)" % (n_local * dim * es / 1e6),
+                       "scan_kernel": {0: "exact_fp64", 1: "simt", 2: "tcgen05"}[int(stats.scan_kernel)],
+                       "scan_ctas": int(stats.scan_ctas), "candidates_per_query": int(stats.candidates),
+                       "exact_rescoring": "binary64, reference summation order (Neumaier)", "timing": "cuda events, max over ranks"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(Q.nbytes),
+                    "d2h_bytes_per_step": int(nq * k * 16 + nq * 4 + 4), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "scan", "kernel_ms": scan_avg, "algorithmic_bytes": alg_bytes,
+                         "peak_source": peak_src},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            qps, ms, desc = cpu_reference_leg(cfg, 1, 1, args.cpu_sample_rows or 100000)
+            line["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        print(json.dumps(line), flush=True)
+    store.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS))
+    ap.add_argument("--rows", type=int, default=None, help="override the total row count (debug)")
+    ap.add_argument("--flags", type=int, default=0, help="extra VM_FLAG_* bits (debug: 4 = force SIMT, 8 = force tcgen05)")
+    ap.add_argument("--cpu-sample-rows", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

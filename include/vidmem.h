@@ -70,7 +70,8 @@ enum {
     VM_FLAG_ASYNC = 1,       /* do not synchronise (device outputs only) */
     VM_FLAG_FORCE_EXACT = 2, /* skip the fast scan: binary64 scan of every row (slow, always exact) */
     VM_FLAG_FORCE_SIMT = 4,  /* use the CUDA-core scan kernel even where the tcgen05 kernel applies */
-    VM_FLAG_FORCE_TC = 8     /* use the tcgen05/TMA scan kernel even for small query batches */
+    VM_FLAG_FORCE_TC = 8,    /* use the tcgen05/TMA scan kernel even for small query batches */
+    VM_FLAG_TIMING = 16      /* bracket the scan kernel with CUDA events on `stream` (see vm_store_last_scan_ms) */
 };
 
 typedef struct vm_store vm_store; /* a row-major embedding store resident in HBM (one shard) */
@@ -83,7 +84,8 @@ typedef struct vm_topk_stats {
     int32_t uncertified;      /* queries the fast scan could not certify and the exact scan re-did */
     int32_t candidates;       /* candidate list length per query (KP) */
     int32_t scan_ctas;
-    int32_t reserved[3];
+    int32_t scan_stages;      /* shared-memory pipeline depth of the tcgen05 scan (0 otherwise) */
+    int32_t reserved[2];
 } vm_topk_stats;
 
 /* ---- library ----------------------------------------------------------------------- */
@@ -129,6 +131,9 @@ int vm_store_invalidate(vm_store *s, const int64_t *rows_host, int64_t n, void *
  * recomputes the cached inverse norms for [row0, n). */
 int vm_store_set_size(vm_store *s, int64_t n, int64_t recompute_from_row, void *stream);
 int vm_store_clear(vm_store *s);
+/* Device time (ms) of the scan kernel(s) of the last vm_topk* call made with VM_FLAG_TIMING,
+ * measured with CUDA events recorded on that call's stream; synchronises on the end event. */
+int vm_store_last_scan_ms(vm_store *s, float *ms);
 
 /* ---- top-k scorer ---------------------------------------------------------------------
  * Replaces the hot loop of PreLLMInjector._calculate_batch_similarities

@@ -20,7 +20,7 @@ VM_F32, VM_BF16, VM_F64 = 0, 1, 2
 VM_MEM_HOST, VM_MEM_DEVICE = 0, 1
 VM_SCORE_RAW, VM_SCORE_NEO4J = 0, 1
 VM_SUM_NAIVE, VM_SUM_NEUMAIER = 0, 1
-VM_FLAG_ASYNC, VM_FLAG_FORCE_EXACT, VM_FLAG_FORCE_SIMT, VM_FLAG_FORCE_TC = 1, 2, 4, 8
+VM_FLAG_ASYNC, VM_FLAG_FORCE_EXACT, VM_FLAG_FORCE_SIMT, VM_FLAG_FORCE_TC, VM_FLAG_TIMING = 1, 2, 4, 8, 16
 
 #: summation order CPython's builtin sum() uses in THIS interpreter (what the reference would compute here)
 DEFAULT_SUM_MODE = VM_SUM_NEUMAIER if sys.version_info >= (3, 12) else VM_SUM_NAIVE
@@ -29,6 +29,7 @@ EXPORTS = [
     "vm_version", "vm_last_error", "vm_device_info", "vm_ld",
     "vm_store_create", "vm_store_attach", "vm_store_destroy", "vm_store_size", "vm_store_capacity", "vm_store_dim",
     "vm_store_ld", "vm_store_append", "vm_store_update", "vm_store_invalidate", "vm_store_set_size", "vm_store_clear",
+    "vm_store_last_scan_ms",
     "vm_topk", "vm_topk_sharded", "vm_merge_topk_lists", "vm_merge_max_by_id", "vm_cosine_pairs", "vm_pairs_above",
     "vm_comm_unique_id", "vm_comm_init_rank", "vm_comm_destroy", "vm_comm_nranks", "vm_comm_rank", "vm_synth_fill",
 ]
@@ -36,7 +37,7 @@ EXPORTS = [
 
 class TopkStats(C.Structure):
     _fields_ = [("scan_kernel", C.c_int32), ("scan_launches", C.c_int32), ("uncertified", C.c_int32),
-                ("candidates", C.c_int32), ("scan_ctas", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("candidates", C.c_int32), ("scan_ctas", C.c_int32), ("scan_stages", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class VidmemError(RuntimeError):
@@ -80,6 +81,7 @@ def load() -> C.CDLL:
         "vm_store_invalidate": (ci, [vp, vp, i64, vp]),
         "vm_store_set_size": (ci, [vp, i64, i64, vp]),
         "vm_store_clear": (ci, [vp]),
+        "vm_store_last_scan_ms": (ci, [vp, P(C.c_float)]),
         "vm_topk": (ci, [vp, vp, ci, ci, ci, ci, dbl, ci, ci, ci, vp, vp, vp, ci, P(TopkStats), vp]),
         "vm_topk_sharded": (ci, [vp, vp, i64, vp, ci, ci, ci, ci, dbl, ci, ci, ci, vp, vp, vp, ci, P(TopkStats), vp]),
         "vm_merge_topk_lists": (ci, [ci, vp, vp, vp, ci, ci, ci, vp, vp, vp, vp]),

@@ -41,6 +41,7 @@ int k_pairs_above(int device, const void *x, int dtype, int64_t n, int dim, int 
                   int64_t *out_i, int64_t *out_j, float *out_score, int64_t *out_count, int part, int nparts, int flags,
                   cudaStream_t st);
 
+extern int g_last_tc_stages;
 static constexpr int MAXQ = 64;   // queries per scan pass
 static constexpr int MAXK = 64;   // k and candidate-list bound
 static constexpr int XCTAS = 148; // exact-scan grid
@@ -100,6 +101,8 @@ struct vm_store {
     bool owns = false;
     Buf stage, stage_idx;
     Workspace ws;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // VM_FLAG_TIMING
+    bool timed = false;
 };
 
 struct vm_comm {
@@ -268,6 +271,8 @@ extern "C" int vm_store_destroy(vm_store *s)
     if (s->owns) { cudaFree(s->rows); cudaFree(s->inv_norms); }
     s->stage.release(); s->stage_idx.release();
     s->ws.release();
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
     delete s;
     return VM_OK;
 }
@@ -339,6 +344,16 @@ extern "C" int vm_store_set_size(vm_store *s, int64_t n, int64_t recompute_from_
     s->size = n;
     if (recompute_from_row >= 0 && recompute_from_row < n)
         return k_row_inv_norms(s->rows, s->dtype, s->inv_norms, recompute_from_row, n, s->ld, (cudaStream_t)stream);
+    return VM_OK;
+}
+
+extern "C" int vm_store_last_scan_ms(vm_store *s, float *ms)
+{
+    VM_REQUIRE(s && ms, VM_ERR_BADARG, "NULL argument");
+    VM_REQUIRE(s->timed, VM_ERR_STATE, "no vm_topk call with VM_FLAG_TIMING has run the scan kernel yet");
+    DeviceGuard g(s->device);
+    VM_CUDA_CHECK(cudaEventSynchronize(s->ev1));
+    VM_CUDA_CHECK(cudaEventElapsedTime(ms, s->ev0, s->ev1));
     return VM_OK;
 }
 
@@ -414,6 +429,11 @@ static int topk_batch(const TopkCall &c)
     ScanArgs a;
     a.rows = s->rows; a.inv_norms = s->inv_norms; a.dtype = s->dtype; a.n = s->size; a.dim = s->dim; a.ld = s->ld;
     a.queries = (const float *)w.q_f32.p; a.nq = c.nq; a.kp = kp; a.cand = (uint64_t *)w.cand.p; a.stream = st;
+    const bool timing = (c.flags & VM_FLAG_TIMING) != 0;
+    if (timing) {
+        if (!s->ev0) { VM_CUDA_CHECK(cudaEventCreate(&s->ev0)); VM_CUDA_CHECK(cudaEventCreate(&s->ev1)); }
+        VM_CUDA_CHECK(cudaEventRecord(s->ev0, st));
+    }
     if (kernel == 1) {
         int64_t need = (s->size + 31) / 32;
         a.ctas = (int)imin64(need, 2 * s->sm_count);
@@ -426,6 +446,7 @@ static int topk_batch(const TopkCall &c)
         launches += 1;
     }
     if (rc != VM_OK) return rc;
+    if (timing) { VM_CUDA_CHECK(cudaEventRecord(s->ev1, st)); s->timed = true; }
 
     rc = k_merge_candidates(a.cand, a.ctas, c.nq, kp, (uint64_t *)w.merged.p, st);
     if (rc != VM_OK) return rc;
@@ -461,6 +482,7 @@ static int topk_batch(const TopkCall &c)
         c.stats->uncertified += n_uncert > 0 ? n_uncert : 0;
         c.stats->candidates = kp;
         c.stats->scan_ctas = a.ctas;
+        c.stats->scan_stages = kernel == 2 ? g_last_tc_stages : 0;
     }
     return VM_OK;
 }

@@ -1,6 +1,285 @@
-// scan_tc.cu -- tcgen05/TMA streaming scorer (placeholder until the kernel lands in this round).
-#include "common.cuh"
+// scan_tc.cu -- tcgen05 / TMA streaming scorer: the bandwidth-bound scan for query batches.
+//
+// One persistent CTA per SM, warp-specialised (192 threads):
+//   warp 0   TMA producer   streams the store as 128-row x 128-byte boxes (SWIZZLE_128B) through a
+//                           ring of 16 KB shared-memory stages, L2 evict-first; loads the
+//                           normalised queries once (evict-last) -- no thread ever touches a row
+//   warp 1   MMA issuer     one thread issues tcgen05.mma (kind::tf32 for an fp32 store, kind::f16
+//                           for bf16): D[128 rows x nq] += A[128 x 32B] * Q[nq x 32B]^T, accumulators
+//                           in TMEM (4 stages x nq columns), tcgen05.commit frees stages / publishes D
+//   warps 2-5 epilogue      tcgen05.ld their 32-lane TMEM quadrant (lane = store row, column = query),
+//                           multiply by the cached 1/||row|| (fused normalisation), compare with the
+//                           per-query running threshold, push the rare survivors into per-query
+//                           queues; thread q then inserts them into query q's sorted top-kp list
+//                           (shared memory).  While a tile overflows a queue its accumulator simply
+//                           stays in TMEM and is re-read after the drain.
+// HBM traffic = the store bytes exactly once per batch of <= 64 queries; the per-CTA lists are
+// merged and exactly rescored by select.cu.
+#include "tc_common.cuh"
+
 namespace vm {
-bool scan_tc_supported(int, int, int, int) { return false; }
-int launch_scan_tc(const ScanArgs &, const void *) { set_error("tcgen05 scan not built"); return VM_ERR_UNSUPPORTED; }
+using namespace tc;
+
+static constexpr int TC_BLOCK_M = 128;
+static constexpr int TC_STAGE_BYTES = TC_BLOCK_M * 128;
+static constexpr int TC_ACC = 4;
+static constexpr int TC_QCAP = 32;
+static constexpr int TC_THREADS = 192;
+static constexpr int TC_TMEM_COLS = 256;
+static constexpr int TC_MAX_STAGES = 8;
+
+struct TcLayout {
+    int nq_pad, KB, stages, kp;
+    uint32_t off_b, off_a, off_list, off_queue, off_tauk, off_tauf, off_qcnt, off_flags, off_bars, off_tmem, total;
+};
+
+static TcLayout make_layout(int dtype, int ld, int nq, int kp)
+{
+    TcLayout L{};
+    const int es = dtype == VM_F32 ? 4 : 2;
+    L.nq_pad = (nq + 15) & ~15;
+    L.KB = (ld * es + 127) / 128;
+    L.kp = kp;
+    uint32_t o = 0;
+    L.off_b = o; o += (uint32_t)L.KB * L.nq_pad * 128;
+    uint32_t epi = (uint32_t)kp * L.nq_pad * 8 + (uint32_t)TC_QCAP * L.nq_pad * 8 + (uint32_t)L.nq_pad * (8 + 4 + 4) + 64 + 512;
+    int64_t room = 227 * 1024 - 1024 - (int64_t)o - epi;
+    L.stages = (int)(room / TC_STAGE_BYTES);
+    if (L.stages > TC_MAX_STAGES) L.stages = TC_MAX_STAGES;
+    if (L.stages < 0) L.stages = 0;
+    L.off_a = o; o += (uint32_t)L.stages * TC_STAGE_BYTES;
+    L.off_list = o; o += (uint32_t)kp * L.nq_pad * 8;
+    L.off_queue = o; o += (uint32_t)TC_QCAP * L.nq_pad * 8;
+    L.off_tauk = o; o += (uint32_t)L.nq_pad * 8;
+    L.off_tauf = o; o += (uint32_t)L.nq_pad * 4;
+    L.off_qcnt = o; o += (uint32_t)L.nq_pad * 4;
+    L.off_flags = o; o += 64;
+    L.off_bars = o; o += 8 * (2 * TC_MAX_STAGES + 1 + 2 * TC_ACC);
+    L.off_tmem = o; o += 16;
+    L.total = o + 1024;  // slack for the 1024-byte alignment of the swizzled tiles
+    return L;
+}
+
+template <bool TF32>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const float *__restrict__ inv_norms, int64_t n, int num_tiles, int nq, TcLayout L, uint64_t *__restrict__ cand)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sB = base + L.off_b;
+    uint8_t *sA = base + L.off_a;
+    uint64_t *list = (uint64_t *)(base + L.off_list);    // [kp][nq_pad] descending per query
+    uint64_t *queue = (uint64_t *)(base + L.off_queue);  // [QCAP][nq_pad]
+    uint64_t *tauk = (uint64_t *)(base + L.off_tauk);
+    float *tauf = (float *)(base + L.off_tauf);
+    int *qcnt = (int *)(base + L.off_qcnt);
+    volatile int *s_hit = (volatile int *)(base + L.off_flags);  // [2]
+    volatile int *s_ovf = s_hit + 2;                             // [2]
+    uint64_t *bars = (uint64_t *)(base + L.off_bars);
+    uint64_t *full = bars, *empty = bars + TC_MAX_STAGES, *qfull = bars + 2 * TC_MAX_STAGES;
+    uint64_t *tfull = qfull + 1, *tempty = tfull + TC_ACC;
+    uint32_t *tmem_slot = (uint32_t *)(base + L.off_tmem);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int nq_pad = L.nq_pad, KB = L.KB, stages = L.stages, kp = L.kp;
+    constexpr int ELEMS = TF32 ? 32 : 64;  // elements per 128-byte K block
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(qfull, 1);
+        for (int a = 0; a < TC_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TC_TMEM_COLS);
+    if (warp >= 2) {
+        const int e = threadIdx.x - 64;
+        if (e < nq_pad) {
+            for (int j = 0; j < kp; ++j) list[j * nq_pad + e] = 0;
+            tauk[e] = 0; tauf[e] = -INFINITY; qcnt[e] = 0;
+        }
+        if (e < 4) s_hit[e] = 0;  // s_hit[0..1], s_ovf[0..1]
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(qfull, (uint32_t)KB * nq_pad * 128);
+            for (int kb = 0; kb < KB; ++kb) tma_load_2d(&tmB, qfull, sB + (size_t)kb * nq_pad * 128, kb * ELEMS, 0, L2_EVICT_LAST);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
+                    tma_load_2d(&tmA, &full[stage], sA + (size_t)stage * TC_STAGE_BYTES, kb * ELEMS, tile * TC_BLOCK_M, L2_EVICT_FIRST);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, TC_BLOCK_M, (uint32_t)nq_pad);
+            mbar_wait(qfull, 0);
+            tc_fence_after();
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * nq_pad);
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = a0 + (uint32_t)stage * TC_STAGE_BYTES;
+                    const uint32_t b_addr = b0 + (uint32_t)kb * nq_pad * 128;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)  // 4 x 32-byte K slices per 128-byte swizzle row
+                        umma<TF32>(d_tmem, make_smem_desc_sw128(a_addr + j * 32), make_smem_desc_sw128(b_addr + j * 32), idesc,
+                                   (uint32_t)((kb | j) != 0));
+                    umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[acc]);  // accumulator complete
+                if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ================================ epilogue =====================================
+        const int e = threadIdx.x - 64;   // 0..127
+        const int quad = warp & 3;        // TMEM lane quadrant this warp may read
+        const int row_in_tile = quad * 32 + lane;
+        uint64_t my_tau = 0;              // threshold key of query e (threads e < nq_pad)
+        int acc = 0, par = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int64_t row = (int64_t)tile * TC_BLOCK_M + row_in_tile;
+            const float inv = row < n ? __ldg(inv_norms + row) : -1.0f;
+            const bool valid = inv >= 0.0f;  // < 0: beyond the shard or a skipped row
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * nq_pad);
+            uint64_t pushed = 0;
+            for (;;) {
+                bool hit_any = false, ovf = false;
+                for (int c = 0; c < nq_pad; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c, v);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int q = c + j;
+                            const float s = __uint_as_float(v[j]) * inv;
+                            if (q < nq && s >= tauf[q] && !((pushed >> q) & 1ull)) {
+                                const uint64_t key = make_key(s, (uint32_t)row);
+                                if (key > tauk[q]) {
+                                    hit_any = true;
+                                    int pos = atomicAdd(&qcnt[q], 1);
+                                    if (pos < TC_QCAP) { queue[pos * nq_pad + q] = key; pushed |= 1ull << q; }
+                                    else ovf = true;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (hit_any) s_hit[par] = 1;
+                if (ovf) s_ovf[par] = 1;
+                if (e == 0) { s_hit[par ^ 1] = 0; s_ovf[par ^ 1] = 0; }  // arm the next round's flags
+                named_bar_sync(1, 128);
+                const int h = s_hit[par], o = s_ovf[par];
+                par ^= 1;
+                if (!h) break;
+                if (e < nq_pad) {
+                    // drain query e's queue into its sorted list
+                    int cnt = qcnt[e];
+                    cnt = cnt < TC_QCAP ? cnt : TC_QCAP;
+                    for (int i = 0; i < cnt; ++i) {
+                        const uint64_t key = queue[i * nq_pad + e];
+                        if (key > my_tau) {
+                            int j = kp - 1;
+                            while (j > 0) {
+                                const uint64_t up = list[(j - 1) * nq_pad + e];
+                                if (up >= key) break;
+                                list[j * nq_pad + e] = up;
+                                --j;
+                            }
+                            list[j * nq_pad + e] = key;
+                            my_tau = list[(kp - 1) * nq_pad + e];
+                        }
+                    }
+                    qcnt[e] = 0;
+                    tauk[e] = my_tau;
+                    tauf[e] = my_tau ? key_score(my_tau) : -INFINITY;
+                }
+                named_bar_sync(1, 128);
+                if (!o) break;
+            }
+            // release the accumulator stage to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1; }
+        }
+        named_bar_sync(1, 128);
+        for (int i = e; i < nq * kp; i += 128) {
+            const int q = i / kp, j = i - q * kp;
+            cand[((int64_t)blockIdx.x * nq + q) * kp + j] = list[j * nq_pad + q];
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    }
+}
+
+bool scan_tc_supported(int dtype, int dim, int nq, int kp)
+{
+    if (dtype != VM_F32 && dtype != VM_BF16) return false;
+    if (nq < 1 || nq > 64 || kp < 1 || kp > 64) return false;
+    TcLayout L = make_layout(dtype, ld_for_dim(dim), nq, kp);
+    return L.stages >= 3;
+}
+
+int g_last_tc_stages = 0;
+
+// queries_store_dtype: the normalised queries [nq_pad][ld] in the STORE dtype (fp32 for the tf32
+// path, bf16 for the bf16 path).
+int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype)
+{
+    VM_REQUIRE(a.n >= 1 && a.n < 0x7FFFFF00LL, VM_ERR_UNSUPPORTED, "tcgen05 scan: shard rows %lld outside [1, 2^31)", (long long)a.n);
+    TcLayout L = make_layout(a.dtype, a.ld, a.nq, a.kp);
+    VM_REQUIRE(L.stages >= 3, VM_ERR_UNSUPPORTED, "tcgen05 scan: dim %d x %d queries does not fit shared memory", a.dim, a.nq);
+    CUtensorMap tmA, tmB;
+    int rc = make_tmap_2d(&tmA, a.rows, a.dtype, (uint64_t)a.n, (uint64_t)a.ld, (uint64_t)a.ld, TC_BLOCK_M);
+    if (rc != VM_OK) return rc;
+    rc = make_tmap_2d(&tmB, queries_store_dtype, a.dtype, (uint64_t)L.nq_pad, (uint64_t)a.ld, (uint64_t)a.ld, (uint32_t)L.nq_pad);
+    if (rc != VM_OK) return rc;
+    const int num_tiles = (int)((a.n + TC_BLOCK_M - 1) / TC_BLOCK_M);
+    g_last_tc_stages = L.stages;
+    if (a.dtype == VM_F32) {
+        static bool set = false;
+        if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+        scan_tc_kernel<true><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand);
+    } else {
+        static bool set = false;
+        if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+        scan_tc_kernel<false><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand);
+    }
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
 }  // namespace vm

@@ -123,6 +123,12 @@ class EmbeddingStore:
         """Declare rows [0, n) of `self.rows` filled in place (e.g. by synth_fill)."""
         L.check(self.lib.vm_store_set_size(self._h, int(n), int(recompute_from_row), _stream_ptr(self.device)))
 
+    def last_scan_ms(self) -> float:
+        """Device time of the scan kernel(s) of the last top-k call made with VM_FLAG_TIMING."""
+        ms = C.c_float(0.0)
+        L.check(self.lib.vm_store_last_scan_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
     def clear(self) -> None:
         L.check(self.lib.vm_store_clear(self._h))
 

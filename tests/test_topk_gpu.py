@@ -197,3 +197,46 @@ def test_merge_max_by_id_golden(vm, golden_dir):
         assert np.array_equal(oi.cpu().numpy()[:m], g[f"idx_{k}_{k2}"])
         assert np.array_equal(os_.cpu().numpy()[:m], g[f"score_{k}_{k2}"])
     st.close()
+
+
+# ---- tcgen05 / TMA scan kernel ----------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("n,d,nq,k", [(1, 8, 1, 1), (100, 384, 5, 10), (129, 64, 16, 3), (5000, 384, 64, 10),
+                                      (4097, 768, 17, 10), (20000, 100, 33, 16), (60000, 384, 64, 10),
+                                      (3000, 1024, 8, 40)])
+def test_tc_vs_oracle(vm, dtype, n, d, nq, k):
+    lib = vm._lib.load()
+    rng = np.random.default_rng(n * 17 + d + nq)
+    X = _quantise(rng.standard_normal((n, d)).astype(np.float32), dtype)
+    Q = rng.standard_normal((nq, d)).astype(np.float32)
+    if n > 10:
+        X[3] = X[1]; X[n - 1] = X[1]; X[5] = 0.0
+        Q[0] = X[1]
+    st = vm.EmbeddingStore(d, n + 5, dtype)
+    st.append(X)
+    ref = oracle.batch_similarities(Q, X, k)
+    idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER, flags=vm.VM_FLAG_FORCE_TC)
+    assert st.last_stats.scan_kernel == 2
+    if n >= 3000:
+        assert st.last_stats.uncertified <= 1  # only the planted-duplicate query may need the exact re-scan
+    _check(idx, score, count, ref, k)
+    st.close()
+
+
+def test_tc_is_used_for_query_batches(vm):
+    d, n, nq, k = 384, 40000, 64, 10
+    X = synth.synth_rows(61, 0, n, d)
+    Q = synth.synth_queries(62, nq, d, 61, n)
+    for dtype in ("f32", "bf16"):
+        st = vm.EmbeddingStore(d, n, dtype)
+        st.append(X)
+        idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)
+        assert st.last_stats.scan_kernel == 2 and st.last_stats.scan_stages >= 3
+        # the tensor-core candidates themselves must be right: nothing may lean on the exact re-scan
+        assert st.last_stats.uncertified == 0
+        _check(idx, score, count, oracle.batch_similarities(Q, X, k), k)
+        # skipped rows and rows beyond the shard never surface from the tensor-core path
+        st.invalidate([int(idx[0, 0]), int(idx[1, 0])])
+        ok = np.ones(n, np.uint8); ok[[int(idx[0, 0]), int(idx[1, 0])]] = 0
+        _check(*st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER), oracle.batch_similarities(Q, X, k, row_ok=ok), k)
+        st.close()
