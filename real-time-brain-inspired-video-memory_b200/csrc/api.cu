@@ -24,7 +24,7 @@ int k_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype, int
 int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, cudaStream_t st);
 int k_invalidate_rows(float *inv_norms, const int64_t *rows_dev, int64_t n, int64_t size, cudaStream_t st);
 int k_normalize_queries(const void *q, int q_dtype, int nq, int nq_pad, int dim, int ld, float *out_f32, void *out_bf16,
-                        cudaStream_t st);
+                        int32_t *zero_me, cudaStream_t st);
 int k_synth_fill(void *rows, int dtype, uint64_t seed, int64_t row0, int64_t n, int dim, int ld, uint64_t dup_period,
                  cudaStream_t st);
 int k_merge_candidates(const uint64_t *cand, int lists, int nq, int kp, uint64_t *merged, cudaStream_t st);
@@ -422,7 +422,8 @@ static int topk_batch(const TopkCall &c)
 
     int nq_pad = kernel == 2 ? ((c.nq + 15) & ~15) : c.nq;
     int rc = k_normalize_queries(q_dev, c.q_dtype, c.nq, nq_pad, s->dim, s->ld, (float *)w.q_f32.p,
-                                 (kernel == 2 && s->dtype == VM_BF16) ? w.q_bf16.p : nullptr, st);
+                                 (kernel == 2 && s->dtype == VM_BF16) ? w.q_bf16.p : nullptr,
+                                 (int32_t *)w.flags.p + c.nq, st);
     if (rc != VM_OK) return rc;
     ++launches;
 
@@ -451,8 +452,7 @@ static int topk_batch(const TopkCall &c)
     rc = k_merge_candidates(a.cand, a.ctas, c.nq, kp, (uint64_t *)w.merged.p, st);
     if (rc != VM_OK) return rc;
     int32_t *flags = (int32_t *)w.flags.p;
-    int32_t *uncert = flags + MAXQ;
-    VM_CUDA_CHECK(cudaMemsetAsync(uncert, 0, 4, st));
+    int32_t *uncert = flags + c.nq;  // counter sits right after the nq flags (zeroed by the normalise kernel)
     RescoreArgs rs{(const uint64_t *)w.merged.p, kp, s->rows, s->inv_norms, s->dtype, s->ld, s->dim, s->size, q_dev,
                    c.q_dtype, c.nq, scan_eps(kernel, s->dtype, s->dim), c.sum_mode, fin, flags, uncert};
     rc = k_rescore(rs, st);

@@ -65,23 +65,26 @@ __host__ __device__ __forceinline__ float key_score(uint64_t k) { return f32_fro
 // keep nvcc from contracting mul+add into FMA, so every step rounds like CPython's doubles.
 struct RefSum {
     double s, c;
-    bool first;
-    __device__ __forceinline__ void init() { s = 0.0; c = 0.0; first = true; }
+    __device__ __forceinline__ void init() { s = 0.0; c = 0.0; }
+    // Branch-free: with s = c = 0 the general step reproduces CPython's first step (0.0 + x)
+    // exactly, so no "first item" case is needed; selects instead of an if keep the loop
+    // unrollable and the loads pipelined.
     template <bool NEUMAIER>
     __device__ __forceinline__ void add(double x)
     {
-        if (first) { s = __dadd_rn(0.0, x); first = false; return; }
-        if (!NEUMAIER) { s = __dadd_rn(s, x); return; }
         double t = __dadd_rn(s, x);
-        if (fabs(s) >= fabs(x)) c = __dadd_rn(c, __dadd_rn(__dadd_rn(s, -t), x));
-        else c = __dadd_rn(c, __dadd_rn(__dadd_rn(x, -t), s));
+        if (NEUMAIER) {
+            const bool big = fabs(s) >= fabs(x);
+            const double hi = big ? s : x, lo = big ? x : s;
+            c = __dadd_rn(c, __dadd_rn(__dadd_rn(hi, -t), lo));
+        }
         s = t;
     }
     template <bool NEUMAIER>
     __device__ __forceinline__ double result() const
     {
         double r = s;
-        if (NEUMAIER && !first && c != 0.0 && isfinite(c)) r = __dadd_rn(r, c);
+        if (NEUMAIER && c != 0.0 && isfinite(c)) r = __dadd_rn(r, c);
         return r;
     }
 };

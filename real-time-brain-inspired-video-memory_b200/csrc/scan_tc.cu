@@ -16,6 +16,7 @@
 // HBM traffic = the store bytes exactly once per batch of <= 64 queries; the per-CTA lists are
 // merged and exactly rescored by select.cu.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace vm {
 using namespace tc;
@@ -63,13 +64,15 @@ static TcLayout make_layout(int dtype, int ld, int nq, int kp)
 template <bool TF32>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const float *__restrict__ inv_norms, int64_t n, int num_tiles, int nq, TcLayout L, uint64_t *__restrict__ cand)
+               const float *__restrict__ inv_norms, int64_t n, int num_tiles, int nq, TcLayout L, uint64_t *__restrict__ cand, int dbg)
 {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    // align to 1024 B with pointer arithmetic on the __shared__ array (an integer round trip would
+    // demote every later access to generic LD/ST)
+    uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *sB = base + L.off_b;
     uint8_t *sA = base + L.off_a;
-    uint64_t *list = (uint64_t *)(base + L.off_list);    // [kp][nq_pad] descending per query
+    uint64_t *list = (uint64_t *)(base + L.off_list);    // [kp][nq_pad] unsorted top-kp set per query
     uint64_t *queue = (uint64_t *)(base + L.off_queue);  // [QCAP][nq_pad]
     uint64_t *tauk = (uint64_t *)(base + L.off_tauk);
     float *tauf = (float *)(base + L.off_tauf);
@@ -144,7 +147,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t b_addr = b0 + (uint32_t)kb * nq_pad * 128;
 #pragma unroll
                     for (int j = 0; j < 4; ++j)  // 4 x 32-byte K slices per 128-byte swizzle row
-                        umma<TF32>(d_tmem, make_smem_desc_sw128(a_addr + j * 32), make_smem_desc_sw128(b_addr + j * 32), idesc,
+                        if (!(dbg & 2) || (kb | j) == 0) umma<TF32>(d_tmem, make_smem_desc_sw128(a_addr + j * 32), make_smem_desc_sw128(b_addr + j * 32), idesc,
                                    (uint32_t)((kb | j) != 0));
                     umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
                     if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -158,7 +161,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int e = threadIdx.x - 64;   // 0..127
         const int quad = warp & 3;        // TMEM lane quadrant this warp may read
         const int row_in_tile = quad * 32 + lane;
-        uint64_t my_tau = 0;              // threshold key of query e (threads e < nq_pad)
+        uint64_t my_tau = 0;              // threshold key (= minimum of the set) of query e (threads e < nq_pad)
+        int my_min = 0;                   // its position in the set
         int acc = 0, par = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -174,20 +178,33 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int c = 0; c < nq_pad; c += 16) {
                     uint32_t v[16];
                     tmem_ld16(taddr + c, v);
-                    tmem_ld_wait();
-                    if (valid) {
+                    // thresholds of these 16 queries, loaded up front (a stale, lower value only lets an
+                    // extra candidate through to the drain, which re-checks against the live key)
+                    float tf[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 t4 = *reinterpret_cast<const float4 *>(tauf + c + 4 * j4);
+                        tf[4 * j4] = t4.x; tf[4 * j4 + 1] = t4.y; tf[4 * j4 + 2] = t4.z; tf[4 * j4 + 3] = t4.w;
+                    }
+                    tmem_ld_wait();
+                    if (valid && !(dbg & 1)) {
+                        uint32_t hits = 0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) hits |= (__uint_as_float(v[j]) * inv >= tf[j]) ? (1u << j) : 0u;
+                        hits &= ~(uint32_t)(pushed >> c) & (nq - c >= 16 ? 0xFFFFu : ((1u << (nq - c > 0 ? nq - c : 0)) - 1u));
+                        while (hits) {  // rare path
+                            const int j = __ffs(hits) - 1;
+                            hits &= hits - 1;
                             const int q = c + j;
-                            const float s = __uint_as_float(v[j]) * inv;
-                            if (q < nq && s >= tauf[q] && !((pushed >> q) & 1ull)) {
-                                const uint64_t key = make_key(s, (uint32_t)row);
-                                if (key > tauk[q]) {
-                                    hit_any = true;
-                                    int pos = atomicAdd(&qcnt[q], 1);
-                                    if (pos < TC_QCAP) { queue[pos * nq_pad + q] = key; pushed |= 1ull << q; }
-                                    else ovf = true;
-                                }
+                            float s = 0.0f;
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) s = (jj == j) ? __uint_as_float(v[jj]) * inv : s;
+                            const uint64_t key = make_key(s, (uint32_t)row);
+                            if (key > tauk[q]) {
+                                hit_any = true;
+                                const int pos = atomicAdd(&qcnt[q], 1);
+                                if (pos < TC_QCAP) { queue[pos * nq_pad + q] = key; pushed |= 1ull << q; }
+                                else ovf = true;
                             }
                         }
                     }
@@ -200,21 +217,23 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 par ^= 1;
                 if (!h) break;
                 if (e < nq_pad) {
-                    // drain query e's queue into its sorted list
+                    // drain query e's queue: replace the current minimum of the (unsorted) top-kp set,
+                    // then rescan for the new minimum with independent, pipelined loads
                     int cnt = qcnt[e];
                     cnt = cnt < TC_QCAP ? cnt : TC_QCAP;
                     for (int i = 0; i < cnt; ++i) {
                         const uint64_t key = queue[i * nq_pad + e];
                         if (key > my_tau) {
-                            int j = kp - 1;
-                            while (j > 0) {
-                                const uint64_t up = list[(j - 1) * nq_pad + e];
-                                if (up >= key) break;
-                                list[j * nq_pad + e] = up;
-                                --j;
+                            list[my_min * nq_pad + e] = key;
+                            uint64_t m = ~0ull;
+                            int p = 0;
+#pragma unroll 8
+                            for (int j = 0; j < kp; ++j) {
+                                const uint64_t x = list[j * nq_pad + e];
+                                if (x < m) { m = x; p = j; }
                             }
-                            list[j * nq_pad + e] = key;
-                            my_tau = list[(kp - 1) * nq_pad + e];
+                            my_tau = m;
+                            my_min = p;
                         }
                     }
                     qcnt[e] = 0;
@@ -268,15 +287,16 @@ int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype)
     rc = make_tmap_2d(&tmB, queries_store_dtype, a.dtype, (uint64_t)L.nq_pad, (uint64_t)a.ld, (uint64_t)a.ld, (uint32_t)L.nq_pad);
     if (rc != VM_OK) return rc;
     const int num_tiles = (int)((a.n + TC_BLOCK_M - 1) / TC_BLOCK_M);
+    static const int dbg = getenv("VIDMEM_TC_DEBUG") ? atoi(getenv("VIDMEM_TC_DEBUG")) : 0;  // perf triage only
     g_last_tc_stages = L.stages;
     if (a.dtype == VM_F32) {
         static bool set = false;
         if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
-        scan_tc_kernel<true><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand);
+        scan_tc_kernel<true><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, dbg);
     } else {
         static bool set = false;
         if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
-        scan_tc_kernel<false><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand);
+        scan_tc_kernel<false><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, dbg);
     }
     VM_CUDA_CHECK(cudaGetLastError());
     return VM_OK;

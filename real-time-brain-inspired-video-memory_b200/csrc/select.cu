@@ -6,48 +6,87 @@
 namespace vm {
 
 // =========================================================================================
-// 1. merge per-CTA candidate lists -> one descending list of kp keys per query
+// 1. merge per-CTA candidate sets -> the kp best keys per query
 // =========================================================================================
-// cand [lists][nq][kp] -> merged [nq][kp] (descending, 0 = empty).  One CTA per query.
-// Each thread owns a strided slice of the lists*kp keys and keeps its local maximum; every
-// round a block-wide max picks the winner (keys are unique), the owner clears it and rescans.
-__global__ void __launch_bounds__(256) merge_candidates_kernel(const uint64_t *__restrict__ cand, int lists, int nq,
-                                                              int kp, uint64_t *__restrict__ merged)
+// cand [lists][nq][kp] -> merged [nq][kp]: the kp largest keys in ARBITRARY order except that
+// slot kp-1 holds the smallest of them (the "worst candidate" the certification needs); unused
+// slots are 0.  One CTA per query.  Keys are unique, so an MSB-first radix select (8 passes of
+// 8 bits, shared-memory histogram + one warp scanning the 256 bins) yields the exact kp-th
+// largest key T; every key >= T is then emitted.  O(n) work instead of kp block-wide arg-max
+// rounds.
+static constexpr int MERGE_THREADS = 512;
+__global__ void __launch_bounds__(MERGE_THREADS) merge_candidates_kernel(const uint64_t *__restrict__ cand, int lists, int nq,
+                                                                       int kp, uint64_t *__restrict__ merged)
 {
     extern __shared__ uint64_t skeys[];  // [lists*kp]
-    __shared__ uint64_t wmax[8];
-    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int hist[256];
+    __shared__ int s_bin, s_need, s_out, s_nz;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int total = lists * kp;
-    for (int e = tid; e < total; e += 256) {
+    if (tid == 0) { s_out = 0; s_nz = 0; }
+    __syncthreads();
+    int nz = 0;
+    for (int e = tid; e < total; e += MERGE_THREADS) {
         int l = e / kp, j = e - l * kp;
-        skeys[e] = cand[((int64_t)l * nq + q) * kp + j];
+        uint64_t k = cand[((int64_t)l * nq + q) * kp + j];
+        skeys[e] = k;
+        nz += k != 0;
+    }
+    if (nz) atomicAdd(&s_nz, nz);
+    __syncthreads();
+    const int nonzero = s_nz;
+    uint64_t T = 1;  // smallest real key is > 0: T = 1 selects every non-empty slot
+    if (nonzero >= kp) {
+        uint64_t prefix = 0;  // bits decided so far (high bits of T)
+        int need = kp;        // rank (1 = largest) of T among the keys matching `prefix`
+        for (int pass = 0; pass < 8; ++pass) {
+            const int shift = 56 - 8 * pass;
+            const uint64_t hmask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+            if (tid < 256) hist[tid] = 0;
+            __syncthreads();
+            for (int e = tid; e < total; e += MERGE_THREADS) {
+                const uint64_t k = skeys[e];
+                if (k != 0 && (k & hmask) == prefix) atomicAdd(&hist[(int)((k >> shift) & 0xFF)], 1);
+            }
+            __syncthreads();
+            if (tid < 32) {
+                // lane owns bins [255-8*lane-7, 255-8*lane] (descending order across lanes)
+                int mine[8], sum = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { mine[i] = hist[255 - (8 * lane + i)]; sum += mine[i]; }
+                int incl = sum;
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                int excl = incl - sum;  // keys in strictly higher bins than this lane's first bin
+                if (excl < need && need <= incl) {
+                    int acc = excl;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (acc < need && need <= acc + mine[i]) { s_bin = 255 - (8 * lane + i); s_need = need - acc; }
+                        acc += mine[i];
+                    }
+                }
+            }
+            __syncthreads();
+            prefix |= (uint64_t)s_bin << shift;
+            need = s_need;
+            __syncthreads();
+        }
+        T = prefix;
+    }
+    for (int e = tid; e < total; e += MERGE_THREADS) {
+        const uint64_t k = skeys[e];
+        if (k >= T && k != 0) {
+            if (nonzero >= kp && k == T) merged[(int64_t)q * kp + kp - 1] = k;  // the worst candidate
+            else merged[(int64_t)q * kp + atomicAdd(&s_out, 1)] = k;
+        }
     }
     __syncthreads();
-    uint64_t best = 0;
-    int bpos = -1;
-    for (int e = tid; e < total; e += 256)
-        if (skeys[e] > best) { best = skeys[e]; bpos = e; }
-    for (int r = 0; r < kp; ++r) {
-        uint64_t m = best;
-        for (int o = 16; o > 0; o >>= 1) {
-            uint64_t t = __shfl_xor_sync(0xffffffffu, m, o);
-            m = t > m ? t : m;
-        }
-        if (lane == 0) wmax[warp] = m;
-        __syncthreads();
-        uint64_t g = wmax[0];
-#pragma unroll
-        for (int w = 1; w < 8; ++w) g = wmax[w] > g ? wmax[w] : g;
-        if (tid == 0) merged[(int64_t)q * kp + r] = g;
-        if (g != 0 && g == best) {  // unique keys: exactly one thread wins
-            skeys[bpos] = 0;
-            best = 0;
-            bpos = -1;
-            for (int e = tid; e < total; e += 256)
-                if (skeys[e] > best) { best = skeys[e]; bpos = e; }
-        }
-        __syncthreads();
-    }
+    const int filled = s_out;
+    const int last = nonzero >= kp ? kp - 1 : kp;
+    for (int e = filled + tid; e < last; e += MERGE_THREADS) merged[(int64_t)q * kp + e] = 0;
 }
 
 // =========================================================================================
@@ -102,32 +141,66 @@ __device__ __forceinline__ bool better(double sa, uint32_t ra, double sb, uint32
     return sa > sb || (sa == sb && ra < rb);
 }
 
-// One CTA (64 threads) per query.  Thread j rescoring candidate j of merged[q][0..kp).
+// One CTA (128 threads) per query; thread j < kp owns candidate j of merged[q][0..kp).
+// The query and the kp candidate rows are staged through shared memory in column chunks
+// (coalesced loads, rows padded to an odd pitch so the per-thread walk is conflict-free); each
+// owner then runs the reference recurrence over its row in index order.
 // eps: bound on |approximate cosine - exact cosine| of the scan that produced the candidates.
+static constexpr int RS_THREADS = 128;
+static constexpr int RS_CHUNK = 128;
 template <bool NEUMAIER, typename T>
-__global__ void __launch_bounds__(64) rescore_kernel(const uint64_t *__restrict__ merged, int kp, const T *__restrict__ rows,
-                                                    const float *__restrict__ inv_norms, int ld, int dim, int64_t n_rows,
-                                                    const void *__restrict__ queries, int q_dtype, double eps,
-                                                    FinalizeArgs f, int32_t *__restrict__ flags,
-                                                    int32_t *__restrict__ uncertified_count)
+__global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const uint64_t *__restrict__ merged, int kp, const T *__restrict__ rows,
+                                                            const float *__restrict__ inv_norms, int ld, int dim, int64_t n_rows,
+                                                            const void *__restrict__ queries, int q_dtype, double eps,
+                                                            FinalizeArgs f, int32_t *__restrict__ flags,
+                                                            int32_t *__restrict__ uncertified_count)
 {
+    __shared__ double sq[RS_CHUNK];
+    __shared__ float srow[64 * (RS_CHUNK + 1)];
     __shared__ double s_score[64];
     __shared__ uint32_t s_row[64];
     __shared__ int s_valid[64];
     __shared__ int s_cnt;
     const int q = blockIdx.x, j = threadIdx.x;
     if (j == 0) s_cnt = 0;
-    uint64_t key = j < kp ? merged[(int64_t)q * kp + j] : 0;
-    bool valid = key != 0;
-    double sc = 0.0;
-    uint32_t row = 0;
-    if (valid) {
-        row = key_row(key);
-        sc = exact_cosine<NEUMAIER, T>(queries, q_dtype, (int64_t)q * dim, rows + (int64_t)row * ld, dim);
+    if (j < 64) {
+        uint64_t key = j < kp ? merged[(int64_t)q * kp + j] : 0;
+        s_valid[j] = key != 0;
+        s_row[j] = key != 0 ? key_row(key) : 0;
     }
-    s_score[j] = sc;
-    s_row[j] = row;
-    s_valid[j] = valid ? 1 : 0;
+    __syncthreads();
+    const bool valid = j < 64 && s_valid[j];
+    RefSum dot, qq, rr;
+    dot.init(); qq.init(); rr.init();
+    for (int c0 = 0; c0 < dim; c0 += RS_CHUNK) {
+        const int len = min(RS_CHUNK, dim - c0);
+        for (int i = j; i < len; i += RS_THREADS) sq[i] = load_as_double(queries, q_dtype, (int64_t)q * dim + c0 + i);
+        for (int e = j; e < kp * len; e += RS_THREADS) {
+            const int r = e / len, col = e - r * len;
+            srow[r * (RS_CHUNK + 1) + col] = s_valid[r] ? load_as_float(rows + (int64_t)s_row[r] * ld, c0 + col) : 0.0f;
+        }
+        __syncthreads();
+        if (valid) {
+            const float *mine = srow + j * (RS_CHUNK + 1);
+#pragma unroll 4
+            for (int i = 0; i < len; ++i) {
+                const double x = sq[i];
+                const double y = (double)mine[i];
+                dot.add<NEUMAIER>(__dmul_rn(x, y));
+                qq.add<NEUMAIER>(__dmul_rn(x, x));
+                rr.add<NEUMAIER>(__dmul_rn(y, y));
+            }
+        }
+        __syncthreads();
+    }
+    double sc = 0.0;
+    const uint32_t row = j < 64 ? s_row[j] : 0;
+    if (valid) {
+        const double n1 = __dsqrt_rn(qq.result<NEUMAIER>());
+        const double n2 = __dsqrt_rn(rr.result<NEUMAIER>());
+        sc = (n1 == 0.0 || n2 == 0.0) ? 0.0 : __ddiv_rn(dot.result<NEUMAIER>(), __dmul_rn(n1, n2));
+    }
+    if (j < 64) s_score[j] = sc;
     __syncthreads();
     int ncand = 0;
     for (int i = 0; i < 64; ++i) ncand += s_valid[i];
@@ -147,6 +220,7 @@ __global__ void __launch_bounds__(64) rescore_kernel(const uint64_t *__restrict_
     // certification: every non-candidate row r has approx(r) <= approx(worst candidate), hence
     // exact(r) <= approx_worst + eps; certified iff that is strictly below the k-th exact score.
     // Fewer than kp candidates means every scorable row of the shard is already a candidate.
+    // (merge_candidates_kernel puts the worst candidate in slot kp-1.)
     if (valid && rank == min(f.k, ncand) - 1) {
         bool cert = true;
         if (ncand >= kp && (int64_t)ncand < n_rows) {
@@ -159,7 +233,7 @@ __global__ void __launch_bounds__(64) rescore_kernel(const uint64_t *__restrict_
     if (ncand == 0 && j == 0) flags[q] = 0;
     if (j == 0) f.out_count[q] = s_cnt;
     int cnt = s_cnt;
-    for (int t = cnt + j; t < f.k; t += 64) {
+    for (int t = cnt + j; t < f.k; t += RS_THREADS) {
         f.out_idx[(int64_t)q * f.k + t] = -1;
         f.out_score[(int64_t)q * f.k + t] = 0.0;
     }
@@ -180,6 +254,8 @@ __global__ void __launch_bounds__(128) exact_scan_kernel(const T *__restrict__ r
                                                         double *__restrict__ xlist_score, uint32_t *__restrict__ xlist_row,
                                                         int32_t *__restrict__ xlist_cnt)
 {
+    // flags[nq] is the uncertified-query counter written by rescore_kernel: nothing to do when 0
+    if (flags && flags[nq] == 0) return;
     extern __shared__ double sq[];  // [dim] query as doubles
     __shared__ double l_score[XK], n_score[XK];
     __shared__ uint32_t l_row[XK], n_row[XK];
@@ -258,7 +334,7 @@ __global__ void __launch_bounds__(256) exact_merge_kernel(const double *__restri
     __shared__ int w_p[8];
     __shared__ int s_out;
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (flags && flags[q] == 0) return;
+    if (flags && (flags[nq] == 0 || flags[q] == 0)) return;
     const int total = lists * k;
     uint8_t *tk = taken + (int64_t)q * total;
     for (int e = tid; e < total; e += 256) tk[e] = 0;
@@ -435,7 +511,7 @@ int k_merge_candidates(const uint64_t *cand, int lists, int nq, int kp, uint64_t
         attr_set = true;
     }
     VM_REQUIRE(smem <= 200 * 1024, VM_ERR_UNSUPPORTED, "candidate merge: %d lists x %d exceeds shared memory", lists, kp);
-    merge_candidates_kernel<<<nq, 256, smem, st>>>(cand, lists, nq, kp, merged);
+    merge_candidates_kernel<<<nq, MERGE_THREADS, smem, st>>>(cand, lists, nq, kp, merged);
     VM_CUDA_CHECK(cudaGetLastError());
     return VM_OK;
 }
@@ -444,7 +520,7 @@ int k_merge_candidates(const uint64_t *cand, int lists, int nq, int kp, uint64_t
 int k_rescore(const RescoreArgs &a, cudaStream_t st)
 {
 #define LAUNCH_RS(NEU, T)                                                                                              \
-    rescore_kernel<NEU, T><<<a.nq, 64, 0, st>>>(a.merged, a.kp, (const T *)a.rows, a.inv_norms, a.ld, a.dim, a.n_rows, \
+    rescore_kernel<NEU, T><<<a.nq, RS_THREADS, 0, st>>>(a.merged, a.kp, (const T *)a.rows, a.inv_norms, a.ld, a.dim, a.n_rows, \
                                                 a.queries, a.q_dtype, a.eps, a.fin, a.flags, a.uncertified_count)
     bool neu = a.sum_mode == VM_SUM_NEUMAIER;
     if (a.dtype == VM_F32) { if (neu) LAUNCH_RS(true, float); else LAUNCH_RS(false, float); }
