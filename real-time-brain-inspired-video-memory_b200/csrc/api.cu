@@ -24,7 +24,7 @@ int k_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype, int
 int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, cudaStream_t st);
 int k_invalidate_rows(float *inv_norms, const int64_t *rows_dev, int64_t n, int64_t size, cudaStream_t st);
 int k_normalize_queries(const void *q, int q_dtype, int nq, int nq_pad, int dim, int ld, float *out_f32, void *out_bf16,
-                        int32_t *zero_me, cudaStream_t st);
+                        int32_t *zero_me, uint32_t *zero_tab, int zero_tab_n, cudaStream_t st);
 int k_synth_fill(void *rows, int dtype, uint64_t seed, int64_t row0, int64_t n, int dim, int ld, uint64_t dup_period,
                  cudaStream_t st);
 int k_merge_candidates(const uint64_t *cand, int lists, int nq, int kp, uint64_t *merged, cudaStream_t st);
@@ -76,11 +76,11 @@ struct Buf {
 struct Workspace {
     bool ready = false;
     int lists_max = 0;
-    Buf q_raw, q_f32, q_bf16, cand, merged, o_idx, o_score, o_count, flags, xs, xr, xc, taken, gather_send, gather_recv, misc;
+    Buf q_raw, q_f32, q_bf16, seed, cand, merged, o_idx, o_score, o_count, flags, xs, xr, xc, taken, gather_send, gather_recv, misc;
     int32_t *h_uncert = nullptr;  // pinned
     void release()
     {
-        Buf *all[] = {&q_raw, &q_f32, &q_bf16, &cand, &merged, &o_idx, &o_score, &o_count, &flags, &xs, &xr, &xc, &taken,
+        Buf *all[] = {&q_raw, &q_f32, &q_bf16, &seed, &cand, &merged, &o_idx, &o_score, &o_count, &flags, &xs, &xr, &xc, &taken,
                       &gather_send, &gather_recv, &misc};
         for (Buf *b : all) b->release();
         if (h_uncert) cudaFreeHost(h_uncert);
@@ -176,7 +176,8 @@ static int ws_prepare(vm_store *s)
     ENS(w.o_idx, (size_t)MAXQ * MAXK * 8);
     ENS(w.o_score, (size_t)MAXQ * MAXK * 8);
     ENS(w.o_count, (size_t)MAXQ * 4);
-    ENS(w.flags, (size_t)(MAXQ + 1) * 4);
+    ENS(w.flags, (size_t)(MAXQ + 2) * 4);
+    ENS(w.seed, (size_t)256 * MAXQ * 4);
     ENS(w.xs, (size_t)XCTAS * MAXQ * MAXK * 8);
     ENS(w.xr, (size_t)XCTAS * MAXQ * MAXK * 4);
     ENS(w.xc, (size_t)XCTAS * MAXQ * 4);
@@ -423,7 +424,8 @@ static int topk_batch(const TopkCall &c)
     int nq_pad = kernel == 2 ? ((c.nq + 15) & ~15) : c.nq;
     int rc = k_normalize_queries(q_dev, c.q_dtype, c.nq, nq_pad, s->dim, s->ld, (float *)w.q_f32.p,
                                  (kernel == 2 && s->dtype == VM_BF16) ? w.q_bf16.p : nullptr,
-                                 (int32_t *)w.flags.p + c.nq, st);
+                                 (int32_t *)w.flags.p + c.nq, kernel == 2 ? (uint32_t *)w.seed.p : nullptr,
+                                 kernel == 2 ? (int)(w.seed.bytes / 4) : 0, st);
     if (rc != VM_OK) return rc;
     ++launches;
 
@@ -443,7 +445,7 @@ static int topk_batch(const TopkCall &c)
     } else {
         int64_t tiles = (s->size + 127) / 128;
         a.ctas = (int)imin64(tiles, s->sm_count);
-        rc = launch_scan_tc(a, s->dtype == VM_BF16 ? w.q_bf16.p : w.q_f32.p);
+        rc = launch_scan_tc(a, s->dtype == VM_BF16 ? w.q_bf16.p : w.q_f32.p, (uint32_t *)w.seed.p, (int *)w.flags.p + c.nq + 1);
         launches += 1;
     }
     if (rc != VM_OK) return rc;

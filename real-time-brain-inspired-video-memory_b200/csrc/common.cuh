@@ -118,7 +118,8 @@ struct ScanArgs {
 };
 int launch_scan_simt(const ScanArgs &a);
 int scan_simt_max_queries();
-int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype);  // tcgen05 path
+// tcgen05 path; seed_tab [ctas][nq_pad] u32 + seed_ctr must be zeroed before the launch (NULL = no seeding)
+int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t *seed_tab, int *seed_ctr);
 bool scan_tc_supported(int dtype, int dim, int nq, int kp);
 
 

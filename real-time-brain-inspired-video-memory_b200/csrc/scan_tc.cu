@@ -13,6 +13,13 @@
 //                           queues; thread q then inserts them into query q's sorted top-kp list
 //                           (shared memory).  While a tile overflows a queue its accumulator simply
 //                           stays in TMEM and is re-read after the drain.
+// Threshold seeding: each CTA starts without a threshold, so for its first tiles every score would
+// be a "survivor".  Instead every CTA first publishes, per query, the maximum score of its first
+// tile; the kp-th largest of those per-CTA maxima is a valid lower bound on the shard's kp-th best
+// score (kp distinct rows reach it), and with ~148 CTAs it is as tight as the kp-th best of the
+// first 19 K rows.  All CTAs adopt it as their initial threshold (bounded wait, no grid barrier
+// semantics needed: a late CTA only makes the bound looser), while TMA/MMA keep streaming into the
+// 8 TMEM stages.  This removes the per-CTA warm-up flood that otherwise dominates small shards.
 // HBM traffic = the store bytes exactly once per batch of <= 64 queries; the per-CTA lists are
 // merged and exactly rescored by select.cu.
 #include "tc_common.cuh"
@@ -23,10 +30,10 @@ using namespace tc;
 
 static constexpr int TC_BLOCK_M = 128;
 static constexpr int TC_STAGE_BYTES = TC_BLOCK_M * 128;
-static constexpr int TC_ACC = 4;
+static constexpr int TC_ACC = 8;      // accumulator stages in TMEM (8 x 64 columns = all 512)
 static constexpr int TC_QCAP = 32;
 static constexpr int TC_THREADS = 192;
-static constexpr int TC_TMEM_COLS = 256;
+static constexpr int TC_TMEM_COLS = 512;
 static constexpr int TC_MAX_STAGES = 8;
 
 struct TcLayout {
@@ -64,7 +71,8 @@ static TcLayout make_layout(int dtype, int ld, int nq, int kp)
 template <bool TF32>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const float *__restrict__ inv_norms, int64_t n, int num_tiles, int nq, TcLayout L, uint64_t *__restrict__ cand, int dbg)
+               const float *__restrict__ inv_norms, int64_t n, int num_tiles, int nq, TcLayout L, uint64_t *__restrict__ cand,
+               uint32_t *__restrict__ seed_tab, int *__restrict__ seed_ctr, int dbg)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     // align to 1024 B with pointer arithmetic on the __shared__ array (an integer round trip would
@@ -163,11 +171,80 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int row_in_tile = quad * 32 + lane;
         uint64_t my_tau = 0;              // threshold key (= minimum of the set) of query e (threads e < nq_pad)
         int my_min = 0;                   // its position in the set
+        float my_seed = -INFINITY;        // seeded lower bound of query e
         int acc = 0, par = 0;
         uint32_t acc_phase = 0;
+        if (seed_tab != nullptr) {
+            // ---- cooperative threshold seeding from the first tile (see file header) ----
+            uint32_t *wmax = reinterpret_cast<uint32_t *>(queue);  // [4][nq_pad] scratch (queue is idle now)
+            float *seedf = reinterpret_cast<float *>(wmax + 4 * nq_pad);
+            const int64_t row0 = (int64_t)blockIdx.x * TC_BLOCK_M + row_in_tile;
+            const float inv0 = row0 < n ? __ldg(inv_norms + row0) : -1.0f;
+            mbar_wait(&tfull[0], 0);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16);
+            for (int c = 0; c < nq_pad; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr0 + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float sc = inv0 >= 0.0f ? __uint_as_float(v[j]) * inv0 : -INFINITY;
+                    const uint32_t mx = __reduce_max_sync(0xffffffffu, f32_ordered(sc));
+                    if (lane == 0) wmax[(warp - 2) * nq_pad + c + j] = mx;
+                }
+            }
+            named_bar_sync(1, 128);
+            if (e < nq_pad) {
+                uint32_t m = wmax[e];
+#pragma unroll
+                for (int w = 1; w < 4; ++w) m = max(m, wmax[w * nq_pad + e]);
+                seed_tab[(size_t)blockIdx.x * nq_pad + e] = m;
+            }
+            __threadfence();
+            named_bar_sync(1, 128);
+            if (e == 0) {
+                atomicAdd(seed_ctr, 1);
+                const long long t0 = clock64();
+                while (*(volatile int *)seed_ctr < (int)gridDim.x)
+                    if (clock64() - t0 > 400000) break;  // ~0.2 ms: late CTAs only loosen the bound
+                __threadfence();
+            }
+            named_bar_sync(1, 128);
+            const int G = (int)gridDim.x;
+            for (int q = warp - 2; q < nq; q += 4) {
+                uint32_t vals[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int i = lane + 32 * t;
+                    vals[t] = i < G ? __ldcg(seed_tab + (size_t)i * nq_pad + q) : 0u;
+                }
+                // bitwise radix select of the kp-th largest; 16 bits are enough (truncation rounds down)
+                uint32_t prefix = 0;
+                int need = kp;
+                for (int bit = 31; bit >= 16; --bit) {
+                    const uint32_t hi = bit == 31 ? 0u : (0xFFFFFFFFu << (bit + 1));
+                    int cnt = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) cnt += ((vals[t] & hi) == prefix && ((vals[t] >> bit) & 1u)) ? 1 : 0;
+                    const int tot = __reduce_add_sync(0xffffffffu, cnt);
+                    if (tot >= need) prefix |= 1u << bit;
+                    else need -= tot;
+                }
+                float sd = f32_from_ordered(prefix);
+                if (!(sd > -INFINITY) || G < kp) sd = -INFINITY;  // also catches NaN patterns
+                if (lane == 0) seedf[q] = sd;
+            }
+            named_bar_sync(1, 128);
+            if (e < nq) { my_seed = seedf[e]; tauf[e] = my_seed; }
+            named_bar_sync(1, 128);
+        }
+        int64_t row = (int64_t)blockIdx.x * TC_BLOCK_M + row_in_tile;
+        float inv = row < n ? __ldg(inv_norms + row) : -1.0f;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int64_t row = (int64_t)tile * TC_BLOCK_M + row_in_tile;
-            const float inv = row < n ? __ldg(inv_norms + row) : -1.0f;
+            // prefetch the next tile's inverse norm so its DRAM latency hides behind this tile
+            const int64_t row_next = row + (int64_t)gridDim.x * TC_BLOCK_M;
+            const float inv_next = (tile + (int)gridDim.x < num_tiles && row_next < n) ? __ldg(inv_norms + row_next) : -1.0f;
             const bool valid = inv >= 0.0f;  // < 0: beyond the shard or a skipped row
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
@@ -238,7 +315,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     qcnt[e] = 0;
                     tauk[e] = my_tau;
-                    tauf[e] = my_tau ? key_score(my_tau) : -INFINITY;
+                    tauf[e] = my_tau ? fmaxf(key_score(my_tau), my_seed) : my_seed;
                 }
                 named_bar_sync(1, 128);
                 if (!o) break;
@@ -248,6 +325,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
             if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1; }
+            row = row_next;
+            inv = inv_next;
         }
         named_bar_sync(1, 128);
         for (int i = e; i < nq * kp; i += 128) {
@@ -276,7 +355,7 @@ int g_last_tc_stages = 0;
 
 // queries_store_dtype: the normalised queries [nq_pad][ld] in the STORE dtype (fp32 for the tf32
 // path, bf16 for the bf16 path).
-int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype)
+int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t *seed_tab, int *seed_ctr)
 {
     VM_REQUIRE(a.n >= 1 && a.n < 0x7FFFFF00LL, VM_ERR_UNSUPPORTED, "tcgen05 scan: shard rows %lld outside [1, 2^31)", (long long)a.n);
     TcLayout L = make_layout(a.dtype, a.ld, a.nq, a.kp);
@@ -289,14 +368,17 @@ int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype)
     const int num_tiles = (int)((a.n + TC_BLOCK_M - 1) / TC_BLOCK_M);
     static const int dbg = getenv("VIDMEM_TC_DEBUG") ? atoi(getenv("VIDMEM_TC_DEBUG")) : 0;  // perf triage only
     g_last_tc_stages = L.stages;
+    // seeding pays off once every CTA streams several tiles and there are at least kp CTAs
+    const bool seed = seed_tab && seed_ctr && a.ctas >= a.kp && a.ctas <= 256 && num_tiles >= 4 * a.ctas && !(dbg & 4);
+    if (!seed) { seed_tab = nullptr; seed_ctr = nullptr; }
     if (a.dtype == VM_F32) {
         static bool set = false;
         if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
-        scan_tc_kernel<true><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, dbg);
+        scan_tc_kernel<true><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, seed_tab, seed_ctr, dbg);
     } else {
         static bool set = false;
         if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
-        scan_tc_kernel<false><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, dbg);
+        scan_tc_kernel<false><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, seed_tab, seed_ctr, dbg);
     }
     VM_CUDA_CHECK(cudaGetLastError());
     return VM_OK;

@@ -46,7 +46,12 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_candidates_kernel(const u
             __syncthreads();
             for (int e = tid; e < total; e += MERGE_THREADS) {
                 const uint64_t k = skeys[e];
-                if (k != 0 && (k & hmask) == prefix) atomicAdd(&hist[(int)((k >> shift) & 0xFF)], 1);
+                const bool act = k != 0 && (k & hmask) == prefix;
+                const int bin = act ? (int)((k >> shift) & 0xFF) : -1;
+                // scores cluster in a few bins (same exponent): aggregate equal bins inside the warp
+                // so a skewed pass costs one atomic per warp instead of 32 serialised ones
+                const unsigned peers = __match_any_sync(__activemask(), bin);
+                if (act && (__ffs(peers) - 1) == lane) atomicAdd(&hist[bin], __popc(peers));
             }
             __syncthreads();
             if (tid < 32) {
@@ -141,13 +146,15 @@ __device__ __forceinline__ bool better(double sa, uint32_t ra, double sb, uint32
     return sa > sb || (sa == sb && ra < rb);
 }
 
-// One CTA (128 threads) per query; thread j < kp owns candidate j of merged[q][0..kp).
-// The query and the kp candidate rows are staged through shared memory in column chunks
-// (coalesced loads, rows padded to an odd pitch so the per-thread walk is conflict-free); each
-// owner then runs the reference recurrence over its row in index order.
+// One CTA per query.  The reference formula needs three sequential binary64 sums per
+// (query, candidate): dot, ||q||^2 and ||row||^2.  Each is an independent chain, so they are
+// spread over threads as TASKS -- task t < kp: dot of candidate t; kp <= t < 2kp: ||row||^2 of
+// candidate t-kp; t == 2kp: ||q||^2 -- and every chain runs in index order (bit-identical to
+// CPython).  Query and candidate rows are staged through shared memory as doubles in column
+// chunks (coalesced loads; odd row pitch -> conflict-free per-thread walks).
 // eps: bound on |approximate cosine - exact cosine| of the scan that produced the candidates.
-static constexpr int RS_THREADS = 128;
-static constexpr int RS_CHUNK = 128;
+static constexpr int RS_THREADS = 160;  // >= 2*64 + 1 tasks
+static constexpr int RS_CHUNK = 96;
 template <bool NEUMAIER, typename T>
 __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const uint64_t *__restrict__ merged, int kp, const T *__restrict__ rows,
                                                             const float *__restrict__ inv_norms, int ld, int dim, int64_t n_rows,
@@ -155,8 +162,10 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const uint64_t *__r
                                                             FinalizeArgs f, int32_t *__restrict__ flags,
                                                             int32_t *__restrict__ uncertified_count)
 {
-    __shared__ double sq[RS_CHUNK];
-    __shared__ float srow[64 * (RS_CHUNK + 1)];
+    extern __shared__ double rs_smem[];
+    double *sq = rs_smem;                 // [RS_CHUNK]
+    double *srow = rs_smem + RS_CHUNK;    // [kp][RS_CHUNK + 1]
+    __shared__ double s_dot[64], s_rr[64], s_qq;
     __shared__ double s_score[64];
     __shared__ uint32_t s_row[64];
     __shared__ int s_valid[64];
@@ -169,36 +178,42 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const uint64_t *__r
         s_row[j] = key != 0 ? key_row(key) : 0;
     }
     __syncthreads();
-    const bool valid = j < 64 && s_valid[j];
-    RefSum dot, qq, rr;
-    dot.init(); qq.init(); rr.init();
+    // task decode
+    const int kind = j < kp ? 0 : (j < 2 * kp ? 1 : (j == 2 * kp ? 2 : 3));
+    const int cand = kind == 0 ? j : (kind == 1 ? j - kp : 0);
+    const bool active = kind == 2 || (kind < 2 && s_valid[cand]);
+    const double *pa = kind == 0 ? sq : (kind == 1 ? srow + cand * (RS_CHUNK + 1) : sq);
+    const double *pb = kind == 2 ? sq : srow + cand * (RS_CHUNK + 1);
+    RefSum acc;
+    acc.init();
     for (int c0 = 0; c0 < dim; c0 += RS_CHUNK) {
         const int len = min(RS_CHUNK, dim - c0);
         for (int i = j; i < len; i += RS_THREADS) sq[i] = load_as_double(queries, q_dtype, (int64_t)q * dim + c0 + i);
         for (int e = j; e < kp * len; e += RS_THREADS) {
             const int r = e / len, col = e - r * len;
-            srow[r * (RS_CHUNK + 1) + col] = s_valid[r] ? load_as_float(rows + (int64_t)s_row[r] * ld, c0 + col) : 0.0f;
+            srow[r * (RS_CHUNK + 1) + col] = s_valid[r] ? (double)load_as_float(rows + (int64_t)s_row[r] * ld, c0 + col) : 0.0;
         }
         __syncthreads();
-        if (valid) {
-            const float *mine = srow + j * (RS_CHUNK + 1);
-#pragma unroll 4
-            for (int i = 0; i < len; ++i) {
-                const double x = sq[i];
-                const double y = (double)mine[i];
-                dot.add<NEUMAIER>(__dmul_rn(x, y));
-                qq.add<NEUMAIER>(__dmul_rn(x, x));
-                rr.add<NEUMAIER>(__dmul_rn(y, y));
-            }
+        if (active) {
+#pragma unroll 8
+            for (int i = 0; i < len; ++i) acc.add<NEUMAIER>(__dmul_rn(pa[i], pb[i]));
         }
         __syncthreads();
     }
+    if (active) {
+        const double r = acc.result<NEUMAIER>();
+        if (kind == 0) s_dot[cand] = r;
+        else if (kind == 1) s_rr[cand] = r;
+        else s_qq = r;
+    }
+    __syncthreads();
+    const bool valid = j < 64 && s_valid[j];
     double sc = 0.0;
     const uint32_t row = j < 64 ? s_row[j] : 0;
     if (valid) {
-        const double n1 = __dsqrt_rn(qq.result<NEUMAIER>());
-        const double n2 = __dsqrt_rn(rr.result<NEUMAIER>());
-        sc = (n1 == 0.0 || n2 == 0.0) ? 0.0 : __ddiv_rn(dot.result<NEUMAIER>(), __dmul_rn(n1, n2));
+        const double n1 = __dsqrt_rn(s_qq);
+        const double n2 = __dsqrt_rn(s_rr[j]);
+        sc = (n1 == 0.0 || n2 == 0.0) ? 0.0 : __ddiv_rn(s_dot[j], __dmul_rn(n1, n2));
     }
     if (j < 64) s_score[j] = sc;
     __syncthreads();
@@ -520,8 +535,17 @@ int k_merge_candidates(const uint64_t *cand, int lists, int nq, int kp, uint64_t
 int k_rescore(const RescoreArgs &a, cudaStream_t st)
 {
 #define LAUNCH_RS(NEU, T)                                                                                              \
-    rescore_kernel<NEU, T><<<a.nq, RS_THREADS, 0, st>>>(a.merged, a.kp, (const T *)a.rows, a.inv_norms, a.ld, a.dim, a.n_rows, \
-                                                a.queries, a.q_dtype, a.eps, a.fin, a.flags, a.uncertified_count)
+    do {                                                                                                               \
+        static bool attr_set = false;                                                                                  \
+        if (!attr_set) {                                                                                               \
+            VM_CUDA_CHECK(cudaFuncSetAttribute(rescore_kernel<NEU, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); \
+            attr_set = true;                                                                                           \
+        }                                                                                                              \
+        rescore_kernel<NEU, T><<<a.nq, RS_THREADS, smem, st>>>(a.merged, a.kp, (const T *)a.rows, a.inv_norms, a.ld, a.dim, \
+                                                               a.n_rows, a.queries, a.q_dtype, a.eps, a.fin, a.flags,    \
+                                                               a.uncertified_count);                                    \
+    } while (0)
+    const size_t smem = ((size_t)a.kp * (RS_CHUNK + 1) + RS_CHUNK) * sizeof(double);
     bool neu = a.sum_mode == VM_SUM_NEUMAIER;
     if (a.dtype == VM_F32) { if (neu) LAUNCH_RS(true, float); else LAUNCH_RS(false, float); }
     else { if (neu) LAUNCH_RS(true, __nv_bfloat16); else LAUNCH_RS(false, __nv_bfloat16); }

@@ -60,9 +60,12 @@ __global__ void invalidate_rows_kernel(float *inv_norms, const int64_t *rows, in
 // stays zero), plus an optional bf16 copy for the tcgen05 bf16 path.  One warp per query.
 __global__ void normalize_queries_kernel(const void *__restrict__ q, int q_dtype, int nq, int nq_pad, int dim, int ld,
                                          float *__restrict__ out_f32, __nv_bfloat16 *__restrict__ out_bf16,
-                                         int32_t *__restrict__ zero_me)
+                                         int32_t *__restrict__ zero_me, uint32_t *__restrict__ zero_tab, int zero_tab_n)
 {
-    if (zero_me && blockIdx.x == 0 && threadIdx.x == 0) *zero_me = 0;  // the uncertified-query counter of this batch
+    // per-batch device state: zero_me[0] = uncertified-query counter, zero_me[1] = seed counter,
+    // zero_tab = the threshold-seeding table of the tcgen05 scan
+    if (zero_me && blockIdx.x == 0 && threadIdx.x < 2) zero_me[threadIdx.x] = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < zero_tab_n; i += gridDim.x * blockDim.x) zero_tab[i] = 0u;
     int lane = threadIdx.x & 31;
     int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= nq_pad) return;
@@ -151,11 +154,11 @@ int k_invalidate_rows(float *inv_norms, const int64_t *rows_dev, int64_t n, int6
 }
 
 int k_normalize_queries(const void *q, int q_dtype, int nq, int nq_pad, int dim, int ld, float *out_f32,
-                        void *out_bf16, int32_t *zero_me, cudaStream_t st)
+                        void *out_bf16, int32_t *zero_me, uint32_t *zero_tab, int zero_tab_n, cudaStream_t st)
 {
     int threads = 128;
     int grid = (nq_pad * 32 + threads - 1) / threads;
-    normalize_queries_kernel<<<grid, threads, 0, st>>>(q, q_dtype, nq, nq_pad, dim, ld, out_f32, (__nv_bfloat16 *)out_bf16, zero_me);
+    normalize_queries_kernel<<<grid, threads, 0, st>>>(q, q_dtype, nq, nq_pad, dim, ld, out_f32, (__nv_bfloat16 *)out_bf16, zero_me, zero_tab, zero_tab_n);
     VM_CUDA_CHECK(cudaGetLastError());
     return VM_OK;
 }
