@@ -1,0 +1,331 @@
+"""Drop-in adapters: the reference's Python seams backed by libvidmem.
+
+Each adapter keeps the signature, return shape and error convention of the reference method it
+replaces (file:line cited per method) and can be bound onto an unmodified reference object
+with `install_*`.  Row identity: chunk ids are strings in the reference
+("{run_uuid}_{batch_idx}_{i}", src/components/pre_llm_injector.py:91); the engine works on dense
+row indices, so the adapters keep the id <-> row table on the host.  Row index == first-seen
+order == the reference's dict insertion order, which is what its stable sort uses to break ties
+(SURVEY.md 9.2).
+"""
+from __future__ import annotations
+
+import math
+import types
+from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _falsy_embedding(emb) -> bool:
+    # `if existing_emb:` (src/components/pre_llm_injector.py:363): None and [] are skipped
+    return emb is None or (hasattr(emb, "__len__") and len(emb) == 0)
+
+
+class ResidentChunkStore:
+    """Host-side id table + one HBM-resident EmbeddingStore that grows by doubling.
+
+    Replaces the dict returned by PreLLMInjector._get_chunk_embeddings
+    (src/components/pre_llm_injector.py:390-412) and is fed by the insert hook S6
+    (src/components/neo4j_handler.py:221-253)."""
+
+    def __init__(self, dtype: str = "f32", device: int = 0, initial_capacity: int = 8192):
+        self.dtype, self.device = dtype, device
+        self.initial_capacity = int(initial_capacity)
+        self.store = None                      # created lazily: the dimension is whatever the embedder returns
+        self.dim: Optional[int] = None
+        self.ids: List[str] = []               # row -> chunk id
+        self.row_of: Dict[str, int] = {}       # chunk id -> row
+        self.meta: Dict[str, Dict[str, Any]] = {}  # chunk id -> {"content", "time"} for vector search results
+
+    def __len__(self) -> int:
+        return len(self.ids)
+
+    # -- storage ---------------------------------------------------------------------------------
+    def _ensure(self, dim: int, extra: int) -> None:
+        from .store import EmbeddingStore
+        if self.store is None:
+            self.dim = int(dim)
+            cap = max(self.initial_capacity, 2 * extra)
+            self.store = EmbeddingStore(self.dim, cap, self.dtype, self.device)
+            return
+        if dim != self.dim:
+            raise ValueError(f"embedding dimension changed from {self.dim} to {dim}")
+        need = len(self.ids) + extra
+        if need > self.store.capacity:
+            old = self.store
+            new = EmbeddingStore(self.dim, max(2 * old.capacity, need), self.dtype, self.device)
+            n = len(old)
+            if n:
+                new.append(old.rows[:n, :self.dim].float().contiguous())      # device -> device, exact for f32/bf16
+                bad = (old.inv_norms[:n] < 0).nonzero().flatten().cpu().numpy()
+                if len(bad):
+                    new.invalidate(bad)
+            old.close()
+            self.store = new
+
+    def clear(self) -> None:
+        if self.store is not None:
+            self.store.clear()
+        self.ids, self.row_of = [], {}
+
+    def upsert(self, items: Iterable[Tuple[str, Any]], meta: Optional[Dict[str, Dict[str, Any]]] = None) -> None:
+        """Insert hook: (chunk_id, embedding) pairs.  Unknown ids are appended, known ids are
+        overwritten in place (the reference MERGEs by id, neo4j_handler.py:229).  A falsy embedding
+        keeps its row slot but is marked skipped."""
+        items = list(items)
+        new_rows, new_ids, invalid = [], [], []
+        dim = next((len(e) for _, e in items if not _falsy_embedding(e)), self.dim)
+        if dim is None:
+            # nothing embeddable seen yet: remember the ids so that store order is preserved
+            dim = 1 if self.store is None else self.dim
+        for cid, emb in items:
+            if cid in self.row_of:
+                row = self.row_of[cid]
+                if _falsy_embedding(emb):
+                    invalid.append(row)
+                else:
+                    self._ensure(len(emb), 0)
+                    self.store.update(row, np.asarray(emb, dtype=np.float64)[None, :])
+            else:
+                new_ids.append(cid)
+                if _falsy_embedding(emb):
+                    new_rows.append(None)
+                else:
+                    new_rows.append(np.asarray(emb, dtype=np.float64))
+        if new_ids:
+            self._ensure(dim, len(new_ids))
+            block = np.zeros((len(new_ids), self.dim), np.float64)
+            for i, r in enumerate(new_rows):
+                if r is None:
+                    invalid.append(len(self.ids) + i)
+                elif len(r) != self.dim:
+                    # the reference scores a length mismatch as 0.0 (:378-379) == a zero row
+                    pass
+                else:
+                    block[i] = r
+            first = self.store.append(block)
+            assert first == len(self.ids)
+            for cid in new_ids:
+                self.row_of[cid] = len(self.ids)
+                self.ids.append(cid)
+        if invalid:
+            self.store.invalidate(invalid)
+        if meta:
+            self.meta.update(meta)
+
+    def sync_from_dict(self, existing: Dict[str, Any]) -> None:
+        """Mirror mode: make the resident rows equal to `existing` (the dict the reference would
+        loop over), in its iteration order.  Fast path: the dict only grew at the end."""
+        keys = list(existing.keys())
+        n = len(self.ids)
+        if keys[:n] != self.ids:
+            self.clear()
+            n = 0
+        if len(keys) > n:
+            self.upsert((k, existing[k]) for k in keys[n:])
+
+    # -- queries ---------------------------------------------------------------------------------
+    def topk(self, queries: Sequence[Any], k: int, min_score: float = -math.inf, score_mode: int = L.VM_SCORE_RAW,
+             flags: int = 0):
+        """queries: list of vectors (or Exception objects).  -> list (per query) of [(chunk_id, score)]."""
+        out: List[List[Tuple[str, float]]] = [[] for _ in queries]
+        if self.store is None or len(self.ids) == 0:
+            return out
+        good = [i for i, q in enumerate(queries)
+                if not isinstance(q, Exception) and not _falsy_embedding(q) and len(q) == self.dim]
+        if good:
+            qa = np.asarray([queries[i] for i in good], dtype=np.float64)
+            idx, score, count = self.store.topk(qa, k, min_score=min_score, score_mode=score_mode, flags=flags)
+            for o, i in enumerate(good):
+                out[i] = [(self.ids[int(idx[o, j])], float(score[o, j])) for j in range(int(count[o]))]
+        # a query of the wrong length scores 0.0 against every row (:378-379): first k rows in store order
+        for i, q in enumerate(queries):
+            if isinstance(q, Exception) or i in good:
+                continue
+            if _falsy_embedding(q) or len(q) != self.dim:
+                valid = (self.store.inv_norms[:len(self.ids)] >= 0).cpu().numpy()
+                rows = np.nonzero(valid)[0][:k]
+                val = 0.0 if score_mode == L.VM_SCORE_RAW else 0.5
+                if val > min_score:
+                    out[i] = [(self.ids[int(r)], val) for r in rows]
+        return out
+
+
+class ChunkSimilarityBackend:
+    """S1 / S2: PreLLMInjector._calculate_batch_similarities and _cosine_similarity
+    (src/components/pre_llm_injector.py:346-388) plus the cross-query merge (:235-249)."""
+
+    def __init__(self, store: Optional[ResidentChunkStore] = None, mirror_fetch: bool = True, **store_kw):
+        self.store = store or ResidentChunkStore(**store_kw)
+        #: True  = behave exactly like the reference: fetch `{id: embedding}` through the injector's own
+        #:         _get_chunk_embeddings (LIMIT 5000) on every call and mirror it into HBM;
+        #: False = rows arrive only through the insert hook; no Bolt fetch on the query path (row f1).
+        self.mirror_fetch = mirror_fetch
+
+    # S1 -- same signature and return type as the reference coroutine
+    async def _calculate_batch_similarities(self, injector, chunk_embeddings, neo4j_handler) -> List[List[Tuple[str, float]]]:
+        if self.mirror_fetch:
+            existing = await injector._get_chunk_embeddings(neo4j_handler)   # reference's own fetch (:353)
+            self.store.sync_from_dict(existing)
+        k = injector.embedder_config.top_k_chunk_with_batch_similarity      # (:370)
+        return self.store.topk(list(chunk_embeddings), k)
+
+    # S2
+    def _cosine_similarity(self, vec1: List[float], vec2: List[float]) -> float:
+        if len(vec1) != len(vec2):                                            # (:378-379)
+            return 0.0
+        if len(vec1) == 0:
+            return 0.0
+        from .store import cosine_pairs
+        return float(cosine_pairs(vec1, vec2, zero_rule=0, device=self.store.device)[0])
+
+    # cross-query merge (:235-249): max score per id, stable sort desc, [:top_k_similar_batch]
+    def merge_top_similar(self, batch_similarities: List[List[Tuple[str, float]]], top_k2: int) -> List[Tuple[str, float]]:
+        import ctypes as C
+        import torch
+        nq = len(batch_similarities)
+        k = max((len(x) for x in batch_similarities), default=0)
+        if nq == 0 or k == 0:
+            return []
+        # ids that are not resident rows (should not happen) get private negative indices
+        extra: Dict[str, int] = {}
+        idx = np.full((nq, k), -1, np.int64)
+        sc = np.zeros((nq, k), np.float64)
+        cnt = np.zeros(nq, np.int32)
+        for i, lst in enumerate(batch_similarities):
+            cnt[i] = len(lst)
+            for j, (cid, s) in enumerate(lst):
+                idx[i, j] = self.store.row_of.get(cid, extra.setdefault(cid, -2 - len(extra)))
+                sc[i, j] = s
+        dev = torch.device("cuda", self.store.device)
+        d_idx, d_sc, d_cnt = (torch.from_numpy(a).to(dev) for a in (idx, sc, cnt))
+        o_idx = torch.full((top_k2,), -1, dtype=torch.int64, device=dev)
+        o_sc = torch.zeros((top_k2,), dtype=torch.float64, device=dev)
+        o_cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+        lib = L.load()
+        L.check(lib.vm_merge_max_by_id(self.store.device, d_idx.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(), nq, k,
+                                       top_k2, o_idx.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(),
+                                       torch.cuda.current_stream(dev).cuda_stream))
+        m = int(o_cnt.item())
+        rev = {v: c for c, v in extra.items()}
+        rows, scores = o_idx[:m].cpu().numpy(), o_sc[:m].cpu().numpy()
+        return [((self.store.ids[int(r)] if r >= 0 else rev[int(r)]), float(s)) for r, s in zip(rows, scores)]
+
+    # S6 -- insert hook, same `text_chunks` list Neo4jHandler._create_chunks_with_embeddings receives
+    def on_chunks_inserted(self, text_chunks: List[Dict[str, Any]]) -> None:
+        self.store.upsert(((c["id"], c.get("embedding")) for c in text_chunks),
+                          meta={c["id"]: {"content": c.get("content"), "time": c.get("time")} for c in text_chunks})
+
+
+class VectorSearchBackend:
+    """S3 / S4: HybridRetriever._vector_search_chunks and _cosine_similarity
+    (src/pipeline/retriever_hybrid.py:284-323, 655-664) plus the post-compression filter (:492-504)."""
+
+    MIN_SCORE = 0.3  # `WHERE similarity > 0.3` (:298), on the Neo4j-normalised score
+
+    def __init__(self, store: ResidentChunkStore):
+        self.store = store
+
+    async def _vector_search_chunks(self, retriever, session, query: str) -> List[Dict[str, Any]]:
+        try:
+            query_embedding = await retriever.neo4j_handler.embedder.aembed_query(query)   # (:290)
+            res = self.store.topk([query_embedding], retriever.config.top_k_chunks, min_score=self.MIN_SCORE,
+                                  score_mode=L.VM_SCORE_NEO4J)[0]
+            chunks = []
+            for cid, score in res:
+                m = self.store.meta.get(cid, {})
+                chunks.append({"id": cid, "time": m.get("time"), "content": m.get("content"),
+                               "score": float(score), "source": "vector"})            # (:310-316)
+            return chunks
+        except Exception:                                                              # (:321-323)
+            return []
+
+    @staticmethod
+    def _cosine_similarity(vec1: List[float], vec2: List[float]) -> float:
+        # zip() truncates the dot product to the shorter vector while the magnitudes use the full
+        # vectors (:658-660): identical to zero-padding the shorter one (a 0.0 product leaves both the
+        # naive and the Neumaier recurrence unchanged)
+        n = max(len(vec1), len(vec2))
+        if min(len(vec1), len(vec2)) == 0:
+            return 0.0
+        a = np.zeros(n, np.float64); a[:len(vec1)] = vec1
+        b = np.zeros(n, np.float64); b[:len(vec2)] = vec2
+        from .store import cosine_pairs
+        return float(cosine_pairs(a, b, zero_rule=1)[0])
+
+    def filter_segments(self, query_embedding: List[float], segment_embeddings: List[List[float]], threshold: float,
+                        top_k: int) -> List[Tuple[int, float]]:
+        """Batch form of the loop at :492-504: (segment index, score) for score >= threshold (inclusive),
+        original order, cut at top_k."""
+        if not segment_embeddings:
+            return []
+        from .store import cosine_pairs
+        q = np.asarray(query_embedding, dtype=np.float64)
+        S = np.asarray(segment_embeddings, dtype=np.float64)
+        scores = cosine_pairs(np.broadcast_to(q, S.shape).copy(), S, zero_rule=1)
+        keep = [(i, float(s)) for i, s in enumerate(scores) if s >= threshold]
+        return keep[:top_k]
+
+
+class PruneBackend:
+    """S5: Graph._are_same_context / _get_representative_relation (src/pipeline/prune.py:56-79)."""
+
+    def __init__(self, device: int = 0):
+        self.device = device
+
+    def _are_same_context(self, graph, relation_sentences, threshold: float = 0.8) -> bool:
+        if len(relation_sentences) <= 1:                                   # (:73-74)
+            return False
+        emb = np.asarray(graph.embedding_model.encode(relation_sentences), dtype=np.float32)
+        from .dedup import pairs_above
+        import torch
+        i, j, s = pairs_above(torch.from_numpy(emb).to(f"cuda:{self.device}"), float(threshold))
+        return bool(len(i) > 0)                                           # np.any(S > threshold) (:79)
+
+    def _get_representative_relation(self, graph, relation_sentences) -> int:
+        emb = np.asarray(graph.embedding_model.encode(relation_sentences), dtype=np.float32)
+        centroid = np.mean(emb, axis=0)                                    # (:61)
+        from .store import EmbeddingStore
+        st = EmbeddingStore(emb.shape[1], len(emb), "f32", self.device)
+        try:
+            st.append(emb)
+            idx, score, count = st.topk(centroid[None, :].astype(np.float32), 1)
+            return int(idx[0, 0]) if count[0] else 0                       # argmax, first maximal index (:64)
+        finally:
+            st.close()
+
+
+# ---- binding onto unmodified reference objects ---------------------------------------------------
+def install_injector(injector, backend: Optional[ChunkSimilarityBackend] = None, **kw) -> ChunkSimilarityBackend:
+    """Rebinds S1/S2 on a reference PreLLMInjector instance; everything else is untouched."""
+    backend = backend or ChunkSimilarityBackend(**kw)
+
+    async def _calc(self, chunk_embeddings, neo4j_handler):
+        return await backend._calculate_batch_similarities(self, chunk_embeddings, neo4j_handler)
+
+    def _cos(self, vec1, vec2):
+        return backend._cosine_similarity(vec1, vec2)
+
+    injector._calculate_batch_similarities = types.MethodType(_calc, injector)
+    injector._cosine_similarity = types.MethodType(_cos, injector)
+    return backend
+
+
+def install_retriever(retriever, store: ResidentChunkStore) -> VectorSearchBackend:
+    backend = VectorSearchBackend(store)
+
+    async def _vs(self, session, query):
+        return await backend._vector_search_chunks(self, session, query)
+
+    retriever._vector_search_chunks = types.MethodType(_vs, retriever)
+    return backend
+
+
+def install_prune(graph, backend: Optional[PruneBackend] = None) -> PruneBackend:
+    backend = backend or PruneBackend()
+    graph._are_same_context = types.MethodType(lambda self, s, threshold=0.8: backend._are_same_context(self, s, threshold), graph)
+    graph._get_representative_relation = types.MethodType(lambda self, s: backend._get_representative_relation(self, s), graph)
+    return backend

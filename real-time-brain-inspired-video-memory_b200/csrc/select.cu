@@ -15,17 +15,79 @@ namespace vm {
 // largest key T; every key >= T is then emitted.  O(n) work instead of kp block-wide arg-max
 // rounds.
 static constexpr int MERGE_THREADS = 512;
+static constexpr int MERGE_SURV = 1024;  // survivors ranked directly
+
+// Exact kp-th largest key of skeys[0..total) by MSB-first radix select (8 passes x 8 bits).
+// Block-wide; returns the same value in every thread.  Used when the cheap bound below does not
+// thin the keys enough (heavily duplicated scores).
+__device__ uint64_t radix_select_kth(const uint64_t *skeys, int total, int kp, int *hist, int *s_bin, int *s_need)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    uint64_t prefix = 0;
+    int need = kp;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        const uint64_t hmask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        for (int e = tid; e < total; e += MERGE_THREADS) {
+            const uint64_t k = skeys[e];
+            const bool act = k != 0 && (k & hmask) == prefix;
+            const int bin = act ? (int)((k >> shift) & 0xFF) : -1;
+            const unsigned peers = __match_any_sync(__activemask(), bin);
+            if (act && (__ffs(peers) - 1) == lane) atomicAdd(&hist[bin], __popc(peers));
+        }
+        __syncthreads();
+        if (tid < 32) {
+            int mine[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { mine[i] = hist[255 - (8 * lane + i)]; sum += mine[i]; }
+            int incl = sum;
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int excl = incl - sum;
+            if (excl < need && need <= incl) {
+                int acc = excl;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (acc < need && need <= acc + mine[i]) { *s_bin = 255 - (8 * lane + i); *s_need = need - acc; }
+                    acc += mine[i];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= (uint64_t)(*s_bin) << shift;
+        need = *s_need;
+        __syncthreads();
+    }
+    return prefix;
+}
+
+// One CTA per query.
+//  1. every list's maximum score is found by one warp (32-bit REDUX); the kp-th largest of those
+//     maxima, L, is a lower bound on the kp-th largest key (kp different lists reach it);
+//  2. keys with score >= L ("survivors", typically ~kp..2kp of the lists*kp keys) are compacted;
+//  3. survivors are ranked against each other and written in descending order, so slot kp-1 is
+//     the worst candidate the certification needs.
+// Falls back to the exact radix select when fewer than kp lists are populated or more than
+// MERGE_SURV keys survive.
 __global__ void __launch_bounds__(MERGE_THREADS) merge_candidates_kernel(const uint64_t *__restrict__ cand, int lists, int nq,
                                                                        int kp, uint64_t *__restrict__ merged)
 {
-    extern __shared__ uint64_t skeys[];  // [lists*kp]
+    extern __shared__ uint64_t skeys[];  // [lists*kp] then [lists] list maxima (u32)
+    __shared__ uint64_t surv[MERGE_SURV];
     __shared__ int hist[256];
-    __shared__ int s_bin, s_need, s_out, s_nz;
-    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    __shared__ int s_bin, s_need, s_m, s_nz;
+    __shared__ uint32_t s_L;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int total = lists * kp;
-    if (tid == 0) { s_out = 0; s_nz = 0; }
+    uint32_t *lmax = reinterpret_cast<uint32_t *>(skeys + total);
+    if (tid == 0) { s_m = 0; s_nz = 0; }
     __syncthreads();
     int nz = 0;
+#pragma unroll 4
     for (int e = tid; e < total; e += MERGE_THREADS) {
         int l = e / kp, j = e - l * kp;
         uint64_t k = cand[((int64_t)l * nq + q) * kp + j];
@@ -36,60 +98,73 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_candidates_kernel(const u
     __syncthreads();
     const int nonzero = s_nz;
     uint64_t T = 1;  // smallest real key is > 0: T = 1 selects every non-empty slot
+    bool ranked_path = false;
     if (nonzero >= kp) {
-        uint64_t prefix = 0;  // bits decided so far (high bits of T)
-        int need = kp;        // rank (1 = largest) of T among the keys matching `prefix`
-        for (int pass = 0; pass < 8; ++pass) {
-            const int shift = 56 - 8 * pass;
-            const uint64_t hmask = pass == 0 ? 0ull : (~0ull << (shift + 8));
-            if (tid < 256) hist[tid] = 0;
-            __syncthreads();
-            for (int e = tid; e < total; e += MERGE_THREADS) {
-                const uint64_t k = skeys[e];
-                const bool act = k != 0 && (k & hmask) == prefix;
-                const int bin = act ? (int)((k >> shift) & 0xFF) : -1;
-                // scores cluster in a few bins (same exponent): aggregate equal bins inside the warp
-                // so a skewed pass costs one atomic per warp instead of 32 serialised ones
-                const unsigned peers = __match_any_sync(__activemask(), bin);
-                if (act && (__ffs(peers) - 1) == lane) atomicAdd(&hist[bin], __popc(peers));
+        if (lists >= kp) {
+            // 1. per-list maximum score (high word of the key)
+            for (int l = warp; l < lists; l += MERGE_THREADS / 32) {
+                uint32_t m = 0;
+                for (int j = lane; j < kp; j += 32) m = max(m, (uint32_t)(skeys[l * kp + j] >> 32));
+                m = __reduce_max_sync(0xffffffffu, m);
+                if (lane == 0) lmax[l] = m;
             }
             __syncthreads();
-            if (tid < 32) {
-                // lane owns bins [255-8*lane-7, 255-8*lane] (descending order across lanes)
-                int mine[8], sum = 0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { mine[i] = hist[255 - (8 * lane + i)]; sum += mine[i]; }
-                int incl = sum;
-                for (int o = 1; o < 32; o <<= 1) {
-                    int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
+            if (warp == 0) {
+                // kp-th largest of the list maxima: bitwise radix select with warp reductions
+                uint32_t prefix = 0;
+                int need = kp;
+                for (int bit = 31; bit >= 0; --bit) {
+                    const uint32_t hi = bit == 31 ? 0u : (0xFFFFFFFFu << (bit + 1));
+                    int cnt = 0;
+                    for (int l = lane; l < lists; l += 32) cnt += ((lmax[l] & hi) == prefix && ((lmax[l] >> bit) & 1u)) ? 1 : 0;
+                    const int tot = __reduce_add_sync(0xffffffffu, cnt);
+                    if (tot >= need) prefix |= 1u << bit;
+                    else need -= tot;
                 }
-                int excl = incl - sum;  // keys in strictly higher bins than this lane's first bin
-                if (excl < need && need <= incl) {
-                    int acc = excl;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (acc < need && need <= acc + mine[i]) { s_bin = 255 - (8 * lane + i); s_need = need - acc; }
-                        acc += mine[i];
+                if (lane == 0) s_L = prefix;
+            }
+            __syncthreads();
+            const uint32_t Lb = s_L;
+            if (Lb != 0) {
+                // 2. compact the survivors
+                for (int e = tid; e < total; e += MERGE_THREADS) {
+                    const uint64_t k = skeys[e];
+                    if ((uint32_t)(k >> 32) >= Lb && k != 0) {
+                        const int p = atomicAdd(&s_m, 1);
+                        if (p < MERGE_SURV) surv[p] = k;
                     }
                 }
+                __syncthreads();
+                const int m = s_m;
+                if (m >= kp && m <= MERGE_SURV) {
+                    // 3. rank survivors (keys are unique) and emit the kp largest in descending order
+                    for (int e = tid; e < m; e += MERGE_THREADS) {
+                        const uint64_t k = surv[e];
+                        int rank = 0;
+                        for (int i = 0; i < m; ++i) rank += surv[i] > k ? 1 : 0;
+                        if (rank < kp) merged[(int64_t)q * kp + rank] = k;
+                    }
+                    ranked_path = true;
+                }
             }
-            __syncthreads();
-            prefix |= (uint64_t)s_bin << shift;
-            need = s_need;
-            __syncthreads();
         }
-        T = prefix;
+        if (!ranked_path) {
+            __syncthreads();
+            T = radix_select_kth(skeys, total, kp, hist, &s_bin, &s_need);
+        }
     }
+    if (ranked_path) return;  // uniform across the block
+    if (tid == 0) s_m = 0;
+    __syncthreads();
     for (int e = tid; e < total; e += MERGE_THREADS) {
         const uint64_t k = skeys[e];
         if (k >= T && k != 0) {
             if (nonzero >= kp && k == T) merged[(int64_t)q * kp + kp - 1] = k;  // the worst candidate
-            else merged[(int64_t)q * kp + atomicAdd(&s_out, 1)] = k;
+            else merged[(int64_t)q * kp + atomicAdd(&s_m, 1)] = k;
         }
     }
     __syncthreads();
-    const int filled = s_out;
+    const int filled = s_m;
     const int last = nonzero >= kp ? kp - 1 : kp;
     for (int e = filled + tid; e < last; e += MERGE_THREADS) merged[(int64_t)q * kp + e] = 0;
 }
@@ -153,18 +228,36 @@ __device__ __forceinline__ bool better(double sa, uint32_t ra, double sb, uint32
 // CPython).  Query and candidate rows are staged through shared memory as doubles in column
 // chunks (coalesced loads; odd row pitch -> conflict-free per-thread walks).
 // eps: bound on |approximate cosine - exact cosine| of the scan that produced the candidates.
-static constexpr int RS_THREADS = 160;  // >= 2*64 + 1 tasks
-static constexpr int RS_CHUNK = 96;
+static constexpr int RS_THREADS = 256;  // >= 2*64 + 1 tasks; the extra threads help staging
+static constexpr int RS_SMEM_ROW_BYTES = 96 * 1024;
+
+// 16-byte global load of 4 (fp32) / 8 (bf16) consecutive row elements -> floats
+__device__ __forceinline__ void load_vec16(const float *p, float *o)
+{
+    const float4 t = *reinterpret_cast<const float4 *>(p);
+    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+}
+__device__ __forceinline__ void load_vec16(const __nv_bfloat16 *p, float *o)
+{
+    const uint4 u = *reinterpret_cast<const uint4 *>(p);
+    o[0] = __uint_as_float(u.x << 16); o[1] = __uint_as_float(u.x & 0xffff0000u);
+    o[2] = __uint_as_float(u.y << 16); o[3] = __uint_as_float(u.y & 0xffff0000u);
+    o[4] = __uint_as_float(u.z << 16); o[5] = __uint_as_float(u.z & 0xffff0000u);
+    o[6] = __uint_as_float(u.w << 16); o[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+
 template <bool NEUMAIER, typename T>
 __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const uint64_t *__restrict__ merged, int kp, const T *__restrict__ rows,
                                                             const float *__restrict__ inv_norms, int ld, int dim, int64_t n_rows,
                                                             const void *__restrict__ queries, int q_dtype, double eps,
                                                             FinalizeArgs f, int32_t *__restrict__ flags,
-                                                            int32_t *__restrict__ uncertified_count)
+                                                            int32_t *__restrict__ uncertified_count, int chunk)
 {
+    constexpr int VEC = 16 / (int)sizeof(T);      // elements per 16-byte load
     extern __shared__ double rs_smem[];
-    double *sq = rs_smem;                 // [RS_CHUNK]
-    double *srow = rs_smem + RS_CHUNK;    // [kp][RS_CHUNK + 1]
+    double *sq = rs_smem;                          // [chunk] query as doubles
+    float *srow = reinterpret_cast<float *>(rs_smem + chunk);  // [kp][chunk + 1] candidate rows (odd pitch)
+    const int pitch = chunk + 1;
     __shared__ double s_dot[64], s_rr[64], s_qq;
     __shared__ double s_score[64];
     __shared__ uint32_t s_row[64];
@@ -182,21 +275,47 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const uint64_t *__r
     const int kind = j < kp ? 0 : (j < 2 * kp ? 1 : (j == 2 * kp ? 2 : 3));
     const int cand = kind == 0 ? j : (kind == 1 ? j - kp : 0);
     const bool active = kind == 2 || (kind < 2 && s_valid[cand]);
-    const double *pa = kind == 0 ? sq : (kind == 1 ? srow + cand * (RS_CHUNK + 1) : sq);
-    const double *pb = kind == 2 ? sq : srow + cand * (RS_CHUNK + 1);
     RefSum acc;
     acc.init();
-    for (int c0 = 0; c0 < dim; c0 += RS_CHUNK) {
-        const int len = min(RS_CHUNK, dim - c0);
+    for (int c0 = 0; c0 < dim; c0 += chunk) {
+        const int len = min(chunk, dim - c0);          // real columns in this chunk
+        const int vlen = (min(chunk, ld - c0) + VEC - 1) / VEC;  // 16-byte groups (rows are zero padded to ld)
         for (int i = j; i < len; i += RS_THREADS) sq[i] = load_as_double(queries, q_dtype, (int64_t)q * dim + c0 + i);
-        for (int e = j; e < kp * len; e += RS_THREADS) {
-            const int r = e / len, col = e - r * len;
-            srow[r * (RS_CHUNK + 1) + col] = s_valid[r] ? (double)load_as_float(rows + (int64_t)s_row[r] * ld, c0 + col) : 0.0;
+        // stage the candidate rows: batches of 4 independent 16-byte loads per thread
+        const int groups = kp * vlen;
+        for (int g0 = j; g0 < groups; g0 += 4 * RS_THREADS) {
+            float buf[4][VEC];
+            int rr_[4], cc_[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int g = g0 + u * RS_THREADS;
+                rr_[u] = g < groups ? g / vlen : -1;
+                cc_[u] = g < groups ? (g - rr_[u] * vlen) * VEC : 0;
+                if (rr_[u] >= 0 && s_valid[rr_[u]]) load_vec16(rows + (int64_t)s_row[rr_[u]] * ld + c0 + cc_[u], buf[u]);
+                else
+#pragma unroll
+                    for (int x = 0; x < VEC; ++x) buf[u][x] = 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (rr_[u] >= 0)
+#pragma unroll
+                    for (int x = 0; x < VEC; ++x)
+                        if (cc_[u] + x < chunk) srow[rr_[u] * pitch + cc_[u] + x] = buf[u][x];
         }
         __syncthreads();
         if (active) {
+            const float *mine = srow + cand * pitch;
+            if (kind == 0) {
 #pragma unroll 8
-            for (int i = 0; i < len; ++i) acc.add<NEUMAIER>(__dmul_rn(pa[i], pb[i]));
+                for (int i = 0; i < len; ++i) acc.add<NEUMAIER>(__dmul_rn(sq[i], (double)mine[i]));
+            } else if (kind == 1) {
+#pragma unroll 8
+                for (int i = 0; i < len; ++i) { const double y = (double)mine[i]; acc.add<NEUMAIER>(__dmul_rn(y, y)); }
+            } else {
+#pragma unroll 8
+                for (int i = 0; i < len; ++i) { const double x = sq[i]; acc.add<NEUMAIER>(__dmul_rn(x, x)); }
+            }
         }
         __syncthreads();
     }
@@ -519,7 +638,7 @@ __global__ void cosine_pairs_kernel(const void *__restrict__ a, const void *__re
 // ---- host wrappers ---------------------------------------------------------------------
 int k_merge_candidates(const uint64_t *cand, int lists, int nq, int kp, uint64_t *merged, cudaStream_t st)
 {
-    size_t smem = (size_t)lists * kp * sizeof(uint64_t);
+    size_t smem = (size_t)lists * kp * sizeof(uint64_t) + (size_t)lists * sizeof(uint32_t) + 16;
     static bool attr_set = false;
     if (!attr_set) {
         VM_CUDA_CHECK(cudaFuncSetAttribute(merge_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -538,14 +657,18 @@ int k_rescore(const RescoreArgs &a, cudaStream_t st)
     do {                                                                                                               \
         static bool attr_set = false;                                                                                  \
         if (!attr_set) {                                                                                               \
-            VM_CUDA_CHECK(cudaFuncSetAttribute(rescore_kernel<NEU, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); \
+            VM_CUDA_CHECK(cudaFuncSetAttribute(rescore_kernel<NEU, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
             attr_set = true;                                                                                           \
         }                                                                                                              \
         rescore_kernel<NEU, T><<<a.nq, RS_THREADS, smem, st>>>(a.merged, a.kp, (const T *)a.rows, a.inv_norms, a.ld, a.dim, \
                                                                a.n_rows, a.queries, a.q_dtype, a.eps, a.fin, a.flags,    \
-                                                               a.uncertified_count);                                    \
+                                                               a.uncertified_count, chunk);                             \
     } while (0)
-    const size_t smem = ((size_t)a.kp * (RS_CHUNK + 1) + RS_CHUNK) * sizeof(double);
+    // column chunk: whole rows when kp rows fit in RS_SMEM_ROW_BYTES, else a multiple of 8 columns
+    int chunk = RS_SMEM_ROW_BYTES / (4 * a.kp) - 1;
+    chunk &= ~7;
+    if (chunk > a.ld) chunk = a.ld;
+    const size_t smem = (size_t)chunk * sizeof(double) + (size_t)a.kp * (chunk + 1) * sizeof(float) + 16;
     bool neu = a.sum_mode == VM_SUM_NEUMAIER;
     if (a.dtype == VM_F32) { if (neu) LAUNCH_RS(true, float); else LAUNCH_RS(false, float); }
     else { if (neu) LAUNCH_RS(true, __nv_bfloat16); else LAUNCH_RS(false, __nv_bfloat16); }

@@ -1,0 +1,124 @@
+"""GPU tests of the reference-facing adapters (S1-S6) against the oracle; the reference objects are
+duck-typed stand-ins because /root/reference does not exist on the GPU box."""
+import asyncio
+import types
+
+import numpy as np
+import pytest
+
+from oracle import oracle, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ad():
+    import torch
+    assert torch.cuda.is_available()
+    from vidmem_b200 import adapters
+    return adapters
+
+
+class FakeInjector:
+    """Duck-typed PreLLMInjector: only what S1 touches (embedder_config, _get_chunk_embeddings)."""
+
+    def __init__(self, store_dict, k, k2=2):
+        self.embedder_config = types.SimpleNamespace(top_k_chunk_with_batch_similarity=k, top_k_similar_batch=k2)
+        self.store_dict = store_dict
+        self.fetches = 0
+
+    async def _get_chunk_embeddings(self, neo4j_handler):
+        self.fetches += 1
+        return self.store_dict
+
+
+def _lists(a):
+    return [[float(v) for v in r] for r in a]
+
+
+def test_s1_mirror_mode_matches_reference_semantics(ad):
+    n, d, k = 300, 96, 3
+    X = synth.synth_rows(71, 0, n, d)
+    X[10] = X[4]
+    row_ok = np.ones(n, np.uint8); row_ok[[7, 200]] = 0
+    store = {f"c{i}": (_lists(X[i:i + 1])[0] if row_ok[i] else (None if i == 7 else [])) for i in range(n)}
+    Q = synth.synth_queries(72, 5, d, 71, n)
+    Q[1] = X[4]
+    queries = _lists(Q)
+    queries[3] = RuntimeError("embedding failed")
+    queries.append([0.5] * (d - 1))                                  # wrong length -> every score 0.0
+    inj = FakeInjector(store, k)
+    backend = ad.install_injector(inj, initial_capacity=64)          # forces the store to grow
+    got = asyncio.run(inj._calculate_batch_similarities(queries, object()))
+    qok = np.array([1, 1, 1, 0, 1], np.uint8)
+    ref = oracle.batch_similarities(Q, X, k, query_ok=qok, row_ok=row_ok)
+    assert len(got) == 6
+    for gi, ri in zip(got[:5], ref):
+        assert gi == [(f"c{r}", s) for r, s in ri]
+    assert got[3] == []
+    assert got[5] == [("c0", 0.0), ("c1", 0.0), ("c2", 0.0)]
+    # second call: the dict grew -> only the new rows are appended, results follow
+    X2 = synth.synth_rows(73, 0, 20, d)
+    for i in range(20):
+        store[f"n{i}"] = _lists(X2[i:i + 1])[0]
+    got2 = asyncio.run(inj._calculate_batch_similarities(_lists(X2[3:4]), object()))
+    assert got2[0][0][0] == "n3" and got2[0][0][1] == oracle.cosine(X2[3], X2[3])
+    assert inj.fetches == 2 and len(backend.store) == n + 20
+    assert inj._cosine_similarity(queries[0], store["c5"]) == oracle.cosine(Q[0], X[5])
+    assert inj._cosine_similarity([1.0, 2.0], [1.0]) == 0.0
+
+
+def test_s6_insert_hook_and_merge(ad):
+    d, k, k2 = 64, 3, 2
+    X = synth.synth_rows(81, 0, 120, d)
+    backend = ad.ChunkSimilarityBackend(mirror_fetch=False, initial_capacity=256)
+    chunks = [{"id": f"u_{i // 4}_{i % 4}", "content": f"text {i}", "index": i, "embedding": _lists(X[i:i + 1])[0]}
+              for i in range(120)]
+    backend.on_chunks_inserted(chunks[:50])
+    backend.on_chunks_inserted(chunks[50:])
+    backend.on_chunks_inserted([{"id": "u_0_1", "content": "new", "embedding": _lists(X[99:100])[0]}])  # upsert by id
+    X2 = X.copy(); X2[1] = X[99]
+    Q = synth.synth_queries(82, 4, d, 81, 120); Q[1] = Q[0]
+    inj = FakeInjector({}, k, k2)
+    got = asyncio.run(backend._calculate_batch_similarities(inj, _lists(Q), object()))
+    ref = oracle.batch_similarities(Q, X2, k)
+    ids = [c["id"] for c in chunks]
+    assert got == [[(ids[r], s) for r, s in lst] for lst in ref]
+    assert inj.fetches == 0                                          # resident mode never fetches
+    merged = backend.merge_top_similar(got, k2)
+    assert merged == [(ids[r], s) for r, s in oracle.merge_max_by_id(ref, k2)]
+
+
+def test_s3_vector_search_and_s4_filter(ad):
+    d = 48
+    X = synth.synth_rows(91, 0, 80, d)
+    store = ad.ResidentChunkStore(initial_capacity=128)
+    store.upsert(((f"c{i}", _lists(X[i:i + 1])[0]) for i in range(80)),
+                 meta={f"c{i}": {"content": f"chunk {i}", "time": float(i)} for i in range(80)})
+    q = X[9].copy(); q[::5] = 0.25
+
+    class Emb:
+        async def aembed_query(self, text):
+            return [float(v) for v in q]
+
+    retr = types.SimpleNamespace(config=types.SimpleNamespace(top_k_chunks=4),
+                                 neo4j_handler=types.SimpleNamespace(embedder=Emb()))
+    backend = ad.install_retriever(retr, store)
+    got = asyncio.run(retr._vector_search_chunks(None, "what happened?"))
+    ref = oracle.vector_search(q, X, 4, 0.3)
+    assert [(g["id"], g["score"]) for g in got] == [(f"c{r}", s) for r, s in ref]
+    assert got[0]["source"] == "vector" and got[0]["content"] == "chunk 9" and got[0]["time"] == 9.0
+    thr = oracle.cosine(q, X[3], "retriever")
+    kept = backend.filter_segments(list(q), _lists(X[:12]), thr, 50)
+    assert kept == oracle.threshold_filter_ge(q, X[:12], thr, 50)
+    assert (3, thr) in kept
+    a, b = [0.3, -0.2, 0.9, 0.4], [0.1, 0.7]
+    assert backend._cosine_similarity(a, b) == oracle.cosine(a, b, "retriever")   # zip-truncated dot
+
+
+def test_s5_representative(ad):
+    E = synth.synth_rows(3, 0, 6, 768, dup_period=2)
+    g = types.SimpleNamespace(embedding_model=types.SimpleNamespace(encode=lambda s: np.asarray(s, np.float32)))
+    backend = ad.PruneBackend()
+    assert backend._get_representative_relation(g, E) == oracle.representative(E)[0]
+    assert backend._are_same_context(g, E[:1], 0.8) is False

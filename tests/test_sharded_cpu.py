@@ -1,0 +1,85 @@
+"""N>1 host logic on CPU: shard bounds, and a world_size-2 gloo run in which every rank scores its
+row shard (with the CPU oracle standing in for the device scan), the per-rank lists are gathered and
+merged exactly like vm_topk_sharded's device merge (score desc, global row asc)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import oracle, synth
+
+
+def _sharded():
+    import vidmem_b200
+    from vidmem_b200 import sharded
+    return sharded
+
+
+def test_shard_bounds_partition_rows():
+    sh = _sharded()
+    for n in (0, 1, 7, 100, 1000003):
+        for g in (1, 2, 3, 8):
+            b = sh.shard_bounds(n, g)
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(g - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+            for row in (0, n // 3, n - 1):
+                if 0 <= row < n:
+                    r = sh.owner_of(row, n, g)
+                    assert b[r][0] <= row < b[r][1]
+
+
+def test_merge_lists_host_ties_and_short_lists():
+    sh = _sharded()
+    a = (np.array([[5, 9, -1]]), np.array([[0.9, 0.5, 0.0]]), np.array([2], np.int32))
+    b = (np.array([[12, 3, 40]]), np.array([[0.9, 0.9, 0.1]]), np.array([3], np.int32))
+    i, s, c = sh.merge_lists_host([a, b], 4)
+    assert list(i[0]) == [3, 5, 12, 9] and list(s[0]) == [0.9, 0.9, 0.9, 0.5] and c[0] == 4
+    i, s, c = sh.merge_lists_host([a, b], 10)
+    assert c[0] == 5 and i[0, 5] == -1
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, d, nq, k, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vidmem_b200 import sharded
+    lo, hi = sharded.shard_bounds(n, world)[rank]
+    X = synth.synth_rows(7, lo, hi - lo, d)
+    X_full = synth.synth_rows(7, 0, n, d)
+    X_full[n - 1] = X_full[0]                      # a tie that straddles the two shards
+    X = X_full[lo:hi]
+    Q = synth.synth_queries(8, nq, d, 7, n)
+    Q[0] = X_full[0]
+    local = oracle.batch_similarities(Q, X, k)     # stand-in for the device scan + exact rescoring
+    idx = np.full((nq, k), -1, np.int64); sc = np.zeros((nq, k)); cnt = np.zeros(nq, np.int32)
+    for qi, lst in enumerate(local):
+        cnt[qi] = len(lst)
+        for j, (r, s) in enumerate(lst):
+            idx[qi, j], sc[qi, j] = r + lo, s    # global row indices, as vm_topk_sharded emits
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (idx, sc, cnt))
+    mi, ms, mc = sharded.merge_lists_host(gathered, k)
+    ref = oracle.batch_similarities(Q, X_full, k)
+    ok = all(list(mi[q, :mc[q]]) == [r for r, _ in ref[q]] and list(ms[q, :mc[q]]) == [s for _, s in ref[q]]
+             for q in range(nq))
+    ok = ok and list(mi[0, :2]) == [0, n - 1]
+    open(os.path.join(out_dir, f"rank{rank}.ok" if ok else f"rank{rank}.bad"), "w").write("x")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, 2001, 64, 5, 10, str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["rank0.ok", "rank1.ok"]

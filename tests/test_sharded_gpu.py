@@ -1,0 +1,60 @@
+"""2-GPU test of vm_topk_sharded: row-sharded store, one ncclAllGather, device merge."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import oracle, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import vidmem_b200 as vm
+    from vidmem_b200.sharded import Communicator, shard_bounds
+    comm = Communicator.from_torch_distributed(rank)
+    ok = True
+    for dtype, n, d, nq, k in (("f32", 50001, 384, 64, 10), ("bf16", 20000, 128, 5, 3)):
+        lo, hi = shard_bounds(n, world)[rank]
+        Xf = synth.synth_rows(17, 0, n, d)
+        Xf[n - 1] = Xf[2]
+        Q = synth.synth_queries(18, nq, d, 17, n)
+        Q[0] = Xf[2]
+        st = vm.EmbeddingStore(d, hi - lo, dtype, device=rank)
+        st.append(Xf[lo:hi])
+        idx, score, count = st.topk(Q, k, comm=comm, row_offset=lo, sum_mode=vm.VM_SUM_NEUMAIER)
+        ref = oracle.batch_similarities(Q, Xf, k)
+        for qi, lst in enumerate(ref):
+            ok = ok and count[qi] == len(lst) and list(idx[qi]) == [r for r, _ in lst] and list(score[qi]) == [s for _, s in lst]
+        ok = ok and list(idx[0, :2]) == [2, n - 1]
+        qd = torch.from_numpy(Q).cuda()
+        di, ds, dc = st.topk_device(qd, k, comm=comm, row_offset=lo, sum_mode=vm.VM_SUM_NEUMAIER, flags=vm.VM_FLAG_ASYNC)
+        torch.cuda.synchronize()
+        ok = ok and np.array_equal(di.cpu().numpy(), idx) and np.array_equal(ds.cpu().numpy(), score)
+        st.close()
+    open(os.path.join(out_dir, f"rank{rank}.ok" if ok else f"rank{rank}.bad"), "w").write("x")
+    dist.barrier()
+    comm.close()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_topk(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["rank0.ok", "rank1.ok"]
