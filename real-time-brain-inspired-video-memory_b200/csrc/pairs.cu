@@ -1,10 +1,335 @@
-// pairs.cu -- all-pairs threshold scorer (placeholder until the kernel lands in this round).
-#include "common.cuh"
+// pairs.cu -- all-pairs cosine threshold scorer (entity / relation dedup): every (i, j), i < j,
+// with cosine(x_i, x_j) > threshold.  Replaces Graph._are_same_context (src/pipeline/prune.py:67-79:
+// S = cosine_similarity(E); fill_diagonal(S, 0); S > threshold) generalised to the pair set.
+//
+// A genuine dense contraction -> tcgen05 tensor cores (bf16 x bf16 -> fp32 in TMEM; kind::tf32 for
+// fp32 rows).  The N x N score matrix (4 TB at N = 1M) never exists: each 128 x 256 accumulator tile
+// is consumed straight out of TMEM by the epilogue, which applies the cached inverse norms, compares
+// against the threshold and appends the (rare) hits with one atomic each.  Only tiles that touch the
+// strict upper triangle are scheduled; tiles are rasterised in groups of 8 column blocks x all row
+// blocks so that the 2048-row column panel stays in L2 while the row panels stream.
+//
+// Persistent, warp-specialised (192 threads): warp 0 TMA producer (A 128-row box + B 256-row box per
+// 128-byte K block, 4 stages of 48 KB), warp 1 MMA issuer (M=128, N=256, 4 MMAs per stage, 2
+// accumulator stages = all 512 TMEM columns), warps 2-5 epilogue.
+// Pairs whose fp32 score lies within eps of the threshold are re-decided in binary64 by
+// pairs_finalize_kernel, so the emitted pair SET is exact for the stored values.
+#include "tc_common.cuh"
+
 namespace vm {
-int k_pairs_above(int, const void *, int, int64_t, int, int, float, int64_t, int64_t *, int64_t *, float *, int64_t *, int, int,
-                  int, cudaStream_t)
+using namespace tc;
+
+static constexpr int P_BM = 128, P_BN = 256;
+static constexpr int P_STAGES = 4, P_ACC = 2, P_THREADS = 192;
+static constexpr int P_A_BYTES = P_BM * 128, P_B_BYTES = P_BN * 128, P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
+static constexpr int P_GJ = 8;  // column blocks per raster group (2048 rows -> 3 MB bf16 panel at D=768)
+
+struct PairsParams {
+    int64_t n;
+    int nbi, nbj, KB;
+    float thr, thr_lo;        // threshold, threshold - eps
+    const float *inv;         // [n] 1/||row||, 0 for a zero row
+    int32_t *st_i, *st_j;     // staging: every pair with approx score > thr_lo
+    float *st_s;
+    unsigned long long *st_cnt;
+    long long st_cap;
+    long long total_tiles;
+    int part, nparts;
+};
+
+__device__ __forceinline__ void tile_coords(long long t, int &bi, int &bj)
 {
-    set_error("pairs kernel not built");
-    return VM_ERR_UNSUPPORTED;
+    // group g holds 16(g+1) row blocks x 8 column blocks; 64 g (g+1) tiles precede it
+    long long g = (long long)((sqrt(1.0 + (double)t / 16.0) - 1.0) * 0.5);
+    while (64 * (g + 1) * (g + 2) <= t) ++g;
+    while (64 * g * (g + 1) > t) --g;
+    const long long r = t - 64 * g * (g + 1);
+    bi = (int)(r >> 3);
+    bj = (int)(g * P_GJ + (r & 7));
 }
+
+template <bool TF32>
+__global__ void __launch_bounds__(P_THREADS, 1)
+pairs_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, PairsParams p)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *stages = base;                                                   // [P_STAGES][A 16K | B 32K]
+    float *sinv = reinterpret_cast<float *>(base + P_STAGES * P_STAGE_BYTES);  // [P_ACC][256]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sinv + P_ACC * P_BN);
+    uint64_t *full = bars, *empty = bars + P_STAGES, *tfull = empty + P_STAGES, *tempty = tfull + P_ACC;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + P_ACC);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    constexpr int ELEMS = TF32 ? 32 : 64;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < P_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile sequence of this CTA: u = blockIdx.x, blockIdx.x + gridDim.x, ... ; t = u * nparts + part
+    auto valid_tile = [&](int bi, int bj) {
+        return bi < p.nbi && bj < p.nbj && ((long long)bj * P_BN + P_BN - 1 > (long long)bi * P_BM);
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long u = blockIdx.x;; u += gridDim.x) {
+                const long long t = u * p.nparts + p.part;
+                if (t >= p.total_tiles) break;
+                int bi, bj;
+                tile_coords(t, bi, bj);
+                if (!valid_tile(bi, bj)) continue;
+                for (int kb = 0; kb < p.KB; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], P_STAGE_BYTES);
+                    uint8_t *sa = stages + (size_t)stage * P_STAGE_BYTES;
+                    tma_load_2d(&tmA, &full[stage], sa, kb * ELEMS, bi * P_BM, L2_EVICT_FIRST);
+                    tma_load_2d(&tmB, &full[stage], sa + P_A_BYTES, kb * ELEMS, bj * P_BN, L2_EVICT_LAST);
+                    if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, P_BM, P_BN);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            const uint32_t s0 = smem_u32(stages);
+            for (long long u = blockIdx.x;; u += gridDim.x) {
+                const long long t = u * p.nparts + p.part;
+                if (t >= p.total_tiles) break;
+                int bi, bj;
+                tile_coords(t, bi, bj);
+                if (!valid_tile(bi, bj)) continue;
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P_BN);
+                for (int kb = 0; kb < p.KB; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = s0 + (uint32_t)stage * P_STAGE_BYTES;
+                    const uint32_t b_addr = a_addr + P_A_BYTES;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        umma<TF32>(d_tmem, make_smem_desc_sw128(a_addr + j * 32), make_smem_desc_sw128(b_addr + j * 32), idesc,
+                                   (uint32_t)((kb | j) != 0));
+                    umma_commit(&empty[stage]);
+                    if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[acc]);
+                if (++acc == P_ACC) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const int e = threadIdx.x - 64;  // 0..127
+        const int quad = warp & 3;
+        const int row_in_tile = quad * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long u = blockIdx.x;; u += gridDim.x) {
+            const long long t = u * p.nparts + p.part;
+            if (t >= p.total_tiles) break;
+            int bi, bj;
+            tile_coords(t, bi, bj);
+            if (!valid_tile(bi, bj)) continue;
+            const long long i = (long long)bi * P_BM + row_in_tile;
+            const long long j0 = (long long)bj * P_BN;
+            const float inv_i = i < p.n ? __ldg(p.inv + i) : -1.0f;
+            // columns' inverse norms for this tile (2 per epilogue thread)
+            float *sj = sinv + acc * P_BN;
+            for (int c = e; c < P_BN; c += 128) sj[c] = (j0 + c < p.n) ? __ldg(p.inv + j0 + c) : 0.0f;
+            // pre-filter threshold on acc * inv_j: (thr_lo / inv_i) nudged down so rounding cannot lose a pair
+            float thr_i;
+            if (inv_i > 0.0f) thr_i = p.thr_lo / inv_i, thr_i -= fabsf(thr_i) * 1e-6f;
+            else thr_i = (inv_i == 0.0f && 0.0f > p.thr_lo) ? -INFINITY : INFINITY;
+            named_bar_sync(1, 128);  // sj visible
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * P_BN);
+#pragma unroll 1
+            for (int c = 0; c < P_BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c, v);
+                float w[32];
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4) {
+                    const float4 t4 = *reinterpret_cast<const float4 *>(sj + c + 4 * q4);
+                    w[4 * q4] = t4.x; w[4 * q4 + 1] = t4.y; w[4 * q4 + 2] = t4.z; w[4 * q4 + 3] = t4.w;
+                }
+                tmem_ld_wait();
+                uint32_t hits = 0;
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) hits |= (__uint_as_float(v[jj]) * w[jj] > thr_i) ? (1u << jj) : 0u;
+                while (hits) {  // rare
+                    const int jj = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    float a = 0.0f, wj = 0.0f;
+#pragma unroll
+                    for (int x = 0; x < 32; ++x) { a = (x == jj) ? __uint_as_float(v[x]) : a; wj = (x == jj) ? w[x] : wj; }
+                    const long long j = j0 + c + jj;
+                    const float s = a * wj * inv_i;
+                    if (j < p.n && j > i && s > p.thr_lo) {
+                        const unsigned long long pos = atomicAdd(p.st_cnt, 1ull);
+                        if ((long long)pos < p.st_cap) { p.st_i[pos] = (int32_t)i; p.st_j[pos] = (int32_t)j; p.st_s[pos] = s; }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == P_ACC) { acc = 0; acc_phase ^= 1; }
+            // sj[acc] is refilled two tiles later, behind the next tile's barrier: no extra sync needed
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// Staged pairs -> output.  Pairs within eps of the threshold are re-decided with a binary64
+// cosine (index-order sums) on the stored values; the rest are kept as they are.
+template <typename T>
+__global__ void pairs_finalize_kernel(const T *__restrict__ x, int ld, int dim, float thr, float eps,
+                                      const int32_t *__restrict__ st_i, const int32_t *__restrict__ st_j,
+                                      const float *__restrict__ st_s, const unsigned long long *__restrict__ st_cnt,
+                                      long long st_cap, int64_t *__restrict__ out_i, int64_t *__restrict__ out_j,
+                                      float *__restrict__ out_s, unsigned long long *__restrict__ out_cnt, long long cap)
+{
+    const unsigned long long staged = *st_cnt;
+    const long long m = (long long)(staged < (unsigned long long)st_cap ? staged : (unsigned long long)st_cap);
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < m; e += (long long)gridDim.x * blockDim.x) {
+        const int i = st_i[e], j = st_j[e];
+        float s = st_s[e];
+        bool keep = s > thr;
+        if (fabsf(s - thr) <= eps) {
+            const T *a = x + (int64_t)i * ld, *b = x + (int64_t)j * ld;
+            double dot = 0.0, aa = 0.0, bb = 0.0;
+            for (int c = 0; c < dim; ++c) {
+                const double u = (double)load_as_float(a, c), v = (double)load_as_float(b, c);
+                dot += u * v; aa += u * u; bb += v * v;
+            }
+            const double den = sqrt(aa) * sqrt(bb);
+            const double ex = den > 0.0 ? dot / den : 0.0;
+            keep = ex > (double)thr;
+            s = (float)ex;
+        }
+        if (keep) {
+            const unsigned long long pos = atomicAdd(out_cnt, 1ull);
+            if ((long long)pos < cap) { out_i[pos] = i; out_j[pos] = j; out_s[pos] = s; }
+        }
+    }
+    // staging overflow: report at least the staged count so the caller sees count > cap
+    if (blockIdx.x == 0 && threadIdx.x == 0 && staged > (unsigned long long)st_cap) atomicMax(out_cnt, staged);
+}
+
+int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, cudaStream_t st);
+
+namespace {
+struct PairsWs {
+    void *inv = nullptr, *st_i = nullptr, *st_j = nullptr, *st_s = nullptr, *cnt = nullptr;
+    size_t inv_bytes = 0, st_entries = 0;
+};
+PairsWs g_pws[16];
+int ensure(void **p, size_t *have, size_t need)
+{
+    if (need <= *have) return VM_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *have = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e)); return VM_ERR_OOM; }
+    *have = need;
+    return VM_OK;
+}
+}  // namespace
+
+int k_pairs_above(int device, const void *x, int dtype, int64_t n, int dim, int ld, float threshold, int64_t cap,
+                  int64_t *out_i, int64_t *out_j, float *out_score, int64_t *out_count, int part, int nparts, int flags,
+                  cudaStream_t st)
+{
+    (void)flags;
+    VM_REQUIRE(device >= 0 && device < 16, VM_ERR_BADARG, "device index %d outside [0, 16)", device);
+    VM_CUDA_CHECK(cudaMemsetAsync(out_count, 0, 8, st));
+    if (n <= 1) return VM_OK;  // prune.py:73-74
+    VM_REQUIRE(((uintptr_t)x & 127) == 0, VM_ERR_BADARG, "rows buffer must be 128-byte aligned");
+    PairsWs &w = g_pws[device];
+    int rc = ensure(&w.inv, &w.inv_bytes, (size_t)n * 4);
+    if (rc != VM_OK) return rc;
+    const size_t st_cap = (size_t)cap + ((size_t)cap / 8 > 65536 ? (size_t)cap / 8 : 65536);
+    if (st_cap > w.st_entries) {
+        size_t have;
+        have = w.st_entries * 4; rc = ensure(&w.st_i, &have, st_cap * 4); if (rc != VM_OK) return rc;
+        have = w.st_entries * 4; rc = ensure(&w.st_j, &have, st_cap * 4); if (rc != VM_OK) return rc;
+        have = w.st_entries * 4; rc = ensure(&w.st_s, &have, st_cap * 4); if (rc != VM_OK) return rc;
+        w.st_entries = st_cap;
+    }
+    if (!w.cnt) VM_CUDA_CHECK(cudaMalloc(&w.cnt, 16));
+    VM_CUDA_CHECK(cudaMemsetAsync(w.cnt, 0, 16, st));
+    rc = k_row_inv_norms(x, dtype, (float *)w.inv, 0, n, ld, st);
+    if (rc != VM_OK) return rc;
+
+    const int es = dtype == VM_F32 ? 4 : 2;
+    const float fp32_acc = (float)(dim + 32) * 1.1920928955078125e-07f;
+    const float eps = dtype == VM_F32 ? 3.90625e-3f + fp32_acc : fp32_acc;  // tf32: both operands truncated twice over i and j
+    PairsParams p{};
+    p.n = n;
+    p.nbi = (int)((n + P_BM - 1) / P_BM);
+    p.nbj = (int)((n + P_BN - 1) / P_BN);
+    p.KB = (ld * es + 127) / 128;
+    p.thr = threshold;
+    p.thr_lo = threshold - eps;
+    p.inv = (const float *)w.inv;
+    p.st_i = (int32_t *)w.st_i; p.st_j = (int32_t *)w.st_j; p.st_s = (float *)w.st_s;
+    p.st_cnt = (unsigned long long *)w.cnt;
+    p.st_cap = (long long)st_cap;
+    const long long groups = (p.nbj + P_GJ - 1) / P_GJ;
+    p.total_tiles = 64 * groups * (groups + 1);  // full groups; tiles outside the matrix are skipped in-kernel
+    p.part = part; p.nparts = nparts;
+
+    CUtensorMap tmA, tmB;
+    rc = make_tmap_2d(&tmA, x, dtype, (uint64_t)n, (uint64_t)ld, (uint64_t)ld, P_BM);
+    if (rc != VM_OK) return rc;
+    rc = make_tmap_2d(&tmB, x, dtype, (uint64_t)n, (uint64_t)ld, (uint64_t)ld, P_BN);
+    if (rc != VM_OK) return rc;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const size_t smem = (size_t)P_STAGES * P_STAGE_BYTES + P_ACC * P_BN * 4 + 8 * (2 * P_STAGES + 2 * P_ACC) + 16 + 1024;
+    const long long my_tiles = (p.total_tiles + nparts - 1) / nparts;
+    const int grid = (int)(my_tiles < sms ? my_tiles : sms);
+    if (dtype == VM_F32) {
+        static bool set = false;
+        if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(pairs_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+        pairs_tc_kernel<true><<<grid, P_THREADS, smem, st>>>(tmA, tmB, p);
+    } else {
+        static bool set = false;
+        if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(pairs_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+        pairs_tc_kernel<false><<<grid, P_THREADS, smem, st>>>(tmA, tmB, p);
+    }
+    VM_CUDA_CHECK(cudaGetLastError());
+    if (dtype == VM_F32)
+        pairs_finalize_kernel<float><<<64, 256, 0, st>>>((const float *)x, ld, dim, threshold, eps, p.st_i, p.st_j, p.st_s, p.st_cnt,
+                                                         p.st_cap, out_i, out_j, out_score, (unsigned long long *)out_count, cap);
+    else
+        pairs_finalize_kernel<__nv_bfloat16><<<64, 256, 0, st>>>((const __nv_bfloat16 *)x, ld, dim, threshold, eps, p.st_i, p.st_j,
+                                                                 p.st_s, p.st_cnt, p.st_cap, out_i, out_j, out_score,
+                                                                 (unsigned long long *)out_count, cap);
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
 }  // namespace vm

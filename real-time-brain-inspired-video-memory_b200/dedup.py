@@ -1,0 +1,43 @@
+"""All-pairs threshold scorer (entity / relation dedup) -- host wrapper of vm_pairs_above.
+
+Replaces `Graph._are_same_context` (src/pipeline/prune.py:67-79): S = cosine_similarity(E);
+fill_diagonal(S, 0); S > threshold -- generalised from `any()` to the set of pairs (i < j)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def pairs_above(x: torch.Tensor, threshold: float, cap: int = 1 << 20, part: int = 0, nparts: int = 1
+                ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """x: CUDA tensor [n, dim], float32 or bfloat16.  -> (i, j, score) numpy arrays sorted by (i, j);
+    raises VidmemError(VM_ERR_OVERFLOW) if more than `cap` pairs exceed the threshold."""
+    if not x.is_cuda or x.dim() != 2:
+        raise TypeError("x must be a 2-D CUDA tensor")
+    lib = L.load()
+    n, dim = x.shape
+    dt = {torch.float32: L.VM_F32, torch.bfloat16: L.VM_BF16}[x.dtype]
+    ld = lib.vm_ld(dim)
+    if ld != dim or not x.is_contiguous():
+        xp = torch.zeros((n, ld), dtype=x.dtype, device=x.device)
+        xp[:, :dim] = x
+        x = xp
+    dev = x.device
+    oi = torch.empty((cap,), dtype=torch.int64, device=dev)
+    oj = torch.empty((cap,), dtype=torch.int64, device=dev)
+    os_ = torch.empty((cap,), dtype=torch.float32, device=dev)
+    cnt = torch.zeros((1,), dtype=torch.int64, device=dev)
+    L.check(lib.vm_pairs_above(dev.index or 0, x.data_ptr(), dt, n, dim, C.c_float(threshold), cap, oi.data_ptr(),
+                               oj.data_ptr(), os_.data_ptr(), cnt.data_ptr(), part, nparts, 0,
+                               torch.cuda.current_stream(dev).cuda_stream))
+    total = int(cnt.item())
+    if total > cap:
+        raise L.VidmemError(L.VM_ERR_OVERFLOW, f"{total} pairs above the threshold exceed cap={cap}")
+    i, j, s = oi[:total].cpu().numpy(), oj[:total].cpu().numpy(), os_[:total].cpu().numpy()
+    order = np.lexsort((j, i))
+    return i[order], j[order], s[order]

@@ -1,0 +1,79 @@
+"""GPU parity of the all-pairs threshold scorer against the sklearn-semantics oracle and the golden
+pair set produced by sklearn itself (tests/golden/prune.npz)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dd():
+    import torch
+    assert torch.cuda.is_available()
+    from vidmem_b200 import dedup
+    return dedup
+
+
+def _check(dd, E, thr, dtype):
+    import torch
+    x = torch.from_numpy(E).cuda().to(dtype)
+    Eq = x.float().cpu().numpy()                       # the stored (rounded) values are what both sides score
+    i, j, s = dd.pairs_above(x, thr)
+    oi, oj, os_ = oracle.pairs_above(Eq, thr)
+    assert list(zip(i.tolist(), j.tolist())) == list(zip(oi.tolist(), oj.tolist()))
+    np.testing.assert_allclose(s, os_, rtol=1e-3 if dtype == torch.float32 else 2e-4, atol=1e-6)
+    return len(oi)
+
+
+def test_golden_sklearn_pair_set(dd, golden_dir):
+    import torch
+    g = np.load(os.path.join(golden_dir, "prune.npz"))
+    E = synth.synth_rows(int(g["pairs_seed"]), 0, int(g["pairs_n"]), int(g["pairs_d"]), int(g["pairs_dup"]))
+    E[50] = 0.0
+    for thr in (0.8, 0.9):
+        t = int(thr * 10)
+        for dtype in (torch.bfloat16, torch.float32):     # synthetic values are exact in bf16 and tf32
+            i, j, s = dd.pairs_above(torch.from_numpy(E).cuda().to(dtype), thr)
+            assert np.array_equal(i, g[f"pairs_i_{t}"]) and np.array_equal(j, g[f"pairs_j_{t}"])
+            np.testing.assert_allclose(s, g[f"pairs_s_{t}"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("n,d,dup", [(2, 8, 1), (100, 64, 3), (129, 768, 4), (257, 384, 5), (1000, 768, 7),
+                                     (2500, 100, 9), (4500, 768, 50)])
+def test_vs_oracle_bf16(dd, n, d, dup):
+    import torch
+    E = synth.synth_rows(1000 + n, 0, n, d, dup_period=dup)
+    if n > 10:
+        E[7] = 0.0
+        E[n - 1] = E[3]
+    found = _check(dd, E, 0.9, torch.bfloat16)
+    assert found > 0 or n < 10
+
+
+def test_vs_oracle_fp32_and_general_values(dd):
+    import torch
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal((40, 256)).astype(np.float32)
+    E = np.concatenate([base + 0.15 * rng.standard_normal((40, 256)).astype(np.float32) for _ in range(20)])
+    _check(dd, E, 0.9, torch.float32)
+    _check(dd, E, 0.97, torch.bfloat16)
+
+
+def test_edge_semantics(dd):
+    import torch
+    x = torch.from_numpy(synth.synth_rows(5, 0, 1, 64)).cuda().to(torch.bfloat16)
+    i, j, s = dd.pairs_above(x, 0.5)
+    assert len(i) == 0                                   # n <= 1 -> no pairs (prune.py:73-74)
+    E = synth.synth_rows(6, 0, 300, 64, dup_period=2)
+    with pytest.raises(Exception):
+        dd.pairs_above(torch.from_numpy(E).cuda().to(torch.bfloat16), 0.5, cap=4)   # overflow is loud
+    # splitting the tile grid across "ranks" partitions the pair set
+    x = torch.from_numpy(synth.synth_rows(7, 0, 3000, 128, dup_period=6)).cuda().to(torch.bfloat16)
+    whole = dd.pairs_above(x, 0.9)
+    parts = [dd.pairs_above(x, 0.9, part=p, nparts=3) for p in range(3)]
+    got = sorted(sum([list(zip(a.tolist(), b.tolist())) for a, b, _ in parts], []))
+    assert got == list(zip(whole[0].tolist(), whole[1].tolist())) and len(got) > 0
