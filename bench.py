@@ -37,6 +37,8 @@ CONFIGS = {
     "c3": (100_000_000, 384, "bf16", 64, 10, 3, 3003),
     "c5": (10_000_000, 384, "f32", 1, 10, 5, 5005),
 }
+# all-pairs dedup: rows, dim, dtype, threshold, seed, planted-duplicate period
+C4 = (1_000_000, 768, "bf16", 0.9, 4, 100)
 
 
 def _peaks():
@@ -311,20 +313,214 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
+        except Exception:
+            pass
+    return 1400.0, "fallback (B200_PROFILING.md sustained)"
+
+
+def run_c4(args):
+    """Config C4: all-pairs dedup, 1M x 768 bf16 vs itself, threshold 0.9 (planted near-duplicates)."""
+    import numpy as np
+    import torch
+    import vidmem_b200 as vm
+    from vidmem_b200 import dedup
+    from vidmem_b200.store import EmbeddingStore
+    rows, dim, dt, thr, seed, dup = C4
+    if args.rows:
+        rows = args.rows
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    st = EmbeddingStore(dim, rows, dt, device=local_rank)     # operand replicated on every rank (1.5 GB)
+    st.synth_fill(seed, rows, dup_period=dup)
+    torch.cuda.synchronize()
+    x = st.rows[:rows]
+    cap = 1 << 22
+    lib = vm._lib.load()
+    import ctypes as C
+    oi = torch.empty((cap,), dtype=torch.int64, device=dev); oj = torch.empty_like(oi)
+    os_ = torch.empty((cap,), dtype=torch.float32, device=dev); cnt = torch.zeros((1,), dtype=torch.int64, device=dev)
+
+    def step():
+        vm._lib.check(lib.vm_pairs_above(local_rank, x.data_ptr(), vm.VM_BF16, rows, dim, C.c_float(thr), cap, oi.data_ptr(),
+                                         oj.data_ptr(), os_.data_ptr(), cnt.data_ptr(), rank, world, 0,
+                                         torch.cuda.current_stream(dev).cuda_stream))
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    steps = max(1, min(args.steps, 5))
+    for _ in range(max(1, min(args.warmup, 3))):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    hits_local = int(cnt.item())
+    # e2e: rows come from pinned host memory every step, pairs go back to the host
+    xh = torch.empty((rows, dim), dtype=torch.bfloat16).pin_memory()
+    xh.copy_(x[:, :dim].cpu())
+    xd = torch.empty_like(x)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        xd[:, :dim].copy_(xh, non_blocking=True)
+        i, j, s = dedup.pairs_above(xd, thr, cap=cap, part=rank, nparts=world)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = [float(v) for v in t.tolist()]
+        h = torch.tensor([hits_local], device=dev, dtype=torch.int64)
+        dist.all_reduce(h)
+        hits = int(h.item())
+    else:
+        hits = hits_local
+    if rank == 0:
+        pairs = rows * (rows - 1) / 2
+        peak, src = _tensor_peak()
+        tf = pairs * 2 * dim / (ms * 1e-3) / 1e12 / world      # per GPU
+        line = {"metric": "dedup_unique_pairs_per_sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world,
+                "steps": steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"c4: all-pairs dedup {rows}x{dim} bf16 vs itself, threshold {thr} (strict), "
+                                       f"1/{dup} rows planted near-duplicates, upper triangle split over {world} GPU(s)",
+                           "hits": hits, "l2_policy": "operand %.0f MB > 126 MB L2" % (rows * dim * 2 / 1e6)},
+                "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": rows * dim * 2,
+                        "d2h_bytes_per_step": hits_local * 20 + 8, "ms_per_step": e2e_ms},
+                "gpu_launches": 3 * steps,
+                "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                             "traffic": None, "kernel": "pairs_tc_kernel", "peak_source": src,
+                             "flops_counted": "2*D per unordered pair (upper triangle only)"},
+                "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle, synth
+            ns = 4096
+            E = synth.synth_rows(seed, 0, ns, dim, dup_period=dup)
+            t0 = time.perf_counter()
+            oracle.pairs_above(E, thr)
+            dt_s = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": (ns * (ns - 1) / 2) / dt_s, "unit": "pairs/s", "cores": os.cpu_count() or 1,
+                                    "kind": "port", "sample": f"{ns} x {dim} rows all-pairs (pairs/s is size-independent for the O(N^2 D) loop)"}
+        print(json.dumps(line), flush=True)
+    st.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier(); dist.destroy_process_group()
+
+
+def run_c5(args):
+    """Config C5: streaming mode -- 4096-row inserts interleaved with single-query top-10 lookups over a
+    10M x 384 store on one GPU; reports p50/p99 latencies (host wall clock around synchronous calls)."""
+    import numpy as np
+    import torch
+    import vidmem_b200 as vm
+    from vidmem_b200.store import EmbeddingStore
+    from oracle import synth
+    rows_total, dim, dt, nq, k, sseed, qseed = CONFIGS["c5"]
+    if args.rows:
+        rows_total = args.rows
+    dt = args.c5_dtype or dt
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    rounds = max(8, min(args.steps, 64))
+    per_round_q = 8
+    ins = 4096
+    st = EmbeddingStore(dim, rows_total + rounds * ins, dt, device=0)
+    st.synth_fill(sseed, rows_total)
+    st.set_size(rows_total)
+    torch.cuda.synchronize()
+    Q = synth.synth_queries(qseed, rounds * per_round_q, dim, sseed, rows_total)
+    qpin = torch.from_numpy(Q).pin_memory().numpy()
+    new_rows = torch.from_numpy(synth.synth_rows(sseed, rows_total, rounds * ins, dim)).pin_memory()
+    for w in range(3):
+        st.topk(qpin[w:w + 1], k)
+    sampler = ClockSampler(0)
+    sampler.start()
+    q_lat, i_lat = [], []
+    t_all = time.perf_counter()
+    for r in range(rounds):
+        t0 = time.perf_counter()
+        st.append(new_rows[r * ins:(r + 1) * ins])          # host -> device, convert, norms; synchronous
+        i_lat.append((time.perf_counter() - t0) * 1e3)
+        for qi in range(per_round_q):
+            t0 = time.perf_counter()
+            st.topk(qpin[r * per_round_q + qi:r * per_round_q + qi + 1], k)
+            q_lat.append((time.perf_counter() - t0) * 1e3)
+    wall = time.perf_counter() - t_all
+    clocks = sampler.stop()
+    scan_ms = []
+    for qi in range(5):
+        st.topk(qpin[qi:qi + 1], k, flags=vm.VM_FLAG_TIMING)
+        scan_ms.append(st.last_scan_ms())
+    es = 4 if dt == "f32" else 2
+    n_now = len(st)
+    peak, src = _peaks()
+    alg = n_now * dim * es + n_now * 4
+    scan = sum(scan_ms) / len(scan_ms)
+    pct = lambda a, p: float(np.percentile(np.asarray(a), p))
+    line = {"metric": "streaming_queries_per_sec_top10_384d", "value": len(q_lat) / (sum(q_lat) * 1e-3), "unit": "queries/s",
+            "n_gpus": 1, "steps": rounds, "warmup": 3, "ms_per_step": wall * 1e3 / rounds, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if dt == "f32" else "bf16", "data": "synthetic",
+            "config": {"workload": f"c5: streaming, {rows_total}x{dim} {dt} store, {ins}-row inserts interleaved with "
+                                   f"{per_round_q} single-query top-{k} lookups per insert, host buffers, synchronous calls",
+                       "scan_kernel": {0: "exact_fp64", 1: "simt", 2: "tcgen05"}[int(st.last_stats.scan_kernel)]},
+            "latency_ms": {"query_p50": pct(q_lat, 50), "query_p99": pct(q_lat, 99), "insert_p50": pct(i_lat, 50),
+                           "insert_p99": pct(i_lat, 99)},
+            "e2e": {"value": len(q_lat) / (sum(q_lat) * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": ins * dim * 4 + per_round_q * dim * 4,
+                    "d2h_bytes_per_step": per_round_q * (k * 16 + 8)},
+            "gpu_launches": int(st.last_stats.scan_launches) * len(q_lat) + 2 * rounds,
+            "roofline": {"bound": "hbm", "achieved": alg / (scan * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (scan * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "scan", "kernel_ms": scan,
+                         "algorithmic_bytes": alg, "peak_source": src},
+            "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    st.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default=None, choices=sorted(CONFIGS))
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS) + ["c4"])
     ap.add_argument("--rows", type=int, default=None, help="override the total row count (debug)")
     ap.add_argument("--flags", type=int, default=0, help="extra VM_FLAG_* bits (debug: 4 = force SIMT, 8 = force tcgen05)")
     ap.add_argument("--cpu-sample-rows", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c5-dtype", default=None, choices=["f32", "bf16"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "c4":
+        run_c4(args)
+    elif args.config == "c5":
+        run_c5(args)
     else:
         run_ours(args)
 

@@ -408,7 +408,10 @@ static int topk_batch(const TopkCall &c)
         int kp_tc = c.k <= 16 ? 32 : (c.k <= 48 ? 64 : 0);
         int kp_simt = c.k <= 24 ? (c.k + 8 > 16 ? ((c.k + 8 + 7) & ~7) : 16) : 0;
         bool tc_ok = kp_tc > 0 && scan_tc_supported(s->dtype, s->dim, c.nq, kp_tc);
-        bool want_tc = (c.flags & VM_FLAG_FORCE_TC) || (c.nq > scan_simt_max_queries() && !(c.flags & VM_FLAG_FORCE_SIMT));
+        // query batches always take the tensor-core scan; so do small batches over big shards, where
+        // the TMA-fed kernel streams at the HBM roofline while the CUDA-core kernel reaches ~half of it
+        bool want_tc = (c.flags & VM_FLAG_FORCE_TC) ||
+                       ((c.nq > scan_simt_max_queries() || s->size >= 65536) && !(c.flags & VM_FLAG_FORCE_SIMT));
         if (want_tc && tc_ok) { kernel = 2; kp = kp_tc; }
         else if (kp_simt > 0) { kernel = 1; kp = kp_simt; }
         else if (tc_ok) { kernel = 2; kp = kp_tc; }
