@@ -380,6 +380,11 @@ struct TopkCall {
     int32_t *d_count;
     cudaStream_t st;
     vm_topk_stats *stats;
+    // optional host destinations: results are copied there inside the same synchronisation that reads
+    // the uncertified-query counter (one stream sync per batch on the host-buffer path)
+    int64_t *h_idx = nullptr;
+    double *h_score = nullptr;
+    int32_t *h_count = nullptr;
 };
 }  // namespace
 
@@ -420,6 +425,12 @@ static int topk_batch(const TopkCall &c)
         int rc = k_exact(ex, st);
         if (rc != VM_OK) return rc;
         launches += 2;
+        if (c.h_idx) {
+            VM_CUDA_CHECK(cudaMemcpyAsync(c.h_idx, c.d_idx, (size_t)c.nq * c.k * 8, cudaMemcpyDeviceToHost, st));
+            VM_CUDA_CHECK(cudaMemcpyAsync(c.h_score, c.d_score, (size_t)c.nq * c.k * 8, cudaMemcpyDeviceToHost, st));
+            VM_CUDA_CHECK(cudaMemcpyAsync(c.h_count, c.d_count, (size_t)c.nq * 4, cudaMemcpyDeviceToHost, st));
+            VM_CUDA_CHECK(cudaStreamSynchronize(st));
+        }
         if (c.stats) { c.stats->scan_kernel = 0; c.stats->scan_launches += launches; }
         return VM_OK;
     }
@@ -472,13 +483,23 @@ static int topk_batch(const TopkCall &c)
         launches += 2;
         n_uncert = -1;
     } else {
+        auto copy_out = [&]() -> int {
+            if (!c.h_idx) return VM_OK;
+            VM_CUDA_CHECK(cudaMemcpyAsync(c.h_idx, c.d_idx, (size_t)c.nq * c.k * 8, cudaMemcpyDeviceToHost, st));
+            VM_CUDA_CHECK(cudaMemcpyAsync(c.h_score, c.d_score, (size_t)c.nq * c.k * 8, cudaMemcpyDeviceToHost, st));
+            VM_CUDA_CHECK(cudaMemcpyAsync(c.h_count, c.d_count, (size_t)c.nq * 4, cudaMemcpyDeviceToHost, st));
+            return VM_OK;
+        };
         VM_CUDA_CHECK(cudaMemcpyAsync(w.h_uncert, uncert, 4, cudaMemcpyDeviceToHost, st));
+        if ((rc = copy_out()) != VM_OK) return rc;
         VM_CUDA_CHECK(cudaStreamSynchronize(st));
         n_uncert = *w.h_uncert;
         if (n_uncert > 0) {
             rc = k_exact(ex, st);
             if (rc != VM_OK) return rc;
             launches += 2;
+            if ((rc = copy_out()) != VM_OK) return rc;
+            if (c.h_idx) VM_CUDA_CHECK(cudaStreamSynchronize(st));
         }
     }
     if (c.stats) {
@@ -516,8 +537,17 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
     const size_t qrow = (size_t)s->dim * dtype_size(q_dtype);
     const bool sharded = comm && comm->nranks > 1;
 
-    for (int q0 = 0; q0 < nq; q0 += MAXQ) {
-        int nb = nq - q0 < MAXQ ? nq - q0 : MAXQ;
+    // queries per scan pass: 64, or fewer when 64 normalised queries of this dimension do not fit the
+    // tcgen05 kernel's shared memory (e.g. 16 for a 1536-d fp32 store)
+    int bq = MAXQ;
+    if (!(flags & (VM_FLAG_FORCE_EXACT | VM_FLAG_FORCE_SIMT)) && (nq > scan_simt_max_queries() || s->size >= 65536 || (flags & VM_FLAG_FORCE_TC))) {
+        const int kp_tc = k <= 16 ? 32 : (k <= 48 ? 64 : 0);
+        if (kp_tc)
+            for (int cand = 64; cand >= 16; cand -= 16)
+                if (scan_tc_supported(s->dtype, s->dim, cand, kp_tc)) { bq = cand; break; }
+    }
+    for (int q0 = 0; q0 < nq; q0 += bq) {
+        int nb = nq - q0 < bq ? nq - q0 : bq;
         // where this batch's local results go
         bool direct = out_mem == VM_MEM_DEVICE && !sharded;
         int64_t *d_idx = direct ? out_idx + (size_t)q0 * k : (int64_t *)w.o_idx.p;
@@ -537,6 +567,8 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
         TopkCall c{s, (const char *)queries + (size_t)q0 * qrow, q_dtype, q_mem, nb, k, min_score, score_mode, sum_mode,
                    flags, row_offset, d_idx, d_score,
                    d_count, st, stats};
+        const bool host_direct = out_mem == VM_MEM_HOST && !sharded && !(flags & VM_FLAG_ASYNC);
+        if (host_direct) { c.h_idx = out_idx + (size_t)q0 * k; c.h_score = out_score + (size_t)q0 * k; c.h_count = out_count + q0; }
         rc = topk_batch(c);
         if (rc != VM_OK) return rc;
         if (sharded) {
@@ -553,7 +585,7 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
             if (stats) stats->scan_launches += 2;
             d_idx = m_idx; d_score = m_score; d_count = m_count;
         }
-        if (out_mem == VM_MEM_HOST) {
+        if (out_mem == VM_MEM_HOST && !host_direct) {
             VM_CUDA_CHECK(cudaMemcpyAsync(out_idx + (size_t)q0 * k, d_idx, (size_t)nb * k * 8, cudaMemcpyDeviceToHost, st));
             VM_CUDA_CHECK(cudaMemcpyAsync(out_score + (size_t)q0 * k, d_score, (size_t)nb * k * 8, cudaMemcpyDeviceToHost, st));
             VM_CUDA_CHECK(cudaMemcpyAsync(out_count + q0, d_count, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));

@@ -240,3 +240,22 @@ def test_tc_is_used_for_query_batches(vm):
         ok = np.ones(n, np.uint8); ok[[int(idx[0, 0]), int(idx[1, 0])]] = 0
         _check(*st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER), oracle.batch_similarities(Q, X, k, row_ok=ok), k)
         st.close()
+
+
+@pytest.mark.parametrize("dtype,d,nq", [("f32", 1536, 64), ("f32", 768, 40), ("bf16", 1536, 64), ("f32", 1024, 70)])
+def test_large_dims_split_query_batches(vm, dtype, d, nq):
+    """64 queries of a 768..1536-d fp32 store do not fit the tensor-core kernel's shared memory at once:
+    the engine splits the batch instead of leaving the tcgen05 path."""
+    n, k = 70000, 10
+    rng = np.random.default_rng(d + nq)
+    X = _quantise(rng.standard_normal((n, d)).astype(np.float32), dtype)
+    Q = rng.standard_normal((nq, d)).astype(np.float32)
+    Q[0] = X[4242]
+    st = vm.EmbeddingStore(d, n, dtype)
+    st.append(X)
+    idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)
+    assert st.last_stats.scan_kernel == 2
+    bi, bs, bc = oracle.topk_blocked(Q, X, k)
+    assert np.array_equal(idx, bi) and np.array_equal(score, bs) and (count == k).all()
+    assert idx[0, 0] == 4242
+    st.close()
