@@ -305,8 +305,36 @@ def run_ours(args):
             cores = os.cpu_count() or 1
             qps, ms, desc = cpu_reference_leg(cfg, 1, 1, args.cpu_sample_rows or 100000)
             line["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
-        print(json.dumps(line), flush=True)
     store.close()
+    if rank == 0:
+        if world == 1 and cfg == "c2" and not args.rows and not args.no_scaling_baseline:
+            # The multi-GPU runs use config C3 (100M x 384 bf16, strong scaling).  Its single-GPU point is
+            # measured here so that the N = 2/4/8 lines have a same-workload N = 1 reference.
+            try:
+                r3, d3, dt3, nq3, k3, ss3, qs3 = CONFIGS["c3"]
+                s3 = EmbeddingStore(d3, r3, dt3, device=local_rank)
+                s3.synth_fill(ss3, r3)
+                s3.set_size(r3)
+                q3 = torch.from_numpy(synth.synth_queries(qs3, nq3, d3, ss3, r3)).to(dev)
+                o3 = (torch.empty((nq3, k3), dtype=torch.int64, device=dev), torch.empty((nq3, k3), dtype=torch.float64, device=dev),
+                      torch.empty((nq3,), dtype=torch.int32, device=dev))
+                for _ in range(3):
+                    s3.topk_device(q3, k3, out=o3, flags=vm.VM_FLAG_ASYNC)
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(10):
+                    s3.topk_device(q3, k3, out=o3, flags=vm.VM_FLAG_ASYNC)
+                a1.record()
+                torch.cuda.synchronize()
+                ms3 = a0.elapsed_time(a1) / 10
+                line["scaling_baseline"] = {"workload": f"c3: {r3}x{d3} {dt3} store on ONE GPU, {nq3}-query batch, top-{k3}",
+                                            "value": nq3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3,
+                                            "hbm_frac": (r3 * d3 * 2 + r3 * 4) / (ms3 * 1e-3) / 1e9 / _peaks()[0]}
+                s3.close()
+            except Exception as e:  # pragma: no cover - e.g. not enough free HBM
+                line["scaling_baseline"] = {"error": repr(e)}
+        print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -513,6 +541,7 @@ def main():
     ap.add_argument("--flags", type=int, default=0, help="extra VM_FLAG_* bits (debug: 4 = force SIMT, 8 = force tcgen05)")
     ap.add_argument("--cpu-sample-rows", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scaling-baseline", action="store_true", help="skip the extra C3-on-one-GPU measurement of the N=1 run")
     ap.add_argument("--c5-dtype", default=None, choices=["f32", "bf16"])
     args = ap.parse_args()
     if args.impl == "reference":

@@ -15,6 +15,7 @@
 // Pairs whose fp32 score lies within eps of the threshold are re-decided in binary64 by
 // pairs_finalize_kernel, so the emitted pair SET is exact for the stored values.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace vm {
 using namespace tc;
@@ -202,6 +203,179 @@ pairs_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
+// =========================================================================================
+// 2-CTA variant: a CTA pair (cluster of 2) computes one 256 x 256 tile with tcgen05.mma.cta_group::2.
+// Each CTA stages only 128 rows of A and HALF of B per K block (32 KB instead of 48 KB) and the
+// tensor core reads B from both shared memories, so shared-memory traffic per SM drops from
+// ~192 B/cycle (the 1-CTA kernel's limiter) to ~128 B/cycle at full MMA rate.
+// =========================================================================================
+static constexpr int P2_STAGES = 6, P2_STAGE_BYTES = 2 * P_A_BYTES;
+
+__device__ __forceinline__ void tile_coords2(long long t, int &bi, int &bj)
+{
+    // 256 x 256 tiles: group g holds 8(g+1) row blocks x 8 column blocks; 32 g (g+1) tiles precede it
+    long long g = (long long)((sqrt(1.0 + (double)t / 8.0) - 1.0) * 0.5);
+    while (32 * (g + 1) * (g + 2) <= t) ++g;
+    while (32 * g * (g + 1) > t) --g;
+    const long long r = t - 32 * g * (g + 1);
+    bi = (int)(r >> 3);
+    bj = (int)(g * P_GJ + (r & 7));
+}
+
+template <bool TF32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
+pairs_tc2_kernel(const __grid_constant__ CUtensorMap tmA, PairsParams p)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *stages = base;                                                     // [P2_STAGES][A 16K | B-half 16K]
+    float *sinv = reinterpret_cast<float *>(base + P2_STAGES * P2_STAGE_BYTES);  // [P_ACC][256]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sinv + P_ACC * P_BN);
+    uint64_t *full = bars, *empty = bars + P2_STAGES, *tfull = empty + P2_STAGES, *tempty = tfull + P_ACC;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + P_ACC);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();  // 0 = leader
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    constexpr int ELEMS = TF32 ? 32 : 64;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        for (int s = 0; s < P2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < P_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }  // 4 local + 4 peer warps
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nb = (int)((p.n + 255) / 256);  // 256-row blocks (rows and columns)
+
+    auto valid_tile = [&](int bi, int bj) { return bi < nb && bj < nb && bj >= bi; };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long u = pair;; u += npairs) {
+                const long long t = u * p.nparts + p.part;
+                if (t >= p.total_tiles) break;
+                int bi, bj;
+                tile_coords2(t, bi, bj);
+                if (!valid_tile(bi, bj)) continue;
+                for (int kb = 0; kb < p.KB; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * P2_STAGE_BYTES);  // both CTAs' bytes
+                    uint8_t *sa = stages + (size_t)stage * P2_STAGE_BYTES;
+                    tma_load_2d_2sm(&tmA, &full[stage], sa, kb * ELEMS, bi * 256 + (int)rank * 128, L2_EVICT_FIRST);
+                    tma_load_2d_2sm(&tmA, &full[stage], sa + P_A_BYTES, kb * ELEMS, bj * 256 + (int)rank * 128, L2_EVICT_LAST);
+                    if (++stage == P2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, 256, 256);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            const uint32_t s0 = smem_u32(stages);
+            for (long long u = pair;; u += npairs) {
+                const long long t = u * p.nparts + p.part;
+                if (t >= p.total_tiles) break;
+                int bi, bj;
+                tile_coords2(t, bi, bj);
+                if (!valid_tile(bi, bj)) continue;
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P_BN);
+                for (int kb = 0; kb < p.KB; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = s0 + (uint32_t)stage * P2_STAGE_BYTES;
+                    const uint32_t b_addr = a_addr + P_A_BYTES;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        umma_2sm<TF32>(d_tmem, make_smem_desc_sw128(a_addr + j * 32), make_smem_desc_sw128(b_addr + j * 32), idesc,
+                                       (uint32_t)((kb | j) != 0));
+                    umma_commit_2sm(&empty[stage]);  // frees the stage in both CTAs
+                    if (++stage == P2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(&tfull[acc]);        // accumulator ready in both CTAs
+                if (++acc == P_ACC) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const int e = threadIdx.x - 64;  // 0..127
+        const int quad = warp & 3;
+        const int row_in_tile = quad * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long u = pair;; u += npairs) {
+            const long long t = u * p.nparts + p.part;
+            if (t >= p.total_tiles) break;
+            int bi, bj;
+            tile_coords2(t, bi, bj);
+            if (!valid_tile(bi, bj)) continue;
+            const long long i = (long long)bi * 256 + rank * 128 + row_in_tile;
+            const long long j0 = (long long)bj * 256;
+            const float inv_i = i < p.n ? __ldg(p.inv + i) : -1.0f;
+            float *sj = sinv + acc * P_BN;
+            for (int c = e; c < P_BN; c += 128) sj[c] = (j0 + c < p.n) ? __ldg(p.inv + j0 + c) : 0.0f;
+            float thr_i;
+            if (inv_i > 0.0f) thr_i = p.thr_lo / inv_i, thr_i -= fabsf(thr_i) * 1e-6f;
+            else thr_i = (inv_i == 0.0f && 0.0f > p.thr_lo) ? -INFINITY : INFINITY;
+            named_bar_sync(1, 128);
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * P_BN);
+#pragma unroll 1
+            for (int c = 0; c < P_BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c, v);
+                float w[32];
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4) {
+                    const float4 t4 = *reinterpret_cast<const float4 *>(sj + c + 4 * q4);
+                    w[4 * q4] = t4.x; w[4 * q4 + 1] = t4.y; w[4 * q4 + 2] = t4.z; w[4 * q4 + 3] = t4.w;
+                }
+                tmem_ld_wait();
+                uint32_t hits = 0;
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) hits |= (__uint_as_float(v[jj]) * w[jj] > thr_i) ? (1u << jj) : 0u;
+                while (hits) {  // rare
+                    const int jj = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    float a = 0.0f, wj = 0.0f;
+#pragma unroll
+                    for (int x = 0; x < 32; ++x) { a = (x == jj) ? __uint_as_float(v[x]) : a; wj = (x == jj) ? w[x] : wj; }
+                    const long long j = j0 + c + jj;
+                    const float s = a * wj * inv_i;
+                    if (j < p.n && j > i && s > p.thr_lo) {
+                        const unsigned long long pos = atomicAdd(p.st_cnt, 1ull);
+                        if ((long long)pos < p.st_cap) { p.st_i[pos] = (int32_t)i; p.st_j[pos] = (int32_t)j; p.st_s[pos] = s; }
+                    }
+                }
+            }
+            // hand the accumulator stage back to the leader's MMA thread (local or remote arrive)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) mbar_arrive(&tempty[acc]);
+                else mbar_arrive_remote(&tempty[acc], 0);
+            }
+            if (++acc == P_ACC) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, 512);
+    }
+}
+
 // Staged pairs -> output.  Pairs within eps of the threshold are re-decided with a binary64
 // cosine (index-order sums) on the stored values; the rest are kept as they are.
 template <typename T>
@@ -304,21 +478,42 @@ int k_pairs_above(int device, const void *x, int dtype, int64_t n, int dim, int 
     CUtensorMap tmA, tmB;
     rc = make_tmap_2d(&tmA, x, dtype, (uint64_t)n, (uint64_t)ld, (uint64_t)ld, P_BM);
     if (rc != VM_OK) return rc;
-    rc = make_tmap_2d(&tmB, x, dtype, (uint64_t)n, (uint64_t)ld, (uint64_t)ld, P_BN);
-    if (rc != VM_OK) return rc;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    const size_t smem = (size_t)P_STAGES * P_STAGE_BYTES + P_ACC * P_BN * 4 + 8 * (2 * P_STAGES + 2 * P_ACC) + 16 + 1024;
-    const long long my_tiles = (p.total_tiles + nparts - 1) / nparts;
-    const int grid = (int)(my_tiles < sms ? my_tiles : sms);
-    if (dtype == VM_F32) {
-        static bool set = false;
-        if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(pairs_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
-        pairs_tc_kernel<true><<<grid, P_THREADS, smem, st>>>(tmA, tmB, p);
+    static const bool one_cta = getenv("VIDMEM_PAIRS_1CTA") != nullptr;  // perf triage: force the 1-CTA kernel
+    if (!one_cta) {
+        // ---- CTA-pair kernel: 256 x 256 tiles ----
+        const long long nb = (n + 255) / 256, groups = (nb + P_GJ - 1) / P_GJ;
+        p.total_tiles = 32 * groups * (groups + 1);
+        const size_t smem = (size_t)P2_STAGES * P2_STAGE_BYTES + P_ACC * P_BN * 4 + 8 * (2 * P2_STAGES + 2 * P_ACC) + 16 + 1024;
+        const long long my_tiles = (p.total_tiles + nparts - 1) / nparts;
+        long long pairs = sms / 2;
+        if (my_tiles < pairs) pairs = my_tiles;
+        const int grid = (int)(2 * pairs);
+        if (dtype == VM_F32) {
+            static bool set = false;
+            if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(pairs_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+            pairs_tc2_kernel<true><<<grid, P_THREADS, smem, st>>>(tmA, p);
+        } else {
+            static bool set = false;
+            if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(pairs_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+            pairs_tc2_kernel<false><<<grid, P_THREADS, smem, st>>>(tmA, p);
+        }
     } else {
-        static bool set = false;
-        if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(pairs_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
-        pairs_tc_kernel<false><<<grid, P_THREADS, smem, st>>>(tmA, tmB, p);
+        rc = make_tmap_2d(&tmB, x, dtype, (uint64_t)n, (uint64_t)ld, (uint64_t)ld, P_BN);
+        if (rc != VM_OK) return rc;
+        const size_t smem = (size_t)P_STAGES * P_STAGE_BYTES + P_ACC * P_BN * 4 + 8 * (2 * P_STAGES + 2 * P_ACC) + 16 + 1024;
+        const long long my_tiles = (p.total_tiles + nparts - 1) / nparts;
+        const int grid = (int)(my_tiles < sms ? my_tiles : sms);
+        if (dtype == VM_F32) {
+            static bool set = false;
+            if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(pairs_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+            pairs_tc_kernel<true><<<grid, P_THREADS, smem, st>>>(tmA, tmB, p);
+        } else {
+            static bool set = false;
+            if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(pairs_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+            pairs_tc_kernel<false><<<grid, P_THREADS, smem, st>>>(tmA, tmB, p);
+        }
     }
     VM_CUDA_CHECK(cudaGetLastError());
     if (dtype == VM_F32)

@@ -41,3 +41,30 @@ def pairs_above(x: torch.Tensor, threshold: float, cap: int = 1 << 20, part: int
     i, j, s = oi[:total].cpu().numpy(), oj[:total].cpu().numpy(), os_[:total].cpu().numpy()
     order = np.lexsort((j, i))
     return i[order], j[order], s[order]
+
+
+def pairs_above_sharded(x: torch.Tensor, threshold: float, cap: int = 1 << 20):
+    """Multi-GPU form: the operand is replicated on every rank, the upper-triangular
+    tile grid is dealt cyclically to the ranks (part = rank), and the per-rank hit lists are
+    concatenated with torch.distributed (counts first, then a padded all_gather).  Every rank
+    returns the full, (i, j)-sorted pair set."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    i, j, s = pairs_above(x, threshold, cap=cap, part=rank, nparts=world)
+    dev = x.device
+    cnt = torch.tensor([len(i)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt)
+    m = int(max(int(c.item()) for c in counts))
+    buf = torch.zeros((m, 3), dtype=torch.float64, device=dev)
+    if len(i):
+        buf[:len(i), 0] = torch.from_numpy(i).to(dev)
+        buf[:len(i), 1] = torch.from_numpy(j).to(dev)
+        buf[:len(i), 2] = torch.from_numpy(s).to(dev)
+    bufs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf)
+    parts = [b[:int(c.item())].cpu().numpy() for b, c in zip(bufs, counts)]
+    allp = np.concatenate(parts) if parts else np.zeros((0, 3))
+    gi, gj, gs = allp[:, 0].astype(np.int64), allp[:, 1].astype(np.int64), allp[:, 2].astype(np.float32)
+    order = np.lexsort((gj, gi))
+    return gi[order], gj[order], gs[order]

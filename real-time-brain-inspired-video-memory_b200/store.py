@@ -139,6 +139,38 @@ class EmbeddingStore:
         L.check(self.lib.vm_synth_fill(self.device.index, dst.data_ptr(), self.dtype_code, seed, row0, n, self.dim,
                                        dup_period, _stream_ptr(self.device)))
 
+    # -- persistence (binary sidecar instead of JSON float lists) ---------------------
+    def save(self, path: str, ids: Optional[Sequence[str]] = None) -> None:
+        """Writes the resident rows as a binary sidecar: `<path>.npz` with the raw row values in the
+        store dtype (bf16 as uint16 bit patterns), the skipped-row mask and, optionally, the chunk ids.
+        The JSON export of src/components/graph_exporter.py:81-108 stores embeddings as float lists;
+        this is the same information without float parsing."""
+        n = len(self)
+        rows = self.rows[:n, :self.dim].contiguous()
+        raw = rows.view(torch.int16).cpu().numpy().view(np.uint16) if self.dtype_code == L.VM_BF16 else rows.cpu().numpy()
+        skipped = (self.inv_norms[:n] < 0).cpu().numpy()
+        np.savez(path, rows=raw, skipped=skipped, dim=self.dim, dtype=self.dtype_code,
+                 ids=np.asarray(list(ids) if ids is not None else [], dtype=object))
+
+    @classmethod
+    def load(cls, path: str, capacity: Optional[int] = None, device: int = 0):
+        """-> (store, ids).  Bit-identical rows, same skipped rows, same order."""
+        z = np.load(path if path.endswith(".npz") else path + ".npz", allow_pickle=True)
+        dim, code = int(z["dim"]), int(z["dtype"])
+        raw = z["rows"]
+        n = raw.shape[0]
+        st = cls(dim, max(int(capacity or n), 1), "bf16" if code == L.VM_BF16 else "f32", device)
+        if n:
+            if code == L.VM_BF16:
+                t = torch.from_numpy(raw.view(np.int16).copy()).view(torch.bfloat16)
+                st.append(t.to(st.device))
+            else:
+                st.append(raw)
+            bad = np.nonzero(z["skipped"])[0]
+            if len(bad):
+                st.invalidate(bad)
+        return st, [str(x) for x in z["ids"].tolist()]
+
     # -- reads ------------------------------------------------------------------------------
     def topk(self, queries, k: int, min_score: float = -math.inf, score_mode: int = L.VM_SCORE_RAW,
              sum_mode: Optional[int] = None, flags: int = 0, comm=None, row_offset: int = 0):

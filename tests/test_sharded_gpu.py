@@ -45,6 +45,13 @@ def _worker(rank, world, port, out_dir):
         torch.cuda.synchronize()
         ok = ok and np.array_equal(di.cpu().numpy(), idx) and np.array_equal(ds.cpu().numpy(), score)
         st.close()
+    # all-pairs dedup split over the ranks == the single-GPU pair set
+    from vidmem_b200 import dedup
+    E = synth.synth_rows(44, 0, 5000, 256, dup_period=6)
+    x = torch.from_numpy(E).cuda().to(torch.bfloat16)
+    gi, gj, gs = dedup.pairs_above_sharded(x, 0.9)
+    oi, oj, _ = oracle.pairs_above(E, 0.9)
+    ok = ok and len(oi) > 0 and list(zip(gi.tolist(), gj.tolist())) == list(zip(oi.tolist(), oj.tolist()))
     open(os.path.join(out_dir, f"rank{rank}.ok" if ok else f"rank{rank}.bad"), "w").write("x")
     dist.barrier()
     comm.close()

@@ -259,3 +259,20 @@ def test_large_dims_split_query_batches(vm, dtype, d, nq):
     assert np.array_equal(idx, bi) and np.array_equal(score, bs) and (count == k).all()
     assert idx[0, 0] == 4242
     st.close()
+
+
+def test_save_load_sidecar_roundtrip(vm, tmp_path):
+    d, n = 96, 500
+    X = synth.synth_rows(55, 0, n, d)
+    Q = synth.synth_queries(56, 4, d, 55, n)
+    for dtype in ("f32", "bf16"):
+        st = vm.EmbeddingStore(d, n, dtype)
+        st.append(X)
+        st.invalidate([3, 77])
+        ref = st.topk(Q, 5)
+        p = str(tmp_path / f"store_{dtype}")
+        st.save(p, ids=[f"c{i}" for i in range(n)])
+        st2, ids = vm.EmbeddingStore.load(p)
+        assert ids[:3] == ["c0", "c1", "c2"] and len(st2) == n
+        assert all(np.array_equal(a, b) for a, b in zip(ref, st2.topk(Q, 5)))
+        st.close(); st2.close()
