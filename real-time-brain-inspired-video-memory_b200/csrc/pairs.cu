@@ -480,6 +480,7 @@ int k_pairs_above(int device, const void *x, int dtype, int64_t n, int dim, int 
     if (rc != VM_OK) return rc;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int dev_idx = device & 63;
     static const bool one_cta = getenv("VIDMEM_PAIRS_1CTA") != nullptr;  // perf triage: force the 1-CTA kernel
     if (!one_cta) {
         // ---- CTA-pair kernel: 256 x 256 tiles ----
@@ -491,12 +492,12 @@ int k_pairs_above(int device, const void *x, int dtype, int64_t n, int dim, int 
         if (my_tiles < pairs) pairs = my_tiles;
         const int grid = (int)(2 * pairs);
         if (dtype == VM_F32) {
-            static bool set = false;
-            if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(pairs_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+            static bool set[64] = {};  // the attribute is per device
+            if (!set[dev_idx]) { VM_CUDA_CHECK(cudaFuncSetAttribute(pairs_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set[dev_idx] = true; }
             pairs_tc2_kernel<true><<<grid, P_THREADS, smem, st>>>(tmA, p);
         } else {
-            static bool set = false;
-            if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(pairs_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+            static bool set[64] = {};  // the attribute is per device
+            if (!set[dev_idx]) { VM_CUDA_CHECK(cudaFuncSetAttribute(pairs_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set[dev_idx] = true; }
             pairs_tc2_kernel<false><<<grid, P_THREADS, smem, st>>>(tmA, p);
         }
     } else {
@@ -506,12 +507,12 @@ int k_pairs_above(int device, const void *x, int dtype, int64_t n, int dim, int 
         const long long my_tiles = (p.total_tiles + nparts - 1) / nparts;
         const int grid = (int)(my_tiles < sms ? my_tiles : sms);
         if (dtype == VM_F32) {
-            static bool set = false;
-            if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(pairs_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+            static bool set[64] = {};  // the attribute is per device
+            if (!set[dev_idx]) { VM_CUDA_CHECK(cudaFuncSetAttribute(pairs_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set[dev_idx] = true; }
             pairs_tc_kernel<true><<<grid, P_THREADS, smem, st>>>(tmA, tmB, p);
         } else {
-            static bool set = false;
-            if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(pairs_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+            static bool set[64] = {};  // the attribute is per device
+            if (!set[dev_idx]) { VM_CUDA_CHECK(cudaFuncSetAttribute(pairs_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set[dev_idx] = true; }
             pairs_tc_kernel<false><<<grid, P_THREADS, smem, st>>>(tmA, tmB, p);
         }
     }

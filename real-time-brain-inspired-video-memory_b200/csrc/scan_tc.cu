@@ -366,18 +366,21 @@ int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t 
     rc = make_tmap_2d(&tmB, queries_store_dtype, a.dtype, (uint64_t)L.nq_pad, (uint64_t)a.ld, (uint64_t)a.ld, (uint32_t)L.nq_pad);
     if (rc != VM_OK) return rc;
     const int num_tiles = (int)((a.n + TC_BLOCK_M - 1) / TC_BLOCK_M);
+    int dev_idx = 0;
+    VM_CUDA_CHECK(cudaGetDevice(&dev_idx));
+    dev_idx &= 63;
     static const int dbg = getenv("VIDMEM_TC_DEBUG") ? atoi(getenv("VIDMEM_TC_DEBUG")) : 0;  // perf triage only
     g_last_tc_stages = L.stages;
     // seeding pays off once every CTA streams several tiles and there are at least kp CTAs
     const bool seed = seed_tab && seed_ctr && a.ctas >= a.kp && a.ctas <= 256 && num_tiles >= 4 * a.ctas && !(dbg & 4);
     if (!seed) { seed_tab = nullptr; seed_ctr = nullptr; }
     if (a.dtype == VM_F32) {
-        static bool set = false;
-        if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+        static bool set[64] = {};  // the attribute is per device
+        if (!set[dev_idx]) { VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set[dev_idx] = true; }
         scan_tc_kernel<true><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, seed_tab, seed_ctr, dbg);
     } else {
-        static bool set = false;
-        if (!set) { VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+        static bool set[64] = {};  // the attribute is per device
+        if (!set[dev_idx]) { VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set[dev_idx] = true; }
         scan_tc_kernel<false><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, seed_tab, seed_ctr, dbg);
     }
     VM_CUDA_CHECK(cudaGetLastError());

@@ -639,7 +639,7 @@ __global__ void cosine_pairs_kernel(const void *__restrict__ a, const void *__re
 int k_merge_candidates(const uint64_t *cand, int lists, int nq, int kp, uint64_t *merged, cudaStream_t st)
 {
     size_t smem = (size_t)lists * kp * sizeof(uint64_t) + (size_t)lists * sizeof(uint32_t) + 16;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};  /* the attribute is per device */ int dev_idx_ = 0; cudaGetDevice(&dev_idx_); bool &attr_set = attr_set_dev[dev_idx_ & 63];
     if (!attr_set) {
         VM_CUDA_CHECK(cudaFuncSetAttribute(merge_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
@@ -655,7 +655,7 @@ int k_rescore(const RescoreArgs &a, cudaStream_t st)
 {
 #define LAUNCH_RS(NEU, T)                                                                                              \
     do {                                                                                                               \
-        static bool attr_set = false;                                                                                  \
+        static bool attr_set_dev[64] = {};  /* the attribute is per device */ int dev_idx_ = 0; cudaGetDevice(&dev_idx_); bool &attr_set = attr_set_dev[dev_idx_ & 63];                                                                                  \
         if (!attr_set) {                                                                                               \
             VM_CUDA_CHECK(cudaFuncSetAttribute(rescore_kernel<NEU, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
             attr_set = true;                                                                                           \
@@ -702,7 +702,7 @@ int k_merge_topk_lists(const void *idx, const void *score, const void *count, si
     int total = lists * k;
     VM_REQUIRE(total <= 4096, VM_ERR_UNSUPPORTED, "merge_topk_lists: lists*k = %d > 4096", total);
     size_t smem = (size_t)total * (8 + 8 + 4);
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};  /* the attribute is per device */ int dev_idx_ = 0; cudaGetDevice(&dev_idx_); bool &attr_set = attr_set_dev[dev_idx_ & 63];
     if (!attr_set) {
         VM_CUDA_CHECK(cudaFuncSetAttribute(merge_topk_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
@@ -719,7 +719,7 @@ int k_merge_max_by_id(const int64_t *idx, const double *score, const int32_t *co
     int total = nq * k;
     VM_REQUIRE(total <= 4096, VM_ERR_UNSUPPORTED, "merge_max_by_id: nq*k = %d > 4096", total);
     size_t smem = (size_t)total * (8 + 8 + 4);
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};  /* the attribute is per device */ int dev_idx_ = 0; cudaGetDevice(&dev_idx_); bool &attr_set = attr_set_dev[dev_idx_ & 63];
     if (!attr_set) {
         VM_CUDA_CHECK(cudaFuncSetAttribute(merge_max_by_id_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;

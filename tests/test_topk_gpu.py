@@ -276,3 +276,48 @@ def test_save_load_sidecar_roundtrip(vm, tmp_path):
         assert ids[:3] == ["c0", "c1", "c2"] and len(st2) == n
         assert all(np.array_equal(a, b) for a, b in zip(ref, st2.topk(Q, 5)))
         st.close(); st2.close()
+
+
+def test_async_device_conditional_exact_rescan(vm):
+    """VM_FLAG_ASYNC never syncs: uncertified queries are re-done by the device-conditional exact scan."""
+    import torch
+    d, n, k = 64, 40000, 10
+    rng = np.random.default_rng(11)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    X[500:900] = X[500]                                     # 400 exact ties: more than any candidate list holds
+    Q = np.stack([X[500], rng.standard_normal(d).astype(np.float32), np.zeros(d, np.float32)] * 3)
+    st = vm.EmbeddingStore(d, n, "f32")
+    st.append(X)
+    for flags in (vm.VM_FLAG_ASYNC, vm.VM_FLAG_ASYNC | vm.VM_FLAG_FORCE_TC, vm.VM_FLAG_ASYNC | vm.VM_FLAG_FORCE_SIMT):
+        idx, score, count = st.topk_device(torch.from_numpy(Q).cuda(), k, sum_mode=vm.VM_SUM_NEUMAIER, flags=flags)
+        torch.cuda.synchronize()
+        _check(idx.cpu().numpy(), score.cpu().numpy(), count.cpu().numpy(), oracle.batch_similarities(Q, X, k), k)
+        assert list(idx[0].cpu().numpy()) == list(range(500, 510))
+    st.close()
+
+
+def test_integration_md_ctypes_example(vm):
+    """The stand-alone ctypes binding shown in INTEGRATION.md section 2, with library-owned store memory."""
+    import ctypes as C
+    lib = C.CDLL(vm._lib.LIB_PATH)
+    lib.vm_last_error.restype = C.c_char_p
+    n, d, k = 3000, 384, 10
+    X = synth.synth_rows(41, 0, n, d).astype(np.float64)
+    Qf = synth.synth_queries(42, 7, d, 41, n)
+    store = C.c_void_p()
+    assert lib.vm_store_create(C.byref(store), 0, d, 0, C.c_int64(n)) == 0, lib.vm_last_error()
+    assert lib.vm_store_append(store, X.ctypes.data_as(C.c_void_p), 2, 0, C.c_int64(n), None, None) == 0, lib.vm_last_error()
+    lib.vm_store_size.restype = C.c_int64
+    assert lib.vm_store_size(store) == n
+    q = Qf.astype(np.float64)
+    idx = np.empty((len(q), k), np.int64); score = np.empty((len(q), k), np.float64); cnt = np.empty(len(q), np.int32)
+    rc = lib.vm_topk(store, q.ctypes.data_as(C.c_void_p), 2, 0, len(q), k, C.c_double(-np.inf), 0, 1, 0,
+                     idx.ctypes.data_as(C.c_void_p), score.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p),
+                     0, None, None)
+    assert rc == 0, lib.vm_last_error()
+    _check(idx, score, cnt, oracle.batch_similarities(Qf, X, k), k)
+    # error convention: status code + message, nothing thrown across the ABI
+    assert lib.vm_store_append(store, X.ctypes.data_as(C.c_void_p), 2, 0, C.c_int64(n), None, None) == vm._lib.VM_ERR_OVERFLOW
+    assert b"capacity" in lib.vm_last_error()
+    assert lib.vm_topk(store, q.ctypes.data_as(C.c_void_p), 2, 0, len(q), 1000, C.c_double(0), 0, 1, 0, None, None, None, 0, None, None) == vm._lib.VM_ERR_BADARG
+    assert lib.vm_store_destroy(store) == 0
