@@ -30,6 +30,7 @@ int k_synth_fill(void *rows, int dtype, uint64_t seed, int64_t row0, int64_t n, 
 int k_merge_candidates(const uint64_t *cand, int lists, int nq, int kp, uint64_t *merged, cudaStream_t st);
 
 int k_rescore(const RescoreArgs &a, cudaStream_t st);
+int k_select_rescore(const uint64_t *cand, int lists, const RescoreArgs &a, cudaStream_t st);
 int k_exact(const ExactArgs &a, cudaStream_t st);
 int k_merge_topk_lists(const void *idx, const void *score, const void *count, size_t stride_bytes, int lists, int nq, int k,
                        int64_t *out_idx, double *out_score, int32_t *out_count, cudaStream_t st);
@@ -465,15 +466,19 @@ static int topk_batch(const TopkCall &c)
     if (rc != VM_OK) return rc;
     if (timing) { VM_CUDA_CHECK(cudaEventRecord(s->ev1, st)); s->timed = true; }
 
-    rc = k_merge_candidates(a.cand, a.ctas, c.nq, kp, (uint64_t *)w.merged.p, st);
-    if (rc != VM_OK) return rc;
     int32_t *flags = (int32_t *)w.flags.p;
     int32_t *uncert = flags + c.nq;  // counter sits right after the nq flags (zeroed by the normalise kernel)
     RescoreArgs rs{(const uint64_t *)w.merged.p, kp, s->rows, s->inv_norms, s->dtype, s->ld, s->dim, s->size, q_dev,
                    c.q_dtype, c.nq, scan_eps(kernel, s->dtype, s->dim), c.sum_mode, fin, flags, uncert};
-    rc = k_rescore(rs, st);
+    rc = k_select_rescore(a.cand, a.ctas, rs, st);  // fused merge + exact rescoring
+    if (rc == VM_ERR_UNSUPPORTED) {                 // rows too large for shared memory: two kernels
+        rc = k_merge_candidates(a.cand, a.ctas, c.nq, kp, (uint64_t *)w.merged.p, st);
+        if (rc != VM_OK) return rc;
+        rc = k_rescore(rs, st);
+        ++launches;
+    }
     if (rc != VM_OK) return rc;
-    launches += 2;
+    launches += 1;
 
     ex.flags = flags;
     int n_uncert = 0;

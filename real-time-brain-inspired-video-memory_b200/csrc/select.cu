@@ -374,6 +374,228 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const uint64_t *__r
 }
 
 // =========================================================================================
+// 2b. fused candidate selection + exact rescoring (the normal path: one launch instead of two)
+// =========================================================================================
+// One CTA (512 threads) per query:
+//   A. the per-CTA candidate sets are loaded into shared memory and thinned with the list-maxima
+//      bound (see merge_candidates_kernel); survivors are ranked -> the kp best keys, descending;
+//   B. the kp candidate rows are pulled into shared memory with cp.async (16-byte, L2-cached) in three
+//      column chunks, the query is converted to doubles;
+//   C. the reference recurrences (dot per candidate, ||row||^2 per candidate, ||q||^2) run as
+//      independent sequential chains on 2kp+1 threads, chunk c overlapping the loads of chunk c+1;
+//   D. rank, emit, certify (as rescore_kernel).
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+static constexpr int SR_THREADS = 512;
+template <bool NEUMAIER, typename T>
+__global__ void __launch_bounds__(SR_THREADS) select_rescore_kernel(const uint64_t *__restrict__ cand, int lists, int nq, int kp,
+                                                                   const T *__restrict__ rows, int ld, int dim, int64_t n_rows,
+                                                                   const void *__restrict__ queries, int q_dtype, double eps,
+                                                                   FinalizeArgs f, int32_t *__restrict__ flags,
+                                                                   int32_t *__restrict__ uncertified_count)
+{
+    extern __shared__ __align__(16) unsigned char sr_smem[];
+    const int total = lists * kp;
+    uint64_t *skeys = reinterpret_cast<uint64_t *>(sr_smem);                       // [total]
+    uint32_t *lmax = reinterpret_cast<uint32_t *>(skeys + total);                  // [lists] (+pad)
+    double *sq = reinterpret_cast<double *>(lmax + ((lists + 3) & ~3));            // [dim]
+    const int pitch = ld * (int)sizeof(T) + 16;                                    // bytes, 16-B aligned rows
+    unsigned char *srow = reinterpret_cast<unsigned char *>(sq + ((dim + 1) & ~1)); // [kp][pitch]
+    __shared__ uint64_t s_top[64];
+    __shared__ uint64_t surv[MERGE_SURV];
+    __shared__ int hist[256];
+    __shared__ int s_bin, s_need, s_m, s_nz, s_cnt;
+    __shared__ uint32_t s_L;
+    __shared__ double s_dot[64], s_rr[64], s_qq, s_score[64];
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---------------- A. candidate selection ----------------
+    if (tid == 0) { s_m = 0; s_nz = 0; s_cnt = 0; }
+    if (tid < 64) s_top[tid] = 0;
+    __syncthreads();
+    int nz = 0;
+#pragma unroll 10
+    for (int e = tid; e < total; e += SR_THREADS) {
+        const int l = e / kp, j = e - l * kp;
+        const uint64_t k = cand[((int64_t)l * nq + q) * kp + j];
+        skeys[e] = k;
+        nz += k != 0;
+    }
+    // the query does not depend on the selection: convert it now
+    for (int i = tid; i < dim; i += SR_THREADS) sq[i] = load_as_double(queries, q_dtype, (int64_t)q * dim + i);
+    if (nz) atomicAdd(&s_nz, nz);
+    __syncthreads();
+    const int nonzero = s_nz;
+    bool done = false;
+    if (nonzero >= kp && lists >= kp && lists <= 256) {
+        for (int l = warp; l < lists; l += SR_THREADS / 32) {
+            uint32_t m = 0;
+            for (int j = lane; j < kp; j += 32) m = max(m, (uint32_t)(skeys[l * kp + j] >> 32));
+            m = __reduce_max_sync(0xffffffffu, m);
+            if (lane == 0) lmax[l] = m;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t vals[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) vals[t] = (lane + 32 * t) < lists ? lmax[lane + 32 * t] : 0u;
+            uint32_t prefix = 0;
+            int need = kp;
+            for (int bit = 31; bit >= 12; --bit) {  // 20 bits: truncation only loosens the bound
+                const uint32_t hi = bit == 31 ? 0u : (0xFFFFFFFFu << (bit + 1));
+                int cnt = 0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) cnt += ((vals[t] & hi) == prefix && ((vals[t] >> bit) & 1u)) ? 1 : 0;
+                const int tot = __reduce_add_sync(0xffffffffu, cnt);
+                if (tot >= need) prefix |= 1u << bit;
+                else need -= tot;
+            }
+            if (lane == 0) s_L = prefix;
+        }
+        __syncthreads();
+        const uint32_t Lb = s_L;
+        if (Lb != 0) {
+            for (int e = tid; e < total; e += SR_THREADS) {
+                const uint64_t k = skeys[e];
+                if ((uint32_t)(k >> 32) >= Lb && k != 0) {
+                    const int p = atomicAdd(&s_m, 1);
+                    if (p < MERGE_SURV) surv[p] = k;
+                }
+            }
+            __syncthreads();
+            const int m = s_m;
+            if (m >= kp && m <= MERGE_SURV) {
+                for (int e = tid; e < m; e += SR_THREADS) {
+                    const uint64_t k = surv[e];
+                    int rank = 0;
+                    for (int i = 0; i < m; ++i) rank += surv[i] > k ? 1 : 0;
+                    if (rank < kp) s_top[rank] = k;
+                }
+                done = true;
+            }
+        }
+    }
+    if (!done) {  // uniform across the block: exact radix select (few lists, heavy duplication)
+        __syncthreads();
+        uint64_t T = 1;
+        if (nonzero >= kp) T = radix_select_kth(skeys, total, kp, hist, &s_bin, &s_need);
+        if (tid == 0) s_m = 0;
+        __syncthreads();
+        for (int e = tid; e < total; e += SR_THREADS) {
+            const uint64_t k = skeys[e];
+            if (k >= T && k != 0) {
+                if (nonzero >= kp && k == T) s_top[kp - 1] = k;  // the worst candidate goes last
+                else s_top[atomicAdd(&s_m, 1)] = k;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- B. stage the candidate rows ----------------
+    const int j = tid;
+    const uint64_t mykey = j < 64 ? s_top[j] : 0;
+    const bool cand_valid = j < kp && mykey != 0;
+    const int gpr = ld * (int)sizeof(T) / 16;                 // 16-byte groups per row
+    const int c1 = gpr / 3, c2 = 2 * gpr / 3;                 // chunk boundaries (in groups)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int g_lo = c == 0 ? 0 : (c == 1 ? c1 : c2), g_hi = c == 0 ? c1 : (c == 1 ? c2 : gpr);
+        const int w = g_hi - g_lo;
+        for (int e = tid; e < kp * w; e += SR_THREADS) {
+            const int r = e / w, g = g_lo + (e - r * w);
+            const uint64_t key = s_top[r];
+            if (key != 0)
+                cp_async16(srow + (size_t)r * pitch + (size_t)g * 16,
+                           reinterpret_cast<const unsigned char *>(rows + (int64_t)key_row(key) * ld) + (size_t)g * 16);
+        }
+        cp_async_commit();
+    }
+
+    // ---------------- C. sequential reference chains ----------------
+    const int kind = j < kp ? 0 : (j < 2 * kp ? 1 : (j == 2 * kp ? 2 : 3));
+    const int cidx = kind == 0 ? j : (kind == 1 ? j - kp : 0);
+    const bool active = kind == 2 || (kind < 2 && s_top[cidx] != 0);
+    const T *mine = reinterpret_cast<const T *>(srow + (size_t)cidx * pitch);
+    constexpr int EPG = 16 / (int)sizeof(T);                  // elements per 16-byte group
+    RefSum acc;
+    acc.init();
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (c == 0) cp_async_wait<2>();
+        else if (c == 1) cp_async_wait<1>();
+        else cp_async_wait<0>();
+        __syncthreads();
+        const int g_lo = c == 0 ? 0 : (c == 1 ? c1 : c2), g_hi = c == 0 ? c1 : (c == 1 ? c2 : gpr);
+        const int i_lo = g_lo * EPG, i_hi = min(g_hi * EPG, dim);
+        if (active) {
+            if (kind == 0) {
+#pragma unroll 8
+                for (int i = i_lo; i < i_hi; ++i) acc.add<NEUMAIER>(__dmul_rn(sq[i], (double)load_as_float(mine, i)));
+            } else if (kind == 1) {
+#pragma unroll 8
+                for (int i = i_lo; i < i_hi; ++i) { const double y = (double)load_as_float(mine, i); acc.add<NEUMAIER>(__dmul_rn(y, y)); }
+            } else {
+#pragma unroll 8
+                for (int i = i_lo; i < i_hi; ++i) { const double x = sq[i]; acc.add<NEUMAIER>(__dmul_rn(x, x)); }
+            }
+        }
+    }
+    if (active) {
+        const double r = acc.result<NEUMAIER>();
+        if (kind == 0) s_dot[cidx] = r;
+        else if (kind == 1) s_rr[cidx] = r;
+        else s_qq = r;
+    }
+    __syncthreads();
+
+    // ---------------- D. rank, emit, certify ----------------
+    double sc = 0.0;
+    const uint32_t row = cand_valid ? key_row(mykey) : 0;
+    if (cand_valid) {
+        const double n1 = __dsqrt_rn(s_qq);
+        const double n2 = __dsqrt_rn(s_rr[j]);
+        sc = (n1 == 0.0 || n2 == 0.0) ? 0.0 : __ddiv_rn(s_dot[j], __dmul_rn(n1, n2));
+    }
+    if (j < 64) s_score[j] = sc;
+    __syncthreads();
+    int ncand = 0;
+    for (int i = 0; i < kp; ++i) ncand += s_top[i] != 0;
+    int rank = 0;
+    if (cand_valid)
+        for (int i = 0; i < kp; ++i)
+            if (s_top[i] != 0 && i != j && better(s_score[i], key_row(s_top[i]), sc, row)) ++rank;
+    const double outv = convert_score(sc, f.score_mode);
+    const bool emit = cand_valid && rank < f.k && outv > f.min_score;
+    if (emit) {
+        f.out_idx[(int64_t)q * f.k + rank] = (int64_t)row + f.row_offset;
+        f.out_score[(int64_t)q * f.k + rank] = outv;
+        atomicAdd(&s_cnt, 1);
+    }
+    __syncthreads();
+    if (cand_valid && rank == min(f.k, ncand) - 1) {
+        bool cert = true;
+        if (ncand >= kp && (int64_t)ncand < n_rows) {
+            const float worst = key_score(s_top[kp - 1]);  // smallest approximate score among the candidates
+            cert = ((double)worst + eps) < sc;
+        }
+        flags[q] = cert ? 0 : 1;
+        if (!cert) atomicAdd(uncertified_count, 1);
+    }
+    if (ncand == 0 && tid == 0) flags[q] = 0;
+    if (tid == 0) f.out_count[q] = s_cnt;
+    const int cnt = s_cnt;
+    for (int t = cnt + tid; t < f.k; t += SR_THREADS) {
+        f.out_idx[(int64_t)q * f.k + t] = -1;
+        f.out_score[(int64_t)q * f.k + t] = 0.0;
+    }
+}
+
+// =========================================================================================
 // 3. always-exact binary64 scan (uncertified queries / VM_FLAG_FORCE_EXACT)
 // =========================================================================================
 // Grid-stride over 128-row tiles; thread t scores row tile*128+t against one flagged query at a
@@ -677,6 +899,36 @@ int k_rescore(const RescoreArgs &a, cudaStream_t st)
     return VM_OK;
 }
 
+
+// Fused path when the candidate keys + kp whole rows fit in shared memory; otherwise the caller falls
+// back to k_merge_candidates + k_rescore.  Returns VM_ERR_UNSUPPORTED (without setting an error the
+// caller must report) when it does not apply.
+int k_select_rescore(const uint64_t *cand, int lists, const RescoreArgs &a, cudaStream_t st)
+{
+    const int es = a.dtype == VM_F32 ? 4 : 2;
+    const size_t smem = (size_t)lists * a.kp * 8 + (size_t)((lists + 3) & ~3) * 4 + (size_t)((a.dim + 1) & ~1) * 8 +
+                        (size_t)a.kp * ((size_t)a.ld * es + 16) + 32;
+    if (smem > 180 * 1024 || a.kp > 64 || 2 * a.kp + 1 > SR_THREADS) return VM_ERR_UNSUPPORTED;
+#define LAUNCH_SR(NEU, T)                                                                                              \
+    do {                                                                                                               \
+        static bool attr_set_dev[64] = {};                                                                             \
+        int dev_idx_ = 0;                                                                                              \
+        cudaGetDevice(&dev_idx_);                                                                                      \
+        if (!attr_set_dev[dev_idx_ & 63]) {                                                                            \
+            VM_CUDA_CHECK(cudaFuncSetAttribute(select_rescore_kernel<NEU, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024)); \
+            attr_set_dev[dev_idx_ & 63] = true;                                                                        \
+        }                                                                                                              \
+        select_rescore_kernel<NEU, T><<<a.nq, SR_THREADS, smem, st>>>(cand, lists, a.nq, a.kp, (const T *)a.rows, a.ld, a.dim, \
+                                                                      a.n_rows, a.queries, a.q_dtype, a.eps, a.fin, a.flags,  \
+                                                                      a.uncertified_count);                            \
+    } while (0)
+    const bool neu = a.sum_mode == VM_SUM_NEUMAIER;
+    if (a.dtype == VM_F32) { if (neu) LAUNCH_SR(true, float); else LAUNCH_SR(false, float); }
+    else { if (neu) LAUNCH_SR(true, __nv_bfloat16); else LAUNCH_SR(false, __nv_bfloat16); }
+#undef LAUNCH_SR
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
 
 int k_exact(const ExactArgs &a, cudaStream_t st)
 {
