@@ -204,12 +204,8 @@ __device__ double exact_cosine_sq(const double *sq, double n1, const T *row, int
 {
     RefSum dot, rr;
     dot.init(); rr.init();
-    for (int i = 0; i < dim; ++i) {
-        double x = sq[i];
-        double y = (double)load_as_float(row, i);
-        dot.add<NEUMAIER>(__dmul_rn(x, y));
-        rr.add<NEUMAIER>(__dmul_rn(y, y));
-    }
+    ref_sum_range<NEUMAIER>(dot, 0, dim, [&](int i) { return __dmul_rn(sq[i], (double)load_as_float(row, i)); });
+    ref_sum_range<NEUMAIER>(rr, 0, dim, [&](int i) { const double y = (double)load_as_float(row, i); return __dmul_rn(y, y); });
     double n2 = __dsqrt_rn(rr.result<NEUMAIER>());
     if (n1 == 0.0 || n2 == 0.0) return 0.0;
     return __ddiv_rn(dot.result<NEUMAIER>(), __dmul_rn(n1, n2));
@@ -247,7 +243,7 @@ __device__ __forceinline__ void load_vec16(const __nv_bfloat16 *p, float *o)
 }
 
 template <bool NEUMAIER, typename T>
-__global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const uint64_t *__restrict__ merged, int kp, const T *__restrict__ rows,
+__global__ void __launch_bounds__(RS_THREADS, 1) rescore_kernel(const uint64_t *__restrict__ merged, int kp, const T *__restrict__ rows,
                                                             const float *__restrict__ inv_norms, int ld, int dim, int64_t n_rows,
                                                             const void *__restrict__ queries, int q_dtype, double eps,
                                                             FinalizeArgs f, int32_t *__restrict__ flags,
@@ -306,16 +302,12 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const uint64_t *__r
         __syncthreads();
         if (active) {
             const float *mine = srow + cand * pitch;
-            if (kind == 0) {
-#pragma unroll 8
-                for (int i = 0; i < len; ++i) acc.add<NEUMAIER>(__dmul_rn(sq[i], (double)mine[i]));
-            } else if (kind == 1) {
-#pragma unroll 8
-                for (int i = 0; i < len; ++i) { const double y = (double)mine[i]; acc.add<NEUMAIER>(__dmul_rn(y, y)); }
-            } else {
-#pragma unroll 8
-                for (int i = 0; i < len; ++i) { const double x = sq[i]; acc.add<NEUMAIER>(__dmul_rn(x, x)); }
-            }
+            if (kind == 0)
+                ref_sum_range<NEUMAIER>(acc, 0, len, [&](int i) { return __dmul_rn(sq[i], (double)mine[i]); });
+            else if (kind == 1)
+                ref_sum_range<NEUMAIER>(acc, 0, len, [&](int i) { const double y = (double)mine[i]; return __dmul_rn(y, y); });
+            else
+                ref_sum_range<NEUMAIER>(acc, 0, len, [&](int i) { const double x = sq[i]; return __dmul_rn(x, x); });
         }
         __syncthreads();
     }
@@ -393,7 +385,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 static constexpr int SR_THREADS = 512;
 template <bool NEUMAIER, typename T>
-__global__ void __launch_bounds__(SR_THREADS) select_rescore_kernel(const uint64_t *__restrict__ cand, int lists, int nq, int kp,
+__global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uint64_t *__restrict__ cand, int lists, int nq, int kp,
                                                                    const T *__restrict__ rows, int ld, int dim, int64_t n_rows,
                                                                    const void *__restrict__ queries, int q_dtype, double eps,
                                                                    FinalizeArgs f, int32_t *__restrict__ flags,
@@ -533,16 +525,12 @@ __global__ void __launch_bounds__(SR_THREADS) select_rescore_kernel(const uint64
         const int g_lo = c == 0 ? 0 : (c == 1 ? c1 : c2), g_hi = c == 0 ? c1 : (c == 1 ? c2 : gpr);
         const int i_lo = g_lo * EPG, i_hi = min(g_hi * EPG, dim);
         if (active) {
-            if (kind == 0) {
-#pragma unroll 8
-                for (int i = i_lo; i < i_hi; ++i) acc.add<NEUMAIER>(__dmul_rn(sq[i], (double)load_as_float(mine, i)));
-            } else if (kind == 1) {
-#pragma unroll 8
-                for (int i = i_lo; i < i_hi; ++i) { const double y = (double)load_as_float(mine, i); acc.add<NEUMAIER>(__dmul_rn(y, y)); }
-            } else {
-#pragma unroll 8
-                for (int i = i_lo; i < i_hi; ++i) { const double x = sq[i]; acc.add<NEUMAIER>(__dmul_rn(x, x)); }
-            }
+            if (kind == 0)
+                ref_sum_range<NEUMAIER>(acc, i_lo, i_hi, [&](int i) { return __dmul_rn(sq[i], (double)load_as_float(mine, i)); });
+            else if (kind == 1)
+                ref_sum_range<NEUMAIER>(acc, i_lo, i_hi, [&](int i) { const double y = (double)load_as_float(mine, i); return __dmul_rn(y, y); });
+            else
+                ref_sum_range<NEUMAIER>(acc, i_lo, i_hi, [&](int i) { const double x = sq[i]; return __dmul_rn(x, x); });
         }
     }
     if (active) {
