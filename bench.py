@@ -153,6 +153,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 in every worker; the reference arm is meant to use every host core
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     cfg = args.config or ("c2" if args.gpus == 1 else "c3")
     cores = os.cpu_count() or 1
     sample = args.cpu_sample_rows or 100000
