@@ -77,15 +77,19 @@ struct Buf {
 struct Workspace {
     bool ready = false;
     int lists_max = 0;
-    Buf q_raw, q_f32, q_bf16, seed, cand, merged, o_idx, o_score, o_count, flags, xs, xr, xc, taken, gather_send, gather_recv, misc;
+    Buf q_raw, q_f32, q_bf16, seed, cand, merged, o_idx, flags, xs, xr, xc, taken, gather_send, gather_recv, misc;
     int32_t *h_uncert = nullptr;  // pinned
+    unsigned char *h_pack = nullptr;  // pinned: packed [idx | score | count] of one batch
+    unsigned char *h_q = nullptr;     // pinned: host queries of one batch
     void release()
     {
-        Buf *all[] = {&q_raw, &q_f32, &q_bf16, &seed, &cand, &merged, &o_idx, &o_score, &o_count, &flags, &xs, &xr, &xc, &taken,
+        Buf *all[] = {&q_raw, &q_f32, &q_bf16, &seed, &cand, &merged, &o_idx, &flags, &xs, &xr, &xc, &taken,
                       &gather_send, &gather_recv, &misc};
         for (Buf *b : all) b->release();
         if (h_uncert) cudaFreeHost(h_uncert);
-        h_uncert = nullptr;
+        if (h_pack) cudaFreeHost(h_pack);
+        if (h_q) cudaFreeHost(h_q);
+        h_uncert = nullptr; h_pack = nullptr; h_q = nullptr;
         ready = false;
     }
 };
@@ -174,9 +178,8 @@ static int ws_prepare(vm_store *s)
     ENS(w.q_bf16, (size_t)MAXQ * s->ld * 2);
     ENS(w.cand, (size_t)lists * MAXQ * MAXK * 8);
     ENS(w.merged, (size_t)MAXQ * MAXK * 8);
-    ENS(w.o_idx, (size_t)MAXQ * MAXK * 8);
-    ENS(w.o_score, (size_t)MAXQ * MAXK * 8);
-    ENS(w.o_count, (size_t)MAXQ * 4);
+    // one contiguous block [idx | score | count] so a host caller gets its results with ONE copy
+    ENS(w.o_idx, (size_t)MAXQ * MAXK * 16 + (size_t)MAXQ * 4 + 64);
     ENS(w.flags, (size_t)(MAXQ + 2) * 4);
     ENS(w.seed, (size_t)256 * MAXQ * 4);
     ENS(w.xs, (size_t)XCTAS * MAXQ * MAXK * 8);
@@ -185,6 +188,8 @@ static int ws_prepare(vm_store *s)
     ENS(w.taken, (size_t)MAXQ * XCTAS * MAXK);
 #undef ENS
     VM_CUDA_CHECK(cudaMallocHost((void **)&w.h_uncert, 64));
+    VM_CUDA_CHECK(cudaMallocHost((void **)&w.h_pack, (size_t)MAXQ * MAXK * 16 + (size_t)MAXQ * 4 + 64));
+    VM_CUDA_CHECK(cudaMallocHost((void **)&w.h_q, (size_t)MAXQ * s->dim * 8));
     w.ready = true;
     return VM_OK;
 }
@@ -389,6 +394,23 @@ struct TopkCall {
 };
 }  // namespace
 
+// Host-output path: the batch's device results are one contiguous block [idx | score | count]
+// (see ws_prepare); one D2H copy into pinned memory, then plain host copies into the caller's arrays.
+static int pack_out_enqueue(const TopkCall &c)
+{
+    const size_t bytes = (size_t)c.nq * c.k * 16 + (size_t)c.nq * 4;
+    VM_CUDA_CHECK(cudaMemcpyAsync(c.s->ws.h_pack, c.d_idx, bytes, cudaMemcpyDeviceToHost, c.st));
+    return VM_OK;
+}
+static void pack_out_finish(const TopkCall &c)
+{
+    const size_t seg = (size_t)c.nq * c.k * 8;
+    const unsigned char *p = c.s->ws.h_pack;
+    memcpy(c.h_idx, p, seg);
+    memcpy(c.h_score, p + seg, seg);
+    memcpy(c.h_count, p + 2 * seg, (size_t)c.nq * 4);
+}
+
 // One batch of <= MAXQ queries; results land in c.d_* (device).  May synchronise the stream
 // (unless VM_FLAG_ASYNC) to learn whether any query needs the exact re-scan.
 static int topk_batch(const TopkCall &c)
@@ -398,8 +420,10 @@ static int topk_batch(const TopkCall &c)
     cudaStream_t st = c.st;
     const void *q_dev = c.queries;
     if (c.q_mem == VM_MEM_HOST) {
-        VM_CUDA_CHECK(cudaMemcpyAsync(w.q_raw.p, c.queries, (size_t)c.nq * s->dim * dtype_size(c.q_dtype),
-                                      cudaMemcpyHostToDevice, st));
+        // pageable host memory would make the copy synchronous: stage through the pinned buffer
+        const size_t qbytes = (size_t)c.nq * s->dim * dtype_size(c.q_dtype);
+        memcpy(w.h_q, c.queries, qbytes);
+        VM_CUDA_CHECK(cudaMemcpyAsync(w.q_raw.p, w.h_q, qbytes, cudaMemcpyHostToDevice, st));
         q_dev = w.q_raw.p;
     }
     FinalizeArgs fin{c.k, c.min_score, c.score_mode, c.row_offset, c.d_idx, c.d_score, c.d_count};
@@ -427,10 +451,9 @@ static int topk_batch(const TopkCall &c)
         if (rc != VM_OK) return rc;
         launches += 2;
         if (c.h_idx) {
-            VM_CUDA_CHECK(cudaMemcpyAsync(c.h_idx, c.d_idx, (size_t)c.nq * c.k * 8, cudaMemcpyDeviceToHost, st));
-            VM_CUDA_CHECK(cudaMemcpyAsync(c.h_score, c.d_score, (size_t)c.nq * c.k * 8, cudaMemcpyDeviceToHost, st));
-            VM_CUDA_CHECK(cudaMemcpyAsync(c.h_count, c.d_count, (size_t)c.nq * 4, cudaMemcpyDeviceToHost, st));
+            if ((rc = pack_out_enqueue(c)) != VM_OK) return rc;
             VM_CUDA_CHECK(cudaStreamSynchronize(st));
+            pack_out_finish(c);
         }
         if (c.stats) { c.stats->scan_kernel = 0; c.stats->scan_launches += launches; }
         return VM_OK;
@@ -488,24 +511,20 @@ static int topk_batch(const TopkCall &c)
         launches += 2;
         n_uncert = -1;
     } else {
-        auto copy_out = [&]() -> int {
-            if (!c.h_idx) return VM_OK;
-            VM_CUDA_CHECK(cudaMemcpyAsync(c.h_idx, c.d_idx, (size_t)c.nq * c.k * 8, cudaMemcpyDeviceToHost, st));
-            VM_CUDA_CHECK(cudaMemcpyAsync(c.h_score, c.d_score, (size_t)c.nq * c.k * 8, cudaMemcpyDeviceToHost, st));
-            VM_CUDA_CHECK(cudaMemcpyAsync(c.h_count, c.d_count, (size_t)c.nq * 4, cudaMemcpyDeviceToHost, st));
-            return VM_OK;
-        };
         VM_CUDA_CHECK(cudaMemcpyAsync(w.h_uncert, uncert, 4, cudaMemcpyDeviceToHost, st));
-        if ((rc = copy_out()) != VM_OK) return rc;
+        if (c.h_idx && (rc = pack_out_enqueue(c)) != VM_OK) return rc;
         VM_CUDA_CHECK(cudaStreamSynchronize(st));
         n_uncert = *w.h_uncert;
         if (n_uncert > 0) {
             rc = k_exact(ex, st);
             if (rc != VM_OK) return rc;
             launches += 2;
-            if ((rc = copy_out()) != VM_OK) return rc;
-            if (c.h_idx) VM_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (c.h_idx) {
+                if ((rc = pack_out_enqueue(c)) != VM_OK) return rc;
+                VM_CUDA_CHECK(cudaStreamSynchronize(st));
+            }
         }
+        if (c.h_idx) pack_out_finish(c);
     }
     if (c.stats) {
         c.stats->scan_kernel = kernel;
@@ -555,9 +574,13 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
         int nb = nq - q0 < bq ? nq - q0 : bq;
         // where this batch's local results go
         bool direct = out_mem == VM_MEM_DEVICE && !sharded;
-        int64_t *d_idx = direct ? out_idx + (size_t)q0 * k : (int64_t *)w.o_idx.p;
-        double *d_score = direct ? out_score + (size_t)q0 * k : (double *)w.o_score.p;
-        int32_t *d_count = direct ? out_count + q0 : (int32_t *)w.o_count.p;
+        // workspace block of this batch: [idx nb*k | score nb*k | count nb], contiguous
+        int64_t *ws_idx = (int64_t *)w.o_idx.p;
+        double *ws_score = (double *)((char *)w.o_idx.p + (size_t)nb * k * 8);
+        int32_t *ws_count = (int32_t *)((char *)w.o_idx.p + (size_t)nb * k * 16);
+        int64_t *d_idx = direct ? out_idx + (size_t)q0 * k : ws_idx;
+        double *d_score = direct ? out_score + (size_t)q0 * k : ws_score;
+        int32_t *d_count = direct ? out_count + q0 : ws_count;
         if (sharded) {
             // pack [idx | score | count] contiguously so ONE all-gather moves the batch
             size_t seg = (size_t)nb * k * 8;
@@ -581,9 +604,9 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
             size_t per_rank = 2 * seg + (((size_t)nb * 4 + 7) & ~(size_t)7);
             VM_NCCL_CHECK(g_nccl.AllGather(w.gather_send.p, w.gather_recv.p, per_rank, /*ncclInt8*/ 0, comm->nccl, st));
             bool dd = out_mem == VM_MEM_DEVICE;
-            int64_t *m_idx = dd ? out_idx + (size_t)q0 * k : (int64_t *)w.o_idx.p;
-            double *m_score = dd ? out_score + (size_t)q0 * k : (double *)w.o_score.p;
-            int32_t *m_count = dd ? out_count + q0 : (int32_t *)w.o_count.p;
+            int64_t *m_idx = dd ? out_idx + (size_t)q0 * k : ws_idx;
+            double *m_score = dd ? out_score + (size_t)q0 * k : ws_score;
+            int32_t *m_count = dd ? out_count + q0 : ws_count;
             const char *rb = (const char *)w.gather_recv.p;
             rc = k_merge_topk_lists(rb, rb + seg, rb + 2 * seg, per_rank, comm->nranks, nb, k, m_idx, m_score, m_count, st);
             if (rc != VM_OK) return rc;

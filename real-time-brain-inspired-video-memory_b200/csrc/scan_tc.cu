@@ -361,9 +361,9 @@ int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t 
     TcLayout L = make_layout(a.dtype, a.ld, a.nq, a.kp);
     VM_REQUIRE(L.stages >= 3, VM_ERR_UNSUPPORTED, "tcgen05 scan: dim %d x %d queries does not fit shared memory", a.dim, a.nq);
     CUtensorMap tmA, tmB;
-    int rc = make_tmap_2d(&tmA, a.rows, a.dtype, (uint64_t)a.n, (uint64_t)a.ld, (uint64_t)a.ld, TC_BLOCK_M);
+    int rc = make_tmap_2d_cached(&tmA, a.rows, a.dtype, (uint64_t)a.n, (uint64_t)a.ld, (uint64_t)a.ld, TC_BLOCK_M);
     if (rc != VM_OK) return rc;
-    rc = make_tmap_2d(&tmB, queries_store_dtype, a.dtype, (uint64_t)L.nq_pad, (uint64_t)a.ld, (uint64_t)a.ld, (uint32_t)L.nq_pad);
+    rc = make_tmap_2d_cached(&tmB, queries_store_dtype, a.dtype, (uint64_t)L.nq_pad, (uint64_t)a.ld, (uint64_t)a.ld, (uint32_t)L.nq_pad);
     if (rc != VM_OK) return rc;
     const int num_tiles = (int)((a.n + TC_BLOCK_M - 1) / TC_BLOCK_M);
     int dev_idx = 0;

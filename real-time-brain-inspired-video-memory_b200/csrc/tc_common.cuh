@@ -285,5 +285,28 @@ static inline int make_tmap_2d(CUtensorMap *out, const void *base, int dtype, ui
     return VM_OK;
 }
 
+// Small per-thread cache in front of make_tmap_2d: a store's descriptors only change when it grows,
+// and the driver call costs a few microseconds -- visible on small, launch-bound stores.
+static inline int make_tmap_2d_cached(CUtensorMap *out, const void *base, int dtype, uint64_t rows, uint64_t cols, uint64_t ld,
+                                      uint32_t box_rows)
+{
+    struct Entry { const void *base; int dtype; uint64_t rows, cols, ld; uint32_t box_rows; CUtensorMap map; bool valid; };
+    static thread_local Entry cache[8] = {};
+    static thread_local int next = 0;
+    for (int i = 0; i < 8; ++i) {
+        const Entry &e = cache[i];
+        if (e.valid && e.base == base && e.dtype == dtype && e.rows == rows && e.cols == cols && e.ld == ld && e.box_rows == box_rows) {
+            *out = e.map;
+            return VM_OK;
+        }
+    }
+    int rc = make_tmap_2d(out, base, dtype, rows, cols, ld, box_rows);
+    if (rc != VM_OK) return rc;
+    Entry &e = cache[next];
+    next = (next + 1) & 7;
+    e.base = base; e.dtype = dtype; e.rows = rows; e.cols = cols; e.ld = ld; e.box_rows = box_rows; e.map = *out; e.valid = true;
+    return VM_OK;
+}
+
 }  // namespace tc
 }  // namespace vm
