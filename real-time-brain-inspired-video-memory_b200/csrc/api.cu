@@ -21,7 +21,7 @@ void set_error(const char *fmt, ...)
 
 // ---- kernels implemented in the other translation units -----------------------------------
 int k_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype, int64_t n, int dim, int ld, cudaStream_t st);
-int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, cudaStream_t st);
+int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, int *extreme, cudaStream_t st);
 int k_invalidate_rows(float *inv_norms, const int64_t *rows_dev, int64_t n, int64_t size, cudaStream_t st);
 int k_normalize_queries(const void *q, int q_dtype, int nq, int nq_pad, int dim, int ld, float *out_f32, void *out_bf16,
                         int32_t *zero_me, uint32_t *zero_tab, int zero_tab_n, cudaStream_t st);
@@ -104,6 +104,7 @@ struct vm_store {
     void *rows = nullptr;
     float *inv_norms = nullptr;
     bool owns = false;
+    int *extreme = nullptr;  // device counter: rows outside the fast scans' numeric range
     Buf stage, stage_idx;
     Workspace ws;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // VM_FLAG_TIMING
@@ -233,6 +234,14 @@ static int store_new(vm_store **out, int device, int dim, int dtype, int64_t cap
     vm_store *s = new (std::nothrow) vm_store();
     VM_REQUIRE(s, VM_ERR_OOM, "host allocation failed");
     s->device = device; s->dim = dim; s->ld = ld_for_dim(dim); s->dtype = dtype; s->capacity = capacity; s->sm_count = sms;
+    {
+        DeviceGuard g(device);
+        if (cudaMalloc((void **)&s->extreme, 4) != cudaSuccess || cudaMemset(s->extreme, 0, 4) != cudaSuccess) {
+            set_error("store allocation failed");
+            delete s;
+            return VM_ERR_OOM;
+        }
+    }
     *out = s;
     return VM_OK;
 }
@@ -249,6 +258,7 @@ extern "C" int vm_store_create(vm_store **out, int device, int dim, int dtype, i
     if (e != cudaSuccess) {
         set_error("store allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
         if (s->rows) cudaFree(s->rows);
+        if (s->extreme) cudaFree(s->extreme);
         delete s;
         *out = nullptr;
         return VM_ERR_OOM;
@@ -276,6 +286,7 @@ extern "C" int vm_store_destroy(vm_store *s)
     DeviceGuard g(s->device);
     cudaDeviceSynchronize();
     if (s->owns) { cudaFree(s->rows); cudaFree(s->inv_norms); }
+    if (s->extreme) cudaFree(s->extreme);
     s->stage.release(); s->stage_idx.release();
     s->ws.release();
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -306,7 +317,7 @@ static int store_write(vm_store *s, int64_t row0, const void *rows, int src_dtyp
     char *dst = (char *)s->rows + (size_t)row0 * s->ld * dtype_size(s->dtype);
     int rc = k_convert_rows(src, src_dtype, dst, s->dtype, n, s->dim, s->ld, st);
     if (rc != VM_OK) return rc;
-    return k_row_inv_norms(s->rows, s->dtype, s->inv_norms, row0, row0 + n, s->ld, st);
+    return k_row_inv_norms(s->rows, s->dtype, s->inv_norms, row0, row0 + n, s->ld, s->extreme, st);
 }
 
 extern "C" int vm_store_append(vm_store *s, const void *rows, int src_dtype, int src_mem, int64_t n, int64_t *first_row,
@@ -350,7 +361,7 @@ extern "C" int vm_store_set_size(vm_store *s, int64_t n, int64_t recompute_from_
     DeviceGuard g(s->device);
     s->size = n;
     if (recompute_from_row >= 0 && recompute_from_row < n)
-        return k_row_inv_norms(s->rows, s->dtype, s->inv_norms, recompute_from_row, n, s->ld, (cudaStream_t)stream);
+        return k_row_inv_norms(s->rows, s->dtype, s->inv_norms, recompute_from_row, n, s->ld, s->extreme, (cudaStream_t)stream);
     return VM_OK;
 }
 
@@ -367,6 +378,8 @@ extern "C" int vm_store_last_scan_ms(vm_store *s, float *ms)
 extern "C" int vm_store_clear(vm_store *s)
 {
     VM_REQUIRE(s, VM_ERR_BADARG, "store is NULL");
+    DeviceGuard g(s->device);
+    VM_CUDA_CHECK(cudaMemset(s->extreme, 0, 4));
     s->size = 0;
     return VM_OK;
 }
@@ -492,7 +505,7 @@ static int topk_batch(const TopkCall &c)
     int32_t *flags = (int32_t *)w.flags.p;
     int32_t *uncert = flags + c.nq;  // counter sits right after the nq flags (zeroed by the normalise kernel)
     RescoreArgs rs{(const uint64_t *)w.merged.p, kp, s->rows, s->inv_norms, s->dtype, s->ld, s->dim, s->size, q_dev,
-                   c.q_dtype, c.nq, scan_eps(kernel, s->dtype, s->dim), c.sum_mode, fin, flags, uncert};
+                   c.q_dtype, c.nq, scan_eps(kernel, s->dtype, s->dim), c.sum_mode, fin, flags, uncert, s->extreme};
     rc = k_select_rescore(a.cand, a.ctas, rs, st);  // fused merge + exact rescoring
     if (rc == VM_ERR_UNSUPPORTED) {                 // rows too large for shared memory: two kernels
         rc = k_merge_candidates(a.cand, a.ctas, c.nq, kp, (uint64_t *)w.merged.p, st);

@@ -183,6 +183,7 @@ struct RescoreArgs {
     int sum_mode;
     FinalizeArgs fin;
     int32_t *flags, *uncertified_count;
+    const int *extreme;  // store-level count of rows outside the scans' numeric range (forces the exact pass)
 };
 struct ExactArgs {
     const void *rows;

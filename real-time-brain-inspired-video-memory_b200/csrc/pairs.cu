@@ -412,7 +412,7 @@ __global__ void pairs_finalize_kernel(const T *__restrict__ x, int ld, int dim, 
     if (blockIdx.x == 0 && threadIdx.x == 0 && staged > (unsigned long long)st_cap) atomicMax(out_cnt, staged);
 }
 
-int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, cudaStream_t st);
+int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, int *extreme, cudaStream_t st);
 
 namespace {
 struct PairsWs {
@@ -454,7 +454,7 @@ int k_pairs_above(int device, const void *x, int dtype, int64_t n, int dim, int 
     }
     if (!w.cnt) VM_CUDA_CHECK(cudaMalloc(&w.cnt, 16));
     VM_CUDA_CHECK(cudaMemsetAsync(w.cnt, 0, 16, st));
-    rc = k_row_inv_norms(x, dtype, (float *)w.inv, 0, n, ld, st);
+    rc = k_row_inv_norms(x, dtype, (float *)w.inv, 0, n, ld, nullptr, st);
     if (rc != VM_OK) return rc;
 
     const int es = dtype == VM_F32 ? 4 : 2;

@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rescore_kernel(const uint64_t *
                                                             const float *__restrict__ inv_norms, int ld, int dim, int64_t n_rows,
                                                             const void *__restrict__ queries, int q_dtype, double eps,
                                                             FinalizeArgs f, int32_t *__restrict__ flags,
-                                                            int32_t *__restrict__ uncertified_count, int chunk)
+                                                            int32_t *__restrict__ uncertified_count, int chunk,
+                                                            const int *__restrict__ extreme)
 {
     constexpr int VEC = 16 / (int)sizeof(T);      // elements per 16-byte load
     extern __shared__ double rs_smem[];
@@ -353,6 +354,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rescore_kernel(const uint64_t *
             float worst = key_score(merged[(int64_t)q * kp + kp - 1]);
             cert = ((double)worst + eps) < sc;
         }
+        if (extreme && *extreme != 0 && (int64_t)ncand < n_rows) cert = false;  // error bound not valid for this store
         flags[q] = cert ? 0 : 1;
         if (!cert) atomicAdd(uncertified_count, 1);
     }
@@ -389,7 +391,8 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uin
                                                                    const T *__restrict__ rows, int ld, int dim, int64_t n_rows,
                                                                    const void *__restrict__ queries, int q_dtype, double eps,
                                                                    FinalizeArgs f, int32_t *__restrict__ flags,
-                                                                   int32_t *__restrict__ uncertified_count)
+                                                                   int32_t *__restrict__ uncertified_count,
+                                                                   const int *__restrict__ extreme)
 {
     extern __shared__ __align__(16) unsigned char sr_smem[];
     const int total = lists * kp;
@@ -571,6 +574,7 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uin
             const float worst = key_score(s_top[kp - 1]);  // smallest approximate score among the candidates
             cert = ((double)worst + eps) < sc;
         }
+        if (extreme && *extreme != 0 && (int64_t)ncand < n_rows) cert = false;  // error bound not valid for this store
         flags[q] = cert ? 0 : 1;
         if (!cert) atomicAdd(uncertified_count, 1);
     }
@@ -872,7 +876,7 @@ int k_rescore(const RescoreArgs &a, cudaStream_t st)
         }                                                                                                              \
         rescore_kernel<NEU, T><<<a.nq, RS_THREADS, smem, st>>>(a.merged, a.kp, (const T *)a.rows, a.inv_norms, a.ld, a.dim, \
                                                                a.n_rows, a.queries, a.q_dtype, a.eps, a.fin, a.flags,    \
-                                                               a.uncertified_count, chunk);                             \
+                                                               a.uncertified_count, chunk, a.extreme);                             \
     } while (0)
     // column chunk: whole rows when kp rows fit in RS_SMEM_ROW_BYTES, else a multiple of 8 columns
     int chunk = RS_SMEM_ROW_BYTES / (4 * a.kp) - 1;
@@ -908,7 +912,7 @@ int k_select_rescore(const uint64_t *cand, int lists, const RescoreArgs &a, cuda
         }                                                                                                              \
         select_rescore_kernel<NEU, T><<<a.nq, SR_THREADS, smem, st>>>(cand, lists, a.nq, a.kp, (const T *)a.rows, a.ld, a.dim, \
                                                                       a.n_rows, a.queries, a.q_dtype, a.eps, a.fin, a.flags,  \
-                                                                      a.uncertified_count);                            \
+                                                                      a.uncertified_count, a.extreme);                            \
     } while (0)
     const bool neu = a.sum_mode == VM_SUM_NEUMAIER;
     if (a.dtype == VM_F32) { if (neu) LAUNCH_SR(true, float); else LAUNCH_SR(false, float); }

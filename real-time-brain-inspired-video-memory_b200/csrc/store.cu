@@ -28,9 +28,13 @@ __global__ void convert_rows_kernel(const void *__restrict__ src, int src_dtype,
 
 // One warp per row: 1/||row|| of the STORED values, accumulated in binary64.
 // 0 for a zero-norm row (its score is 0.0: pre_llm_injector.py:385-386).
+// `extreme` (may be NULL) counts rows whose squared norm lies outside [2^-120, 2^120]: the fast scans'
+// error bound assumes normal-range arithmetic (tensor cores flush fp32 denormals, huge rows overflow the
+// fp32 accumulator), so any such row makes the exact pass re-do every query of this store.
+// Rows with a non-finite norm (NaN / Inf elements) are marked skipped.
 template <typename T>
 __global__ void row_inv_norms_kernel(const T *__restrict__ rows, float *__restrict__ inv_norms, int64_t row0,
-                                     int64_t n, int ld)
+                                     int64_t n, int ld, int *__restrict__ extreme)
 {
     int lane = threadIdx.x & 31;
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -44,8 +48,13 @@ __global__ void row_inv_norms_kernel(const T *__restrict__ rows, float *__restri
         }
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         if (lane == 0) {
-            // keep an earlier "skipped" mark (negative) only when the caller re-marks it; fresh rows get the norm
-            inv_norms[r] = ss > 0.0 ? (float)(1.0 / sqrt(ss)) : 0.0f;
+            float inv = 0.0f;
+            if (!isfinite(ss)) inv = -1.0f;
+            else if (ss > 0.0) {
+                inv = (float)(1.0 / sqrt(ss));
+                if (extreme && (ss < 7.52316384526264e-37 || ss > 1.329227995784916e+36)) atomicAdd(extreme, 1);
+            }
+            inv_norms[r] = inv;
         }
     }
 }
@@ -134,13 +143,13 @@ int k_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype, int
     return VM_OK;
 }
 
-int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, cudaStream_t st)
+int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, int *extreme, cudaStream_t st)
 {
     if (n <= row0) return VM_OK;
     int64_t warps = n - row0;
     int grid = (int)vm::imin64((warps * 32 + 255) / 256, 148 * 16);
-    if (dtype == VM_F32) row_inv_norms_kernel<float><<<grid, 256, 0, st>>>((const float *)rows, inv_norms, row0, n, ld);
-    else row_inv_norms_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)rows, inv_norms, row0, n, ld);
+    if (dtype == VM_F32) row_inv_norms_kernel<float><<<grid, 256, 0, st>>>((const float *)rows, inv_norms, row0, n, ld, extreme);
+    else row_inv_norms_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)rows, inv_norms, row0, n, ld, extreme);
     VM_CUDA_CHECK(cudaGetLastError());
     return VM_OK;
 }

@@ -321,3 +321,37 @@ def test_integration_md_ctypes_example(vm):
     assert b"capacity" in lib.vm_last_error()
     assert lib.vm_topk(store, q.ctypes.data_as(C.c_void_p), 2, 0, len(q), 1000, C.c_double(0), 0, 1, 0, None, None, None, 0, None, None) == vm._lib.VM_ERR_BADARG
     assert lib.vm_store_destroy(store) == 0
+
+
+@pytest.mark.parametrize("scale", [1e-30, 1e-42, 1e25])
+def test_extreme_magnitudes_stay_exact(vm, scale):
+    """Rows far outside the fast scans' numeric range (fp32 denormals are flushed by the tensor cores,
+    huge rows overflow fp32 accumulation) must not break exactness: the store flags them and the
+    binary64 pass re-does the queries."""
+    d, n, k = 128, 20000, 10
+    rng = np.random.default_rng(7)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    X[100:140] = (X[100:140].astype(np.float64) * scale).astype(np.float32)   # 40 rows at an extreme scale
+    Q = rng.standard_normal((6, d)).astype(np.float32)
+    Q[0] = (X[120].astype(np.float64) / scale).astype(np.float32)             # points at one of them
+    st = vm.EmbeddingStore(d, n, "f32")
+    st.append(X)
+    ref = oracle.batch_similarities(Q, X, k)
+    for flags in (0, vm.VM_FLAG_FORCE_TC, vm.VM_FLAG_FORCE_SIMT):
+        idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER, flags=flags)
+        _check(idx, score, count, ref, k)
+    assert st.last_stats.uncertified == len(Q)          # every query went through the exact pass
+    assert ref[0][0][0] == 120
+    st.close()
+
+
+def test_non_finite_rows_are_skipped(vm):
+    d, n = 32, 500
+    X = synth.synth_rows(5, 0, n, d)
+    Xbad = X.copy(); Xbad[10, 3] = np.nan; Xbad[20, 0] = np.inf
+    st = vm.EmbeddingStore(d, n, "f32")
+    st.append(Xbad)
+    ok = np.ones(n, np.uint8); ok[[10, 20]] = 0
+    Q = X[[10, 20, 30]]
+    _check(*st.topk(Q, 5, sum_mode=vm.VM_SUM_NEUMAIER), oracle.batch_similarities(Q, X, 5, row_ok=ok), 5)
+    st.close()
