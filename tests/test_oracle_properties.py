@@ -1,0 +1,66 @@
+"""Property tests (hypothesis) of the C oracle against an inline restatement of the reference's three
+scalar formulas in plain Python floats -- the same expressions as src/components/pre_llm_injector.py:374-388,
+src/pipeline/retriever_hybrid.py:655-664 and src/utils/embedding_utils.py:29-39, evaluated by THIS
+interpreter's builtin sum() (Neumaier on CPython >= 3.12)."""
+import math
+import sys
+
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from oracle import oracle
+
+MODE = oracle.SUM_NEUMAIER if sys.version_info >= (3, 12) else oracle.SUM_NAIVE
+finite = st.floats(min_value=-1e6, max_value=1e6, allow_nan=False, allow_infinity=False, width=64)
+vec = st.lists(finite, min_size=0, max_size=40)
+
+
+def py_injector(vec1, vec2):
+    if len(vec1) != len(vec2):
+        return 0.0
+    dot_product = sum(a * b for a, b in zip(vec1, vec2))
+    norm1 = math.sqrt(sum(a * a for a in vec1))
+    norm2 = math.sqrt(sum(b * b for b in vec2))
+    if norm1 == 0 or norm2 == 0:
+        return 0.0
+    return dot_product / (norm1 * norm2)
+
+
+def py_retriever(vec1, vec2):
+    dot_product = sum(a * b for a, b in zip(vec1, vec2))
+    mag1 = math.sqrt(sum(a * a for a in vec1))
+    mag2 = math.sqrt(sum(b * b for b in vec2))
+    if mag1 * mag2 == 0:
+        return 0.0
+    return dot_product / (mag1 * mag2)
+
+
+def py_utils(vec1, vec2):
+    dot_product = sum(a * b for a, b in zip(vec1, vec2))
+    magnitude1 = sum(a * a for a in vec1) ** 0.5
+    magnitude2 = sum(b * b for b in vec2) ** 0.5
+    if magnitude1 == 0 or magnitude2 == 0:
+        return 0.0
+    return dot_product / (magnitude1 * magnitude2)
+
+
+@settings(max_examples=300, deadline=None)
+@given(vec, vec)
+def test_scalar_variants_bit_exact(v1, v2):
+    for name, fn in (("injector", py_injector), ("retriever", py_retriever), ("utils", py_utils)):
+        got = oracle.cosine(v1, v2, name, MODE)
+        want = fn(v1, v2)
+        assert got == want or (math.isnan(got) and math.isnan(want)), (name, v1, v2, got, want)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 40), st.integers(1, 12), st.integers(1, 5), st.integers(1, 12), st.integers(0, 2 ** 31 - 1))
+def test_topk_matches_python_sort(n, d, q, k, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.integers(-3, 4, size=(n, d)).astype(np.float64) / 4.0     # few distinct values -> many exact ties
+    Q = rng.integers(-3, 4, size=(q, d)).astype(np.float64) / 4.0
+    got = oracle.batch_similarities(Q, X, k, sum_mode=MODE)
+    for qi in range(q):
+        sims = [(i, float(py_injector(list(Q[qi]), list(X[i])))) for i in range(n)]
+        sims.sort(key=lambda x: x[1], reverse=True)                    # stable, like the reference (:369)
+        assert got[qi] == sims[:k]

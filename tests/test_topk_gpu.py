@@ -355,3 +355,32 @@ def test_non_finite_rows_are_skipped(vm):
     Q = X[[10, 20, 30]]
     _check(*st.topk(Q, 5, sum_mode=vm.VM_SUM_NEUMAIER), oracle.batch_similarities(Q, X, 5, row_ok=ok), 5)
     st.close()
+
+
+def test_randomised_differential(vm):
+    """Fuzz: random shapes / dtypes / k / duplicate structure, every scan path against the oracle."""
+    rng = np.random.default_rng(20261018)
+    for case in range(36):
+        n = int(rng.choice([1, 2, 31, 128, 129, 700, 3001, 9000]))
+        d = int(rng.choice([8, 24, 100, 384, 520]))
+        nq = int(rng.choice([1, 3, 8, 9, 40, 64, 70]))
+        k = int(rng.choice([1, 3, 10, 16, 24, 33]))
+        dtype = "bf16" if case % 3 == 0 else "f32"
+        vals = rng.integers(-2, 3, size=(n, d)).astype(np.float32) if case % 4 == 0 else rng.standard_normal((n, d)).astype(np.float32)
+        X = _quantise(vals, dtype)
+        if n > 40:
+            X[rng.integers(0, n, 6)] = X[7]                # duplicates -> exact ties
+            X[rng.integers(0, n, 2)] = 0.0
+        Q = rng.standard_normal((nq, d)).astype(np.float32)
+        if n > 8:
+            Q[0] = X[7]
+        st = vm.EmbeddingStore(d, n, dtype)
+        st.append(X)
+        ref = oracle.batch_similarities(Q, X, k)
+        for flags in (0, vm.VM_FLAG_FORCE_TC, vm.VM_FLAG_FORCE_SIMT, vm.VM_FLAG_FORCE_EXACT):
+            idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER, flags=flags)
+            try:
+                _check(idx, score, count, ref, k)
+            except AssertionError as e:
+                raise AssertionError(f"case {case}: n={n} d={d} nq={nq} k={k} {dtype} flags={flags}: {e}")
+        st.close()
