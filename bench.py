@@ -149,6 +149,25 @@ def cpu_reference_leg(cfg_name: str, steps: int, warmup: int, sample_rows: int):
                                        f"time scaled linearly in rows to the full store")
 
 
+def cpu_blas_leg(cfg_name: str, sample_rows: int):
+    """The reference's own vectorised idiom (src/pipeline/prune.py:62,76): sklearn cosine_similarity (BLAS
+    sgemm over every host core, store re-normalised on every call) + argpartition/sort for the top-k, on the
+    same bounded sample.  Context only: float32, not the bit-exact reference order."""
+    import numpy as np
+    from sklearn.metrics.pairwise import cosine_similarity
+    from oracle import synth
+    rows_total, dim, _dt, nq, k, sseed, qseed = CONFIGS[cfg_name]
+    X = synth.synth_rows(sseed, 0, sample_rows, dim)
+    Q = synth.synth_queries(qseed, nq, dim, sseed, rows_total)
+    cosine_similarity(Q[:2], X[:1000])
+    t0 = time.perf_counter()
+    S = cosine_similarity(Q, X)
+    part = np.argpartition(-S, k - 1, axis=1)[:, :k]
+    np.take_along_axis(S, part, 1).sort(axis=1)
+    dt = time.perf_counter() - t0
+    return nq / (dt * rows_total / sample_rows)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -190,11 +209,13 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     comm = None
+    peer_exchange = False
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
         from vidmem_b200.sharded import Communicator
         comm = Communicator.from_torch_distributed(local_rank)
+        peer_exchange = args.peer_exchange and comm.enable_peer_exchange()
 
     cfg = args.config or ("c2" if world == 1 else "c3")
     rows_total, dim, dt, nq, k, sseed, qseed = CONFIGS[cfg]
@@ -294,7 +315,9 @@ def run_ours(args):
                        "rows_per_gpu": n_local, "l2_policy": "inputs larger than L2 (%.0f MB store per GPU vs 126 MB L2)" % (n_local * dim * es / 1e6),
                        "scan_kernel": {0: "exact_fp64", 1: "simt", 2: "tcgen05"}[int(stats.scan_kernel)],
                        "scan_ctas": int(stats.scan_ctas), "candidates_per_query": int(stats.candidates),
-                       "exact_rescoring": "binary64, reference summation order (Neumaier)", "timing": "cuda events, max over ranks"},
+                       "exact_rescoring": "binary64, reference summation order (Neumaier)", "timing": "cuda events, max over ranks",
+                       "exchange": ("peer memory (symmetric buffers, NVLink pull-merge kernel)" if peer_exchange else
+                                    "ncclAllGather + merge kernel") if world > 1 else "none"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(Q.nbytes),
                     "d2h_bytes_per_step": int(nq * k * 16 + nq * 4 + 4), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
@@ -307,6 +330,10 @@ def run_ours(args):
             cores = os.cpu_count() or 1
             qps, ms, desc = cpu_reference_leg(cfg, 1, 1, args.cpu_sample_rows or 100000)
             line["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+            try:
+                line["cpu_baseline"]["sklearn_blas_value"] = cpu_blas_leg(cfg, args.cpu_sample_rows or 100000)
+            except Exception as e:  # pragma: no cover
+                line["cpu_baseline"]["sklearn_blas_value"] = None
     store.close()
     if rank == 0:
         if world == 1 and cfg == "c2" and not args.rows and not args.no_scaling_baseline:
@@ -543,6 +570,8 @@ def main():
     ap.add_argument("--flags", type=int, default=0, help="extra VM_FLAG_* bits (debug: 4 = force SIMT, 8 = force tcgen05)")
     ap.add_argument("--cpu-sample-rows", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--peer-exchange", action="store_true",
+                    help="multi-GPU: replace ncclAllGather + merge by the peer-memory pull-merge kernel (symmetric memory)")
     ap.add_argument("--no-scaling-baseline", action="store_true", help="skip the extra C3-on-one-GPU measurement of the N=1 run")
     ap.add_argument("--c5-dtype", default=None, choices=["f32", "bf16"])
     args = ap.parse_args()

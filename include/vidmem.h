@@ -212,6 +212,15 @@ int vm_pairs_above(int device, const void *x_dev, int dtype, int64_t n, int dim,
 int vm_comm_unique_id(void *out128);
 int vm_comm_init_rank(vm_comm **out, int device, int nranks, int rank, const void *id128);
 int vm_comm_destroy(vm_comm *c);
+/* Optional peer-memory exchange (NVLink loads instead of the NCCL all-gather): bufs[r] is rank r's
+ * exchange buffer as mapped into THIS process (e.g. torch symmetric memory `buffer_ptrs`), each
+ * vm_comm_exchange_bytes() long and zero-filled before first use on every rank.  Once attached,
+ * vm_topk_sharded writes each batch's exact local lists into its own buffer, publishes a generation
+ * flag with system scope, and ONE kernel per batch waits for every peer's flag, pulls the peers' lists
+ * over NVLink and merges them (ties -> lowest global row).  Every rank must make the same sequence of
+ * vm_topk_sharded calls. */
+size_t vm_comm_exchange_bytes(void);
+int vm_comm_attach_peer_buffers(vm_comm *c, void *const *bufs, int nranks);
 int vm_comm_nranks(const vm_comm *c);
 int vm_comm_rank(const vm_comm *c);
 

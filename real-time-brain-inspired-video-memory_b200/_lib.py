@@ -31,7 +31,7 @@ EXPORTS = [
     "vm_store_ld", "vm_store_append", "vm_store_update", "vm_store_invalidate", "vm_store_set_size", "vm_store_clear",
     "vm_store_last_scan_ms",
     "vm_topk", "vm_topk_sharded", "vm_merge_topk_lists", "vm_merge_max_by_id", "vm_cosine_pairs", "vm_pairs_above",
-    "vm_comm_unique_id", "vm_comm_init_rank", "vm_comm_destroy", "vm_comm_nranks", "vm_comm_rank", "vm_synth_fill",
+    "vm_comm_unique_id", "vm_comm_init_rank", "vm_comm_destroy", "vm_comm_exchange_bytes", "vm_comm_attach_peer_buffers", "vm_comm_nranks", "vm_comm_rank", "vm_synth_fill",
 ]
 
 
@@ -91,6 +91,8 @@ def load() -> C.CDLL:
         "vm_comm_unique_id": (ci, [vp]),
         "vm_comm_init_rank": (ci, [P(vp), ci, ci, ci, vp]),
         "vm_comm_destroy": (ci, [vp]),
+        "vm_comm_exchange_bytes": (sz, []),
+        "vm_comm_attach_peer_buffers": (ci, [vp, P(vp), ci]),
         "vm_comm_nranks": (ci, [vp]),
         "vm_comm_rank": (ci, [vp]),
         "vm_synth_fill": (ci, [ci, vp, ci, u64, i64, i64, ci, u64, vp]),

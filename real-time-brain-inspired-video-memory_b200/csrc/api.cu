@@ -34,6 +34,9 @@ int k_select_rescore(const uint64_t *cand, int lists, const RescoreArgs &a, cuda
 int k_exact(const ExactArgs &a, cudaStream_t st);
 int k_merge_topk_lists(const void *idx, const void *score, const void *count, size_t stride_bytes, int lists, int nq, int k,
                        int64_t *out_idx, double *out_score, int32_t *out_count, cudaStream_t st);
+int k_p2p_publish(void *flag, unsigned long long gen, cudaStream_t st);
+int k_merge_topk_p2p(void *const *peers, int nranks, size_t slot_off, size_t flag_off, unsigned long long gen, int nq, int k,
+                     int64_t *out_idx, double *out_score, int32_t *out_count, cudaStream_t st);
 int k_merge_max_by_id(const int64_t *idx, const double *score, const int32_t *count, int nq, int k, int k2,
                       int64_t *out_idx, double *out_score, int32_t *out_count, cudaStream_t st);
 int k_cosine_pairs(const void *a, const void *b, int dtype, int64_t n, int dim, int zero_rule, int sum_mode, double *out,
@@ -111,9 +114,17 @@ struct vm_store {
     bool timed = false;
 };
 
+// exchange buffer of one rank: two result slots + a generation flag
+static constexpr size_t XCHG_SLOT_BYTES = ((size_t)MAXQ * MAXK * 16 + (size_t)MAXQ * 4 + 255) & ~(size_t)255;
+static constexpr size_t XCHG_FLAG_OFF = 2 * XCHG_SLOT_BYTES;
+static constexpr size_t XCHG_BYTES = XCHG_FLAG_OFF + 256;
+
 struct vm_comm {
     void *nccl = nullptr;  // ncclComm_t
     int nranks = 1, rank = 0, device = 0;
+    void *peer[16] = {};   // peer-mapped exchange buffers (optional, see vm_comm_attach_peer_buffers)
+    bool p2p = false;
+    unsigned long long gen = 0;
 };
 
 // ---- NCCL, resolved at run time so the library loads on hosts without it --------------------
@@ -594,7 +605,18 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
         int64_t *d_idx = direct ? out_idx + (size_t)q0 * k : ws_idx;
         double *d_score = direct ? out_score + (size_t)q0 * k : ws_score;
         int32_t *d_count = direct ? out_count + q0 : ws_count;
-        if (sharded) {
+        const bool p2p = sharded && comm->p2p;
+        unsigned long long gen = 0;
+        size_t slot_off = 0;
+        if (p2p) {
+            // peer-memory exchange: results go straight into this rank's slot of the symmetric buffer
+            gen = ++comm->gen;
+            slot_off = (size_t)(gen & 1) * XCHG_SLOT_BYTES;
+            char *slot = (char *)comm->peer[comm->rank] + slot_off;
+            d_idx = (int64_t *)slot;
+            d_score = (double *)(slot + (size_t)nb * k * 8);
+            d_count = (int32_t *)(slot + (size_t)nb * k * 16);
+        } else if (sharded) {
             // pack [idx | score | count] contiguously so ONE all-gather moves the batch
             size_t seg = (size_t)nb * k * 8;
             size_t per_rank = 2 * seg + (((size_t)nb * 4 + 7) & ~(size_t)7);
@@ -613,15 +635,21 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
         rc = topk_batch(c);
         if (rc != VM_OK) return rc;
         if (sharded) {
-            size_t seg = (size_t)nb * k * 8;
-            size_t per_rank = 2 * seg + (((size_t)nb * 4 + 7) & ~(size_t)7);
-            VM_NCCL_CHECK(g_nccl.AllGather(w.gather_send.p, w.gather_recv.p, per_rank, /*ncclInt8*/ 0, comm->nccl, st));
             bool dd = out_mem == VM_MEM_DEVICE;
             int64_t *m_idx = dd ? out_idx + (size_t)q0 * k : ws_idx;
             double *m_score = dd ? out_score + (size_t)q0 * k : ws_score;
             int32_t *m_count = dd ? out_count + q0 : ws_count;
-            const char *rb = (const char *)w.gather_recv.p;
-            rc = k_merge_topk_lists(rb, rb + seg, rb + 2 * seg, per_rank, comm->nranks, nb, k, m_idx, m_score, m_count, st);
+            if (p2p) {
+                rc = k_p2p_publish((char *)comm->peer[comm->rank] + XCHG_FLAG_OFF, gen, st);
+                if (rc == VM_OK)
+                    rc = k_merge_topk_p2p(comm->peer, comm->nranks, slot_off, XCHG_FLAG_OFF, gen, nb, k, m_idx, m_score, m_count, st);
+            } else {
+                size_t seg = (size_t)nb * k * 8;
+                size_t per_rank = 2 * seg + (((size_t)nb * 4 + 7) & ~(size_t)7);
+                VM_NCCL_CHECK(g_nccl.AllGather(w.gather_send.p, w.gather_recv.p, per_rank, /*ncclInt8*/ 0, comm->nccl, st));
+                const char *rb = (const char *)w.gather_recv.p;
+                rc = k_merge_topk_lists(rb, rb + seg, rb + 2 * seg, per_rank, comm->nranks, nb, k, m_idx, m_score, m_count, st);
+            }
             if (rc != VM_OK) return rc;
             if (stats) stats->scan_launches += 2;
             d_idx = m_idx; d_score = m_score; d_count = m_count;
@@ -768,6 +796,21 @@ extern "C" int vm_comm_init_rank(vm_comm **out, int device, int nranks, int rank
     }
     c->nranks = nranks; c->rank = rank; c->device = device;
     *out = c;
+    return VM_OK;
+}
+
+extern "C" size_t vm_comm_exchange_bytes(void) { return XCHG_BYTES; }
+
+extern "C" int vm_comm_attach_peer_buffers(vm_comm *c, void *const *bufs, int nranks)
+{
+    VM_REQUIRE(c && bufs, VM_ERR_BADARG, "NULL argument");
+    VM_REQUIRE(nranks == c->nranks && nranks <= 16, VM_ERR_BADARG, "peer buffers for %d ranks, communicator has %d (max 16)", nranks, c->nranks);
+    for (int r = 0; r < nranks; ++r) {
+        VM_REQUIRE(bufs[r] && ((uintptr_t)bufs[r] & 255) == 0, VM_ERR_BADARG, "peer buffer %d is NULL or not 256-byte aligned", r);
+        c->peer[r] = bufs[r];
+    }
+    c->p2p = true;
+    c->gen = 0;
     return VM_OK;
 }
 

@@ -779,6 +779,72 @@ __global__ void __launch_bounds__(256) merge_topk_lists_kernel(const char *__res
 }
 
 // =========================================================================================
+// 4b. cross-shard merge over peer memory: the all-gather and the merge in ONE kernel
+// =========================================================================================
+// Every rank has written its exact local lists [idx nq*k | score nq*k | count nq] into slot
+// (gen & 1) of its own exchange buffer and then published `gen` in that buffer's flag word
+// (p2p_publish_kernel, system-scope release).  This kernel -- one CTA per query -- waits until every
+// peer's flag has reached `gen` (acquire loads over NVLink, bounded), pulls the peers' entries for its
+// query with plain peer loads and ranks them.  Slot reuse two batches later is safe: a rank only
+// reaches batch gen+2 after its merge of gen+1 saw every peer's flag gen+1, which each peer publishes
+// after finishing its own merge of gen (stream order).
+struct PeerPtrs { const unsigned char *p[16]; };
+
+__global__ void p2p_publish_kernel(unsigned long long *flag, unsigned long long gen)
+{
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(gen) : "memory");
+}
+
+__global__ void __launch_bounds__(256) merge_topk_p2p_kernel(PeerPtrs peers, int nranks, size_t slot_off, size_t flag_off,
+                                                            unsigned long long gen, int nq, int k,
+                                                            int64_t *__restrict__ out_idx, double *__restrict__ out_score,
+                                                            int32_t *__restrict__ out_count)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int total = nranks * k;
+    double *s_s = (double *)smem_raw;
+    int64_t *s_i = (int64_t *)(s_s + total);
+    int *s_v = (int *)(s_i + total);
+    if (tid < nranks) {
+        const unsigned long long *f = reinterpret_cast<const unsigned long long *>(peers.p[tid] + flag_off);
+        unsigned long long v;
+        const long long t0 = clock64();
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= gen) break;
+            if (clock64() - t0 > 4000000000LL) { printf("vidmem: peer %d never published batch %llu\n", tid, gen); __trap(); }
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < total; e += 256) {
+        const int l = e / k, j = e - l * k;
+        const unsigned char *b = peers.p[l] + slot_off;
+        const int64_t *idx = reinterpret_cast<const int64_t *>(b);
+        const double *score = reinterpret_cast<const double *>(b + (size_t)nq * k * 8);
+        const int32_t *count = reinterpret_cast<const int32_t *>(b + (size_t)nq * k * 16);
+        const bool v = j < __ldcv(count + q);
+        s_s[e] = v ? __ldcv(score + (size_t)q * k + j) : 0.0;
+        s_i[e] = v ? __ldcv(idx + (size_t)q * k + j) : -1;
+        s_v[e] = v ? 1 : 0;
+    }
+    __syncthreads();
+    int nvalid = 0;
+    for (int e = 0; e < total; ++e) nvalid += s_v[e];
+    for (int e = tid; e < total; e += 256) {
+        if (!s_v[e]) continue;
+        int rank = 0;
+        for (int i = 0; i < total; ++i)
+            if (s_v[i] && (s_s[i] > s_s[e] || (s_s[i] == s_s[e] && s_i[i] < s_i[e]))) ++rank;
+        if (rank < k) { out_idx[(int64_t)q * k + rank] = s_i[e]; out_score[(int64_t)q * k + rank] = s_s[e]; }
+    }
+    const int cnt = min(nvalid, k);
+    if (tid == 0) out_count[q] = cnt;
+    for (int t = cnt + tid; t < k; t += 256) { out_idx[(int64_t)q * k + t] = -1; out_score[(int64_t)q * k + t] = 0.0; }
+}
+
+// =========================================================================================
 // 5. cross-query merge (pre_llm_injector.py:235-249): max score per id, stable sort desc, [:k2]
 // =========================================================================================
 __global__ void __launch_bounds__(256) merge_max_by_id_kernel(const int64_t *__restrict__ idx, const double *__restrict__ score,
@@ -953,6 +1019,34 @@ int k_merge_topk_lists(const void *idx, const void *score, const void *count, si
     }
     merge_topk_lists_kernel<<<nq, 256, smem, st>>>((const char *)idx, (const char *)score, (const char *)count, stride_bytes, lists, nq, k,
                                                   out_idx, out_score, out_count);
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
+int k_p2p_publish(void *flag, unsigned long long gen, cudaStream_t st)
+{
+    p2p_publish_kernel<<<1, 1, 0, st>>>((unsigned long long *)flag, gen);
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
+int k_merge_topk_p2p(void *const *peers, int nranks, size_t slot_off, size_t flag_off, unsigned long long gen, int nq, int k,
+                     int64_t *out_idx, double *out_score, int32_t *out_count, cudaStream_t st)
+{
+    VM_REQUIRE(nranks >= 1 && nranks <= 16, VM_ERR_UNSUPPORTED, "peer exchange supports up to 16 ranks");
+    const int total = nranks * k;
+    VM_REQUIRE(total <= 4096, VM_ERR_UNSUPPORTED, "merge: nranks*k = %d > 4096", total);
+    PeerPtrs pp{};
+    for (int r = 0; r < nranks; ++r) pp.p[r] = (const unsigned char *)peers[r];
+    const size_t smem = (size_t)total * (8 + 8 + 4);
+    static bool attr_set_dev[64] = {};
+    int dev_idx_ = 0;
+    cudaGetDevice(&dev_idx_);
+    if (!attr_set_dev[dev_idx_ & 63]) {
+        VM_CUDA_CHECK(cudaFuncSetAttribute(merge_topk_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set_dev[dev_idx_ & 63] = true;
+    }
+    merge_topk_p2p_kernel<<<nq, 256, smem, st>>>(pp, nranks, slot_off, flag_off, gen, nq, k, out_idx, out_score, out_count);
     VM_CUDA_CHECK(cudaGetLastError());
     return VM_OK;
 }

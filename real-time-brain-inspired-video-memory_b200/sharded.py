@@ -77,6 +77,29 @@ class Communicator:
         torch.cuda.set_device(device)
         return cls(device, world, rank, uid[0])
 
+    def enable_peer_exchange(self) -> bool:
+        """Switches the cross-shard exchange from ncclAllGather to the peer-memory kernel: allocates this
+        rank's exchange buffer in torch symmetric memory (NVLink-mapped into every rank of the node),
+        zero-fills it and hands the peer pointers to the library.  Returns False (NCCL path stays) when
+        symmetric memory is unavailable."""
+        import torch
+        import torch.distributed as dist
+        try:
+            import torch.distributed._symmetric_memory as symm
+            nbytes = int(self.lib.vm_comm_exchange_bytes())
+            buf = symm.empty(nbytes, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+            hdl = symm.rendezvous(buf, dist.group.WORLD)
+            buf.zero_()
+            torch.cuda.synchronize()
+            dist.barrier()
+            ptrs = (C.c_void_p * self.nranks)(*[int(p) for p in hdl.buffer_ptrs])
+            L.check(self.lib.vm_comm_attach_peer_buffers(self.handle, ptrs, self.nranks))
+            self._xchg = (buf, hdl)   # keep the mapping alive
+            return True
+        except Exception as e:  # pragma: no cover - depends on the platform
+            self.peer_exchange_error = repr(e)
+            return False
+
     def close(self):
         if self.handle:
             self.lib.vm_comm_destroy(self.handle)

@@ -45,6 +45,30 @@ def _worker(rank, world, port, out_dir):
         torch.cuda.synchronize()
         ok = ok and np.array_equal(di.cpu().numpy(), idx) and np.array_equal(ds.cpu().numpy(), score)
         st.close()
+    # peer-memory exchange (symmetric memory + one pull-merge kernel) == NCCL all-gather path, across
+    # several consecutive batches so both slots are reused
+    n, d, nq, k = 30011, 256, 150, 10
+    lo, hi = shard_bounds(n, world)[rank]
+    Xf = synth.synth_rows(19, 0, n, d)
+    Q = synth.synth_queries(20, nq, d, 19, n)
+    st = vm.EmbeddingStore(d, hi - lo, "f32", device=rank)
+    st.append(Xf[lo:hi])
+    base = st.topk(Q, k, comm=comm, row_offset=lo, sum_mode=vm.VM_SUM_NEUMAIER)
+    ref = oracle.batch_similarities(Q, Xf, k)
+    ok = ok and all(list(base[0][qi]) == [r for r, _ in ref[qi]] for qi in range(nq))
+    enabled = comm.enable_peer_exchange()
+    peer_state = "p2p" if enabled else "nccl-only:" + getattr(comm, "peer_exchange_error", "?")
+    if enabled:
+        for rep in range(5):
+            got = st.topk(Q, k, comm=comm, row_offset=lo, sum_mode=vm.VM_SUM_NEUMAIER)
+            ok = ok and all(np.array_equal(a, b) for a, b in zip(base, got))
+        qd = torch.from_numpy(Q).cuda()
+        for rep in range(4):
+            di, ds, dc = st.topk_device(qd, k, comm=comm, row_offset=lo, sum_mode=vm.VM_SUM_NEUMAIER, flags=vm.VM_FLAG_ASYNC)
+        torch.cuda.synchronize()
+        ok = ok and np.array_equal(di.cpu().numpy(), base[0]) and np.array_equal(ds.cpu().numpy(), base[1])
+    open(os.path.join(out_dir, f"rank{rank}.{peer_state[:3]}"), "w").write(peer_state)
+    st.close()
     # all-pairs dedup split over the ranks == the single-GPU pair set
     from vidmem_b200 import dedup
     E = synth.synth_rows(44, 0, 5000, 256, dup_period=6)
@@ -64,4 +88,6 @@ def test_two_gpu_sharded_topk(tmp_path):
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
-    assert sorted(os.listdir(tmp_path)) == ["rank0.ok", "rank1.ok"]
+    files = sorted(os.listdir(tmp_path))
+    assert "rank0.ok" in files and "rank1.ok" in files, files
+    assert "rank0.p2p" in files and "rank1.p2p" in files, [open(os.path.join(tmp_path, f)).read() for f in files]
