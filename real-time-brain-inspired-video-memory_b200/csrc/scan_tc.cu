@@ -6,13 +6,14 @@
 //                           normalised queries once (evict-last) -- no thread ever touches a row
 //   warp 1   MMA issuer     one thread issues tcgen05.mma (kind::tf32 for an fp32 store, kind::f16
 //                           for bf16): D[128 rows x nq] += A[128 x 32B] * Q[nq x 32B]^T, accumulators
-//                           in TMEM (4 stages x nq columns), tcgen05.commit frees stages / publishes D
+//                           in TMEM (8 stages x nq columns), tcgen05.commit frees stages / publishes D
 //   warps 2-5 epilogue      tcgen05.ld their 32-lane TMEM quadrant (lane = store row, column = query),
 //                           multiply by the cached 1/||row|| (fused normalisation), compare with the
 //                           per-query running threshold, push the rare survivors into per-query
-//                           queues; thread q then inserts them into query q's sorted top-kp list
-//                           (shared memory).  While a tile overflows a queue its accumulator simply
-//                           stays in TMEM and is re-read after the drain.
+//                           queues; thread q then folds them into query q's unsorted top-kp set in
+//                           shared memory (replace the minimum, rescan with pipelined loads).  While a
+//                           tile overflows a queue its accumulator simply stays in TMEM and is re-read
+//                           after the drain.
 // Threshold seeding: each CTA starts without a threshold, so for its first tiles every score would
 // be a "survivor".  Instead every CTA first publishes, per query, the maximum score of its first
 // tile; the kp-th largest of those per-CTA maxima is a valid lower bound on the shard's kp-th best
