@@ -4,6 +4,7 @@
 
 #include <dlfcn.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 
@@ -112,6 +113,18 @@ struct vm_store {
     Workspace ws;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // VM_FLAG_TIMING
     bool timed = false;
+    // CUDA-graph cache of the host-buffer top-k pipeline (launch-bound small stores / small batches)
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;
+        uint64_t version = 0;
+        int nq = 0, k = 0, flags = 0, score_mode = 0, sum_mode = 0, q_dtype = 0;
+        double min_score = 0.0;
+        vm_topk_stats stats{};
+    };
+    GraphEntry graphs[4];
+    int graph_next = 0;
+    uint64_t version = 1;         // bumped by every mutation: cached graphs bake in row counts and TMA descriptors
+    cudaStream_t gstream = nullptr;  // blocking stream the graphs run on (ordered with the legacy default stream)
 };
 
 // exchange buffer of one rank: two result slots + a generation flag
@@ -302,6 +315,8 @@ extern "C" int vm_store_destroy(vm_store *s)
     s->ws.release();
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    for (auto &ge : s->graphs) if (ge.exec) cudaGraphExecDestroy(ge.exec);
+    if (s->gstream) cudaStreamDestroy(s->gstream);
     delete s;
     return VM_OK;
 }
@@ -342,6 +357,7 @@ extern "C" int vm_store_append(vm_store *s, const void *rows, int src_dtype, int
     if (rc != VM_OK) return rc;
     if (first_row) *first_row = s->size;
     s->size += n;
+    ++s->version;
     return VM_OK;
 }
 
@@ -350,6 +366,7 @@ extern "C" int vm_store_update(vm_store *s, int64_t row0, const void *rows, int 
     VM_REQUIRE(s, VM_ERR_BADARG, "store is NULL");
     VM_REQUIRE(row0 >= 0 && n >= 0 && row0 + n <= s->size, VM_ERR_BADARG, "update range [%lld, %lld) outside [0, %lld)",
                (long long)row0, (long long)(row0 + n), (long long)s->size);
+    ++s->version;
     return store_write(s, row0, rows, src_dtype, src_mem, n, (cudaStream_t)stream);
 }
 
@@ -362,6 +379,7 @@ extern "C" int vm_store_invalidate(vm_store *s, const int64_t *rows_host, int64_
     int rc = s->stage_idx.ensure((size_t)n * 8);
     if (rc != VM_OK) return rc;
     VM_CUDA_CHECK(cudaMemcpyAsync(s->stage_idx.p, rows_host, (size_t)n * 8, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    ++s->version;
     return k_invalidate_rows(s->inv_norms, (const int64_t *)s->stage_idx.p, n, s->size, (cudaStream_t)stream);
 }
 
@@ -371,6 +389,7 @@ extern "C" int vm_store_set_size(vm_store *s, int64_t n, int64_t recompute_from_
     VM_REQUIRE(n >= 0 && n <= s->capacity, VM_ERR_BADARG, "size %lld outside [0, capacity]", (long long)n);
     DeviceGuard g(s->device);
     s->size = n;
+    ++s->version;
     if (recompute_from_row >= 0 && recompute_from_row < n)
         return k_row_inv_norms(s->rows, s->dtype, s->inv_norms, recompute_from_row, n, s->ld, s->extreme, (cudaStream_t)stream);
     return VM_OK;
@@ -392,6 +411,7 @@ extern "C" int vm_store_clear(vm_store *s)
     DeviceGuard g(s->device);
     VM_CUDA_CHECK(cudaMemset(s->extreme, 0, 4));
     s->size = 0;
+    ++s->version;
     return VM_OK;
 }
 
@@ -584,6 +604,78 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
     Workspace &w = s->ws;
     const size_t qrow = (size_t)s->dim * dtype_size(q_dtype);
     const bool sharded = comm && comm->nranks > 1;
+
+    // ---- CUDA-graph fast path: one graph launch for H2D -> normalise -> scan -> select/rescore ->
+    // (device-conditional exact re-scan) -> packed D2H.  Host buffers, one batch, caller on the legacy
+    // default stream (the graph runs on a library-owned blocking stream, which the legacy stream orders
+    // with).  The graph bakes in row count and TMA descriptors, so it is keyed on the store version.
+    static const bool no_graph = getenv("VIDMEM_NO_GRAPH") != nullptr;
+    if (!no_graph && !sharded && st == nullptr && q_mem == VM_MEM_HOST && out_mem == VM_MEM_HOST && nq <= MAXQ &&
+        !(flags & (VM_FLAG_ASYNC | VM_FLAG_TIMING | VM_FLAG_FORCE_EXACT)) && s->size > 0) {
+        if (!s->gstream) VM_CUDA_CHECK(cudaStreamCreate(&s->gstream));
+        vm_store::GraphEntry *ge = nullptr;
+        for (auto &e : s->graphs)
+            if (e.exec && e.version == s->version && e.nq == nq && e.k == k && e.flags == flags && e.score_mode == score_mode &&
+                e.sum_mode == sum_mode && e.q_dtype == q_dtype && e.min_score == min_score) { ge = &e; break; }
+        int bq_g = MAXQ;
+        if (nq > scan_simt_max_queries() || s->size >= 65536 || (flags & VM_FLAG_FORCE_TC)) {
+            const int kp_tc = k <= 16 ? 32 : (k <= 48 ? 64 : 0);
+            bq_g = 0;
+            if (kp_tc)
+                for (int cand = 64; cand >= 16; cand -= 16)
+                    if (scan_tc_supported(s->dtype, s->dim, cand, kp_tc)) { bq_g = cand; break; }
+            if (bq_g == 0) bq_g = MAXQ;
+        }
+        if (nq <= bq_g) {
+            const size_t qbytes = (size_t)nq * qrow, obytes = (size_t)nq * k * 16 + (size_t)nq * 4;
+            int64_t *ws_idx = (int64_t *)w.o_idx.p;
+            double *ws_score = (double *)((char *)w.o_idx.p + (size_t)nq * k * 8);
+            int32_t *ws_count = (int32_t *)((char *)w.o_idx.p + (size_t)nq * k * 16);
+            if (!ge) {
+                ge = &s->graphs[s->graph_next];
+                s->graph_next = (s->graph_next + 1) & 3;
+                if (ge->exec) { cudaGraphExecDestroy(ge->exec); ge->exec = nullptr; }
+                vm_topk_stats cs{};
+                cudaGraph_t graph = nullptr;
+                VM_CUDA_CHECK(cudaStreamBeginCapture(s->gstream, cudaStreamCaptureModeRelaxed));
+                rc = VM_OK;
+                if (cudaMemcpyAsync(w.q_raw.p, w.h_q, qbytes, cudaMemcpyHostToDevice, s->gstream) != cudaSuccess) rc = VM_ERR_CUDA;
+                if (rc == VM_OK) {
+                    TopkCall c{s, w.q_raw.p, q_dtype, VM_MEM_DEVICE, nq, k, min_score, score_mode, sum_mode, flags | VM_FLAG_ASYNC,
+                               row_offset, ws_idx, ws_score, ws_count, s->gstream, &cs};
+                    rc = topk_batch(c);
+                }
+                if (rc == VM_OK && cudaMemcpyAsync(w.h_pack, ws_idx, obytes, cudaMemcpyDeviceToHost, s->gstream) != cudaSuccess) rc = VM_ERR_CUDA;
+                // number of queries the exact pass re-did (counter written by the rescoring kernel)
+                if (rc == VM_OK && cs.scan_kernel != 0 &&
+                    cudaMemcpyAsync(w.h_uncert, (int32_t *)w.flags.p + nq, 4, cudaMemcpyDeviceToHost, s->gstream) != cudaSuccess) rc = VM_ERR_CUDA;
+                cudaError_t ce = cudaStreamEndCapture(s->gstream, &graph);
+                if (rc != VM_OK || ce != cudaSuccess || !graph) {
+                    if (graph) cudaGraphDestroy(graph);
+                    if (rc == VM_OK) { set_error("graph capture failed: %s", cudaGetErrorString(ce)); rc = VM_ERR_CUDA; }
+                    cudaGetLastError();
+                    return rc;
+                }
+                ce = cudaGraphInstantiate(&ge->exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) { ge->exec = nullptr; set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return VM_ERR_CUDA; }
+                ge->version = s->version; ge->nq = nq; ge->k = k; ge->flags = flags; ge->score_mode = score_mode;
+                ge->sum_mode = sum_mode; ge->q_dtype = q_dtype; ge->min_score = min_score; ge->stats = cs;
+            }
+            memcpy(w.h_q, queries, qbytes);
+            VM_CUDA_CHECK(cudaGraphLaunch(ge->exec, s->gstream));
+            VM_CUDA_CHECK(cudaStreamSynchronize(s->gstream));
+            const size_t seg = (size_t)nq * k * 8;
+            memcpy(out_idx, w.h_pack, seg);
+            memcpy(out_score, w.h_pack + seg, seg);
+            memcpy(out_count, w.h_pack + 2 * seg, (size_t)nq * 4);
+            if (stats) {
+                *stats = ge->stats;
+                stats->uncertified = ge->stats.scan_kernel != 0 ? *w.h_uncert : 0;
+            }
+            return VM_OK;
+        }
+    }
 
     // queries per scan pass: 64, or fewer when 64 normalised queries of this dimension do not fit the
     // tcgen05 kernel's shared memory (e.g. 16 for a 1536-d fp32 store)
