@@ -79,16 +79,31 @@ class ResidentChunkStore:
         new_rows, new_ids, invalid = [], [], []
         dim = next((len(e) for _, e in items if not _falsy_embedding(e)), self.dim)
         if dim is None:
-            # nothing embeddable seen yet: remember the ids so that store order is preserved
-            dim = 1 if self.store is None else self.dim
+            # no embeddable vector seen yet, so the dimension is still unknown: only remember the ids (they
+            # keep their place in store order and become skipped rows once the store exists)
+            for cid, _ in items:
+                if cid not in self.row_of:
+                    self.row_of[cid] = len(self.ids)
+                    self.ids.append(cid)
+            if meta:
+                self.meta.update(meta)
+            return
+        if self.store is None and self.ids:
+            # ids registered before the dimension was known: materialise them as skipped rows
+            self._ensure(dim, len(self.ids) + len(items))
+            self.store.append(np.zeros((len(self.ids), dim), np.float64))
+            self.store.invalidate(range(len(self.ids)))
         for cid, emb in items:
             if cid in self.row_of:
                 row = self.row_of[cid]
                 if _falsy_embedding(emb):
                     invalid.append(row)
-                else:
+                elif len(emb) == self.dim or self.dim is None:
                     self._ensure(len(emb), 0)
                     self.store.update(row, np.asarray(emb, dtype=np.float64)[None, :])
+                else:
+                    self._ensure(self.dim, 0)
+                    self.store.update(row, np.zeros((1, self.dim), np.float64))   # length mismatch scores 0.0 (:378-379)
             else:
                 new_ids.append(cid)
                 if _falsy_embedding(emb):

@@ -122,3 +122,20 @@ def test_s5_representative(ad):
     backend = ad.PruneBackend()
     assert backend._get_representative_relation(g, E) == oracle.representative(E)[0]
     assert backend._are_same_context(g, E[:1], 0.8) is False
+
+
+def test_ids_before_first_embedding_and_boundaries(ad):
+    """Chunks whose embeddings failed arrive first: the dimension is not known yet, yet store order holds."""
+    store = ad.ResidentChunkStore(initial_capacity=8)
+    store.upsert([("a", None), ("b", [])])
+    assert len(store) == 2 and store.store is None
+    assert store.topk([[1.0, 2.0]], 3) == [[]]                       # nothing scorable yet
+    X = synth.synth_rows(3, 0, 20, 16)
+    store.upsert((f"c{i}", [float(v) for v in X[i]]) for i in range(20))
+    assert store.ids[:3] == ["a", "b", "c0"] and len(store) == 22
+    got = store.topk([[float(v) for v in X[4]]], 3)[0]
+    ref = oracle.batch_similarities(X[4:5], X, 3)[0]
+    assert got == [(f"c{r}", s) for r, s in ref]
+    store.upsert([("a", [float(v) for v in X[4]])])                 # the failed chunk is re-embedded later (MERGE by id)
+    got = store.topk([[float(v) for v in X[4]]], 2)[0]
+    assert [g[0] for g in got] == ["a", "c4"] and got[0][1] == got[1][1] == oracle.cosine(X[4], X[4])

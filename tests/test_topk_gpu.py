@@ -384,3 +384,24 @@ def test_randomised_differential(vm):
             except AssertionError as e:
                 raise AssertionError(f"case {case}: n={n} d={d} nq={nq} k={k} {dtype} flags={flags}: {e}")
         st.close()
+
+
+def test_boundaries_empty_store_large_k_no_queries(vm):
+    d = 32
+    st = vm.EmbeddingStore(d, 100, "f32")
+    Q = synth.synth_queries(1, 3, d, 2, 100)
+    idx, score, count = st.topk(Q, 5)                                # empty store -> nothing, no error
+    assert (count == 0).all() and (idx == -1).all()
+    X = synth.synth_rows(2, 0, 70, d)
+    st.append(X)
+    idx, score, count = st.topk(Q[:0], 5)                            # no queries
+    assert idx.shape == (0, 5)
+    for k in (49, 64):                                               # beyond the fast scans' candidate lists: exact scan
+        idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)
+        _check(idx, score, count, oracle.batch_similarities(Q, X, k), k)
+        assert st.last_stats.scan_kernel == 0
+    with pytest.raises(vm.VidmemError):
+        st.topk(Q, 65)
+    with pytest.raises(ValueError):
+        st.topk(np.zeros((2, d + 1), np.float32), 3)
+    st.close()
