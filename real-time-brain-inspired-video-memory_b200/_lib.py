@@ -11,7 +11,7 @@ import os
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvidmem.so")
+LIB_PATH = os.environ.get("VIDMEM_LIB", os.path.join(HERE, "libvidmem.so"))  # override: A/B builds
 
 # enums (include/vidmem.h)
 VM_OK = 0

@@ -253,9 +253,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint64_t pushed = 0;
             for (;;) {
                 bool hit_any = false, ovf = false;
-                for (int c = 0; c < nq_pad; c += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(taddr + c, v);
+                // 16 queries (TMEM columns) at a time; the load of chunk c+1 is issued before chunk c is
+                // processed so its TMEM latency hides behind the compares
+                auto process = [&](const uint32_t (&v)[16], int c) {
                     // thresholds of these 16 queries, loaded up front (a stale, lower value only lets an
                     // extra candidate through to the drain, which re-checks against the live key)
                     float tf[16];
@@ -264,7 +264,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const float4 t4 = *reinterpret_cast<const float4 *>(tauf + c + 4 * j4);
                         tf[4 * j4] = t4.x; tf[4 * j4 + 1] = t4.y; tf[4 * j4 + 2] = t4.z; tf[4 * j4 + 3] = t4.w;
                     }
-                    tmem_ld_wait();
                     if (valid && !(dbg & 1)) {
                         uint32_t hits = 0;
 #pragma unroll
@@ -285,6 +284,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 else ovf = true;
                             }
                         }
+                    }
+                };
+                uint32_t va[16], vb[16];
+                tmem_ld16(taddr, va);
+                for (int c = 0; c < nq_pad; c += 32) {
+                    tmem_ld_wait();
+                    if (c + 16 < nq_pad) tmem_ld16(taddr + c + 16, vb);
+                    process(va, c);
+                    if (c + 16 < nq_pad) {
+                        tmem_ld_wait();
+                        if (c + 32 < nq_pad) tmem_ld16(taddr + c + 32, va);
+                        process(vb, c + 16);
                     }
                 }
                 if (hit_any) s_hit[par] = 1;
