@@ -81,11 +81,13 @@ typedef struct vm_comm vm_comm;   /* an NCCL communicator wrapper (one rank) */
 typedef struct vm_topk_stats {
     int32_t scan_kernel;      /* 0 = exact only, 1 = SIMT scan, 2 = tcgen05 scan */
     int32_t scan_launches;    /* kernels launched by the call (all kinds) */
-    int32_t uncertified;      /* queries the fast scan could not certify and the exact scan re-did */
+    int32_t uncertified;      /* queries the fast scan could not certify (settled by the collect pass or the exact scan) */
     int32_t candidates;       /* candidate list length per query (KP) */
     int32_t scan_ctas;
     int32_t scan_stages;      /* shared-memory pipeline depth of the tcgen05 scan (0 otherwise) */
-    int32_t reserved[2];
+    int32_t full_rescans;     /* of the uncertified queries, how many the collect pass could not settle and the
+                                 binary64 scan of every row re-did (-1: not read back, e.g. graph replay) */
+    int32_t reserved[1];
 } vm_topk_stats;
 
 /* ---- library ----------------------------------------------------------------------- */

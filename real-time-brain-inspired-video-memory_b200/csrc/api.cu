@@ -32,6 +32,7 @@ int k_merge_candidates(const uint64_t *cand, int lists, int nq, int kp, uint64_t
 
 int k_rescore(const RescoreArgs &a, cudaStream_t st);
 int k_select_rescore(const uint64_t *cand, int lists, const RescoreArgs &a, cudaStream_t st);
+int k_collect_rescore(const uint64_t *buf, const int *cnt, int cap, const RescoreArgs &a, cudaStream_t st);
 int k_exact(const ExactArgs &a, cudaStream_t st);
 int k_merge_topk_lists(const void *idx, const void *score, const void *count, size_t stride_bytes, int lists, int nq, int k,
                        int64_t *out_idx, double *out_score, int32_t *out_count, cudaStream_t st);
@@ -50,6 +51,8 @@ extern int g_last_tc_stages;
 static constexpr int MAXQ = 64;   // queries per scan pass
 static constexpr int MAXK = 64;   // k and candidate-list bound
 static constexpr int XCTAS = 148; // exact-scan grid
+static constexpr int COLLECT_CAP = 4096;         // rows per query the collect pass may gather
+static constexpr int FLAG_INTERNAL_CAPTURE = 1 << 30;  // set by the CUDA-graph path while capturing
 
 struct DeviceGuard {
     int prev = -1;
@@ -81,13 +84,13 @@ struct Buf {
 struct Workspace {
     bool ready = false;
     int lists_max = 0;
-    Buf q_raw, q_f32, q_bf16, seed, cand, merged, o_idx, flags, xs, xr, xc, taken, gather_send, gather_recv, misc;
+    Buf q_raw, q_f32, q_bf16, seed, cand, merged, o_idx, flags, col_thr, col_cnt, col_buf, xs, xr, xc, taken, gather_send, gather_recv, misc;
     int32_t *h_uncert = nullptr;  // pinned
     unsigned char *h_pack = nullptr;  // pinned: packed [idx | score | count] of one batch
     unsigned char *h_q = nullptr;     // pinned: host queries of one batch
     void release()
     {
-        Buf *all[] = {&q_raw, &q_f32, &q_bf16, &seed, &cand, &merged, &o_idx, &flags, &xs, &xr, &xc, &taken,
+        Buf *all[] = {&q_raw, &q_f32, &q_bf16, &seed, &cand, &merged, &o_idx, &flags, &col_thr, &col_cnt, &col_buf, &xs, &xr, &xc, &taken,
                       &gather_send, &gather_recv, &misc};
         for (Buf *b : all) b->release();
         if (h_uncert) cudaFreeHost(h_uncert);
@@ -207,6 +210,9 @@ static int ws_prepare(vm_store *s)
     ENS(w.o_idx, (size_t)MAXQ * MAXK * 16 + (size_t)MAXQ * 4 + 64);
     ENS(w.flags, (size_t)(MAXQ + 2) * 4);
     ENS(w.seed, (size_t)256 * MAXQ * 4);
+    ENS(w.col_thr, (size_t)MAXQ * 4);
+    ENS(w.col_cnt, (size_t)MAXQ * 4);
+    ENS(w.col_buf, (size_t)MAXQ * COLLECT_CAP * 8);
     ENS(w.xs, (size_t)XCTAS * MAXQ * MAXK * 8);
     ENS(w.xr, (size_t)XCTAS * MAXQ * MAXK * 4);
     ENS(w.xc, (size_t)XCTAS * MAXQ * 4);
@@ -536,7 +542,8 @@ static int topk_batch(const TopkCall &c)
     int32_t *flags = (int32_t *)w.flags.p;
     int32_t *uncert = flags + c.nq;  // counter sits right after the nq flags (zeroed by the normalise kernel)
     RescoreArgs rs{(const uint64_t *)w.merged.p, kp, s->rows, s->inv_norms, s->dtype, s->ld, s->dim, s->size, q_dev,
-                   c.q_dtype, c.nq, scan_eps(kernel, s->dtype, s->dim), c.sum_mode, fin, flags, uncert, s->extreme};
+                   c.q_dtype, c.nq, scan_eps(kernel, s->dtype, s->dim), c.sum_mode, fin, flags, uncert, s->extreme,
+                   kernel == 2 ? (float *)w.col_thr.p : nullptr};
     rc = k_select_rescore(a.cand, a.ctas, rs, st);  // fused merge + exact rescoring
     if (rc == VM_ERR_UNSUPPORTED) {                 // rows too large for shared memory: two kernels
         rc = k_merge_candidates(a.cand, a.ctas, c.nq, kp, (uint64_t *)w.merged.p, st);
@@ -548,8 +555,27 @@ static int topk_batch(const TopkCall &c)
     launches += 1;
 
     ex.flags = flags;
-    int n_uncert = 0;
+    int n_uncert = 0, n_full = -1;
+    // Second chance for uncertified queries of the tensor-core scan: one more scan in collect mode
+    // (every row within 2 eps of the exact k-th candidate score) + exact rescoring of what it gathered.
+    // Both kernels exit at once when nothing is flagged.  Whatever they cannot settle (buffer overflow,
+    // stores with out-of-range rows) is left to the binary64 scan of every row.
+    auto run_collect = [&]() -> int {
+        VM_CUDA_CHECK(cudaMemsetAsync(w.col_cnt.p, 0, (size_t)c.nq * 4, st));
+        ScanCollect sc{(const float *)w.col_thr.p, (uint64_t *)w.col_buf.p, (int *)w.col_cnt.p, COLLECT_CAP, uncert};
+        int r = launch_scan_tc(a, s->dtype == VM_BF16 ? w.q_bf16.p : w.q_f32.p, nullptr, nullptr, &sc);
+        if (r != VM_OK) return r;
+        return k_collect_rescore((const uint64_t *)w.col_buf.p, (const int *)w.col_cnt.p, COLLECT_CAP, rs, st);
+    };
     if (c.flags & VM_FLAG_ASYNC) {
+        if (c.flags & FLAG_INTERNAL_CAPTURE) {
+            // graph replay: everything is device-conditional; the count after the first pass goes to the host
+            VM_CUDA_CHECK(cudaMemcpyAsync(w.h_uncert, uncert, 4, cudaMemcpyDeviceToHost, st));
+            if (kernel == 2) {
+                if ((rc = run_collect()) != VM_OK) return rc;
+                launches += 2;
+            }
+        }
         rc = k_exact(ex, st);  // device-side conditional: returns immediately when nothing is flagged
         if (rc != VM_OK) return rc;
         launches += 2;
@@ -559,10 +585,22 @@ static int topk_batch(const TopkCall &c)
         if (c.h_idx && (rc = pack_out_enqueue(c)) != VM_OK) return rc;
         VM_CUDA_CHECK(cudaStreamSynchronize(st));
         n_uncert = *w.h_uncert;
+        n_full = 0;
         if (n_uncert > 0) {
-            rc = k_exact(ex, st);
-            if (rc != VM_OK) return rc;
-            launches += 2;
+            int left = n_uncert;
+            if (kernel == 2) {
+                if ((rc = run_collect()) != VM_OK) return rc;
+                launches += 2;
+                VM_CUDA_CHECK(cudaMemcpyAsync(w.h_uncert, uncert, 4, cudaMemcpyDeviceToHost, st));
+                VM_CUDA_CHECK(cudaStreamSynchronize(st));
+                left = *w.h_uncert;
+            }
+            n_full = left;
+            if (left > 0) {
+                rc = k_exact(ex, st);
+                if (rc != VM_OK) return rc;
+                launches += 2;
+            }
             if (c.h_idx) {
                 if ((rc = pack_out_enqueue(c)) != VM_OK) return rc;
                 VM_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -574,6 +612,7 @@ static int topk_batch(const TopkCall &c)
         c.stats->scan_kernel = kernel;
         c.stats->scan_launches += launches;
         c.stats->uncertified += n_uncert > 0 ? n_uncert : 0;
+        c.stats->full_rescans = n_full;
         c.stats->candidates = kp;
         c.stats->scan_ctas = a.ctas;
         c.stats->scan_stages = kernel == 2 ? g_last_tc_stages : 0;
@@ -641,14 +680,13 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
                 rc = VM_OK;
                 if (cudaMemcpyAsync(w.q_raw.p, w.h_q, qbytes, cudaMemcpyHostToDevice, s->gstream) != cudaSuccess) rc = VM_ERR_CUDA;
                 if (rc == VM_OK) {
-                    TopkCall c{s, w.q_raw.p, q_dtype, VM_MEM_DEVICE, nq, k, min_score, score_mode, sum_mode, flags | VM_FLAG_ASYNC,
+                    TopkCall c{s, w.q_raw.p, q_dtype, VM_MEM_DEVICE, nq, k, min_score, score_mode, sum_mode,
+                               flags | VM_FLAG_ASYNC | FLAG_INTERNAL_CAPTURE,
                                row_offset, ws_idx, ws_score, ws_count, s->gstream, &cs};
                     rc = topk_batch(c);
                 }
                 if (rc == VM_OK && cudaMemcpyAsync(w.h_pack, ws_idx, obytes, cudaMemcpyDeviceToHost, s->gstream) != cudaSuccess) rc = VM_ERR_CUDA;
-                // number of queries the exact pass re-did (counter written by the rescoring kernel)
-                if (rc == VM_OK && cs.scan_kernel != 0 &&
-                    cudaMemcpyAsync(w.h_uncert, (int32_t *)w.flags.p + nq, 4, cudaMemcpyDeviceToHost, s->gstream) != cudaSuccess) rc = VM_ERR_CUDA;
+
                 cudaError_t ce = cudaStreamEndCapture(s->gstream, &graph);
                 if (rc != VM_OK || ce != cudaSuccess || !graph) {
                     if (graph) cudaGraphDestroy(graph);

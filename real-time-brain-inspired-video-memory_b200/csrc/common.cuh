@@ -155,8 +155,18 @@ struct ScanArgs {
 };
 int launch_scan_simt(const ScanArgs &a);
 int scan_simt_max_queries();
-// tcgen05 path; seed_tab [ctas][nq_pad] u32 + seed_ctr must be zeroed before the launch (NULL = no seeding)
-int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t *seed_tab, int *seed_ctr);
+// second pass of the tcgen05 scan for uncertified queries (see scan_tc.cu "collect mode")
+struct ScanCollect {
+    const float *thr;    // [nq] thresholds written by the rescoring kernel (+inf = query is done)
+    uint64_t *buf;       // [nq][cap]
+    int *cnt;            // [nq], zeroed before the launch
+    int cap;
+    const int *pending;  // uncertified-query counter
+};
+// tcgen05 path; seed_tab [ctas][nq_pad] u32 + seed_ctr must be zeroed before the launch (NULL = no seeding);
+// sc != NULL runs the collect pass instead of the top-kp pass
+int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t *seed_tab, int *seed_ctr,
+                   const ScanCollect *sc = nullptr);
 bool scan_tc_supported(int dtype, int dim, int nq, int kp);
 
 
@@ -184,6 +194,7 @@ struct RescoreArgs {
     FinalizeArgs fin;
     int32_t *flags, *uncertified_count;
     const int *extreme;  // store-level count of rows outside the scans' numeric range (forces the exact pass)
+    float *collect_thr;  // [nq] out: threshold of the collect pass for uncertified queries (+inf otherwise); may be NULL
 };
 struct ExactArgs {
     const void *rows;

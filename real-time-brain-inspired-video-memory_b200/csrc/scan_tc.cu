@@ -23,6 +23,9 @@
 // 8 TMEM stages.  This removes the per-CTA warm-up flood that otherwise dominates small shards.
 // HBM traffic = the store bytes exactly once per batch of <= 64 queries; the per-CTA lists are
 // merged and exactly rescored by select.cu.
+// Collect mode (second pass for queries the first pass could not certify): thresholds are fixed per
+// query (exact k-th candidate score - 2 eps; +inf for queries that need nothing) and every row at or
+// above its query's threshold is appended to that query's global buffer -- no lists, no drains.
 #include "tc_common.cuh"
 #include <stdlib.h>
 
@@ -36,6 +39,15 @@ static constexpr int TC_QCAP = 32;
 static constexpr int TC_THREADS = 192;
 static constexpr int TC_TMEM_COLS = 512;
 static constexpr int TC_MAX_STAGES = 8;
+
+// second-pass ("collect") arguments; thr == nullptr selects the normal top-kp mode
+struct CollectArgs {
+    const float *thr;      // [nq] per-query score threshold (+inf: ignore the query)
+    uint64_t *buf;         // [nq][cap] collected keys
+    int *cnt;              // [nq] number of rows at or above the threshold (may exceed cap)
+    int cap;
+    const int *pending;    // device counter of uncertified queries: 0 -> the kernel exits at once
+};
 
 struct TcLayout {
     int nq_pad, KB, stages, kp;
@@ -73,8 +85,11 @@ template <bool TF32>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const float *__restrict__ inv_norms, int64_t n, int num_tiles, int nq, TcLayout L, uint64_t *__restrict__ cand,
-               uint32_t *__restrict__ seed_tab, int *__restrict__ seed_ctr, int dbg)
+               uint32_t *__restrict__ seed_tab, int *__restrict__ seed_ctr, int dbg, CollectArgs col)
 {
+    const bool collect = col.thr != nullptr;
+    if (collect && *col.pending == 0) return;  // nothing left to refine (uniform across the grid)
+
     extern __shared__ __align__(16) uint8_t smem_raw[];
     // align to 1024 B with pointer arithmetic on the __shared__ array (an integer round trip would
     // demote every later access to generic LD/ST)
@@ -111,7 +126,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int e = threadIdx.x - 64;
         if (e < nq_pad) {
             for (int j = 0; j < kp; ++j) list[j * nq_pad + e] = 0;
-            tauk[e] = 0; tauf[e] = -INFINITY; qcnt[e] = 0;
+            tauk[e] = 0; qcnt[e] = 0;
+            tauf[e] = collect ? (e < nq ? col.thr[e] : INFINITY) : -INFINITY;
         }
         if (e < 4) s_hit[e] = 0;  // s_hit[0..1], s_ovf[0..1]
     }
@@ -175,7 +191,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float my_seed = -INFINITY;        // seeded lower bound of query e
         int acc = 0, par = 0;
         uint32_t acc_phase = 0;
-        if (seed_tab != nullptr) {
+        if (seed_tab != nullptr && !collect) {
             // ---- cooperative threshold seeding from the first tile (see file header) ----
             uint32_t *wmax = reinterpret_cast<uint32_t *>(queue);  // [4][nq_pad] scratch (queue is idle now)
             float *seedf = reinterpret_cast<float *>(wmax + 4 * nq_pad);
@@ -277,7 +293,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int jj = 0; jj < 16; ++jj) s = (jj == j) ? __uint_as_float(v[jj]) * inv : s;
                             const uint64_t key = make_key(s, (uint32_t)row);
-                            if (key > tauk[q]) {
+                            if (collect) {
+                                const int pos = atomicAdd(col.cnt + q, 1);
+                                if (pos < col.cap) col.buf[(size_t)q * col.cap + pos] = key;
+                            } else if (key > tauk[q]) {
                                 hit_any = true;
                                 const int pos = atomicAdd(&qcnt[q], 1);
                                 if (pos < TC_QCAP) { queue[pos * nq_pad + q] = key; pushed |= 1ull << q; }
@@ -341,7 +360,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             inv = inv_next;
         }
         named_bar_sync(1, 128);
-        for (int i = e; i < nq * kp; i += 128) {
+        for (int i = e; i < nq * kp && !collect; i += 128) {
             const int q = i / kp, j = i - q * kp;
             cand[((int64_t)blockIdx.x * nq + q) * kp + j] = list[j * nq_pad + q];
         }
@@ -367,7 +386,7 @@ int g_last_tc_stages = 0;
 
 // queries_store_dtype: the normalised queries [nq_pad][ld] in the STORE dtype (fp32 for the tf32
 // path, bf16 for the bf16 path).
-int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t *seed_tab, int *seed_ctr)
+int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t *seed_tab, int *seed_ctr, const ScanCollect *sc)
 {
     VM_REQUIRE(a.n >= 1 && a.n < 0x7FFFFF00LL, VM_ERR_UNSUPPORTED, "tcgen05 scan: shard rows %lld outside [1, 2^31)", (long long)a.n);
     TcLayout L = make_layout(a.dtype, a.ld, a.nq, a.kp);
@@ -385,15 +404,17 @@ int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t 
     g_last_tc_stages = L.stages;
     // seeding pays off once every CTA streams several tiles and there are at least kp CTAs
     const bool seed = seed_tab && seed_ctr && a.ctas >= a.kp && a.ctas <= 256 && num_tiles >= 4 * a.ctas && !(dbg & 4);
-    if (!seed) { seed_tab = nullptr; seed_ctr = nullptr; }
+    if (!seed || sc) { seed_tab = nullptr; seed_ctr = nullptr; }
+    CollectArgs col{};
+    if (sc) { col.thr = sc->thr; col.buf = sc->buf; col.cnt = sc->cnt; col.cap = sc->cap; col.pending = sc->pending; }
     if (a.dtype == VM_F32) {
         static bool set[64] = {};  // the attribute is per device
         if (!set[dev_idx]) { VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set[dev_idx] = true; }
-        scan_tc_kernel<true><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, seed_tab, seed_ctr, dbg);
+        scan_tc_kernel<true><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, seed_tab, seed_ctr, dbg, col);
     } else {
         static bool set[64] = {};  // the attribute is per device
         if (!set[dev_idx]) { VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set[dev_idx] = true; }
-        scan_tc_kernel<false><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, seed_tab, seed_ctr, dbg);
+        scan_tc_kernel<false><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, seed_tab, seed_ctr, dbg, col);
     }
     VM_CUDA_CHECK(cudaGetLastError());
     return VM_OK;

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rescore_kernel(const uint64_t *
                                                             const void *__restrict__ queries, int q_dtype, double eps,
                                                             FinalizeArgs f, int32_t *__restrict__ flags,
                                                             int32_t *__restrict__ uncertified_count, int chunk,
-                                                            const int *__restrict__ extreme)
+                                                            const int *__restrict__ extreme, float *__restrict__ collect_thr)
 {
     constexpr int VEC = 16 / (int)sizeof(T);      // elements per 16-byte load
     extern __shared__ double rs_smem[];
@@ -354,11 +354,19 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rescore_kernel(const uint64_t *
             float worst = key_score(merged[(int64_t)q * kp + kp - 1]);
             cert = ((double)worst + eps) < sc;
         }
-        if (extreme && *extreme != 0 && (int64_t)ncand < n_rows) cert = false;  // error bound not valid for this store
-        flags[q] = cert ? 0 : 1;
+        // flag 1: a collect pass (all rows within 2 eps of this score) can settle the query;
+        // flag 2: the error bound does not hold for this store -> binary64 scan of every row
+        const bool bound_ok = !(extreme && *extreme != 0);
+        if (!bound_ok && (int64_t)ncand < n_rows) cert = false;
+        flags[q] = cert ? 0 : (bound_ok ? 1 : 2);
+        if (collect_thr) {
+            float t = (float)(sc - 2.0 * eps);
+            t = nextafterf(nextafterf(t, -INFINITY), -INFINITY);  // the cast may have rounded up
+            collect_thr[q] = (!cert && bound_ok) ? t : INFINITY;
+        }
         if (!cert) atomicAdd(uncertified_count, 1);
     }
-    if (ncand == 0 && j == 0) flags[q] = 0;
+    if (ncand == 0 && j == 0) { flags[q] = 0; if (collect_thr) collect_thr[q] = INFINITY; }
     if (j == 0) f.out_count[q] = s_cnt;
     int cnt = s_cnt;
     for (int t = cnt + j; t < f.k; t += RS_THREADS) {
@@ -392,7 +400,7 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uin
                                                                    const void *__restrict__ queries, int q_dtype, double eps,
                                                                    FinalizeArgs f, int32_t *__restrict__ flags,
                                                                    int32_t *__restrict__ uncertified_count,
-                                                                   const int *__restrict__ extreme)
+                                                                   const int *__restrict__ extreme, float *__restrict__ collect_thr)
 {
     extern __shared__ __align__(16) unsigned char sr_smem[];
     const int total = lists * kp;
@@ -574,14 +582,112 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uin
             const float worst = key_score(s_top[kp - 1]);  // smallest approximate score among the candidates
             cert = ((double)worst + eps) < sc;
         }
-        if (extreme && *extreme != 0 && (int64_t)ncand < n_rows) cert = false;  // error bound not valid for this store
-        flags[q] = cert ? 0 : 1;
+        const bool bound_ok = !(extreme && *extreme != 0);
+        if (!bound_ok && (int64_t)ncand < n_rows) cert = false;
+        flags[q] = cert ? 0 : (bound_ok ? 1 : 2);  // 1: collect pass can settle it, 2: needs the full binary64 scan
+        if (collect_thr) {
+            float t = (float)(sc - 2.0 * eps);
+            t = nextafterf(nextafterf(t, -INFINITY), -INFINITY);
+            collect_thr[q] = (!cert && bound_ok) ? t : INFINITY;
+        }
         if (!cert) atomicAdd(uncertified_count, 1);
     }
-    if (ncand == 0 && tid == 0) flags[q] = 0;
+    if (ncand == 0 && tid == 0) { flags[q] = 0; if (collect_thr) collect_thr[q] = INFINITY; }
     if (tid == 0) f.out_count[q] = s_cnt;
     const int cnt = s_cnt;
     for (int t = cnt + tid; t < f.k; t += SR_THREADS) {
+        f.out_idx[(int64_t)q * f.k + t] = -1;
+        f.out_score[(int64_t)q * f.k + t] = 0.0;
+    }
+}
+
+// =========================================================================================
+// 2c. collect pass: exact top-k among the rows the second scan gathered for an uncertified query
+// =========================================================================================
+// One CTA (512 threads) per query with flag 1.  The collect scan stored every row whose approximate
+// score reached (exact k-th candidate score - 2 eps): that set contains the reference's top-k (a row
+// outside it is more than eps below the k-th candidate).  All gathered rows are scored with the
+// reference recurrence (one sequential chain pair per thread and row) and the best k by (score desc,
+// row asc) are emitted; the query's flag is cleared.  If the buffer overflowed the flag becomes 2 and
+// the binary64 scan of every row takes over.
+static constexpr int CR_THREADS = 512;
+template <bool NEUMAIER, typename T>
+__global__ void __launch_bounds__(CR_THREADS, 1) collect_rescore_kernel(const uint64_t *__restrict__ buf, const int *__restrict__ cnt, int cap,
+                                                                       const T *__restrict__ rows, int ld, int dim,
+                                                                       const void *__restrict__ queries, int q_dtype, FinalizeArgs f,
+                                                                       int32_t *__restrict__ flags, int32_t *__restrict__ uncertified_count,
+                                                                       int nq)
+{
+    extern __shared__ __align__(16) unsigned char cr_smem[];
+    double *sq = reinterpret_cast<double *>(cr_smem);               // [dim]
+    double *s_sc = sq + ((dim + 1) & ~1);                           // [cap]
+    uint32_t *s_row = reinterpret_cast<uint32_t *>(s_sc + cap);     // [cap]
+    unsigned char *s_taken = reinterpret_cast<unsigned char *>(s_row + cap);  // [cap]
+    __shared__ double w_s[CR_THREADS / 32];
+    __shared__ uint32_t w_r[CR_THREADS / 32];
+    __shared__ int w_p[CR_THREADS / 32];
+    __shared__ double s_n1;
+    __shared__ int s_out;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (flags[nq] == 0 || flags[q] != 1) return;
+    const int m = cnt[q];
+    if (m > cap) {  // too many rows inside the band: leave it to the full binary64 scan
+        if (tid == 0) flags[q] = 2;
+        return;
+    }
+    for (int i = tid; i < dim; i += CR_THREADS) sq[i] = load_as_double(queries, q_dtype, (int64_t)q * dim + i);
+    if (tid == 0) s_out = 0;
+    __syncthreads();
+    if (tid == 0) {
+        RefSum qq; qq.init();
+        ref_sum_range<NEUMAIER>(qq, 0, dim, [&](int i) { return __dmul_rn(sq[i], sq[i]); });
+        s_n1 = __dsqrt_rn(qq.result<NEUMAIER>());
+    }
+    __syncthreads();
+    const double n1 = s_n1;
+    for (int e = tid; e < m; e += CR_THREADS) {
+        const uint32_t r = key_row(buf[(size_t)q * cap + e]);
+        s_row[e] = r;
+        s_sc[e] = exact_cosine_sq<NEUMAIER, T>(sq, n1, rows + (int64_t)r * ld, dim);
+        s_taken[e] = 0;
+    }
+    __syncthreads();
+    // k rounds of block-wide arg-best over the m scored rows
+    for (int r = 0; r < f.k; ++r) {
+        double bs = 0.0; uint32_t br = 0; int bp = -1;
+        for (int e = tid; e < m; e += CR_THREADS)
+            if (!s_taken[e] && (bp < 0 || better(s_sc[e], s_row[e], bs, br))) { bs = s_sc[e]; br = s_row[e]; bp = e; }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ts = __shfl_xor_sync(0xffffffffu, bs, o);
+            const uint32_t tr = __shfl_xor_sync(0xffffffffu, br, o);
+            const int tp = __shfl_xor_sync(0xffffffffu, bp, o);
+            if (tp >= 0 && (bp < 0 || better(ts, tr, bs, br))) { bs = ts; br = tr; bp = tp; }
+        }
+        if (lane == 0) { w_s[warp] = bs; w_r[warp] = br; w_p[warp] = bp; }
+        __syncthreads();
+        bs = w_s[0]; br = w_r[0]; bp = w_p[0];
+        for (int w = 1; w < CR_THREADS / 32; ++w)
+            if (w_p[w] >= 0 && (bp < 0 || better(w_s[w], w_r[w], bs, br))) { bs = w_s[w]; br = w_r[w]; bp = w_p[w]; }
+        if (bp < 0) break;  // uniform
+        if (tid == 0) {
+            s_taken[bp] = 1;
+            const double outv = convert_score(bs, f.score_mode);
+            if (outv > f.min_score) {
+                f.out_idx[(int64_t)q * f.k + r] = (int64_t)br + f.row_offset;
+                f.out_score[(int64_t)q * f.k + r] = outv;
+                s_out = r + 1;
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    const int cntv = s_out;
+    if (tid == 0) {
+        f.out_count[q] = cntv;
+        flags[q] = 0;
+        atomicSub(uncertified_count, 1);
+    }
+    for (int t = cntv + tid; t < f.k; t += CR_THREADS) {
         f.out_idx[(int64_t)q * f.k + t] = -1;
         f.out_score[(int64_t)q * f.k + t] = 0.0;
     }
@@ -942,7 +1048,7 @@ int k_rescore(const RescoreArgs &a, cudaStream_t st)
         }                                                                                                              \
         rescore_kernel<NEU, T><<<a.nq, RS_THREADS, smem, st>>>(a.merged, a.kp, (const T *)a.rows, a.inv_norms, a.ld, a.dim, \
                                                                a.n_rows, a.queries, a.q_dtype, a.eps, a.fin, a.flags,    \
-                                                               a.uncertified_count, chunk, a.extreme);                             \
+                                                               a.uncertified_count, chunk, a.extreme, a.collect_thr);                             \
     } while (0)
     // column chunk: whole rows when kp rows fit in RS_SMEM_ROW_BYTES, else a multiple of 8 columns
     int chunk = RS_SMEM_ROW_BYTES / (4 * a.kp) - 1;
@@ -978,12 +1084,36 @@ int k_select_rescore(const uint64_t *cand, int lists, const RescoreArgs &a, cuda
         }                                                                                                              \
         select_rescore_kernel<NEU, T><<<a.nq, SR_THREADS, smem, st>>>(cand, lists, a.nq, a.kp, (const T *)a.rows, a.ld, a.dim, \
                                                                       a.n_rows, a.queries, a.q_dtype, a.eps, a.fin, a.flags,  \
-                                                                      a.uncertified_count, a.extreme);                            \
+                                                                      a.uncertified_count, a.extreme, a.collect_thr);             \
     } while (0)
     const bool neu = a.sum_mode == VM_SUM_NEUMAIER;
     if (a.dtype == VM_F32) { if (neu) LAUNCH_SR(true, float); else LAUNCH_SR(false, float); }
     else { if (neu) LAUNCH_SR(true, __nv_bfloat16); else LAUNCH_SR(false, __nv_bfloat16); }
 #undef LAUNCH_SR
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
+int k_collect_rescore(const uint64_t *buf, const int *cnt, int cap, const RescoreArgs &a, cudaStream_t st)
+{
+    const size_t smem = (size_t)((a.dim + 1) & ~1) * 8 + (size_t)cap * (8 + 4 + 1) + 32;
+    VM_REQUIRE(smem <= 200 * 1024, VM_ERR_UNSUPPORTED, "collect pass: buffer of %d rows exceeds shared memory", cap);
+#define LAUNCH_CR(NEU, T)                                                                                               \
+    do {                                                                                                                \
+        static bool attr_set_dev[64] = {};                                                                              \
+        int dev_idx_ = 0;                                                                                               \
+        cudaGetDevice(&dev_idx_);                                                                                       \
+        if (!attr_set_dev[dev_idx_ & 63]) {                                                                             \
+            VM_CUDA_CHECK(cudaFuncSetAttribute(collect_rescore_kernel<NEU, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+            attr_set_dev[dev_idx_ & 63] = true;                                                                         \
+        }                                                                                                               \
+        collect_rescore_kernel<NEU, T><<<a.nq, CR_THREADS, smem, st>>>(buf, cnt, cap, (const T *)a.rows, a.ld, a.dim, a.queries, \
+                                                                       a.q_dtype, a.fin, a.flags, a.uncertified_count, a.nq);    \
+    } while (0)
+    const bool neu = a.sum_mode == VM_SUM_NEUMAIER;
+    if (a.dtype == VM_F32) { if (neu) LAUNCH_CR(true, float); else LAUNCH_CR(false, float); }
+    else { if (neu) LAUNCH_CR(true, __nv_bfloat16); else LAUNCH_CR(false, __nv_bfloat16); }
+#undef LAUNCH_CR
     VM_CUDA_CHECK(cudaGetLastError());
     return VM_OK;
 }

@@ -405,3 +405,36 @@ def test_boundaries_empty_store_large_k_no_queries(vm):
     with pytest.raises(ValueError):
         st.topk(np.zeros((2, d + 1), np.float32), 3)
     st.close()
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_near_duplicate_cluster_uses_collect_pass(vm, dtype):
+    """A cluster of near-identical rows (video chunks of a static scene) puts more rows inside the scan's
+    error band than the candidate list holds: the query is uncertified, and the collect pass -- not the
+    binary64 scan of every row -- settles it exactly."""
+    import torch
+    d, n, k = 384, 120000, 10
+    rng = np.random.default_rng(23)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    base = rng.standard_normal(d).astype(np.float32)
+    X[5000:5300] = base + 1e-3 * rng.standard_normal((300, d)).astype(np.float32)   # cosines within ~1e-6 of each other
+    X = _quantise(X, dtype)
+    Q = np.stack([base, rng.standard_normal(d).astype(np.float32), X[77]])
+    st = vm.EmbeddingStore(d, n, dtype)
+    st.append(X)
+    ref = oracle.topk_blocked(Q, X, k, slack=400)
+    with torch.cuda.stream(torch.cuda.Stream()):                      # non-default stream: plain (non-graph) sync path, stats are read back
+        idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)
+    assert np.array_equal(idx, ref[0]) and np.array_equal(score, ref[1])
+    assert st.last_stats.scan_kernel == 2 and st.last_stats.uncertified >= 1
+    assert st.last_stats.full_rescans == 0                            # settled by the collect pass
+    idx2, score2, _ = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)      # default stream: CUDA-graph replay, same answer
+    assert np.array_equal(idx2, idx) and np.array_equal(score2, score)
+    # more near-ties than the collect buffer holds -> the binary64 scan takes over, still exact
+    X2 = X.copy(); X2[20000:25000] = X2[5000]
+    st2 = vm.EmbeddingStore(d, n, dtype); st2.append(X2)
+    ref2 = oracle.topk_blocked(Q[:1], X2, k, slack=6000)
+    with torch.cuda.stream(torch.cuda.Stream()):
+        i3, s3, _ = st2.topk(Q[:1], k, sum_mode=vm.VM_SUM_NEUMAIER)
+    assert np.array_equal(i3, ref2[0]) and np.array_equal(s3, ref2[1]) and st2.last_stats.full_rescans == 1
+    st.close(); st2.close()
