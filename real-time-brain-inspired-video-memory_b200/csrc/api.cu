@@ -127,6 +127,8 @@ struct vm_store {
     GraphEntry graphs[4];
     int graph_next = 0;
     uint64_t version = 1;         // bumped by every mutation: cached graphs bake in row counts and TMA descriptors
+    uint64_t seen_version = 0;    // version at the previous top-k call
+    int stable_calls = 0;         // consecutive top-k calls without a mutation in between
     cudaStream_t gstream = nullptr;  // blocking stream the graphs run on (ordered with the legacy default stream)
 };
 
@@ -569,16 +571,14 @@ static int topk_batch(const TopkCall &c)
     };
     if (c.flags & VM_FLAG_ASYNC) {
         if (c.flags & FLAG_INTERNAL_CAPTURE) {
-            // graph replay: everything is device-conditional; the count after the first pass goes to the host
+            // graph replay carries only the common path; the uncertified count goes to the host, which
+            // re-runs the batch through the plain path in the rare case it is non-zero
             VM_CUDA_CHECK(cudaMemcpyAsync(w.h_uncert, uncert, 4, cudaMemcpyDeviceToHost, st));
-            if (kernel == 2) {
-                if ((rc = run_collect()) != VM_OK) return rc;
-                launches += 2;
-            }
+        } else {
+            rc = k_exact(ex, st);  // device-side conditional: returns immediately when nothing is flagged
+            if (rc != VM_OK) return rc;
+            launches += 2;
         }
-        rc = k_exact(ex, st);  // device-side conditional: returns immediately when nothing is flagged
-        if (rc != VM_OK) return rc;
-        launches += 2;
         n_uncert = -1;
     } else {
         VM_CUDA_CHECK(cudaMemcpyAsync(w.h_uncert, uncert, 4, cudaMemcpyDeviceToHost, st));
@@ -649,7 +649,11 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
     // default stream (the graph runs on a library-owned blocking stream, which the legacy stream orders
     // with).  The graph bakes in row count and TMA descriptors, so it is keyed on the store version.
     static const bool no_graph = getenv("VIDMEM_NO_GRAPH") != nullptr;
-    if (!no_graph && !sharded && st == nullptr && q_mem == VM_MEM_HOST && out_mem == VM_MEM_HOST && nq <= MAXQ &&
+    // capturing costs a few hundred microseconds: only worth it for a store that is being queried, not
+    // one that is mutated every few calls (streaming inserts)
+    if (s->seen_version == s->version) { if (s->stable_calls < 1 << 20) ++s->stable_calls; }
+    else { s->seen_version = s->version; s->stable_calls = 0; }
+    if (!no_graph && s->stable_calls >= 16 && !sharded && st == nullptr && q_mem == VM_MEM_HOST && out_mem == VM_MEM_HOST && nq <= MAXQ &&
         !(flags & (VM_FLAG_ASYNC | VM_FLAG_TIMING | VM_FLAG_FORCE_EXACT)) && s->size > 0) {
         if (!s->gstream) VM_CUDA_CHECK(cudaStreamCreate(&s->gstream));
         vm_store::GraphEntry *ge = nullptr;
@@ -703,6 +707,13 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
             memcpy(w.h_q, queries, qbytes);
             VM_CUDA_CHECK(cudaGraphLaunch(ge->exec, s->gstream));
             VM_CUDA_CHECK(cudaStreamSynchronize(s->gstream));
+            if (ge->stats.scan_kernel != 0 && *w.h_uncert > 0) {
+                // some query was not certified: run this batch through the plain path (collect pass / exact scan)
+                TopkCall c{s, queries, q_dtype, VM_MEM_HOST, nq, k, min_score, score_mode, sum_mode, flags, row_offset,
+                           ws_idx, ws_score, ws_count, s->gstream, stats};
+                c.h_idx = out_idx; c.h_score = out_score; c.h_count = out_count;
+                return topk_batch(c);
+            }
             const size_t seg = (size_t)nq * k * 8;
             memcpy(out_idx, w.h_pack, seg);
             memcpy(out_score, w.h_pack + seg, seg);
