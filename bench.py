@@ -194,6 +194,24 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def make_queries(store, n_rows: int, nq: int, dim: int, seed: int, dev, world: int = 1):
+    """Synthetic query batch for the timed arm (no oracle code on this path): even queries are copies of a
+    resident row with every 4th column redrawn, odd queries are independent draws; all values are multiples
+    of 1/128 like the store rows.  Under torchrun rank 0's batch is broadcast so every rank scores the same
+    queries.  -> float32 CPU tensor [nq, dim]."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    ridx = torch.randint(0, max(n_rows, 1), (nq,), generator=g)
+    base = store.rows[ridx.to(dev), :dim].float()
+    noise = (torch.randint(-127, 128, (nq, dim), generator=g).float() / 128.0).to(dev)
+    redraw = (torch.arange(dim, device=dev) % 4 == 0)[None, :] | (torch.arange(nq, device=dev) % 2 == 1)[:, None]
+    q = torch.where(redraw, noise, base).contiguous()
+    if world > 1:
+        import torch.distributed as dist
+        dist.broadcast(q, src=0)
+    return q.cpu()
+
+
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
@@ -202,7 +220,6 @@ def run_ours(args):
     import torch
     import vidmem_b200 as vm
     from vidmem_b200.store import EmbeddingStore
-    from oracle import synth  # synthetic query generator only (numpy); nothing from the oracle is timed here
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -233,8 +250,8 @@ def run_ours(args):
     store.synth_fill(sseed, n_local, row0=row_lo)
     store.set_size(n_local)
     torch.cuda.synchronize()
-    Q = synth.synth_queries(qseed, nq, dim, sseed, rows_total)
-    q_pinned = torch.from_numpy(Q).pin_memory()
+    q_pinned = make_queries(store, n_local, nq, dim, qseed, dev, world).pin_memory()
+    Q = q_pinned.numpy()
     q_dev = q_pinned.to(dev)
     out = (torch.empty((nq, k), dtype=torch.int64, device=dev), torch.empty((nq, k), dtype=torch.float64, device=dev),
            torch.empty((nq,), dtype=torch.int32, device=dev))
@@ -365,7 +382,7 @@ def run_ours(args):
                 s3 = EmbeddingStore(d3, r3, dt3, device=local_rank)
                 s3.synth_fill(ss3, r3)
                 s3.set_size(r3)
-                q3 = torch.from_numpy(synth.synth_queries(qs3, nq3, d3, ss3, r3)).to(dev)
+                q3 = make_queries(s3, r3, nq3, d3, qs3, dev).to(dev)
                 o3 = (torch.empty((nq3, k3), dtype=torch.int64, device=dev), torch.empty((nq3, k3), dtype=torch.float64, device=dev),
                       torch.empty((nq3,), dtype=torch.int32, device=dev))
                 for _ in range(3):
@@ -518,7 +535,6 @@ def run_c5(args):
     import torch
     import vidmem_b200 as vm
     from vidmem_b200.store import EmbeddingStore
-    from oracle import synth
     rows_total, dim, dt, nq, k, sseed, qseed = CONFIGS["c5"]
     if args.rows:
         rows_total = args.rows
@@ -532,9 +548,9 @@ def run_c5(args):
     st.synth_fill(sseed, rows_total)
     st.set_size(rows_total)
     torch.cuda.synchronize()
-    Q = synth.synth_queries(qseed, rounds * per_round_q, dim, sseed, rows_total)
-    qpin = torch.from_numpy(Q).pin_memory().numpy()
-    new_rows = torch.from_numpy(synth.synth_rows(sseed, rows_total, rounds * ins, dim)).pin_memory()
+    qpin = make_queries(st, rows_total, rounds * per_round_q, dim, qseed, dev).pin_memory().numpy()
+    g = torch.Generator(device="cpu").manual_seed(sseed + 1)
+    new_rows = (torch.randint(-127, 128, (rounds * ins, dim), generator=g).float() / 128.0).pin_memory()
     for w in range(3):
         st.topk(qpin[w:w + 1], k)
     sampler = ClockSampler(0)
