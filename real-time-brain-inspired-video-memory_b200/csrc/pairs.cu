@@ -38,16 +38,28 @@ struct PairsParams {
     int part, nparts;
 };
 
-__device__ __forceinline__ void tile_coords(long long t, int &bi, int &bj)
-{
-    // group g holds 16(g+1) row blocks x 8 column blocks; 64 g (g+1) tiles precede it
-    long long g = (long long)((sqrt(1.0 + (double)t / 16.0) - 1.0) * 0.5);
-    while (64 * (g + 1) * (g + 2) <= t) ++g;
-    while (64 * g * (g + 1) > t) --g;
-    const long long r = t - 64 * g * (g + 1);
-    bi = (int)(r >> 3);
-    bj = (int)(g * P_GJ + (r & 7));
-}
+// Tile sequence of one CTA (pair): t = first, first + stride, ...  Tiles are numbered group by group;
+// group g holds GB*(g+1) row blocks x P_GJ column blocks (GB = 16 for 128-row blocks, 8 for 256-row
+// blocks), i.e. GB*P_GJ*(g+1) tiles.  The iterator keeps (group, offset in group) and advances with
+// integer arithmetic only -- this runs on the single MMA-issuing thread between tiles.
+template <int GB>
+struct TileIter {
+    long long t, stride, total;
+    long long g, r;  // group and offset of t inside it
+    __device__ __forceinline__ void init(long long first, long long stride_, long long total_)
+    {
+        t = first; stride = stride_; total = total_; g = 0; r = first;
+        settle();
+    }
+    __device__ __forceinline__ void settle()
+    {
+        while (r >= (long long)GB * P_GJ * (g + 1)) { r -= (long long)GB * P_GJ * (g + 1); ++g; }
+    }
+    __device__ __forceinline__ bool valid() const { return t < total; }
+    __device__ __forceinline__ void next() { t += stride; r += stride; settle(); }
+    __device__ __forceinline__ int bi() const { return (int)(r >> 3); }
+    __device__ __forceinline__ int bj() const { return (int)(g * P_GJ + (r & 7)); }
+};
 
 template <bool TF32>
 __global__ void __launch_bounds__(P_THREADS, 1)
@@ -87,11 +99,9 @@ pairs_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (long long u = blockIdx.x;; u += gridDim.x) {
-                const long long t = u * p.nparts + p.part;
-                if (t >= p.total_tiles) break;
-                int bi, bj;
-                tile_coords(t, bi, bj);
+            TileIter<16> ti;
+            for (ti.init((long long)blockIdx.x * p.nparts + p.part, (long long)gridDim.x * p.nparts, p.total_tiles); ti.valid(); ti.next()) {
+                const int bi = ti.bi(), bj = ti.bj();
                 if (!valid_tile(bi, bj)) continue;
                 for (int kb = 0; kb < p.KB; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -109,11 +119,9 @@ pairs_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             const uint32_t s0 = smem_u32(stages);
-            for (long long u = blockIdx.x;; u += gridDim.x) {
-                const long long t = u * p.nparts + p.part;
-                if (t >= p.total_tiles) break;
-                int bi, bj;
-                tile_coords(t, bi, bj);
+            TileIter<16> ti;
+            for (ti.init((long long)blockIdx.x * p.nparts + p.part, (long long)gridDim.x * p.nparts, p.total_tiles); ti.valid(); ti.next()) {
+                const int bi = ti.bi(), bj = ti.bj();
                 if (!valid_tile(bi, bj)) continue;
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -140,11 +148,9 @@ pairs_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int row_in_tile = quad * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (long long u = blockIdx.x;; u += gridDim.x) {
-            const long long t = u * p.nparts + p.part;
-            if (t >= p.total_tiles) break;
-            int bi, bj;
-            tile_coords(t, bi, bj);
+        TileIter<16> ti;
+        for (ti.init((long long)blockIdx.x * p.nparts + p.part, (long long)gridDim.x * p.nparts, p.total_tiles); ti.valid(); ti.next()) {
+            const int bi = ti.bi(), bj = ti.bj();
             if (!valid_tile(bi, bj)) continue;
             const long long i = (long long)bi * P_BM + row_in_tile;
             const long long j0 = (long long)bj * P_BN;
@@ -211,17 +217,6 @@ pairs_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // =========================================================================================
 static constexpr int P2_STAGES = 6, P2_STAGE_BYTES = 2 * P_A_BYTES;
 
-__device__ __forceinline__ void tile_coords2(long long t, int &bi, int &bj)
-{
-    // 256 x 256 tiles: group g holds 8(g+1) row blocks x 8 column blocks; 32 g (g+1) tiles precede it
-    long long g = (long long)((sqrt(1.0 + (double)t / 8.0) - 1.0) * 0.5);
-    while (32 * (g + 1) * (g + 2) <= t) ++g;
-    while (32 * g * (g + 1) > t) --g;
-    const long long r = t - 32 * g * (g + 1);
-    bi = (int)(r >> 3);
-    bj = (int)(g * P_GJ + (r & 7));
-}
-
 template <bool TF32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 pairs_tc2_kernel(const __grid_constant__ CUtensorMap tmA, PairsParams p)
@@ -259,11 +254,9 @@ pairs_tc2_kernel(const __grid_constant__ CUtensorMap tmA, PairsParams p)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (long long u = pair;; u += npairs) {
-                const long long t = u * p.nparts + p.part;
-                if (t >= p.total_tiles) break;
-                int bi, bj;
-                tile_coords2(t, bi, bj);
+            TileIter<8> ti;
+            for (ti.init((long long)pair * p.nparts + p.part, (long long)npairs * p.nparts, p.total_tiles); ti.valid(); ti.next()) {
+                const int bi = ti.bi(), bj = ti.bj();
                 if (!valid_tile(bi, bj)) continue;
                 for (int kb = 0; kb < p.KB; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -281,11 +274,9 @@ pairs_tc2_kernel(const __grid_constant__ CUtensorMap tmA, PairsParams p)
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             const uint32_t s0 = smem_u32(stages);
-            for (long long u = pair;; u += npairs) {
-                const long long t = u * p.nparts + p.part;
-                if (t >= p.total_tiles) break;
-                int bi, bj;
-                tile_coords2(t, bi, bj);
+            TileIter<8> ti;
+            for (ti.init((long long)pair * p.nparts + p.part, (long long)npairs * p.nparts, p.total_tiles); ti.valid(); ti.next()) {
+                const int bi = ti.bi(), bj = ti.bj();
                 if (!valid_tile(bi, bj)) continue;
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -312,11 +303,9 @@ pairs_tc2_kernel(const __grid_constant__ CUtensorMap tmA, PairsParams p)
         const int row_in_tile = quad * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (long long u = pair;; u += npairs) {
-            const long long t = u * p.nparts + p.part;
-            if (t >= p.total_tiles) break;
-            int bi, bj;
-            tile_coords2(t, bi, bj);
+        TileIter<8> ti;
+        for (ti.init((long long)pair * p.nparts + p.part, (long long)npairs * p.nparts, p.total_tiles); ti.valid(); ti.next()) {
+            const int bi = ti.bi(), bj = ti.bj();
             if (!valid_tile(bi, bj)) continue;
             const long long i = (long long)bi * 256 + rank * 128 + row_in_tile;
             const long long j0 = (long long)bj * 256;
