@@ -1,5 +1,5 @@
 import sys, time, torch, numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, ".")
 import vidmem_b200 as vm
 from vidmem_b200 import dedup
 from vidmem_b200.store import EmbeddingStore
