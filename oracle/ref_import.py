@@ -39,7 +39,14 @@ def _stub(name: str, **attrs) -> None:
         return
     m = types.ModuleType(name)
     m.__dict__.update(attrs)
-    m.__getattr__ = lambda attr: _Anything  # any other symbol resolves to a dummy class
+    def _missing(attr):
+        # any ordinary symbol resolves to a dummy class; dunders (__file__, __path__, ...) must stay absent so
+        # that tools which introspect sys.modules (hypothesis, importlib) see a normal, file-less module
+        if attr.startswith("__") and attr.endswith("__"):
+            raise AttributeError(attr)
+        return _Anything
+
+    m.__getattr__ = _missing
     sys.modules[name] = m
     if "." in name:
         parent, child = name.rsplit(".", 1)
