@@ -142,6 +142,49 @@ class ResidentChunkStore:
         if len(keys) > n:
             self.upsert((k, existing[k]) for k in keys[n:])
 
+    # -- persistence ------------------------------------------------------
+    def save(self, path: str) -> None:
+        """Binary sidecar next to the JSON export of src/components/graph_exporter.py:81-108: rows in the
+        store dtype, the skipped mask, the id table and the per-chunk metadata."""
+        import json
+        if self.store is None:
+            raise ValueError("nothing to save: the store has no rows yet")
+        self.store.save(path, ids=self.ids, extra={"meta": json.dumps(self.meta, ensure_ascii=False, default=str)})
+
+    @classmethod
+    def load(cls, path: str, device: int = 0, initial_capacity: int = 8192) -> "ResidentChunkStore":
+        """Re-hydrates the HBM store from a sidecar: bit-identical rows, same row order, same ids."""
+        import json
+        from .store import EmbeddingStore
+        st, ids, extra = EmbeddingStore.load(path, capacity=None, device=device, with_extra=True, min_capacity=initial_capacity)
+        self = cls("bf16" if st.dtype_code == L.VM_BF16 else "f32", device, initial_capacity)
+        self.store, self.dim = st, st.dim
+        if len(ids) != len(st):
+            raise ValueError(f"sidecar holds {len(st)} rows but {len(ids)} ids")
+        self.ids = list(ids)
+        self.row_of = {c: i for i, c in enumerate(self.ids)}
+        self.meta = json.loads(extra.get("meta", "{}"))
+        return self
+
+    def load_export(self, export: Any) -> int:
+        """Hydrates from a graph export (the dict GraphExporter.export_graph writes, or its path;
+        src/components/graph_exporter.py:59-68): every node labelled Chunk with an id and a list-valued
+        embedding -- the filter of _get_chunk_embeddings (pre_llm_injector.py:394-409) -- in file order.
+        -> number of chunk rows taken."""
+        import json
+        if isinstance(export, (str, bytes)) or hasattr(export, "__fspath__"):
+            with open(export, "r", encoding="utf-8") as f:
+                export = json.load(f)
+        items, meta = [], {}
+        for node in export.get("nodes", []):
+            props = node.get("properties") or {}
+            cid, emb = props.get("id"), props.get("embedding")
+            if "Chunk" in (node.get("labels") or []) and cid and isinstance(emb, list):
+                items.append((cid, emb))
+                meta[cid] = {"content": props.get("content"), "time": props.get("time")}
+        self.upsert(items, meta=meta)
+        return len(items)
+
     # -- queries ---------------------------------------------------------------------------------
     def topk(self, queries: Sequence[Any], k: int, min_score: float = -math.inf, score_mode: int = L.VM_SCORE_RAW,
              flags: int = 0):
@@ -174,7 +217,7 @@ class ChunkSimilarityBackend:
     (src/components/pre_llm_injector.py:346-388) plus the cross-query merge (:235-249)."""
 
     def __init__(self, store: Optional[ResidentChunkStore] = None, mirror_fetch: bool = True, **store_kw):
-        self.store = store or ResidentChunkStore(**store_kw)
+        self.store = store if store is not None else ResidentChunkStore(**store_kw)
         #: True  = behave exactly like the reference: fetch `{id: embedding}` through the injector's own
         #:         _get_chunk_embeddings (LIMIT 5000) on every call and mirror it into HBM;
         #: False = rows arrive only through the insert hook; no Bolt fetch on the query path (row f1).
@@ -187,6 +230,41 @@ class ChunkSimilarityBackend:
             self.store.sync_from_dict(existing)
         k = injector.embedder_config.top_k_chunk_with_batch_similarity      # (:370)
         return self.store.topk(list(chunk_embeddings), k)
+
+    # row f1: one bulk read instead of a full fetch per batch
+    HYDRATE_QUERY = """
+        MATCH (c:Chunk:GraphNode)
+        WHERE c.graph_uuid = $graph_uuid AND c.id IS NOT NULL AND c.embedding IS NOT NULL
+        RETURN c.id as chunk_id, c.embedding as embedding, c.content as content
+    """
+
+    async def hydrate(self, neo4j_handler, limit: Optional[int] = None, page_rows: int = 4096) -> int:
+        """Fills the resident store once from Neo4j with the MATCH/WHERE/RETURN of the reference's
+        _get_chunk_embeddings (src/components/pre_llm_injector.py:394-399) -- without its `LIMIT 5000`
+        unless `limit` is given -- streaming the result in pages of `page_rows` rows so that no
+        Python dict of the whole store is ever built.  Row order = the order Neo4j returns, exactly as
+        in the reference.  Afterwards the query path needs no Bolt fetch (mirror_fetch is switched
+        off); new rows arrive through on_chunks_inserted.  -> rows read."""
+        query = self.HYDRATE_QUERY + (f"        LIMIT {int(limit)}\n" if limit is not None else "")
+        total = 0
+        self.store.clear()
+        async with neo4j_handler.driver.session() as session:
+            result = await session.run(query, graph_uuid=neo4j_handler.run_uuid)
+            page, meta = [], {}
+            async for record in result:
+                chunk_id, embedding = record["chunk_id"], record["embedding"]
+                if isinstance(embedding, list) and chunk_id:               # the reference's row filter (:405)
+                    page.append((chunk_id, embedding))
+                    meta[chunk_id] = {"content": record.get("content") if hasattr(record, "get") else None, "time": None}
+                    if len(page) >= page_rows:
+                        self.store.upsert(page, meta=meta)
+                        total += len(page)
+                        page, meta = [], {}
+            if page:
+                self.store.upsert(page, meta=meta)
+                total += len(page)
+        self.mirror_fetch = False
+        return total
 
     # S2
     def _cosine_similarity(self, vec1: List[float], vec2: List[float]) -> float:

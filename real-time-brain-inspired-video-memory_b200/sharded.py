@@ -104,3 +104,120 @@ class Communicator:
         if self.handle:
             self.lib.vm_comm_destroy(self.handle)
             self.handle = None
+
+
+class ShardedChunkStore:
+    """Streaming inserts over the GPUs of one box ("streaming inserts"): every rank runs
+    the same call sequence (SPMD); each insert batch's NEW ids go to the least-full rank as one
+    block, an id that is already known is overwritten on the rank that owns it (the reference
+    MERGEs by id, src/components/neo4j_handler.py:229).  No collective on the insert path.
+
+    Every rank keeps the whole id table (global row -> chunk id, owner rank); only the owner holds
+    the embedding in HBM.  Global row == first-seen order over all ranks == the reference's dict
+    insertion order, so the tie rule "earliest row wins"  holds across shards: local
+    rows are in increasing global order, and the cross-rank merge orders by (score desc, global
+    row asc).
+
+    Queries: local exact top-k (vm_topk) -> local rows renamed to global rows -> ONE all-gather of
+    the [nq][k] lists -> device merge (vm_merge_topk_lists); identical results on every rank.
+    Exposes the ResidentChunkStore surface the adapters use (upsert / sync_from_dict / topk / ids /
+    row_of / meta / device), so it plugs into ChunkSimilarityBackend and VectorSearchBackend."""
+
+    def __init__(self, dtype: str = "f32", device: int = 0, rank: int = None, world: int = None, group=None,
+                 initial_capacity: int = 8192):
+        import torch.distributed as dist
+        from .adapters import ResidentChunkStore
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else int(rank)
+        self.world = dist.get_world_size(group) if world is None else int(world)
+        self.device = device
+        self.local = ResidentChunkStore(dtype, device, initial_capacity)
+        self.ids: List[str] = []            # global row -> chunk id
+        self.row_of = {}                    # chunk id -> global row
+        self.owner: List[int] = []          # global row -> rank
+        self.load = [0] * self.world        # rows per rank
+        self.meta = self.local.meta         # replicated on every rank (host only)
+
+    def __len__(self) -> int:
+        return len(self.ids)
+
+    def clear(self) -> None:
+        self.local.clear()
+        self.ids, self.row_of, self.owner = [], {}, []
+        self.load = [0] * self.world
+
+    def upsert(self, items, meta=None) -> None:
+        items = list(items)
+        fresh = [cid for cid, _ in items if cid not in self.row_of]
+        fresh = list(dict.fromkeys(fresh))  # an id repeated inside one batch is one row
+        target = min(range(self.world), key=lambda r: (self.load[r], r)) if fresh else -1
+        for cid in fresh:
+            self.row_of[cid] = len(self.ids)
+            self.ids.append(cid)
+            self.owner.append(target)
+        if fresh:
+            self.load[target] += len(fresh)
+        mine = [(cid, emb) for cid, emb in items if self.owner[self.row_of[cid]] == self.rank]
+        if mine:
+            self.local.upsert(mine)
+        if meta:
+            self.meta.update(meta)
+
+    def sync_from_dict(self, existing) -> None:
+        keys = list(existing.keys())
+        n = len(self.ids)
+        if keys[:n] != self.ids:
+            self.clear()
+            n = 0
+        if len(keys) > n:
+            self.upsert((k, existing[k]) for k in keys[n:])
+
+    # -- the exchange -------------------------------------------------------------------------
+    def _gather(self, idx: np.ndarray, score: np.ndarray, count: np.ndarray):
+        """One all-gather of this rank's lists; -> per-rank (idx, score, count), idx global."""
+        import torch
+        import torch.distributed as dist
+        nq, k = idx.shape
+        packed = np.concatenate([idx.reshape(-1), score.reshape(-1).view(np.int64), count.astype(np.int64)])
+        on_gpu = dist.get_backend(self.group) == "nccl"
+        t = torch.from_numpy(packed)
+        if on_gpu:
+            t = t.to(torch.device("cuda", self.device))
+        out = torch.empty((self.world * packed.size,), dtype=torch.int64, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=self.group)
+        return out.view(self.world, packed.size), nq, k
+
+    def _merge(self, gathered, nq: int, k: int):
+        """Device merge of the gathered lists (vm_merge_topk_lists): (score desc, global row asc)."""
+        import torch
+        lib = L.load()
+        dev = torch.device("cuda", self.device)
+        g = gathered.to(dev)
+        idx = g[:, :nq * k].contiguous()
+        score = g[:, nq * k:2 * nq * k].contiguous().view(torch.float64)
+        count = g[:, 2 * nq * k:].to(torch.int32).contiguous()
+        o_idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        o_score = torch.empty((nq, k), dtype=torch.float64, device=dev)
+        o_count = torch.empty((nq,), dtype=torch.int32, device=dev)
+        L.check(lib.vm_merge_topk_lists(self.device, idx.data_ptr(), score.data_ptr(), count.data_ptr(), self.world, nq, k,
+                                        o_idx.data_ptr(), o_score.data_ptr(), o_count.data_ptr(),
+                                        torch.cuda.current_stream(dev).cuda_stream))
+        return o_idx.cpu().numpy(), o_score.cpu().numpy(), o_count.cpu().numpy()
+
+    def topk(self, queries, k: int, min_score: float = -np.inf, score_mode: int = L.VM_SCORE_RAW, flags: int = 0):
+        """Same contract as ResidentChunkStore.topk: list (per query) of [(chunk_id, score)]."""
+        queries = list(queries)
+        nq = len(queries)
+        if nq == 0 or not self.ids:
+            return [[] for _ in queries]
+        local = self.local.topk(queries, k, min_score=min_score, score_mode=score_mode, flags=flags)
+        idx = np.full((nq, k), -1, np.int64)
+        score = np.zeros((nq, k), np.float64)
+        count = np.zeros(nq, np.int32)
+        for i, lst in enumerate(local):
+            count[i] = len(lst)
+            for j, (cid, s) in enumerate(lst):
+                idx[i, j], score[i, j] = self.row_of[cid], s
+        gathered, nq, k = self._gather(idx, score, count)
+        m_idx, m_score, m_count = self._merge(gathered, nq, k)
+        return [[(self.ids[int(m_idx[i, j])], float(m_score[i, j])) for j in range(int(m_count[i]))] for i in range(nq)]

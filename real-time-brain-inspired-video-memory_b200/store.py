@@ -140,26 +140,31 @@ class EmbeddingStore:
                                        dup_period, _stream_ptr(self.device)))
 
     # -- persistence (binary sidecar instead of JSON float lists) ---------------------
-    def save(self, path: str, ids: Optional[Sequence[str]] = None) -> None:
+    def save(self, path: str, ids: Optional[Sequence[str]] = None, extra: Optional[dict] = None) -> None:
         """Writes the resident rows as a binary sidecar: `<path>.npz` with the raw row values in the
-        store dtype (bf16 as uint16 bit patterns), the skipped-row mask and, optionally, the chunk ids.
-        The JSON export of src/components/graph_exporter.py:81-108 stores embeddings as float lists;
-        this is the same information without float parsing."""
+        store dtype (bf16 as uint16 bit patterns), the skipped-row mask and, optionally, the chunk ids
+        and caller strings (`extra`: name -> str).  The JSON export of
+        src/components/graph_exporter.py:81-108 stores embeddings as float lists; this is the same
+        information without float parsing.  Plain arrays only -- nothing in the file is pickled."""
         n = len(self)
         rows = self.rows[:n, :self.dim].contiguous()
         raw = rows.view(torch.int16).cpu().numpy().view(np.uint16) if self.dtype_code == L.VM_BF16 else rows.cpu().numpy()
         skipped = (self.inv_norms[:n] < 0).cpu().numpy()
-        np.savez(path, rows=raw, skipped=skipped, dim=self.dim, dtype=self.dtype_code,
-                 ids=np.asarray(list(ids) if ids is not None else [], dtype=object))
+        arrays = {"rows": raw, "skipped": skipped, "dim": np.int64(self.dim), "dtype": np.int64(self.dtype_code),
+                  "ids": np.asarray([str(x) for x in ids] if ids is not None else [], dtype=np.str_)}
+        for name, text in (extra or {}).items():
+            arrays["extra_" + name] = np.frombuffer(str(text).encode("utf-8"), dtype=np.uint8)
+        np.savez(path, **arrays)
 
     @classmethod
-    def load(cls, path: str, capacity: Optional[int] = None, device: int = 0):
-        """-> (store, ids).  Bit-identical rows, same skipped rows, same order."""
-        z = np.load(path if path.endswith(".npz") else path + ".npz", allow_pickle=True)
+    def load(cls, path: str, capacity: Optional[int] = None, device: int = 0, with_extra: bool = False,
+             min_capacity: int = 1):
+        """-> (store, ids) or (store, ids, extra).  Bit-identical rows, same skipped rows, same order."""
+        z = np.load(path if path.endswith(".npz") else path + ".npz", allow_pickle=False)
         dim, code = int(z["dim"]), int(z["dtype"])
         raw = z["rows"]
         n = raw.shape[0]
-        st = cls(dim, max(int(capacity or n), 1), "bf16" if code == L.VM_BF16 else "f32", device)
+        st = cls(dim, max(int(capacity or n), int(min_capacity), 1), "bf16" if code == L.VM_BF16 else "f32", device)
         if n:
             if code == L.VM_BF16:
                 t = torch.from_numpy(raw.view(np.int16).copy()).view(torch.bfloat16)
@@ -169,7 +174,11 @@ class EmbeddingStore:
             bad = np.nonzero(z["skipped"])[0]
             if len(bad):
                 st.invalidate(bad)
-        return st, [str(x) for x in z["ids"].tolist()]
+        ids = [str(x) for x in z["ids"].tolist()]
+        if not with_extra:
+            return st, ids
+        extra = {k[len("extra_"):]: bytes(z[k].tobytes()).decode("utf-8") for k in z.files if k.startswith("extra_")}
+        return st, ids, extra
 
     # -- reads ------------------------------------------------------------------------------
     def topk(self, queries, k: int, min_score: float = -math.inf, score_mode: int = L.VM_SCORE_RAW,

@@ -1,0 +1,43 @@
+"""Test doubles shared by the CPU suites (never imported by the product)."""
+import numpy as np
+
+from oracle import oracle
+
+
+class OracleBackedStore:
+    """Stands in for vidmem_b200.store.EmbeddingStore inside ResidentChunkStore (tests only)."""
+
+    def __init__(self, dim, capacity, dtype="f32", device=0):
+        self.dim, self.capacity = dim, capacity
+        self.X = np.zeros((0, dim))
+        self.ok = np.zeros(0, np.uint8)
+
+    def __len__(self):
+        return len(self.X)
+
+    def append(self, rows):
+        first = len(self.X)
+        rows = np.asarray(rows, np.float64).astype(np.float32).astype(np.float64)   # fp32 store rounding
+        self.X = np.concatenate([self.X, rows]); self.ok = np.concatenate([self.ok, np.ones(len(rows), np.uint8)])
+        return first
+
+    def update(self, row0, rows):
+        self.X[row0:row0 + len(rows)] = np.asarray(rows, np.float64).astype(np.float32); self.ok[row0:row0 + len(rows)] = 1
+
+    def invalidate(self, rows):
+        self.ok[list(rows)] = 0
+
+    def clear(self):
+        self.X = self.X[:0]; self.ok = self.ok[:0]
+
+    def topk(self, q, k, min_score=-np.inf, score_mode=0, flags=0):
+        res = oracle.batch_similarities(q, self.X, k, row_ok=self.ok)
+        idx = np.full((len(q), k), -1, np.int64); sc = np.zeros((len(q), k)); cnt = np.zeros(len(q), np.int32)
+        for i, lst in enumerate(res):
+            cnt[i] = len(lst)
+            for j, (r, s) in enumerate(lst):
+                idx[i, j], sc[i, j] = r, s
+        return idx, sc, cnt
+
+    def close(self):
+        pass

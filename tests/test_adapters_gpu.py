@@ -139,3 +139,38 @@ def test_ids_before_first_embedding_and_boundaries(ad):
     store.upsert([("a", [float(v) for v in X[4]])])                 # the failed chunk is re-embedded later (MERGE by id)
     got = store.topk([[float(v) for v in X[4]]], 2)[0]
     assert [g[0] for g in got] == ["a", "c4"] and got[0][1] == got[1][1] == oracle.cosine(X[4], X[4])
+
+
+def test_f1_hydrate_and_f3_sidecar_roundtrip(ad, tmp_path):
+    """Bulk hydration from a (fake) Neo4j session, then save -> load of the resident store: same ids, bit-identical
+    answers; and re-hydration from a JSON graph export."""
+    import json
+    from test_hydrate_cpu import _Handler, _records
+    n, d, k = 700, 64, 5
+    X, recs = _records(n, d)
+    backend = ad.ChunkSimilarityBackend(initial_capacity=64)               # forces several growth steps
+    assert asyncio.run(backend.hydrate(_Handler(recs), page_rows=128)) == n - 2
+    kept = [r for r in recs if isinstance(r["embedding"], list) and r["chunk_id"]]
+    Q = _lists(synth.synth_queries(6, 4, d, 5, n))
+    want = oracle.batch_similarities(np.array(Q), np.array([r["embedding"] if r["embedding"] else [0.0] * d for r in kept]), k,
+                                     row_ok=np.array([1 if r["embedding"] else 0 for r in kept], np.uint8))
+    want = [[(kept[r]["chunk_id"], s) for r, s in lst] for lst in want]
+    assert backend.store.topk(Q, k) == want
+    for dt in ("f32", "bf16"):
+        src = backend.store if dt == "f32" else ad.ResidentChunkStore("bf16")
+        if dt == "bf16":
+            src.upsert([(r["chunk_id"], r["embedding"]) for r in kept])
+        p = str(tmp_path / f"chunks_{dt}")
+        src.save(p)
+        back = ad.ResidentChunkStore.load(p)
+        assert back.ids == src.ids and back.dtype == dt and back.meta == src.meta
+        assert back.topk(Q, k) == src.topk(Q, k)
+        fresh = _lists(synth.synth_rows(99, 0, 1, d))
+        back.upsert([("late", fresh[0])])                                  # still growable after a load
+        assert back.topk(fresh, 1)[0][0][0] == "late"
+    nodes = [{"name": None, "labels": ["Chunk"], "properties": {"id": r["chunk_id"], "content": r["content"], "embedding": r["embedding"]}}
+             for r in kept]
+    path = tmp_path / "export.json"
+    path.write_text(json.dumps({"graph_uuid": "g", "nodes": nodes, "relationships": []}))
+    st = ad.ResidentChunkStore()
+    assert st.load_export(str(path)) == len(kept) and st.topk(Q, k) == want

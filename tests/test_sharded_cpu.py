@@ -83,3 +83,75 @@ def test_world_size_2_gloo(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, 2001, 64, 5, 10, str(tmp_path)), nprocs=2, join=True)
     assert sorted(os.listdir(tmp_path)) == ["rank0.ok", "rank1.ok"]
+
+
+def _stream_scenario(d=48):
+    """Insert batches (ids, rows) + queries shared by the CPU (gloo) and the 2-GPU test."""
+    X = synth.synth_rows(31, 0, 200, d)
+    batches, row = [], 0
+    for b, size in enumerate((5, 40, 3, 17, 64, 1, 30)):
+        items = [(f"u_{b}_{i}", [float(v) for v in X[row + i]]) for i in range(size)]
+        row += size
+        batches.append(items)
+    batches[3][2] = ("u_3_2", [])                                         # falsy embedding: a skipped row (:363)
+    batches[5][0] = ("u_5_0", batches[0][1][1])                           # duplicate of an earlier row -> a cross-rank tie
+    batches.append([("u_1_7", [float(v) for v in X[190]]), ("u_7_0", [float(v) for v in X[191]])])  # upsert + new
+    Q = synth.synth_queries(32, 6, d, 31, 160)
+    Q[0] = X[1]
+    Q[1] = X[190]
+    return batches, [[float(v) for v in q] for q in Q]
+
+
+def _stream_expected(batches, queries, k):
+    order, emb = [], {}
+    for items in batches:
+        for cid, e in items:
+            if cid not in emb:
+                order.append(cid)
+            emb[cid] = e
+    d = len(queries[0])
+    Xg = np.array([emb[c] if emb[c] else [0.0] * d for c in order], np.float64).astype(np.float32).astype(np.float64)
+    ok = np.array([1 if emb[c] else 0 for c in order], np.uint8)
+    ref = oracle.batch_similarities(np.array(queries), Xg, k, row_ok=ok)
+    return [[(order[r], s) for r, s in lst] for lst in ref], order
+
+
+def _stream_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import vidmem_b200.store as vstore
+    from vidmem_b200 import sharded
+    from doubles import OracleBackedStore
+    vstore.EmbeddingStore = OracleBackedStore                            # no GPU here: the oracle answers for the shard
+
+    def host_merge(self, gathered, nq, k):                               # stands in for vm_merge_topk_lists
+        g = gathered.numpy()
+        lists = [(g[r, :nq * k].reshape(nq, k), g[r, nq * k:2 * nq * k].copy().view(np.float64).reshape(nq, k),
+                  g[r, 2 * nq * k:].astype(np.int32)) for r in range(g.shape[0])]
+        return sharded.merge_lists_host(lists, k)
+
+    sharded.ShardedChunkStore._merge = host_merge
+    batches, queries = _stream_scenario()
+    st = sharded.ShardedChunkStore("f32", device=0)
+    for items in batches:
+        st.upsert(items)
+    k = 4
+    got = st.topk(queries, k)
+    want, order = _stream_expected(batches, queries, k)
+    ok = got == want and st.ids == order
+    ok = ok and [c for c, _ in got[0][:2]] == ["u_0_1", "u_5_0"]          # the tie resolves to the earlier global row
+    ok = ok and got[1][0][0] == "u_1_7"                                   # the overwritten row answers with its new vector
+    ok = ok and sorted(set(st.owner)) == [0, 1] and abs(st.load[0] - st.load[1]) <= 64
+    ok = ok and len(st.local) == st.load[rank]
+    open(os.path.join(out_dir, f"rank{rank}.ok" if ok else f"rank{rank}.bad"), "w").write("x")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_streaming_inserts_world_size_2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_stream_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["rank0.ok", "rank1.ok"]

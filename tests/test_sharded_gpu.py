@@ -76,6 +76,17 @@ def _worker(rank, world, port, out_dir):
     gi, gj, gs = dedup.pairs_above_sharded(x, 0.9)
     oi, oj, _ = oracle.pairs_above(E, 0.9)
     ok = ok and len(oi) > 0 and list(zip(gi.tolist(), gj.tolist())) == list(zip(oi.tolist(), oj.tolist()))
+    # streaming inserts routed over the ranks + one all-gather + vm_merge_topk_lists
+    from vidmem_b200.sharded import ShardedChunkStore
+    from test_sharded_cpu import _stream_scenario, _stream_expected
+    batches, queries = _stream_scenario()
+    for dt in ("f32", "bf16"):
+        sst = ShardedChunkStore(dt, device=rank)
+        for items in batches:
+            sst.upsert(items)
+        got = sst.topk(queries, 4)
+        want, order = _stream_expected(batches, queries, 4)                 # values are exact in bf16 too (ints / 128)
+        ok = ok and got == want and sst.ids == order and len(sst.local) == sst.load[rank]
     open(os.path.join(out_dir, f"rank{rank}.ok" if ok else f"rank{rank}.bad"), "w").write("x")
     dist.barrier()
     comm.close()
