@@ -31,7 +31,8 @@ int k_synth_fill(void *rows, int dtype, uint64_t seed, int64_t row0, int64_t n, 
 int k_merge_candidates(const uint64_t *cand, int lists, int nq, int kp, uint64_t *merged, cudaStream_t st);
 
 int k_rescore(const RescoreArgs &a, cudaStream_t st);
-int k_select_rescore(const uint64_t *cand, int lists, const RescoreArgs &a, cudaStream_t st);
+int k_select_rescore(const uint64_t *cand, int lists, int list_len, const RescoreArgs &a, cudaStream_t st);
+bool select_rescore_fits(int lists, int list_len, int kp, int dtype, int dim, int ld);
 int k_collect_rescore(const uint64_t *buf, const int *cnt, int cap, const RescoreArgs &a, cudaStream_t st);
 int k_exact(const ExactArgs &a, cudaStream_t st);
 int k_merge_topk_lists(const void *idx, const void *score, const void *count, size_t stride_bytes, int lists, int nq, int k,
@@ -535,6 +536,10 @@ static int topk_batch(const TopkCall &c)
     } else {
         int64_t tiles = (s->size + 127) / 128;
         a.ctas = (int)imin64(tiles, s->sm_count);
+        // small store: too few tiles per CTA for a threshold to form -> rank every row's key instead
+        a.dump = tiles <= s->sm_count && tiles * SCAN_DUMP_TILE <= SCAN_DUMP_MAX_KEYS &&
+                 (size_t)tiles * c.nq * SCAN_DUMP_TILE * 8 <= w.cand.bytes &&
+                 select_rescore_fits((int)tiles, SCAN_DUMP_TILE, kp, s->dtype, s->dim, s->ld);
         rc = launch_scan_tc(a, s->dtype == VM_BF16 ? w.q_bf16.p : w.q_f32.p, (uint32_t *)w.seed.p, (int *)w.flags.p + c.nq + 1);
         launches += 1;
     }
@@ -546,8 +551,8 @@ static int topk_batch(const TopkCall &c)
     RescoreArgs rs{(const uint64_t *)w.merged.p, kp, s->rows, s->inv_norms, s->dtype, s->ld, s->dim, s->size, q_dev,
                    c.q_dtype, c.nq, scan_eps(kernel, s->dtype, s->dim), c.sum_mode, fin, flags, uncert, s->extreme,
                    kernel == 2 ? (float *)w.col_thr.p : nullptr};
-    rc = k_select_rescore(a.cand, a.ctas, rs, st);  // fused merge + exact rescoring
-    if (rc == VM_ERR_UNSUPPORTED) {                 // rows too large for shared memory: two kernels
+    rc = k_select_rescore(a.cand, a.ctas, a.dump ? SCAN_DUMP_TILE : kp, rs, st);  // fused merge + exact rescoring
+    if (rc == VM_ERR_UNSUPPORTED && !a.dump) {                 // rows too large for shared memory: two kernels
         rc = k_merge_candidates(a.cand, a.ctas, c.nq, kp, (uint64_t *)w.merged.p, st);
         if (rc != VM_OK) return rc;
         rc = k_rescore(rs, st);

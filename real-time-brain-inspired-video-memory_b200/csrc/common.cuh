@@ -152,7 +152,10 @@ struct ScanArgs {
     uint64_t *cand;          // [ctas][nq][kp] keys out
     int ctas;                // number of CTAs to launch (lists produced)
     cudaStream_t stream;
+    int dump = 0;            // tcgen05 scan only: small store -- emit EVERY row's key, cand = [tiles][nq][128] (see scan_tc.cu)
 };
+static constexpr int SCAN_DUMP_TILE = 128;     // rows (= keys per query) per dumped tile
+static constexpr int SCAN_DUMP_MAX_KEYS = 9472;  // per query: what the fused select kernel ranks in shared memory (148 x 64)
 int launch_scan_simt(const ScanArgs &a);
 int scan_simt_max_queries();
 // second pass of the tcgen05 scan for uncertified queries (see scan_tc.cu "collect mode")

@@ -26,6 +26,11 @@
 // Collect mode (second pass for queries the first pass could not certify): thresholds are fixed per
 // query (exact k-th candidate score - 2 eps; +inf for queries that need nothing) and every row at or
 // above its query's threshold is appended to that query's global buffer -- no lists, no drains.
+// Dump mode (template DUMP, stores of <= 9472 rows): with one or two tiles per CTA there is no
+// threshold to filter with -- every row of a first tile is a "survivor" and the serial per-query
+// drain dominates (measured 82 us for 5000 rows x 30 queries).  Instead the epilogue writes the
+// key of EVERY row, [tile][query][128], and select.cu ranks all of them per query; nothing is
+// dropped before the exact rescoring, so the certification bound is the kp-th best approximate score.
 #include "tc_common.cuh"
 #include <stdlib.h>
 
@@ -81,13 +86,13 @@ static TcLayout make_layout(int dtype, int ld, int nq, int kp)
     return L;
 }
 
-template <bool TF32>
+template <bool TF32, bool DUMP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const float *__restrict__ inv_norms, int64_t n, int num_tiles, int nq, TcLayout L, uint64_t *__restrict__ cand,
                uint32_t *__restrict__ seed_tab, int *__restrict__ seed_ctr, int dbg, CollectArgs col)
 {
-    const bool collect = col.thr != nullptr;
+    const bool collect = !DUMP && col.thr != nullptr;
     if (collect && *col.pending == 0) return;  // nothing left to refine (uniform across the grid)
 
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -191,6 +196,29 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float my_seed = -INFINITY;        // seeded lower bound of query e
         int acc = 0, par = 0;
         uint32_t acc_phase = 0;
+        if constexpr (DUMP) {
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int64_t r = (int64_t)tile * TC_BLOCK_M + row_in_tile;
+                const float iv = r < n ? __ldg(inv_norms + r) : -1.0f;
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * nq_pad);
+                uint64_t *out = cand + (int64_t)tile * nq * TC_BLOCK_M + row_in_tile;
+                for (int c = 0; c < nq_pad; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c + j < nq)  // coalesced: 32 consecutive rows of one query per warp store
+                            out[(int64_t)(c + j) * TC_BLOCK_M] = iv >= 0.0f ? make_key(__uint_as_float(v[j]) * iv, (uint32_t)r) : 0ull;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1; }
+            }
+        } else {
         if (seed_tab != nullptr && !collect) {
             // ---- cooperative threshold seeding from the first tile (see file header) ----
             uint32_t *wmax = reinterpret_cast<uint32_t *>(queue);  // [4][nq_pad] scratch (queue is idle now)
@@ -364,6 +392,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int q = i / kp, j = i - q * kp;
             cand[((int64_t)blockIdx.x * nq + q) * kp + j] = list[j * nq_pad + q];
         }
+        }  // !DUMP
     }
 
     tc_fence_before();
@@ -407,15 +436,22 @@ int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t 
     if (!seed || sc) { seed_tab = nullptr; seed_ctr = nullptr; }
     CollectArgs col{};
     if (sc) { col.thr = sc->thr; col.buf = sc->buf; col.cnt = sc->cnt; col.cap = sc->cap; col.pending = sc->pending; }
-    if (a.dtype == VM_F32) {
-        static bool set[64] = {};  // the attribute is per device
-        if (!set[dev_idx]) { VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set[dev_idx] = true; }
-        scan_tc_kernel<true><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, seed_tab, seed_ctr, dbg, col);
-    } else {
-        static bool set[64] = {};  // the attribute is per device
-        if (!set[dev_idx]) { VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set[dev_idx] = true; }
-        scan_tc_kernel<false><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, seed_tab, seed_ctr, dbg, col);
-    }
+    const bool dump = a.dump && !sc;
+    if (dump) VM_REQUIRE(TC_BLOCK_M == SCAN_DUMP_TILE && (int64_t)num_tiles * TC_BLOCK_M <= SCAN_DUMP_MAX_KEYS && a.ctas == num_tiles,
+                         VM_ERR_UNSUPPORTED, "tcgen05 scan: dump mode needs one CTA per tile and at most %d rows", SCAN_DUMP_MAX_KEYS);
+#define LAUNCH_TC(TF, DU)                                                                                                  \
+    do {                                                                                                                   \
+        static bool set[64] = {}; /* the attribute is per device */                                                        \
+        if (!set[dev_idx]) {                                                                                               \
+            VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<TF, DU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            set[dev_idx] = true;                                                                                           \
+        }                                                                                                                  \
+        scan_tc_kernel<TF, DU><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, \
+                                                                          seed_tab, seed_ctr, dbg, col);                  \
+    } while (0)
+    if (a.dtype == VM_F32) { if (dump) LAUNCH_TC(true, true); else LAUNCH_TC(true, false); }
+    else { if (dump) LAUNCH_TC(false, true); else LAUNCH_TC(false, false); }
+#undef LAUNCH_TC
     VM_CUDA_CHECK(cudaGetLastError());
     return VM_OK;
 }

@@ -395,7 +395,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 static constexpr int SR_THREADS = 512;
 template <bool NEUMAIER, typename T>
-__global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uint64_t *__restrict__ cand, int lists, int nq, int kp,
+__global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uint64_t *__restrict__ cand, int lists, int list_len, int nq, int kp,
                                                                    const T *__restrict__ rows, int ld, int dim, int64_t n_rows,
                                                                    const void *__restrict__ queries, int q_dtype, double eps,
                                                                    FinalizeArgs f, int32_t *__restrict__ flags,
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uin
                                                                    const int *__restrict__ extreme, float *__restrict__ collect_thr)
 {
     extern __shared__ __align__(16) unsigned char sr_smem[];
-    const int total = lists * kp;
+    const int total = lists * list_len;  // list_len == kp for per-CTA top-kp lists, 128 for dumped tiles
     uint64_t *skeys = reinterpret_cast<uint64_t *>(sr_smem);                       // [total]
     uint32_t *lmax = reinterpret_cast<uint32_t *>(skeys + total);                  // [lists] (+pad)
     double *sq = reinterpret_cast<double *>(lmax + ((lists + 3) & ~3));            // [dim]
@@ -424,8 +424,8 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uin
     int nz = 0;
 #pragma unroll 10
     for (int e = tid; e < total; e += SR_THREADS) {
-        const int l = e / kp, j = e - l * kp;
-        const uint64_t k = cand[((int64_t)l * nq + q) * kp + j];
+        const int l = e / list_len, j = e - l * list_len;
+        const uint64_t k = cand[((int64_t)l * nq + q) * list_len + j];
         skeys[e] = k;
         nz += k != 0;
     }
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uin
     if (nonzero >= kp && lists >= kp && lists <= 256) {
         for (int l = warp; l < lists; l += SR_THREADS / 32) {
             uint32_t m = 0;
-            for (int j = lane; j < kp; j += 32) m = max(m, (uint32_t)(skeys[l * kp + j] >> 32));
+            for (int j = lane; j < list_len; j += 32) m = max(m, (uint32_t)(skeys[l * list_len + j] >> 32));
             m = __reduce_max_sync(0xffffffffu, m);
             if (lane == 0) lmax[l] = m;
         }
@@ -1067,12 +1067,20 @@ int k_rescore(const RescoreArgs &a, cudaStream_t st)
 // Fused path when the candidate keys + kp whole rows fit in shared memory; otherwise the caller falls
 // back to k_merge_candidates + k_rescore.  Returns VM_ERR_UNSUPPORTED (without setting an error the
 // caller must report) when it does not apply.
-int k_select_rescore(const uint64_t *cand, int lists, const RescoreArgs &a, cudaStream_t st)
+bool select_rescore_fits(int lists, int list_len, int kp, int dtype, int dim, int ld)
+{
+    const int es = dtype == VM_F32 ? 4 : 2;
+    const size_t smem = (size_t)lists * list_len * 8 + (size_t)((lists + 3) & ~3) * 4 + (size_t)((dim + 1) & ~1) * 8 +
+                        (size_t)kp * ((size_t)ld * es + 16) + 32;
+    return smem <= 180 * 1024 && kp <= 64 && 2 * kp + 1 <= SR_THREADS;
+}
+
+int k_select_rescore(const uint64_t *cand, int lists, int list_len, const RescoreArgs &a, cudaStream_t st)
 {
     const int es = a.dtype == VM_F32 ? 4 : 2;
-    const size_t smem = (size_t)lists * a.kp * 8 + (size_t)((lists + 3) & ~3) * 4 + (size_t)((a.dim + 1) & ~1) * 8 +
+    const size_t smem = (size_t)lists * list_len * 8 + (size_t)((lists + 3) & ~3) * 4 + (size_t)((a.dim + 1) & ~1) * 8 +
                         (size_t)a.kp * ((size_t)a.ld * es + 16) + 32;
-    if (smem > 180 * 1024 || a.kp > 64 || 2 * a.kp + 1 > SR_THREADS) return VM_ERR_UNSUPPORTED;
+    if (!select_rescore_fits(lists, list_len, a.kp, a.dtype, a.dim, a.ld)) return VM_ERR_UNSUPPORTED;
 #define LAUNCH_SR(NEU, T)                                                                                              \
     do {                                                                                                               \
         static bool attr_set_dev[64] = {};                                                                             \
@@ -1082,7 +1090,7 @@ int k_select_rescore(const uint64_t *cand, int lists, const RescoreArgs &a, cuda
             VM_CUDA_CHECK(cudaFuncSetAttribute(select_rescore_kernel<NEU, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024)); \
             attr_set_dev[dev_idx_ & 63] = true;                                                                        \
         }                                                                                                              \
-        select_rescore_kernel<NEU, T><<<a.nq, SR_THREADS, smem, st>>>(cand, lists, a.nq, a.kp, (const T *)a.rows, a.ld, a.dim, \
+        select_rescore_kernel<NEU, T><<<a.nq, SR_THREADS, smem, st>>>(cand, lists, list_len, a.nq, a.kp, (const T *)a.rows, a.ld, a.dim, \
                                                                       a.n_rows, a.queries, a.q_dtype, a.eps, a.fin, a.flags,  \
                                                                       a.uncertified_count, a.extreme, a.collect_thr);             \
     } while (0)

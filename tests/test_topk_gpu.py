@@ -438,3 +438,46 @@ def test_near_duplicate_cluster_uses_collect_pass(vm, dtype):
         i3, s3, _ = st2.topk(Q[:1], k, sum_mode=vm.VM_SUM_NEUMAIER)
     assert np.array_equal(i3, ref2[0]) and np.array_equal(s3, ref2[1]) and st2.last_stats.full_rescans == 1
     st.close(); st2.close()
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("n", [127, 128, 129, 4095, 4097, 9472, 9473])
+def test_small_store_dump_mode_boundaries(vm, dtype, n):
+    """Stores of <= 9472 rows take the tcgen05 scan's dump mode (every row's key is ranked, no per-CTA lists);
+    9473 rows is the first size on the list path.  Skipped, zero and duplicate rows, partial last tile."""
+    d, nq, k = 96, 19, 10
+    rng = np.random.default_rng(n)
+    X = _quantise(rng.standard_normal((n, d)).astype(np.float32), dtype)
+    X[n - 1] = X[1]; X[50] = X[1]; X[7] = 0.0
+    Q = rng.standard_normal((nq, d)).astype(np.float32)
+    Q[0] = X[1]; Q[1] = 0.0
+    st = vm.EmbeddingStore(d, n, dtype)
+    st.append(X)
+    st.invalidate([2, n - 2])
+    ok = np.ones(n, np.uint8); ok[[2, n - 2]] = 0
+    ref = oracle.batch_similarities(Q, X, k, row_ok=ok)
+    idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)
+    assert st.last_stats.scan_kernel == 2
+    _check(idx, score, count, ref, k)
+    assert list(idx[0, :3]) == [1, 50, n - 1]                       # three-way tie -> lowest rows first
+    st.close()
+
+
+def test_small_store_near_ties_collect_after_dump(vm):
+    """More near-identical rows than the candidate list holds, in a store small enough for dump mode: the
+    query is uncertified and the (list-mode) collect pass settles it exactly."""
+    import torch
+    d, n, k = 384, 6000, 10
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    base = rng.standard_normal(d).astype(np.float32)
+    X[1000:1200] = base + 1e-3 * rng.standard_normal((200, d)).astype(np.float32)
+    Q = np.stack([base] + [rng.standard_normal(d).astype(np.float32) for _ in range(11)])
+    st = vm.EmbeddingStore(d, n, "f32")
+    st.append(X)
+    ref = oracle.batch_similarities(Q, X, k)
+    with torch.cuda.stream(torch.cuda.Stream()):
+        idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)
+    _check(idx, score, count, ref, k)
+    assert st.last_stats.scan_kernel == 2 and st.last_stats.uncertified >= 1 and st.last_stats.full_rescans == 0
+    st.close()
