@@ -431,8 +431,9 @@ int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t 
     dev_idx &= 63;
     static const int dbg = getenv("VIDMEM_TC_DEBUG") ? atoi(getenv("VIDMEM_TC_DEBUG")) : 0;  // perf triage only
     g_last_tc_stages = L.stages;
-    // seeding pays off once every CTA streams several tiles and there are at least kp CTAs
-    const bool seed = seed_tab && seed_ctr && a.ctas >= a.kp && a.ctas <= 256 && num_tiles >= 4 * a.ctas && !(dbg & 4);
+    // seeding needs at least kp CTAs (kp first-tile maxima); it pays off even with a single tile per CTA,
+    // because a first tile without a threshold costs ~80 us of serial drains (stores below that use dump mode)
+    const bool seed = seed_tab && seed_ctr && a.ctas >= a.kp && a.ctas <= 256 && !(dbg & 4);
     if (!seed || sc) { seed_tab = nullptr; seed_ctr = nullptr; }
     CollectArgs col{};
     if (sc) { col.thr = sc->thr; col.buf = sc->buf; col.cnt = sc->cnt; col.cap = sc->cap; col.pending = sc->pending; }
