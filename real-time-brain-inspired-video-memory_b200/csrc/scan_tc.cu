@@ -1,6 +1,6 @@
 // scan_tc.cu -- tcgen05 / TMA streaming scorer: the bandwidth-bound scan for query batches.
 //
-// One persistent CTA per SM, warp-specialised (192 threads):
+// One persistent CTA per SM, warp-specialised (192 threads; 288 with the threshold warp, see below):
 //   warp 0   TMA producer   streams the store as 128-row x 128-byte boxes (SWIZZLE_128B) through a
 //                           ring of 16 KB shared-memory stages, L2 evict-first; loads the
 //                           normalised queries once (evict-last) -- no thread ever touches a row
@@ -21,6 +21,13 @@
 // first 19 K rows.  All CTAs adopt it as their initial threshold (bounded wait, no grid barrier
 // semantics needed: a late CTA only makes the bound looser), while TMA/MMA keep streaming into the
 // 8 TMEM stages.  This removes the per-CTA warm-up flood that otherwise dominates small shards.
+// Threshold warp (template TW, long scans of narrow tiles): a CTA's own kp-th best is a weak filter -- it
+// has seen 1/148 of the shard -- so ~every tile still produced a survivor and paid the two-barrier drain,
+// and the epilogue, not HBM, paced bf16 scans.  With TW the drains keep each CTA's RUNNING maximum per
+// query current in the seed table and one extra warp per CTA keeps re-deriving, query by query, the kp-th
+// largest of all CTAs' maxima (same proof as the first seed: kp distinct rows reach it), raising the
+// shared-memory thresholds with a CAS-max.  The bound then follows the shard-wide top-kp (~40th best of
+// everything scanned so far), survivors become rare, and the epilogue drops off the critical path.
 // HBM traffic = the store bytes exactly once per batch of <= 64 queries; the per-CTA lists are
 // merged and exactly rescored by select.cu.
 // Collect mode (second pass for queries the first pass could not certify): thresholds are fixed per
@@ -41,7 +48,10 @@ static constexpr int TC_BLOCK_M = 128;
 static constexpr int TC_STAGE_BYTES = TC_BLOCK_M * 128;
 static constexpr int TC_ACC = 8;      // accumulator stages in TMEM (8 x 64 columns = all 512)
 static constexpr int TC_QCAP = 32;
-static constexpr int TC_THREADS = 192;
+static constexpr int TC_THREADS_TW = 288;  // with the threshold warp (TW)
+static constexpr int TC_THREADS = 192;     // without: TMA warp, MMA warp, 4 epilogue warps
+// 288:  // TMA warp, MMA warp, 4 epilogue warps, (2 idle), threshold warp 8 -> scheduler 0,
+                                         // away from the schedulers of the warps that run the drains (2 and 3)
 static constexpr int TC_TMEM_COLS = 512;
 static constexpr int TC_MAX_STAGES = 8;
 
@@ -56,7 +66,7 @@ struct CollectArgs {
 
 struct TcLayout {
     int nq_pad, KB, stages, kp;
-    uint32_t off_b, off_a, off_list, off_queue, off_tauk, off_tauf, off_qcnt, off_flags, off_bars, off_tmem, total;
+    uint32_t off_b, off_a, off_list, off_queue, off_tauk, off_tauf, off_seedf, off_qcnt, off_flags, off_bars, off_tmem, total;
 };
 
 static TcLayout make_layout(int dtype, int ld, int nq, int kp)
@@ -68,7 +78,7 @@ static TcLayout make_layout(int dtype, int ld, int nq, int kp)
     L.kp = kp;
     uint32_t o = 0;
     L.off_b = o; o += (uint32_t)L.KB * L.nq_pad * 128;
-    uint32_t epi = (uint32_t)kp * L.nq_pad * 8 + (uint32_t)TC_QCAP * L.nq_pad * 8 + (uint32_t)L.nq_pad * (8 + 4 + 4) + 64 + 512;
+    uint32_t epi = (uint32_t)kp * L.nq_pad * 8 + (uint32_t)TC_QCAP * L.nq_pad * 8 + (uint32_t)L.nq_pad * (8 + 4 + 4 + 4) + 64 + 512;
     int64_t room = 227 * 1024 - 1024 - (int64_t)o - epi;
     L.stages = (int)(room / TC_STAGE_BYTES);
     if (L.stages > TC_MAX_STAGES) L.stages = TC_MAX_STAGES;
@@ -78,6 +88,7 @@ static TcLayout make_layout(int dtype, int ld, int nq, int kp)
     L.off_queue = o; o += (uint32_t)TC_QCAP * L.nq_pad * 8;
     L.off_tauk = o; o += (uint32_t)L.nq_pad * 8;
     L.off_tauf = o; o += (uint32_t)L.nq_pad * 4;
+    L.off_seedf = o; o += (uint32_t)L.nq_pad * 4;
     L.off_qcnt = o; o += (uint32_t)L.nq_pad * 4;
     L.off_flags = o; o += 64;
     L.off_bars = o; o += 8 * (2 * TC_MAX_STAGES + 1 + 2 * TC_ACC);
@@ -86,11 +97,50 @@ static TcLayout make_layout(int dtype, int ld, int nq, int kp)
     return L;
 }
 
-template <bool TF32, bool DUMP>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+
+// monotone update of a shared-memory float (several writers, values only grow)
+__device__ __forceinline__ void smem_fmax(float *addr, float v)
+{
+    uint32_t *a = reinterpret_cast<uint32_t *>(addr);
+    uint32_t old = *reinterpret_cast<volatile uint32_t *>(a);
+    while (!(__uint_as_float(old) >= v)) {
+        const uint32_t prev = atomicCAS(a, old, __float_as_uint(v));
+        if (prev == old) break;
+        old = prev;
+    }
+}
+
+// kp-th largest of the per-CTA maxima of query q (one warp, G <= 256 CTAs): a lower bound on the shard's
+// kp-th best score, because kp distinct rows (one per CTA) reach it.  16 radix bits; truncation rounds down.
+__device__ __forceinline__ float seed_select(const uint32_t *seed_tab, int G, int nq_pad, int q, int kp, int lane)
+{
+    uint32_t vals[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int i = lane + 32 * t;
+        vals[t] = i < G ? __ldcg(seed_tab + (size_t)i * nq_pad + q) : 0u;
+    }
+    uint32_t prefix = 0;
+    int need = kp;
+    for (int bit = 31; bit >= 16; --bit) {
+        const uint32_t hi = bit == 31 ? 0u : (0xFFFFFFFFu << (bit + 1));
+        int cnt = 0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) cnt += ((vals[t] & hi) == prefix && ((vals[t] >> bit) & 1u)) ? 1 : 0;
+        const int tot = __reduce_add_sync(0xffffffffu, cnt);
+        if (tot >= need) prefix |= 1u << bit;
+        else need -= tot;
+    }
+    float sd = f32_from_ordered(prefix);
+    if (!(sd > -INFINITY) || G < kp) sd = -INFINITY;  // also catches NaN patterns
+    return sd;
+}
+
+template <bool TF32, bool DUMP, bool TW>
+__global__ void __launch_bounds__(TW ? TC_THREADS_TW : TC_THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const float *__restrict__ inv_norms, int64_t n, int num_tiles, int nq, TcLayout L, uint64_t *__restrict__ cand,
-               uint32_t *__restrict__ seed_tab, int *__restrict__ seed_ctr, int dbg, CollectArgs col)
+               uint32_t *__restrict__ seed_tab, int *__restrict__ seed_ctr, int dbg, CollectArgs col, int tw_sleep)
 {
     const bool collect = !DUMP && col.thr != nullptr;
     if (collect && *col.pending == 0) return;  // nothing left to refine (uniform across the grid)
@@ -105,9 +155,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t *queue = (uint64_t *)(base + L.off_queue);  // [QCAP][nq_pad]
     uint64_t *tauk = (uint64_t *)(base + L.off_tauk);
     float *tauf = (float *)(base + L.off_tauf);
+    float *seedf = (float *)(base + L.off_seedf);         // [nq_pad] seeded lower bound per query (only grows)
     int *qcnt = (int *)(base + L.off_qcnt);
     volatile int *s_hit = (volatile int *)(base + L.off_flags);  // [2]
     volatile int *s_ovf = s_hit + 2;                             // [2]
+    volatile int *s_done = s_hit + 4;                            // epilogue finished (stops the threshold warp)
     uint64_t *bars = (uint64_t *)(base + L.off_bars);
     uint64_t *full = bars, *empty = bars + TC_MAX_STAGES, *qfull = bars + 2 * TC_MAX_STAGES;
     uint64_t *tfull = qfull + 1, *tempty = tfull + TC_ACC;
@@ -131,10 +183,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int e = threadIdx.x - 64;
         if (e < nq_pad) {
             for (int j = 0; j < kp; ++j) list[j * nq_pad + e] = 0;
-            tauk[e] = 0; qcnt[e] = 0;
+            tauk[e] = 0; qcnt[e] = 0; seedf[e] = -INFINITY;
             tauf[e] = collect ? (e < nq ? col.thr[e] : INFINITY) : -INFINITY;
         }
-        if (e < 4) s_hit[e] = 0;  // s_hit[0..1], s_ovf[0..1]
+        if (e < 5) s_hit[e] = 0;  // s_hit[0..1], s_ovf[0..1], s_done
     }
     tc_fence_before();
     __syncthreads();
@@ -186,14 +238,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else {
+    } else if (warp < 6) {
         // ================================ epilogue =====================================
         const int e = threadIdx.x - 64;   // 0..127
         const int quad = warp & 3;        // TMEM lane quadrant this warp may read
         const int row_in_tile = quad * 32 + lane;
         uint64_t my_tau = 0;              // threshold key (= minimum of the set) of query e (threads e < nq_pad)
         int my_min = 0;                   // its position in the set
-        float my_seed = -INFINITY;        // seeded lower bound of query e
+        uint32_t my_max = 0;              // best score (ordered bits) in query e's set == this CTA's entry in seed_tab
         int acc = 0, par = 0;
         uint32_t acc_phase = 0;
         if constexpr (DUMP) {
@@ -222,7 +274,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (seed_tab != nullptr && !collect) {
             // ---- cooperative threshold seeding from the first tile (see file header) ----
             uint32_t *wmax = reinterpret_cast<uint32_t *>(queue);  // [4][nq_pad] scratch (queue is idle now)
-            float *seedf = reinterpret_cast<float *>(wmax + 4 * nq_pad);
             const int64_t row0 = (int64_t)blockIdx.x * TC_BLOCK_M + row_in_tile;
             const float inv0 = row0 < n ? __ldg(inv_norms + row0) : -1.0f;
             mbar_wait(&tfull[0], 0);
@@ -245,6 +296,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int w = 1; w < 4; ++w) m = max(m, wmax[w * nq_pad + e]);
                 seed_tab[(size_t)blockIdx.x * nq_pad + e] = m;
+                my_max = m;
             }
             __threadfence();
             named_bar_sync(1, 128);
@@ -258,30 +310,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             named_bar_sync(1, 128);
             const int G = (int)gridDim.x;
             for (int q = warp - 2; q < nq; q += 4) {
-                uint32_t vals[8];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const int i = lane + 32 * t;
-                    vals[t] = i < G ? __ldcg(seed_tab + (size_t)i * nq_pad + q) : 0u;
-                }
-                // bitwise radix select of the kp-th largest; 16 bits are enough (truncation rounds down)
-                uint32_t prefix = 0;
-                int need = kp;
-                for (int bit = 31; bit >= 16; --bit) {
-                    const uint32_t hi = bit == 31 ? 0u : (0xFFFFFFFFu << (bit + 1));
-                    int cnt = 0;
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) cnt += ((vals[t] & hi) == prefix && ((vals[t] >> bit) & 1u)) ? 1 : 0;
-                    const int tot = __reduce_add_sync(0xffffffffu, cnt);
-                    if (tot >= need) prefix |= 1u << bit;
-                    else need -= tot;
-                }
-                float sd = f32_from_ordered(prefix);
-                if (!(sd > -INFINITY) || G < kp) sd = -INFINITY;  // also catches NaN patterns
-                if (lane == 0) seedf[q] = sd;
+                const float sd = seed_select(seed_tab, G, nq_pad, q, kp, lane);
+                if (lane == 0) { smem_fmax(&seedf[q], sd); smem_fmax(&tauf[q], sd); }
             }
-            named_bar_sync(1, 128);
-            if (e < nq) { my_seed = seedf[e]; tauf[e] = my_seed; }
             named_bar_sync(1, 128);
         }
         int64_t row = (int64_t)blockIdx.x * TC_BLOCK_M + row_in_tile;
@@ -357,9 +388,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // then rescan for the new minimum with independent, pipelined loads
                     int cnt = qcnt[e];
                     cnt = cnt < TC_QCAP ? cnt : TC_QCAP;
+                    const uint32_t max_before = my_max;
                     for (int i = 0; i < cnt; ++i) {
                         const uint64_t key = queue[i * nq_pad + e];
                         if (key > my_tau) {
+                            if (TW) my_max = max(my_max, (uint32_t)(key >> 32));
                             list[my_min * nq_pad + e] = key;
                             uint64_t m = ~0ull;
                             int p = 0;
@@ -374,7 +407,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     qcnt[e] = 0;
                     tauk[e] = my_tau;
-                    tauf[e] = my_tau ? fmaxf(key_score(my_tau), my_seed) : my_seed;
+                    const float sd = seedf[e];
+                    if (TW) {
+                        smem_fmax(&tauf[e], my_tau ? fmaxf(key_score(my_tau), sd) : sd);
+                        if (seed_tab != nullptr && my_max != max_before) __stcg(seed_tab + (size_t)blockIdx.x * nq_pad + e, my_max);
+                    } else {
+                        tauf[e] = my_tau ? fmaxf(key_score(my_tau), sd) : sd;
+                    }
                 }
                 named_bar_sync(1, 128);
                 if (!o) break;
@@ -393,6 +432,24 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             cand[((int64_t)blockIdx.x * nq + q) * kp + j] = list[j * nq_pad + q];
         }
         }  // !DUMP
+        if (e == 0) *s_done = 1;
+    } else {
+        // ================================ threshold warp ================================
+        // Keeps re-deriving, query by query, the kp-th largest of all CTAs' RUNNING maxima (seed_tab, kept
+        // current by the drains) and raises the query's threshold to it: the bound then follows the
+        // shard-wide top-kp instead of this CTA's own, so survivors -- and the per-tile drains they cause --
+        // become rare.  Off the epilogue's critical path; a stale table entry only loosens the bound.
+        if (TW && !DUMP && warp == 8 && seed_tab != nullptr && !collect) {
+            int q = 0;
+            // the exit test is a warp vote: a lane that lags behind (lane 0 does the updates) must not leave
+            // the loop while the others are already inside the next select's warp reductions
+            while (!__any_sync(0xffffffffu, *s_done != 0)) {
+                const float sd = seed_select(seed_tab, (int)gridDim.x, nq_pad, q, kp, lane);
+                if (lane == 0 && sd > seedf[q]) { smem_fmax(&seedf[q], sd); smem_fmax(&tauf[q], sd); }
+                if (++q == nq) q = 0;
+                __nanosleep(tw_sleep);
+            }
+        }
     }
 
     tc_fence_before();
@@ -437,21 +494,30 @@ int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t 
     if (!seed || sc) { seed_tab = nullptr; seed_ctr = nullptr; }
     CollectArgs col{};
     if (sc) { col.thr = sc->thr; col.buf = sc->buf; col.cnt = sc->cnt; col.cap = sc->cap; col.pending = sc->pending; }
+    // Threshold warp: pays off where the epilogue, not HBM, paces the scan -- tiles of <= 128 KB (bf16 rows
+    // of 384 dims stream in 2.2 us, an fp32 tile in 4.4 us hides the drains) -- and once every CTA streams
+    // enough tiles for the shared bound to pull ahead of its own.  Measured on 64-query batches: bf16 4M rows
+    // 0.68 -> 0.56 ms, 12.5M rows 1.68 -> 1.55 ms; fp32 1M rows would lose 3 %, larger fp32 stores are HBM-bound.
+    static const int tw_min_tiles = getenv("VIDMEM_TC_TW_MIN_TILES") ? atoi(getenv("VIDMEM_TC_TW_MIN_TILES")) : 64;
+    static const int tw_max_tile_kb = getenv("VIDMEM_TC_TW_MAX_TILE_KB") ? atoi(getenv("VIDMEM_TC_TW_MAX_TILE_KB")) : 128;
+    const int tw_sleep = 200;
+    const bool tw = seed_tab != nullptr && !sc && !a.dump && (int64_t)num_tiles >= (int64_t)tw_min_tiles * a.ctas &&
+                    (int64_t)TC_BLOCK_M * a.ld * (a.dtype == VM_F32 ? 4 : 2) <= (int64_t)tw_max_tile_kb * 1024;
     const bool dump = a.dump && !sc;
     if (dump) VM_REQUIRE(TC_BLOCK_M == SCAN_DUMP_TILE && (int64_t)num_tiles * TC_BLOCK_M <= SCAN_DUMP_MAX_KEYS && a.ctas == num_tiles,
                          VM_ERR_UNSUPPORTED, "tcgen05 scan: dump mode needs one CTA per tile and at most %d rows", SCAN_DUMP_MAX_KEYS);
-#define LAUNCH_TC(TF, DU)                                                                                                  \
+#define LAUNCH_TC(TF, DU, TWV)                                                                                                \
     do {                                                                                                                   \
         static bool set[64] = {}; /* the attribute is per device */                                                        \
         if (!set[dev_idx]) {                                                                                               \
-            VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<TF, DU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<TF, DU, TWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
             set[dev_idx] = true;                                                                                           \
         }                                                                                                                  \
-        scan_tc_kernel<TF, DU><<<a.ctas, TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, \
-                                                                          seed_tab, seed_ctr, dbg, col);                  \
+        scan_tc_kernel<TF, DU, TWV><<<a.ctas, TWV ? TC_THREADS_TW : TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, \
+                                                                          seed_tab, seed_ctr, dbg, col, tw_sleep);        \
     } while (0)
-    if (a.dtype == VM_F32) { if (dump) LAUNCH_TC(true, true); else LAUNCH_TC(true, false); }
-    else { if (dump) LAUNCH_TC(false, true); else LAUNCH_TC(false, false); }
+    if (a.dtype == VM_F32) { if (dump) LAUNCH_TC(true, true, false); else if (tw) LAUNCH_TC(true, false, true); else LAUNCH_TC(true, false, false); }
+    else { if (dump) LAUNCH_TC(false, true, false); else if (tw) LAUNCH_TC(false, false, true); else LAUNCH_TC(false, false, false); }
 #undef LAUNCH_TC
     VM_CUDA_CHECK(cudaGetLastError());
     return VM_OK;
