@@ -136,6 +136,10 @@ int vm_store_clear(vm_store *s);
 /* Device time (ms) of the scan kernel(s) of the last vm_topk* call made with VM_FLAG_TIMING,
  * measured with CUDA events recorded on that call's stream; synchronises on the end event. */
 int vm_store_last_scan_ms(vm_store *s, float *ms);
+/* Average scan-kernel time (ms) over the VM_FLAG_TIMING calls made since the previous read (the most
+ * recent 64 at most), each bracketed by its own event pair on its stream -- nothing is synchronised
+ * until this call, so a back-to-back timed loop is measured as it ran.  *calls (optional) = how many. */
+int vm_store_avg_scan_ms(vm_store *s, float *ms, int *calls);
 
 /* ---- top-k scorer ---------------------------------------------------------------------
  * Replaces the hot loop of PreLLMInjector._calculate_batch_similarities

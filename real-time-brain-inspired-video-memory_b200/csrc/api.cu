@@ -115,7 +115,12 @@ struct vm_store {
     int *extreme = nullptr;  // device counter: rows outside the fast scans' numeric range
     Buf stage, stage_idx;
     Workspace ws;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // VM_FLAG_TIMING
+    // VM_FLAG_TIMING: a ring of event pairs, one per timed call, so a whole timed loop can be read back afterwards
+    static constexpr int EV_RING = 64;
+    cudaEvent_t evr[EV_RING][2] = {};
+    int ev_next = 0;     // slot the next timed call records into
+    int ev_pending = 0;  // timed calls since the last vm_store_avg_scan_ms (capped at EV_RING)
+    int ev_cur = -1;     // slot of the call in flight / most recent call
     bool timed = false;
     // CUDA-graph cache of the host-buffer top-k pipeline (launch-bound small stores / small batches)
     struct GraphEntry {
@@ -322,8 +327,7 @@ extern "C" int vm_store_destroy(vm_store *s)
     if (s->extreme) cudaFree(s->extreme);
     s->stage.release(); s->stage_idx.release();
     s->ws.release();
-    if (s->ev0) cudaEventDestroy(s->ev0);
-    if (s->ev1) cudaEventDestroy(s->ev1);
+    for (auto &pr : s->evr) { if (pr[0]) cudaEventDestroy(pr[0]); if (pr[1]) cudaEventDestroy(pr[1]); }
     for (auto &ge : s->graphs) if (ge.exec) cudaGraphExecDestroy(ge.exec);
     if (s->gstream) cudaStreamDestroy(s->gstream);
     delete s;
@@ -409,8 +413,28 @@ extern "C" int vm_store_last_scan_ms(vm_store *s, float *ms)
     VM_REQUIRE(s && ms, VM_ERR_BADARG, "NULL argument");
     VM_REQUIRE(s->timed, VM_ERR_STATE, "no vm_topk call with VM_FLAG_TIMING has run the scan kernel yet");
     DeviceGuard g(s->device);
-    VM_CUDA_CHECK(cudaEventSynchronize(s->ev1));
-    VM_CUDA_CHECK(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+    VM_CUDA_CHECK(cudaEventSynchronize(s->evr[s->ev_cur][1]));
+    VM_CUDA_CHECK(cudaEventElapsedTime(ms, s->evr[s->ev_cur][0], s->evr[s->ev_cur][1]));
+    return VM_OK;
+}
+
+extern "C" int vm_store_avg_scan_ms(vm_store *s, float *ms, int *calls)
+{
+    VM_REQUIRE(s && ms, VM_ERR_BADARG, "NULL argument");
+    VM_REQUIRE(s->timed && s->ev_pending > 0, VM_ERR_STATE, "no vm_topk call with VM_FLAG_TIMING since the last read");
+    DeviceGuard g(s->device);
+    VM_CUDA_CHECK(cudaEventSynchronize(s->evr[s->ev_cur][1]));
+    double sum = 0.0;
+    const int n = s->ev_pending;
+    for (int i = 0; i < n; ++i) {
+        const int slot = (s->ev_cur - i + 2 * vm_store::EV_RING) % vm_store::EV_RING;
+        float t = 0.0f;
+        VM_CUDA_CHECK(cudaEventElapsedTime(&t, s->evr[slot][0], s->evr[slot][1]));
+        sum += t;
+    }
+    *ms = (float)(sum / n);
+    if (calls) *calls = n;
+    s->ev_pending = 0;
     return VM_OK;
 }
 
@@ -525,8 +549,11 @@ static int topk_batch(const TopkCall &c)
     a.queries = (const float *)w.q_f32.p; a.nq = c.nq; a.kp = kp; a.cand = (uint64_t *)w.cand.p; a.stream = st;
     const bool timing = (c.flags & VM_FLAG_TIMING) != 0;
     if (timing) {
-        if (!s->ev0) { VM_CUDA_CHECK(cudaEventCreate(&s->ev0)); VM_CUDA_CHECK(cudaEventCreate(&s->ev1)); }
-        VM_CUDA_CHECK(cudaEventRecord(s->ev0, st));
+        s->ev_cur = s->ev_next;
+        s->ev_next = (s->ev_next + 1) % vm_store::EV_RING;
+        if (s->ev_pending < vm_store::EV_RING) ++s->ev_pending;
+        if (!s->evr[s->ev_cur][0]) { VM_CUDA_CHECK(cudaEventCreate(&s->evr[s->ev_cur][0])); VM_CUDA_CHECK(cudaEventCreate(&s->evr[s->ev_cur][1])); }
+        VM_CUDA_CHECK(cudaEventRecord(s->evr[s->ev_cur][0], st));
     }
     if (kernel == 1) {
         int64_t need = (s->size + 31) / 32;
@@ -544,7 +571,7 @@ static int topk_batch(const TopkCall &c)
         launches += 1;
     }
     if (rc != VM_OK) return rc;
-    if (timing) { VM_CUDA_CHECK(cudaEventRecord(s->ev1, st)); s->timed = true; }
+    if (timing) { VM_CUDA_CHECK(cudaEventRecord(s->evr[s->ev_cur][1], st)); s->timed = true; }
 
     int32_t *flags = (int32_t *)w.flags.p;
     int32_t *uncert = flags + c.nq;  // counter sits right after the nq flags (zeroed by the normalise kernel)

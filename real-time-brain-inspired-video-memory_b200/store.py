@@ -129,6 +129,13 @@ class EmbeddingStore:
         L.check(self.lib.vm_store_last_scan_ms(self._h, C.byref(ms)))
         return float(ms.value)
 
+    def avg_scan_ms(self):
+        """-> (mean scan-kernel ms, calls) over the VM_FLAG_TIMING calls since the previous read (at most the
+        last 64): every call carries its own event pair, so a back-to-back loop is measured as it ran."""
+        ms, n = C.c_float(0.0), C.c_int(0)
+        L.check(self.lib.vm_store_avg_scan_ms(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     def clear(self) -> None:
         L.check(self.lib.vm_store_clear(self._h))
 

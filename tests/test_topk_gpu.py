@@ -481,3 +481,24 @@ def test_small_store_near_ties_collect_after_dump(vm):
     _check(idx, score, count, ref, k)
     assert st.last_stats.scan_kernel == 2 and st.last_stats.uncertified >= 1 and st.last_stats.full_rescans == 0
     st.close()
+
+
+def test_avg_scan_ms_covers_every_timed_call(vm):
+    import torch
+    n, d = 20000, 64
+    X = np.random.default_rng(1).standard_normal((n, d)).astype(np.float32)
+    st = vm.EmbeddingStore(d, n, "f32"); st.append(X)
+    q = torch.from_numpy(X[:16].copy()).cuda()
+    with pytest.raises(vm.VidmemError):
+        st.avg_scan_ms()                                             # nothing timed yet
+    for _ in range(5):
+        st.topk_device(q, 10, flags=vm.VM_FLAG_ASYNC | vm.VM_FLAG_TIMING)
+    ms, calls = st.avg_scan_ms()
+    assert calls == 5 and 0.0 < ms < 50.0
+    for _ in range(70):                                              # more than the ring holds: the last 64 are averaged
+        st.topk_device(q, 10, flags=vm.VM_FLAG_ASYNC | vm.VM_FLAG_TIMING)
+    ms2, calls2 = st.avg_scan_ms()
+    assert calls2 == 64 and 0.0 < ms2 < 50.0 and abs(st.last_scan_ms() - ms2) < 10 * ms2
+    with pytest.raises(vm.VidmemError):
+        st.avg_scan_ms()                                             # already consumed
+    st.close()
