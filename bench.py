@@ -110,13 +110,15 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def _ncu_traffic(cfg: str, scan_kernel: int):
+def _ncu_traffic(cfg: str, scan_kernel: int, rows_local: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel from the committed ncu --set full
-    capture of this workload (profiles/), per launch; None when no capture exists for it."""
+    capture of this workload (profiles/), per launch; None when no capture exists for this shard size."""
     p = os.path.join(ROOT, "profiles", f"r1_scan_tc_{cfg}_summary.json")
     if scan_kernel == 2 and os.path.exists(p):
         try:
             d = json.load(open(p))
+            if int(d.get("rows", rows_local)) != int(rows_local):
+                return None
             return d["dram_bytes_read"] + d["dram_bytes_write"]
         except Exception:
             return None
@@ -360,7 +362,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(nq * k * 16 + nq * 4 + 4), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": _ncu_traffic(cfg, int(stats.scan_kernel)), "kernel": "scan", "kernel_ms": scan_avg, "kernel_ms_samples": scan_calls, "algorithmic_bytes": alg_bytes,
+                         "traffic": _ncu_traffic(cfg, int(stats.scan_kernel), n_local), "kernel": "scan", "kernel_ms": scan_avg, "kernel_ms_samples": scan_calls, "algorithmic_bytes": alg_bytes,
                          "peak_source": peak_src},
             "clocks": clocks,
         }
