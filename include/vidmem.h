@@ -87,7 +87,7 @@ typedef struct vm_topk_stats {
     int32_t scan_stages;      /* shared-memory pipeline depth of the tcgen05 scan (0 otherwise) */
     int32_t full_rescans;     /* of the uncertified queries, how many the collect pass could not settle and the
                                  binary64 scan of every row re-did (-1: not read back, e.g. graph replay) */
-    int32_t reserved[1];
+    int32_t scan_variant;     /* tcgen05 scan: 0 = per-CTA lists, 1 = dump mode (small store), 2 = lists + threshold warp */
 } vm_topk_stats;
 
 /* ---- library ----------------------------------------------------------------------- */

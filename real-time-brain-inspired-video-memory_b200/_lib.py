@@ -38,7 +38,7 @@ EXPORTS = [
 
 class TopkStats(C.Structure):
     _fields_ = [("scan_kernel", C.c_int32), ("scan_launches", C.c_int32), ("uncertified", C.c_int32),
-                ("candidates", C.c_int32), ("scan_ctas", C.c_int32), ("scan_stages", C.c_int32), ("full_rescans", C.c_int32), ("reserved", C.c_int32 * 1)]
+                ("candidates", C.c_int32), ("scan_ctas", C.c_int32), ("scan_stages", C.c_int32), ("full_rescans", C.c_int32), ("scan_variant", C.c_int32)]
 
 
 class VidmemError(RuntimeError):

@@ -49,6 +49,7 @@ int k_pairs_above(int device, const void *x, int dtype, int64_t n, int dim, int 
                   cudaStream_t st);
 
 extern int g_last_tc_stages;
+extern int g_last_tc_variant;
 static constexpr int MAXQ = 64;   // queries per scan pass
 static constexpr int MAXK = 64;   // k and candidate-list bound
 static constexpr int XCTAS = 148; // exact-scan grid
@@ -648,6 +649,7 @@ static int topk_batch(const TopkCall &c)
         c.stats->candidates = kp;
         c.stats->scan_ctas = a.ctas;
         c.stats->scan_stages = kernel == 2 ? g_last_tc_stages : 0;
+        c.stats->scan_variant = kernel == 2 ? g_last_tc_variant : 0;
     }
     return VM_OK;
 }

@@ -469,6 +469,7 @@ bool scan_tc_supported(int dtype, int dim, int nq, int kp)
 }
 
 int g_last_tc_stages = 0;
+int g_last_tc_variant = 0;  // 0 lists, 1 dump, 2 lists + threshold warp (reported in vm_topk_stats)
 
 // queries_store_dtype: the normalised queries [nq_pad][ld] in the STORE dtype (fp32 for the tf32
 // path, bf16 for the bf16 path).
@@ -507,6 +508,7 @@ int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t 
     const bool dump = a.dump && !sc;
     if (dump) VM_REQUIRE(TC_BLOCK_M == SCAN_DUMP_TILE && (int64_t)num_tiles * TC_BLOCK_M <= SCAN_DUMP_MAX_KEYS && a.ctas == num_tiles,
                          VM_ERR_UNSUPPORTED, "tcgen05 scan: dump mode needs one CTA per tile and at most %d rows", SCAN_DUMP_MAX_KEYS);
+    if (!sc) g_last_tc_variant = dump ? 1 : (tw ? 2 : 0);
 #define LAUNCH_TC(TF, DU, TWV)                                                                                                \
     do {                                                                                                                   \
         static bool set[64] = {}; /* the attribute is per device */                                                        \

@@ -457,7 +457,7 @@ def test_small_store_dump_mode_boundaries(vm, dtype, n):
     ok = np.ones(n, np.uint8); ok[[2, n - 2]] = 0
     ref = oracle.batch_similarities(Q, X, k, row_ok=ok)
     idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)
-    assert st.last_stats.scan_kernel == 2
+    assert st.last_stats.scan_kernel == 2 and st.last_stats.scan_variant == (1 if n <= 9472 else 0)
     _check(idx, score, count, ref, k)
     assert list(idx[0, :3]) == [1, 50, n - 1]                       # three-way tie -> lowest rows first
     st.close()
@@ -501,4 +501,23 @@ def test_avg_scan_ms_covers_every_timed_call(vm):
     assert calls2 == 64 and 0.0 < ms2 < 50.0 and abs(st.last_scan_ms() - ms2) < 10 * ms2
     with pytest.raises(vm.VidmemError):
         st.avg_scan_ms()                                             # already consumed
+    st.close()
+
+
+def test_threshold_warp_scan_vs_blocked_oracle(vm):
+    """bf16, 1.3 M rows, 40 queries: long enough for the threshold-warp variant of the tcgen05 scan (shared bound
+    from every CTA's running maxima).  All queries checked against the blocked oracle, incl. planted duplicates."""
+    import torch
+    n, d, nq, k = 1_300_000, 384, 40, 10
+    st = vm.EmbeddingStore(d, n, "bf16")
+    st.synth_fill(11, n, dup_period=50_000)                          # planted exact duplicates -> cross-CTA ties
+    st.set_size(n)
+    X = st.rows[:n, :d].float().cpu().numpy()
+    Q = synth.synth_queries(12, nq, d, 11, n)
+    Q[0] = X[123_456]; Q[1] = X[n - 1]
+    with torch.cuda.stream(torch.cuda.Stream()):
+        idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)
+    assert st.last_stats.scan_kernel == 2 and st.last_stats.scan_variant == 2
+    bi, bs, bc = oracle.topk_blocked(Q, X, k, slack=64)
+    assert np.array_equal(idx, bi) and np.array_equal(score, bs) and (count == k).all()
     st.close()
