@@ -38,7 +38,13 @@ def _torch_dtype_code(t: torch.Tensor) -> int:
     raise TypeError(f"unsupported tensor dtype {t.dtype}")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream_ptr(device: torch.device) -> int:
+    # the caller's current stream on `device`; the raw accessor skips building a Stream object (~5 us per call)
+    if _raw_stream is not None:
+        return _raw_stream(device.index)
     return torch.cuda.current_stream(device).cuda_stream
 
 
@@ -62,6 +68,7 @@ class EmbeddingStore:
                                          self.rows.data_ptr(), self.inv_norms.data_ptr()))
         self._h = h
         self.last_stats = L.TopkStats()
+        self._stats_ref = C.byref(self.last_stats)
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self) -> None:
@@ -209,12 +216,12 @@ class EmbeddingStore:
         if comm is None:
             rc = self.lib.vm_topk(self._h, q.ctypes.data, _np_dtype_code(q), L.VM_MEM_HOST, nq, k, float(min_score),
                                   score_mode, sm, flags, idx.ctypes.data, score.ctypes.data, count.ctypes.data,
-                                  L.VM_MEM_HOST, C.byref(self.last_stats), st)
+                                  L.VM_MEM_HOST, self._stats_ref, st)
         else:
             rc = self.lib.vm_topk_sharded(self._h, comm.handle, int(row_offset), q.ctypes.data, _np_dtype_code(q),
                                           L.VM_MEM_HOST, nq, k, float(min_score), score_mode, sm, flags,
                                           idx.ctypes.data, score.ctypes.data, count.ctypes.data, L.VM_MEM_HOST,
-                                          C.byref(self.last_stats), st)
+                                          self._stats_ref, st)
         L.check(rc)
         return idx, score, count
 
@@ -236,12 +243,12 @@ class EmbeddingStore:
         if comm is None:
             rc = self.lib.vm_topk(self._h, q.data_ptr(), _torch_dtype_code(q), L.VM_MEM_DEVICE, nq, k, float(min_score),
                                   score_mode, sm, flags, idx.data_ptr(), score.data_ptr(), count.data_ptr(),
-                                  L.VM_MEM_DEVICE, C.byref(self.last_stats), st)
+                                  L.VM_MEM_DEVICE, self._stats_ref, st)
         else:
             rc = self.lib.vm_topk_sharded(self._h, comm.handle, int(row_offset), q.data_ptr(), _torch_dtype_code(q),
                                           L.VM_MEM_DEVICE, nq, k, float(min_score), score_mode, sm, flags,
                                           idx.data_ptr(), score.data_ptr(), count.data_ptr(), L.VM_MEM_DEVICE,
-                                          C.byref(self.last_stats), st)
+                                          self._stats_ref, st)
         L.check(rc)
         return idx, score, count
 
