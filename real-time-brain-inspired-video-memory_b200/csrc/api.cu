@@ -516,10 +516,11 @@ static int topk_batch(const TopkCall &c)
         int kp_tc = c.k <= 16 ? 32 : (c.k <= 48 ? 64 : 0);
         int kp_simt = c.k <= 24 ? (c.k + 8 > 16 ? ((c.k + 8 + 7) & ~7) : 16) : 0;
         bool tc_ok = kp_tc > 0 && scan_tc_supported(s->dtype, s->dim, c.nq, kp_tc);
-        // query batches always take the tensor-core scan; so do small batches over big shards, where
-        // the TMA-fed kernel streams at the HBM roofline while the CUDA-core kernel reaches ~half of it
-        bool want_tc = (c.flags & VM_FLAG_FORCE_TC) ||
-                       ((c.nq > scan_simt_max_queries() || s->size >= 65536) && !(c.flags & VM_FLAG_FORCE_SIMT));
+        // The tcgen05 scan is the default at every size: it streams big shards at the HBM roofline (the CUDA-core
+        // kernel reaches ~half of it) and is also the lower-latency choice for a few queries over a small store
+        // (measured fp32, 1-8 queries: 5 K rows 39 vs 45-54 us, 60 K rows 55-57 vs 74-123 us).  The CUDA-core kernel
+        // serves the shapes the tensor path does not fit (k > 48, dims beyond its shared memory) and cross-checks it.
+        bool want_tc = !(c.flags & VM_FLAG_FORCE_SIMT);
         if (want_tc && tc_ok) { kernel = 2; kp = kp_tc; }
         else if (kp_simt > 0) { kernel = 1; kp = kp_simt; }
         else if (tc_ok) { kernel = 2; kp = kp_tc; }
@@ -695,7 +696,7 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
             if (e.exec && e.version == s->version && e.nq == nq && e.k == k && e.flags == flags && e.score_mode == score_mode &&
                 e.sum_mode == sum_mode && e.q_dtype == q_dtype && e.min_score == min_score) { ge = &e; break; }
         int bq_g = MAXQ;
-        if (nq > scan_simt_max_queries() || s->size >= 65536 || (flags & VM_FLAG_FORCE_TC)) {
+        if (!(flags & VM_FLAG_FORCE_SIMT)) {
             const int kp_tc = k <= 16 ? 32 : (k <= 48 ? 64 : 0);
             bq_g = 0;
             if (kp_tc)
@@ -763,7 +764,7 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
     // queries per scan pass: 64, or fewer when 64 normalised queries of this dimension do not fit the
     // tcgen05 kernel's shared memory (e.g. 16 for a 1536-d fp32 store)
     int bq = MAXQ;
-    if (!(flags & (VM_FLAG_FORCE_EXACT | VM_FLAG_FORCE_SIMT)) && (nq > scan_simt_max_queries() || s->size >= 65536 || (flags & VM_FLAG_FORCE_TC))) {
+    if (!(flags & (VM_FLAG_FORCE_EXACT | VM_FLAG_FORCE_SIMT))) {
         const int kp_tc = k <= 16 ? 32 : (k <= 48 ? 64 : 0);
         if (kp_tc)
             for (int cand = 64; cand >= 16; cand -= 16)
