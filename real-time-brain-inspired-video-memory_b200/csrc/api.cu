@@ -218,7 +218,7 @@ static int ws_prepare(vm_store *s)
     // one contiguous block [idx | score | count] so a host caller gets its results with ONE copy
     ENS(w.o_idx, (size_t)MAXQ * MAXK * 16 + (size_t)MAXQ * 4 + 64);
     ENS(w.flags, (size_t)(MAXQ + 2) * 4);
-    ENS(w.seed, (size_t)256 * MAXQ * 4);
+    ENS(w.seed, (size_t)(256 * MAXQ + 2 * MAXQ) * 4);  // per-CTA maxima + published per-query bounds + their counter (scan_tc.cu)
     ENS(w.col_thr, (size_t)MAXQ * 4);
     ENS(w.col_cnt, (size_t)MAXQ * 4);
     ENS(w.col_buf, (size_t)MAXQ * COLLECT_CAP * 8);

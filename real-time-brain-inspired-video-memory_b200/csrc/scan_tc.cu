@@ -21,13 +21,16 @@
 // first 19 K rows.  All CTAs adopt it as their initial threshold (bounded wait, no grid barrier
 // semantics needed: a late CTA only makes the bound looser), while TMA/MMA keep streaming into the
 // 8 TMEM stages.  This removes the per-CTA warm-up flood that otherwise dominates small shards.
-// Threshold warp (template TW, long scans of narrow tiles): a CTA's own kp-th best is a weak filter -- it
-// has seen 1/148 of the shard -- so ~every tile still produced a survivor and paid the two-barrier drain,
-// and the epilogue, not HBM, paced bf16 scans.  With TW the drains keep each CTA's RUNNING maximum per
-// query current in the seed table and one extra warp per CTA keeps re-deriving, query by query, the kp-th
-// largest of all CTAs' maxima (same proof as the first seed: kp distinct rows reach it), raising the
-// shared-memory thresholds with a CAS-max.  The bound then follows the shard-wide top-kp (~40th best of
-// everything scanned so far), survivors become rare, and the epilogue drops off the critical path.
+// Threshold warp (template TW, narrow tiles): a CTA's own kp-th best is a weak filter -- it has seen
+// 1/148 of the shard -- so ~every tile still produced a survivor and paid the two-barrier drain, and the
+// epilogue, not HBM, paced bf16 scans.  With TW the drains keep each CTA's RUNNING maximum per query
+// current in the seed table and one extra warp per CTA runs a distributed bound service: the CTA that
+// owns query q (q mod G) keeps re-deriving the exact kp-th largest of all CTAs' maxima (same proof as the
+// first seed: kp distinct rows reach it) and publishes it with an atomic max; every CTA adopts the
+// published bounds of all queries with a CAS-max on its shared-memory thresholds.  The bound then follows
+// the shard-wide top-kp (~40th best of everything scanned so far), survivors become rare, and the epilogue
+// drops off the critical path.  The first seed is derived the same way (one select per owner CTA, a second
+// short bounded wait) instead of 64 selects in every CTA.
 // HBM traffic = the store bytes exactly once per batch of <= 64 queries; the per-CTA lists are
 // merged and exactly rescored by select.cu.
 // Collect mode (second pass for queries the first pass could not certify): thresholds are fixed per
@@ -54,6 +57,7 @@ static constexpr int TC_THREADS = 192;     // without: TMA warp, MMA warp, 4 epi
                                          // away from the schedulers of the warps that run the drains (2 and 3)
 static constexpr int TC_TMEM_COLS = 512;
 static constexpr int TC_MAX_STAGES = 8;
+static constexpr int SEED_TAB_WORDS = 256 * 64;  // per-CTA maxima [<= 256 CTAs][<= 64 queries]; the published bounds follow
 
 // second-pass ("collect") arguments; thr == nullptr selects the normal top-kp mode
 struct CollectArgs {
@@ -108,6 +112,28 @@ __device__ __forceinline__ void smem_fmax(float *addr, float v)
         if (prev == old) break;
         old = prev;
     }
+}
+
+// Cheap lower bound on the kp-th largest of the per-CTA maxima of query q (one warp, kp <= 64 <= G <= 256... or
+// kp <= 32 <= G): lane l holds the entries of CTAs l, l+32, ...; the minimum over the lanes of each lane's
+// largest (kp <= 32) or second largest (kp <= 64) entry is reached by at least kp distinct CTAs.  ~40 cycles
+// after the loads instead of ~1000 for the exact select; typically the ~2*kp-th largest instead of the kp-th.
+__device__ __forceinline__ uint32_t seed_bound_fast(const uint32_t *seed_tab, int G, int nq_pad, int q, int kp, int lane)
+{
+    uint32_t m1 = 0, m2 = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int i = lane + 32 * t;
+        const uint32_t x = i < G ? __ldcg(seed_tab + (size_t)i * nq_pad + q) : 0u;
+        m2 = max(m2, min(m1, x));
+        m1 = max(m1, x);
+    }
+    return __reduce_min_sync(0xffffffffu, kp > 32 ? m2 : m1);
+}
+__device__ __forceinline__ float seed_from_ordered(uint32_t o)
+{
+    const float sd = f32_from_ordered(o);
+    return sd > -INFINITY ? sd : -INFINITY;  // 0 (an empty slot) maps to a NaN pattern
 }
 
 // kp-th largest of the per-CTA maxima of query q (one warp, G <= 256 CTAs): a lower bound on the shard's
@@ -308,10 +334,35 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __threadfence();
             }
             named_bar_sync(1, 128);
+            // The bound of query q is derived once, by the CTA that owns it (q mod G), and published; a second,
+            // short bounded wait lets every CTA adopt all nq bounds (64 exact selects in every CTA cost ~15 us).
             const int G = (int)gridDim.x;
-            for (int q = warp - 2; q < nq; q += 4) {
-                const float sd = seed_select(seed_tab, G, nq_pad, q, kp, lane);
-                if (lane == 0) { smem_fmax(&seedf[q], sd); smem_fmax(&tauf[q], sd); }
+            uint32_t *gbound = seed_tab + SEED_TAB_WORDS;
+            int *pub_ctr = reinterpret_cast<int *>(gbound + 64);
+            if (warp == 2) {
+                for (int q = blockIdx.x; q < nq; q += G) {
+                    const float sd = seed_select(seed_tab, G, nq_pad, q, kp, lane);
+                    if (lane == 0) {
+                        if (sd > -INFINITY) atomicMax(gbound + q, f32_ordered(sd));
+                        __threadfence();
+                        atomicAdd(pub_ctr, 1);
+                    }
+                }
+                if (lane == 0) {
+                    const long long t0 = clock64();
+                    while (*(volatile int *)pub_ctr < nq)
+                        if (clock64() - t0 > 200000) break;  // ~0.1 ms: a missing bound only means "no threshold yet"
+                    __threadfence();
+                }
+            }
+            named_bar_sync(1, 128);
+            if (e < nq) {
+                const uint32_t o = __ldcg(gbound + e);
+                if (o != 0u) {
+                    const float f = f32_from_ordered(o);
+                    smem_fmax(&seedf[e], f);
+                    smem_fmax(&tauf[e], f);
+                }
             }
             named_bar_sync(1, 128);
         }
@@ -440,13 +491,26 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // shard-wide top-kp instead of this CTA's own, so survivors -- and the per-tile drains they cause --
         // become rare.  Off the epilogue's critical path; a stale table entry only loosens the bound.
         if (TW && !DUMP && warp == 8 && seed_tab != nullptr && !collect) {
-            int q = 0;
-            // the exit test is a warp vote: a lane that lags behind (lane 0 does the updates) must not leave
-            // the loop while the others are already inside the next select's warp reductions
+            // A distributed bound service: CTA b owns queries b, b+G, ... (at most one with G >= nq), keeps
+            // re-deriving their exact kp-th largest running maximum and publishes it with an atomic max; every
+            // CTA adopts the published bounds of all queries.  One table column per owner per round instead of
+            // every column in every CTA keeps the shared 38 KB table from becoming an L2 hot spot.
+            const int G = (int)gridDim.x;
+            uint32_t *gbound = seed_tab + SEED_TAB_WORDS;
+            // the exit test is a warp vote: a lane that lags behind must not leave the loop while the others
+            // are already inside the next round's warp reductions
             while (!__any_sync(0xffffffffu, *s_done != 0)) {
-                const float sd = seed_select(seed_tab, (int)gridDim.x, nq_pad, q, kp, lane);
-                if (lane == 0 && sd > seedf[q]) { smem_fmax(&seedf[q], sd); smem_fmax(&tauf[q], sd); }
-                if (++q == nq) q = 0;
+                for (int q = blockIdx.x; q < nq; q += G) {
+                    const float sd = seed_select(seed_tab, G, nq_pad, q, kp, lane);
+                    if (lane == 0 && sd > -INFINITY) atomicMax(gbound + q, f32_ordered(sd));
+                }
+                for (int q = lane; q < nq; q += 32) {
+                    const uint32_t o = __ldcg(gbound + q);
+                    if (o != 0u) {
+                        const float f = f32_from_ordered(o);
+                        if (f > seedf[q]) { smem_fmax(&seedf[q], f); smem_fmax(&tauf[q], f); }
+                    }
+                }
                 __nanosleep(tw_sleep);
             }
         }
@@ -496,10 +560,10 @@ int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t 
     CollectArgs col{};
     if (sc) { col.thr = sc->thr; col.buf = sc->buf; col.cnt = sc->cnt; col.cap = sc->cap; col.pending = sc->pending; }
     // Threshold warp: pays off where the epilogue, not HBM, paces the scan -- tiles of <= 128 KB (bf16 rows
-    // of 384 dims stream in 2.2 us, an fp32 tile in 4.4 us hides the drains) -- and once every CTA streams
-    // enough tiles for the shared bound to pull ahead of its own.  Measured on 64-query batches: bf16 4M rows
-    // 0.68 -> 0.56 ms, 12.5M rows 1.68 -> 1.55 ms; fp32 1M rows would lose 3 %, larger fp32 stores are HBM-bound.
-    static const int tw_min_tiles = getenv("VIDMEM_TC_TW_MIN_TILES") ? atoi(getenv("VIDMEM_TC_TW_MIN_TILES")) : 64;
+    // of 384 dims stream in 2.2 us; an fp32 tile takes 4.4 us and hides the drains, and measures 3 % slower
+    // with the extra warp) -- once a CTA streams enough tiles for the shared bound to matter.  Measured on
+    // 64-query batches, bf16: 1M rows 0.247 -> 0.172 ms, 4M rows 0.68 -> 0.49 ms, 12.5M rows 1.68 -> 1.49 ms.
+    static const int tw_min_tiles = getenv("VIDMEM_TC_TW_MIN_TILES") ? atoi(getenv("VIDMEM_TC_TW_MIN_TILES")) : 16;
     static const int tw_max_tile_kb = getenv("VIDMEM_TC_TW_MAX_TILE_KB") ? atoi(getenv("VIDMEM_TC_TW_MAX_TILE_KB")) : 128;
     const int tw_sleep = 200;
     // (a single-query scan has no epilogue pressure: C5 bf16 measured 1.11 ms without vs 1.16 ms with it)
