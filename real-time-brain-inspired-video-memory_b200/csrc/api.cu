@@ -474,6 +474,22 @@ struct TopkCall {
 
 // Host-output path: the batch's device results are one contiguous block [idx | score | count]
 // (see ws_prepare); one D2H copy into pinned memory, then plain host copies into the caller's arrays.
+// Result wait of the synchronous (host-buffer) calls.  cudaStreamSynchronize may park the thread for work longer
+// than ~1 ms and then pays a 0.1-0.2 ms wake-up; a top-k call is latency-critical and short, so poll instead
+// (VIDMEM_SYNC=block restores the blocking wait, e.g. on oversubscribed hosts).
+static cudaError_t wait_stream(cudaStream_t st)
+{
+    static const bool block = [] { const char *e = getenv("VIDMEM_SYNC"); return e && !strcmp(e, "block"); }();
+    if (block) return cudaStreamSynchronize(st);
+    for (;;) {
+        const cudaError_t e = cudaStreamQuery(st);
+        if (e != cudaErrorNotReady) return e;
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+}
+
 static int pack_out_enqueue(const TopkCall &c)
 {
     const size_t bytes = (size_t)c.nq * c.k * 16 + (size_t)c.nq * 4;
@@ -531,7 +547,7 @@ static int topk_batch(const TopkCall &c)
         launches += 2;
         if (c.h_idx) {
             if ((rc = pack_out_enqueue(c)) != VM_OK) return rc;
-            VM_CUDA_CHECK(cudaStreamSynchronize(st));
+            VM_CUDA_CHECK(wait_stream(st));
             pack_out_finish(c);
         }
         if (c.stats) { c.stats->scan_kernel = 0; c.stats->scan_launches += launches; }
@@ -617,7 +633,7 @@ static int topk_batch(const TopkCall &c)
     } else {
         VM_CUDA_CHECK(cudaMemcpyAsync(w.h_uncert, uncert, 4, cudaMemcpyDeviceToHost, st));
         if (c.h_idx && (rc = pack_out_enqueue(c)) != VM_OK) return rc;
-        VM_CUDA_CHECK(cudaStreamSynchronize(st));
+        VM_CUDA_CHECK(wait_stream(st));
         n_uncert = *w.h_uncert;
         n_full = 0;
         if (n_uncert > 0) {
@@ -626,7 +642,7 @@ static int topk_batch(const TopkCall &c)
                 if ((rc = run_collect()) != VM_OK) return rc;
                 launches += 2;
                 VM_CUDA_CHECK(cudaMemcpyAsync(w.h_uncert, uncert, 4, cudaMemcpyDeviceToHost, st));
-                VM_CUDA_CHECK(cudaStreamSynchronize(st));
+                VM_CUDA_CHECK(wait_stream(st));
                 left = *w.h_uncert;
             }
             n_full = left;
@@ -637,7 +653,7 @@ static int topk_batch(const TopkCall &c)
             }
             if (c.h_idx) {
                 if ((rc = pack_out_enqueue(c)) != VM_OK) return rc;
-                VM_CUDA_CHECK(cudaStreamSynchronize(st));
+                VM_CUDA_CHECK(wait_stream(st));
             }
         }
         if (c.h_idx) pack_out_finish(c);
@@ -741,7 +757,7 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
             }
             memcpy(w.h_q, queries, qbytes);
             VM_CUDA_CHECK(cudaGraphLaunch(ge->exec, s->gstream));
-            VM_CUDA_CHECK(cudaStreamSynchronize(s->gstream));
+            VM_CUDA_CHECK(wait_stream(s->gstream));
             if (ge->stats.scan_kernel != 0 && *w.h_uncert > 0) {
                 // some query was not certified: run this batch through the plain path (collect pass / exact scan)
                 TopkCall c{s, queries, q_dtype, VM_MEM_HOST, nq, k, min_score, score_mode, sum_mode, flags, row_offset,
@@ -803,8 +819,12 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
             d_score = (double *)((char *)w.gather_send.p + seg);
             d_count = (int32_t *)((char *)w.gather_send.p + 2 * seg);
         }
+        // Sharded call with host outputs: enqueue the local pass without a host round trip (uncertified queries
+        // are settled by the device-conditional binary64 scan), so scan -> exchange -> merge -> one packed D2H run
+        // back to back and the ranks reach the all-gather together; the only synchronisation is the final one.
+        const bool sharded_host = sharded && out_mem == VM_MEM_HOST && !(flags & VM_FLAG_ASYNC);
         TopkCall c{s, (const char *)queries + (size_t)q0 * qrow, q_dtype, q_mem, nb, k, min_score, score_mode, sum_mode,
-                   flags, row_offset, d_idx, d_score,
+                   sharded_host ? (flags | VM_FLAG_ASYNC) : flags, row_offset, d_idx, d_score,
                    d_count, st, stats};
         const bool host_direct = out_mem == VM_MEM_HOST && !sharded && !(flags & VM_FLAG_ASYNC);
         if (host_direct) { c.h_idx = out_idx + (size_t)q0 * k; c.h_score = out_score + (size_t)q0 * k; c.h_count = out_count + q0; }
@@ -830,11 +850,19 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
             if (stats) stats->scan_launches += 2;
             d_idx = m_idx; d_score = m_score; d_count = m_count;
         }
-        if (out_mem == VM_MEM_HOST && !host_direct) {
+        if (sharded_host) {
+            // merged results sit in the contiguous workspace block [idx | score | count]: one D2H into pinned memory
+            const size_t seg = (size_t)nb * k * 8;
+            VM_CUDA_CHECK(cudaMemcpyAsync(w.h_pack, ws_idx, 2 * seg + (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+            VM_CUDA_CHECK(wait_stream(st));
+            memcpy(out_idx + (size_t)q0 * k, w.h_pack, seg);
+            memcpy(out_score + (size_t)q0 * k, w.h_pack + seg, seg);
+            memcpy(out_count + q0, w.h_pack + 2 * seg, (size_t)nb * 4);
+        } else if (out_mem == VM_MEM_HOST && !host_direct) {
             VM_CUDA_CHECK(cudaMemcpyAsync(out_idx + (size_t)q0 * k, d_idx, (size_t)nb * k * 8, cudaMemcpyDeviceToHost, st));
             VM_CUDA_CHECK(cudaMemcpyAsync(out_score + (size_t)q0 * k, d_score, (size_t)nb * k * 8, cudaMemcpyDeviceToHost, st));
             VM_CUDA_CHECK(cudaMemcpyAsync(out_count + q0, d_count, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-            VM_CUDA_CHECK(cudaStreamSynchronize(st));
+            VM_CUDA_CHECK(wait_stream(st));
         }
     }
     return VM_OK;
