@@ -156,12 +156,13 @@ int vm_store_avg_scan_ms(vm_store *s, float *ms, int *calls);
  *  out_count  [nq] number of valid entries (rows may be fewer than k: no padding, :370)
  *  out_mem    where the three outputs live
  *
- * How: a fast scan (tcgen05/TMA tensor-core kernel, or the CUDA-core kernel for small query
- * batches) streams the store once and keeps, per query, a candidate list by approximate fp32
+ * How: a fast scan (the tcgen05/TMA tensor-core kernel; the CUDA-core kernel only for shapes it
+ * does not fit) streams the store once and keeps, per query, a candidate list by approximate fp32
  * score; an exact binary64 pass rescores the candidates in the reference's summation order,
  * sorts them and CERTIFIES that no other row can reach the k-th score (approximation error
- * bound); uncertified queries (rare: more near-ties than the candidate list holds) are redone
- * by a binary64 scan of all rows.  Results are therefore exact, not approximate. */
+ * bound); uncertified queries (rare: more near-ties than the candidate list holds) get a second
+ * scan that collects every row inside the error band, or, failing that, a binary64 scan of all
+ * rows.  Results are therefore exact, not approximate. */
 int vm_topk(vm_store *s, const void *queries, int q_dtype, int q_mem, int nq, int k, double min_score,
             int score_mode, int sum_mode, int flags, int64_t *out_idx, double *out_score, int32_t *out_count,
             int out_mem, vm_topk_stats *stats, void *stream);
