@@ -457,7 +457,7 @@ def test_small_store_dump_mode_boundaries(vm, dtype, n):
     ok = np.ones(n, np.uint8); ok[[2, n - 2]] = 0
     ref = oracle.batch_similarities(Q, X, k, row_ok=ok)
     idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)
-    assert st.last_stats.scan_kernel == 2 and st.last_stats.scan_variant == (1 if n <= 9472 else 0)
+    assert st.last_stats.scan_kernel == 2 and (st.last_stats.scan_variant == 1) == (n <= 9472)
     _check(idx, score, count, ref, k)
     assert list(idx[0, :3]) == [1, 50, n - 1]                       # three-way tie -> lowest rows first
     st.close()
