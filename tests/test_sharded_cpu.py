@@ -155,3 +155,36 @@ def test_streaming_inserts_world_size_2_gloo(tmp_path):
     import torch.multiprocessing as mp
     mp.spawn(_stream_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert sorted(os.listdir(tmp_path)) == ["rank0.ok", "rank1.ok"]
+
+
+def _dedup_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vidmem_b200 import dedup
+    E = synth.synth_rows(44, 0, 900, 64, dup_period=5)
+    oi, oj, os_ = oracle.pairs_above(E, 0.9)
+
+    def part_of_oracle(x, threshold, cap=1 << 20, part=0, nparts=1):
+        # stands in for vm_pairs_above(part, nparts): this rank's share of the upper-triangular 128x128 tile grid
+        mine = ((oi // 128) * 7 + (oj // 128)) % nparts == part
+        return oi[mine], oj[mine], os_[mine].astype(np.float32)
+
+    dedup.pairs_above = part_of_oracle
+    gi, gj, gs = dedup.pairs_above_sharded(torch.from_numpy(E), 0.9)
+    ok = len(oi) > 20 and np.array_equal(gi, oi) and np.array_equal(gj, oj) and np.array_equal(gs, os_.astype(np.float32))
+    shares = [int((((oi // 128) * 7 + (oj // 128)) % world == r).sum()) for r in range(world)]
+    ok = ok and min(shares) > 0                                           # both ranks really contributed
+    open(os.path.join(out_dir, f"rank{rank}.ok" if ok else f"rank{rank}.bad"), "w").write("x")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_dedup_concatenation_world_size_2_gloo(tmp_path):
+    """Host side of the multi-GPU all-pairs path: per-rank hit lists of different lengths are exchanged (counts,
+    then a padded all-gather), concatenated and sorted by (i, j) -- identical on every rank."""
+    import torch.multiprocessing as mp
+    mp.spawn(_dedup_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["rank0.ok", "rank1.ok"]
