@@ -146,6 +146,18 @@ def _stream_worker(rank, world, port, out_dir):
     ok = ok and got[1][0][0] == "u_1_7"                                   # the overwritten row answers with its new vector
     ok = ok and sorted(set(st.owner)) == [0, 1] and abs(st.load[0] - st.load[1]) <= 64
     ok = ok and len(st.local) == st.load[rank]
+    # the S1 / S6 adapters take the sharded store unchanged (same surface as ResidentChunkStore)
+    import asyncio
+    import types
+    from vidmem_b200 import adapters
+    st2 = sharded.ShardedChunkStore("f32", device=0)
+    backend = adapters.ChunkSimilarityBackend(store=st2, mirror_fetch=False)
+    assert backend.store is st2                                           # an empty store must not be replaced
+    for items in batches:
+        backend.on_chunks_inserted([{"id": cid, "content": f"text of {cid}", "embedding": emb} for cid, emb in items])
+    inj = types.SimpleNamespace(embedder_config=types.SimpleNamespace(top_k_chunk_with_batch_similarity=k))
+    got2 = asyncio.run(backend._calculate_batch_similarities(inj, queries + [RuntimeError("embed failed")], None))
+    ok = ok and got2[:-1] == want and got2[-1] == [] and st2.meta["u_1_7"]["content"] == "text of u_1_7"
     open(os.path.join(out_dir, f"rank{rank}.ok" if ok else f"rank{rank}.bad"), "w").write("x")
     dist.barrier()
     dist.destroy_process_group()
