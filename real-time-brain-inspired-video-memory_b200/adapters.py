@@ -75,7 +75,12 @@ class ResidentChunkStore:
         """Insert hook: (chunk_id, embedding) pairs.  Unknown ids are appended, known ids are
         overwritten in place (the reference MERGEs by id, neo4j_handler.py:229).  A falsy embedding
         keeps its row slot but is marked skipped."""
-        items = list(items)
+        # an id written twice in one batch is ONE row: first-seen position, last value (dict semantics, like the
+        # reference's {id: embedding} and its MERGE-by-id inserts)
+        merged: Dict[str, Any] = {}
+        for cid, emb in items:
+            merged[cid] = emb
+        items = list(merged.items())
         new_rows, new_ids, invalid = [], [], []
         dim = next((len(e) for _, e in items if not _falsy_embedding(e)), self.dim)
         if dim is None:
@@ -106,10 +111,7 @@ class ResidentChunkStore:
                     self.store.update(row, np.zeros((1, self.dim), np.float64))   # length mismatch scores 0.0 (:378-379)
             else:
                 new_ids.append(cid)
-                if _falsy_embedding(emb):
-                    new_rows.append(None)
-                else:
-                    new_rows.append(np.asarray(emb, dtype=np.float64))
+                new_rows.append(None if _falsy_embedding(emb) else np.asarray(emb, dtype=np.float64))
         if new_ids:
             self._ensure(dim, len(new_ids))
             block = np.zeros((len(new_ids), self.dim), np.float64)

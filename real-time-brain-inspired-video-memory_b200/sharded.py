@@ -147,9 +147,11 @@ class ShardedChunkStore:
         self.load = [0] * self.world
 
     def upsert(self, items, meta=None) -> None:
-        items = list(items)
+        merged = {}
+        for cid, emb in items:              # an id written twice in one batch is one row: first position, last value
+            merged[cid] = emb
+        items = list(merged.items())
         fresh = [cid for cid, _ in items if cid not in self.row_of]
-        fresh = list(dict.fromkeys(fresh))  # an id repeated inside one batch is one row
         target = min(range(self.world), key=lambda r: (self.load[r], r)) if fresh else -1
         for cid in fresh:
             self.row_of[cid] = len(self.ids)
@@ -204,12 +206,9 @@ class ShardedChunkStore:
                                         torch.cuda.current_stream(dev).cuda_stream))
         return o_idx.cpu().numpy(), o_score.cpu().numpy(), o_count.cpu().numpy()
 
-    def topk(self, queries, k: int, min_score: float = -np.inf, score_mode: int = L.VM_SCORE_RAW, flags: int = 0):
-        """Same contract as ResidentChunkStore.topk: list (per query) of [(chunk_id, score)]."""
-        queries = list(queries)
+    def _local_lists(self, queries, k: int, min_score: float, score_mode: int, flags: int):
+        """This rank's exact top-k per query with rows renamed to GLOBAL rows: (idx [nq,k], score, count)."""
         nq = len(queries)
-        if nq == 0 or not self.ids:
-            return [[] for _ in queries]
         local = self.local.topk(queries, k, min_score=min_score, score_mode=score_mode, flags=flags)
         idx = np.full((nq, k), -1, np.int64)
         score = np.zeros((nq, k), np.float64)
@@ -218,6 +217,16 @@ class ShardedChunkStore:
             count[i] = len(lst)
             for j, (cid, s) in enumerate(lst):
                 idx[i, j], score[i, j] = self.row_of[cid], s
+        return idx, score, count
+
+    def _named(self, m_idx, m_score, m_count):
+        return [[(self.ids[int(m_idx[i, j])], float(m_score[i, j])) for j in range(int(m_count[i]))] for i in range(len(m_count))]
+
+    def topk(self, queries, k: int, min_score: float = -np.inf, score_mode: int = L.VM_SCORE_RAW, flags: int = 0):
+        """Same contract as ResidentChunkStore.topk: list (per query) of [(chunk_id, score)]."""
+        queries = list(queries)
+        if len(queries) == 0 or not self.ids:
+            return [[] for _ in queries]
+        idx, score, count = self._local_lists(queries, k, min_score, score_mode, flags)
         gathered, nq, k = self._gather(idx, score, count)
-        m_idx, m_score, m_count = self._merge(gathered, nq, k)
-        return [[(self.ids[int(m_idx[i, j])], float(m_score[i, j])) for j in range(int(m_count[i]))] for i in range(nq)]
+        return self._named(*self._merge(gathered, nq, k))
