@@ -39,6 +39,7 @@ class ResidentChunkStore:
         self.ids: List[str] = []               # row -> chunk id
         self.row_of: Dict[str, int] = {}       # chunk id -> row
         self.meta: Dict[str, Dict[str, Any]] = {}  # chunk id -> {"content", "time"} for vector search results
+        self._mirror_prev: Optional[Dict[str, Any]] = None   # last dict handed to sync_from_dict (mirror mode)
 
     def __len__(self) -> int:
         return len(self.ids)
@@ -70,6 +71,7 @@ class ResidentChunkStore:
         if self.store is not None:
             self.store.clear()
         self.ids, self.row_of = [], {}
+        self._mirror_prev = None
 
     def upsert(self, items: Iterable[Tuple[str, Any]], meta: Optional[Dict[str, Dict[str, Any]]] = None) -> None:
         """Insert hook: (chunk_id, embedding) pairs.  Unknown ids are appended, known ids are
@@ -135,14 +137,24 @@ class ResidentChunkStore:
 
     def sync_from_dict(self, existing: Dict[str, Any]) -> None:
         """Mirror mode: make the resident rows equal to `existing` (the dict the reference would
-        loop over), in its iteration order.  Fast path: the dict only grew at the end."""
+        loop over), in its iteration order.  Fast path: same leading keys -> only rows whose value
+        differs from the previous snapshot are rewritten and new keys are appended; a removed or
+        reordered key rebuilds the store (the reference re-reads everything on every call anyway)."""
         keys = list(existing.keys())
         n = len(self.ids)
+        prev = self._mirror_prev
         if keys[:n] != self.ids:
             self.clear()
-            n = 0
-        if len(keys) > n:
-            self.upsert((k, existing[k]) for k in keys[n:])
+            n, prev = 0, None
+        changed = []
+        if n:
+            if prev is None:
+                changed = keys[:n]                                            # no snapshot to compare with: rewrite
+            else:
+                changed = [c for c in keys[:n] if existing[c] is not prev.get(c) and existing[c] != prev.get(c)]
+        if changed or len(keys) > n:
+            self.upsert([(c, existing[c]) for c in changed] + [(c, existing[c]) for c in keys[n:]])
+        self._mirror_prev = existing
 
     # -- persistence (SURVEY.md 8f, row f3) ------------------------------------------------------
     def save(self, path: str) -> None:

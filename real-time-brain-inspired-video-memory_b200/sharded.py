@@ -137,6 +137,7 @@ class ShardedChunkStore:
         self.owner: List[int] = []          # global row -> rank
         self.load = [0] * self.world        # rows per rank
         self.meta = self.local.meta         # replicated on every rank (host only)
+        self._mirror_prev = None            # last dict handed to sync_from_dict
 
     def __len__(self) -> int:
         return len(self.ids)
@@ -145,6 +146,7 @@ class ShardedChunkStore:
         self.local.clear()
         self.ids, self.row_of, self.owner = [], {}, []
         self.load = [0] * self.world
+        self._mirror_prev = None
 
     def upsert(self, items, meta=None) -> None:
         merged = {}
@@ -166,13 +168,20 @@ class ShardedChunkStore:
             self.meta.update(meta)
 
     def sync_from_dict(self, existing) -> None:
+        """Mirror mode, same contract as ResidentChunkStore.sync_from_dict (changed values are rewritten on
+        their owner, new keys are routed, a removed or reordered key rebuilds the store)."""
         keys = list(existing.keys())
         n = len(self.ids)
+        prev = self._mirror_prev
         if keys[:n] != self.ids:
             self.clear()
-            n = 0
-        if len(keys) > n:
-            self.upsert((k, existing[k]) for k in keys[n:])
+            n, prev = 0, None
+        changed = []
+        if n:
+            changed = keys[:n] if prev is None else [c for c in keys[:n] if existing[c] is not prev.get(c) and existing[c] != prev.get(c)]
+        if changed or len(keys) > n:
+            self.upsert([(c, existing[c]) for c in changed] + [(c, existing[c]) for c in keys[n:]])
+        self._mirror_prev = existing
 
     # -- the exchange -------------------------------------------------------------------------
     def _gather(self, idx: np.ndarray, score: np.ndarray, count: np.ndarray):
