@@ -15,6 +15,17 @@ class OracleBackedStore:
     def __len__(self):
         return len(self.X)
 
+    # what ResidentChunkStore reads directly from the real store (torch tensors there)
+    @property
+    def inv_norms(self):
+        import torch
+        return torch.from_numpy(np.where(self.ok > 0, 1.0, -1.0).astype(np.float32))
+
+    @property
+    def rows(self):
+        import torch
+        return torch.from_numpy(self.X.astype(np.float32))
+
     def append(self, rows):
         first = len(self.X)
         rows = np.asarray(rows, np.float64).astype(np.float32).astype(np.float64)   # fp32 store rounding

@@ -44,3 +44,30 @@ def test_install_on_real_reference_injector(monkeypatch):
     assert got == want and got[-1] == []
     assert all(isinstance(cid, str) and isinstance(s, float) for lst in got for cid, s in lst)
     assert len(backend.store) == n + 1 and backend.store.ids[-1] == "u_bad"
+
+
+def test_ragged_queries_and_growth_match_the_reference(monkeypatch):
+    """Wrong-length, empty and Exception queries, falsy rows, and a store that outgrows its capacity several
+    times: the adapter returns what the UNMODIFIED reference method returns on the same dict."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import ref_import
+    from vidmem_b200 import adapters
+    import vidmem_b200.store as vstore
+    monkeypatch.setattr(vstore, "EmbeddingStore", OracleBackedStore)
+    d = 6
+    vec = st.lists(st.integers(-3, 3).map(float), min_size=d, max_size=d)
+    anyq = st.one_of(vec, st.lists(st.integers(-3, 3).map(float), min_size=0, max_size=d + 2), st.just(RuntimeError("embed failed")))
+    rows = st.lists(st.one_of(vec, st.just([])), min_size=1, max_size=40)
+
+    @settings(max_examples=40, deadline=None)
+    @given(rows, st.lists(anyq, min_size=1, max_size=4), st.integers(1, 5))
+    def run(row_list, queries, k):
+        store = {f"u_{i}": list(r) for i, r in enumerate(row_list)}
+        want = ref_import.run_batch_similarities(queries, store, k)
+        res = adapters.ResidentChunkStore(initial_capacity=4)                    # forces repeated growth
+        for i in range(0, len(row_list), 3):                                     # rows arrive in small insert batches
+            res.upsert([(f"u_{j}", row_list[j]) for j in range(i, min(i + 3, len(row_list)))])
+        assert res.topk(queries, k) == want
+        assert res.ids == list(store)
+
+    run()
