@@ -42,7 +42,12 @@ class OracleBackedStore:
         self.X = self.X[:0]; self.ok = self.ok[:0]
 
     def topk(self, q, k, min_score=-np.inf, score_mode=0, flags=0):
-        res = oracle.batch_similarities(q, self.X, k, row_ok=self.ok)
+        if score_mode == 1:                                            # VM_SCORE_NEO4J: (1 + cos) / 2, strict > min_score
+            res = [oracle.vector_search(qi, self.X, k, min_score=min_score, row_ok=self.ok) for qi in np.asarray(q, np.float64)]
+        else:
+            res = oracle.batch_similarities(q, self.X, k, row_ok=self.ok)
+            if min_score > -np.inf:
+                res = [[(r, s) for r, s in lst if s > min_score] for lst in res]
         idx = np.full((len(q), k), -1, np.int64); sc = np.zeros((len(q), k)); cnt = np.zeros(len(q), np.int32)
         for i, lst in enumerate(res):
             cnt[i] = len(lst)

@@ -71,3 +71,31 @@ def test_ragged_queries_and_growth_match_the_reference(monkeypatch):
         assert res.ids == list(store)
 
     run()
+
+
+def test_scalar_cosine_seams_ragged_lengths_match_the_reference(monkeypatch):
+    """S2 / S4 with vectors of different lengths, zero vectors and empty vectors: the adapters' length handling
+    (0.0 on mismatch for the injector; zip-truncation == zero padding for the retriever) against the reference's
+    own methods.  The device kernel behind cosine_pairs is replaced by the oracle (its GPU parity is a GPU test)."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import ref_import
+    from vidmem_b200 import adapters
+    import vidmem_b200.store as vstore
+
+    def oracle_pairs(a, b, zero_rule=0, sum_mode=None, device=0):
+        a, b = np.atleast_2d(np.asarray(a, np.float64)), np.atleast_2d(np.asarray(b, np.float64))
+        return np.array([oracle.cosine(x, y, variant="injector" if zero_rule == 0 else "retriever") for x, y in zip(a, b)])
+
+    monkeypatch.setattr(vstore, "cosine_pairs", oracle_pairs)
+    ref = ref_import.load()
+    inj = ref_import.make_injector(3)
+    backend = adapters.ChunkSimilarityBackend(store=adapters.ResidentChunkStore())
+    vec = st.lists(st.one_of(st.integers(-5, 5).map(float), st.floats(-1e3, 1e3, allow_nan=False, width=32)), min_size=0, max_size=9)
+
+    @settings(max_examples=150, deadline=None)
+    @given(vec, vec)
+    def run(v1, v2):
+        assert backend._cosine_similarity(v1, v2) == inj._cosine_similarity(v1, v2)
+        assert adapters.VectorSearchBackend._cosine_similarity(v1, v2) == ref["HybridRetriever"]._cosine_similarity(v1, v2)
+
+    run()

@@ -102,3 +102,34 @@ def test_load_export_takes_chunk_nodes_in_file_order(monkeypatch, tmp_path):
     assert st.load_export(str(path)) == 6
     assert st.ids == [f"c{i}" for i in range(6)] and st.meta["c3"]["content"] == "t3"
     assert np.array_equal(st.store.X, X.astype(np.float32).astype(np.float64))
+
+
+def test_s3_vector_search_adapter_shape_threshold_and_error_convention(monkeypatch):
+    """S3 on CPU (device store replaced by the oracle): result dict keys, Neo4j-normalised score with the strict
+    > 0.3 filter, best first, content/time from the insert hook's metadata, [] on any error (:321-323)."""
+    import types
+    import vidmem_b200.store as vstore
+    from vidmem_b200 import adapters
+    monkeypatch.setattr(vstore, "EmbeddingStore", OracleBackedStore)
+    n, d = 40, 16
+    X = synth.synth_rows(3, 0, n, d)
+    backend = adapters.ChunkSimilarityBackend(mirror_fetch=False)
+    backend.on_chunks_inserted([{"id": f"u_{i}", "content": f"text {i}", "time": f"00:{i:02d}", "embedding": [float(v) for v in X[i]]}
+                                for i in range(n)])
+    q = [float(v) for v in X[7]]
+
+    class Embedder:
+        async def aembed_query(self, text):
+            if text == "boom":
+                raise RuntimeError("embedding service down")
+            return q
+
+    retriever = types.SimpleNamespace(neo4j_handler=types.SimpleNamespace(embedder=Embedder()), config=types.SimpleNamespace(top_k_chunks=5))
+    vs = adapters.install_retriever(retriever, backend.store)
+    got = asyncio.run(retriever._vector_search_chunks(None, "what happened?"))
+    want = oracle.vector_search(np.array(q), X.astype(np.float32).astype(np.float64), 5, min_score=0.3)
+    assert [g["id"] for g in got] == [f"u_{r}" for r, _ in want] and [g["score"] for g in got] == [s for _, s in want]
+    assert got[0]["id"] == "u_7" and got[0]["score"] == 1.0 and got[0]["content"] == "text 7" and got[0]["time"] == "00:07"
+    assert all(set(g) == {"id", "time", "content", "score", "source"} and g["source"] == "vector" and g["score"] > 0.3 for g in got)
+    assert asyncio.run(retriever._vector_search_chunks(None, "boom")) == []
+    assert isinstance(vs, adapters.VectorSearchBackend)
