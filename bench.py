@@ -598,6 +598,12 @@ def run_c5(args):
     st.close()
 
 
+def torchrun_argv(gpus: int, argv, port: int):
+    """The launch line of the bench contract for N > 1 (one rank per GPU, 127.0.0.1 rendezvous)."""
+    return [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={gpus}", "--master-addr", "127.0.0.1",
+            "--master-port", str(port), os.path.abspath(__file__), *argv]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -614,6 +620,13 @@ def main():
     ap.add_argument("--no-scaling-baseline", action="store_true", help="skip the extra C3-on-one-GPU measurement of the N=1 run")
     ap.add_argument("--c5-dtype", default=None, choices=["f32", "bf16"])
     args = ap.parse_args()
+    if args.gpus > 1 and args.impl == "ours" and "WORLD_SIZE" not in os.environ:
+        # started as plain `python bench.py --gpus N`: re-launch under torchrun, one rank per GPU
+        import socket
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        os.execv(sys.executable, torchrun_argv(args.gpus, sys.argv[1:], port))
     if args.impl == "reference":
         run_reference(args)
     elif args.config == "c4":

@@ -52,3 +52,16 @@ def test_methods_quoted_in_integration_md_exist():
             assert hasattr(cls, name), f"INTEGRATION.md calls {var}.{name}(), which {cls.__name__} does not have"
             checked += 1
     assert checked >= 5
+
+
+def test_bench_self_launch_line_follows_the_contract():
+    import importlib.util
+    import sys
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    argv = bench.torchrun_argv(4, ["--gpus", "4", "--steps", "10"], 29517)
+    assert argv[:3] == [sys.executable, "-m", "torch.distributed.run"]
+    assert "--nnodes=1" in argv and "--nproc-per-node=4" in argv
+    assert argv[argv.index("--master-addr") + 1] == "127.0.0.1" and argv[argv.index("--master-port") + 1] == "29517"
+    assert argv[-5].endswith("bench.py") and argv[-4:] == ["--gpus", "4", "--steps", "10"]
