@@ -194,7 +194,10 @@ int vm_merge_max_by_id(int device, const int64_t *idx_dev, const double *score_d
  * device) -> out[i] binary64, bit-identical to PreLLMInjector._cosine_similarity
  * (pre_llm_injector.py:374-388) / HybridRetriever._cosine_similarity
  * (retriever_hybrid.py:655-664; used by _post_compress_chunks :492-504).
- * zero_rule 0: norm1 == 0 or norm2 == 0 -> 0.0 ; zero_rule 1: mag1 * mag2 == 0 -> 0.0. */
+ * zero_rule 0: norm1 == 0 or norm2 == 0 -> 0.0 ; zero_rule 1: mag1 * mag2 == 0 -> 0.0 ;
+ * zero_rule 2: EmbeddingUtils.cosine_similarity (src/utils/embedding_utils.py:29-39): zero test as
+ * rule 0, magnitudes through `** 0.5` (pow instead of sqrt: agrees with CPython's libm pow to a
+ * few ulp, not bit-pinned -- the only entry point of this header whose scores carry a tolerance). */
 int vm_cosine_pairs(int device, const void *a, const void *b, int dtype, int mem, int64_t n, int dim, int zero_rule,
                     int sum_mode, double *out, int out_mem, void *stream);
 
@@ -207,8 +210,10 @@ int vm_cosine_pairs(int device, const void *a, const void *b, int dtype, int mem
  * which case the call reports VM_ERR_OVERFLOW on sync paths and only the first cap hits are
  * written.  part/nparts split the upper-triangular tile grid across ranks (0/1 = all).
  * Scores are fp32 (bf16 x bf16 products accumulated in fp32 on the tensor cores), rows
- * normalised by cached fp32 inverse norms; pairs whose score lies within tie_eps of the
- * threshold are re-decided in binary64 so the pair SET is exact for the stored values. */
+ * normalised by cached fp32 inverse norms; pairs whose fp32 score lies within the kernel's own
+ * error bound of the threshold ((dim + 32) * 2^-23 for bf16 rows, + 2^-8 for tf32-truncated fp32
+ * rows; not a parameter) are re-decided in binary64, so the pair SET is exact for the stored
+ * values.  Re-entrant: scratch is kept per (device, stream). */
 int vm_pairs_above(int device, const void *x_dev, int dtype, int64_t n, int dim, float threshold, int64_t cap,
                    int64_t *out_i_dev, int64_t *out_j_dev, float *out_score_dev, int64_t *out_count_dev, int part,
                    int nparts, int flags, void *stream);

@@ -40,6 +40,11 @@ class ResidentChunkStore:
         self.row_of: Dict[str, int] = {}       # chunk id -> row
         self.meta: Dict[str, Dict[str, Any]] = {}  # chunk id -> {"content", "time"} for vector search results
         self._mirror_prev: Optional[Dict[str, Any]] = None   # last dict handed to sync_from_dict (mirror mode)
+        #: True while the resident rows are known to be ALL chunks of the graph (fed by the insert hook from an
+        #: empty graph, or hydrated without a LIMIT).  A mirror of _get_chunk_embeddings is not: that query is
+        #: capped at 5000 rows and only re-read at ingest (pre_llm_injector.py:394-399), whereas the Cypher scan of
+        #: _vector_search_chunks sees every chunk -- VectorSearchBackend serves searches from HBM only when True.
+        self.complete = True
 
     def __len__(self) -> int:
         return len(self.ids)
@@ -72,6 +77,7 @@ class ResidentChunkStore:
             self.store.clear()
         self.ids, self.row_of = [], {}
         self._mirror_prev = None
+        self.complete = True
 
     def upsert(self, items: Iterable[Tuple[str, Any]], meta: Optional[Dict[str, Dict[str, Any]]] = None) -> None:
         """Insert hook: (chunk_id, embedding) pairs.  Unknown ids are appended, known ids are
@@ -84,7 +90,13 @@ class ResidentChunkStore:
             merged[cid] = emb
         items = list(merged.items())
         new_rows, new_ids, invalid = [], [], []
-        dim = next((len(e) for _, e in items if not _falsy_embedding(e)), self.dim)
+        if self.dim is not None:
+            dim = self.dim                                    # fixed once the store exists: other lengths score 0.0
+        else:
+            # first embeddable batch: the store dimension is the most common length of the batch (ties -> the
+            # earliest), so one malformed vector cannot fix a wrong dimension for good
+            lens = [len(e) for _, e in items if not _falsy_embedding(e)]
+            dim = max(sorted(set(lens), key=lens.index), key=lens.count) if lens else None
         if dim is None:
             # no embeddable vector seen yet, so the dimension is still unknown: only remember the ids (they
             # keep their place in store order and become skipped rows once the store exists)
@@ -105,12 +117,12 @@ class ResidentChunkStore:
                 row = self.row_of[cid]
                 if _falsy_embedding(emb):
                     invalid.append(row)
-                elif len(emb) == self.dim or self.dim is None:
-                    self._ensure(len(emb), 0)
+                elif len(emb) == dim:
+                    self._ensure(dim, 0)
                     self.store.update(row, np.asarray(emb, dtype=np.float64)[None, :])
                 else:
-                    self._ensure(self.dim, 0)
-                    self.store.update(row, np.zeros((1, self.dim), np.float64))   # length mismatch scores 0.0 (:378-379)
+                    self._ensure(dim, 0)
+                    self.store.update(row, np.zeros((1, dim), np.float64))        # length mismatch scores 0.0 (:378-379)
             else:
                 new_ids.append(cid)
                 new_rows.append(None if _falsy_embedding(emb) else np.asarray(emb, dtype=np.float64))
@@ -155,6 +167,7 @@ class ResidentChunkStore:
         if changed or len(keys) > n:
             self.upsert([(c, existing[c]) for c in changed] + [(c, existing[c]) for c in keys[n:]])
         self._mirror_prev = existing
+        self.complete = False          # a LIMIT-5000, ingest-time snapshot: not the whole graph
 
     # -- persistence ------------------------------------------------------
     def save(self, path: str) -> None:
@@ -249,7 +262,7 @@ class ChunkSimilarityBackend:
     HYDRATE_QUERY = """
         MATCH (c:Chunk:GraphNode)
         WHERE c.graph_uuid = $graph_uuid AND c.id IS NOT NULL AND c.embedding IS NOT NULL
-        RETURN c.id as chunk_id, c.embedding as embedding, c.content as content
+        RETURN c.id as chunk_id, c.embedding as embedding, c.content as content, c.time as time
     """
 
     async def hydrate(self, neo4j_handler, limit: Optional[int] = None, page_rows: int = 4096) -> int:
@@ -269,7 +282,8 @@ class ChunkSimilarityBackend:
                 chunk_id, embedding = record["chunk_id"], record["embedding"]
                 if isinstance(embedding, list) and chunk_id:               # the reference's row filter (:405)
                     page.append((chunk_id, embedding))
-                    meta[chunk_id] = {"content": record.get("content") if hasattr(record, "get") else None, "time": None}
+                    get = record.get if hasattr(record, "get") else (lambda key: None)
+                    meta[chunk_id] = {"content": get("content"), "time": get("time")}
                     if len(page) >= page_rows:
                         self.store.upsert(page, meta=meta)
                         total += len(page)
@@ -278,6 +292,7 @@ class ChunkSimilarityBackend:
                 self.store.upsert(page, meta=meta)
                 total += len(page)
         self.mirror_fetch = False
+        self.store.complete = limit is None
         return total
 
     # S2
@@ -329,29 +344,49 @@ class ChunkSimilarityBackend:
 
 class VectorSearchBackend:
     """S3 / S4: HybridRetriever._vector_search_chunks and _cosine_similarity
-    (src/pipeline/retriever_hybrid.py:284-323, 655-664) plus the post-compression filter (:492-504)."""
+    (src/pipeline/retriever_hybrid.py:284-323, 655-664) plus post-compression (:465-514)."""
 
     MIN_SCORE = 0.3  # `WHERE similarity > 0.3` (:298), on the Neo4j-normalised score (SURVEY.md 9.3)
 
-    def __init__(self, store: ResidentChunkStore):
+    #: content/time of the returned ids when the resident store does not hold them (mirror mode keeps vectors
+    #: only): the RETURN clause of the reference's Cypher (:299) restricted to the hits
+    META_QUERY = """
+        MATCH (c:Chunk {graph_uuid: $graph_uuid})
+        WHERE c.id IN $ids
+        RETURN c.id AS chunk_id, c.time AS chunk_time, c.content AS content
+    """
+
+    def __init__(self, store: ResidentChunkStore, fallback=None):
         self.store = store
+        #: the reference's own bound _vector_search_chunks (set by install_retriever): used whenever the resident
+        #: store is not known to hold every chunk of the graph (ResidentChunkStore.complete)
+        self.fallback = fallback
+
+    async def _fetch_meta(self, retriever, session, ids: List[str]) -> None:
+        result = await session.run(self.META_QUERY, graph_uuid=retriever.neo4j_handler.run_uuid, ids=list(ids))
+        async for record in result:
+            self.store.meta[record["chunk_id"]] = {"content": record["content"], "time": record["chunk_time"]}
 
     async def _vector_search_chunks(self, retriever, session, query: str) -> List[Dict[str, Any]]:
+        if not getattr(self.store, "complete", True) and self.fallback is not None:
+            return await self.fallback(session, query)       # partial mirror: the reference's exhaustive Cypher scan
         try:
             query_embedding = await retriever.neo4j_handler.embedder.aembed_query(query)   # (:290)
             res = self.store.topk([query_embedding], retriever.config.top_k_chunks, min_score=self.MIN_SCORE,
                                   score_mode=L.VM_SCORE_NEO4J)[0]
+            missing = [cid for cid, _ in res if "content" not in self.store.meta.get(cid, {})]
+            if missing:
+                await self._fetch_meta(retriever, session, missing)
             chunks = []
             for cid, score in res:
-                m = self.store.meta.get(cid, {})
+                m = self.store.meta[cid]                     # KeyError (no such chunk in Neo4j) -> [] like any failure
                 chunks.append({"id": cid, "time": m.get("time"), "content": m.get("content"),
                                "score": float(score), "source": "vector"})            # (:310-316)
             return chunks
         except Exception:                                                              # (:321-323)
             return []
 
-    @staticmethod
-    def _cosine_similarity(vec1: List[float], vec2: List[float]) -> float:
+    def _cosine_similarity(self, vec1: List[float], vec2: List[float]) -> float:
         # zip() truncates the dot product to the shorter vector while the magnitudes use the full
         # vectors (:658-660): identical to zero-padding the shorter one (a 0.0 product leaves both the
         # naive and the Neumaier recurrence unchanged)
@@ -361,20 +396,71 @@ class VectorSearchBackend:
         a = np.zeros(n, np.float64); a[:len(vec1)] = vec1
         b = np.zeros(n, np.float64); b[:len(vec2)] = vec2
         from .store import cosine_pairs
-        return float(cosine_pairs(a, b, zero_rule=1)[0])
+        return float(cosine_pairs(a, b, zero_rule=1, device=self.store.device)[0])
 
     def filter_segments(self, query_embedding: List[float], segment_embeddings: List[List[float]], threshold: float,
-                        top_k: int) -> List[Tuple[int, float]]:
+                        top_k: Optional[int] = None) -> List[Tuple[int, float]]:
         """Batch form of the loop at :492-504: (segment index, score) for score >= threshold (inclusive),
-        original order, cut at top_k."""
+        original order, cut at top_k.  Segments may differ in length from the query (zip truncation, see
+        _cosine_similarity): every pair is zero-padded to the longest vector of the batch."""
         if not segment_embeddings:
             return []
         from .store import cosine_pairs
-        q = np.asarray(query_embedding, dtype=np.float64)
-        S = np.asarray(segment_embeddings, dtype=np.float64)
-        scores = cosine_pairs(np.broadcast_to(q, S.shape).copy(), S, zero_rule=1)
-        keep = [(i, float(s)) for i, s in enumerate(scores) if s >= threshold]
-        return keep[:top_k]
+        n = max([len(query_embedding)] + [len(e) for e in segment_embeddings])
+        S = np.zeros((len(segment_embeddings), n), np.float64)
+        for i, e in enumerate(segment_embeddings):
+            S[i, :len(e)] = e
+        q = np.zeros(n, np.float64)
+        q[:len(query_embedding)] = query_embedding
+        if n == 0:
+            scores = np.zeros(len(segment_embeddings))
+        else:
+            scores = cosine_pairs(np.broadcast_to(q, S.shape).copy(), S, zero_rule=1, device=self.store.device)
+        keep = [(i, float(sc)) for i, sc in enumerate(scores) if sc >= threshold]
+        return keep if top_k is None else keep[:top_k]
+
+    async def _post_compress_chunks(self, retriever, query: str, chunks: List[Dict]) -> List[Dict]:
+        """S4 caller (:465-514): same splitter, same dict shape, same order and `[:top_k]` cut -- but the segment
+        embeddings are requested together (one asyncio.gather instead of a sequential HTTP loop) and scored by ONE
+        batched device call instead of a Python loop per segment."""
+        import asyncio
+        import sys
+        if not retriever.embedder or not chunks:                                       # (:467-468)
+            return chunks
+        try:
+            query_embedding = await retriever.embedder.aembed_query(query)             # (:474)
+            splitter_cls = getattr(sys.modules.get(type(retriever).__module__), "RecursiveCharacterTextSplitter")
+            splitter = splitter_cls(chunk_size=256, chunk_overlap=32, separators=["\n\n", "\n", ". ", " "])   # (:478-482)
+            owners, segments = [], []
+            for chunk in chunks:
+                for segment in splitter.split_text(chunk["content"]):                  # (:486-489)
+                    owners.append(chunk)
+                    segments.append(segment)
+            embedded = await asyncio.gather(*(retriever.embedder.aembed_query(sg) for sg in segments),
+                                            return_exceptions=True)
+            ok = [i for i, e in enumerate(embedded) if not isinstance(e, BaseException)]   # a failed segment is skipped (:505-507)
+            kept = self.filter_segments(query_embedding, [embedded[i] for i in ok], retriever.config.compression_threshold)
+            out = [{**owners[ok[i]], "content": segments[ok[i]], "compression_score": float(sc)} for i, sc in kept]
+            return out[:retriever.config.top_k]                                        # (:510)
+        except Exception:                                                              # (:512-514)
+            return chunks
+
+
+class EmbeddingUtilsBackend:
+    """EmbeddingUtils.cosine_similarity (src/utils/embedding_utils.py:29-39) -- zip-truncated
+    dot product, magnitudes through `** 0.5`, 0.0 when either magnitude is zero."""
+
+    def __init__(self, device: int = 0):
+        self.device = device
+
+    def cosine_similarity(self, vec1: List[float], vec2: List[float]) -> float:
+        n = max(len(vec1), len(vec2))
+        if min(len(vec1), len(vec2)) == 0:
+            return 0.0
+        a = np.zeros(n, np.float64); a[:len(vec1)] = vec1
+        b = np.zeros(n, np.float64); b[:len(vec2)] = vec2
+        from .store import cosine_pairs
+        return float(cosine_pairs(a, b, zero_rule=2, device=self.device)[0])
 
 
 class PruneBackend:
@@ -422,12 +508,31 @@ def install_injector(injector, backend: Optional[ChunkSimilarityBackend] = None,
 
 
 def install_retriever(retriever, store: ResidentChunkStore) -> VectorSearchBackend:
-    backend = VectorSearchBackend(store)
+    """Rebinds S3 (_vector_search_chunks), S4 (_cosine_similarity) and S4's caller (_post_compress_chunks) on a
+    reference HybridRetriever instance.  The instance's own _vector_search_chunks is kept as the fallback for a
+    store that does not hold the whole graph (mirror mode)."""
+    backend = VectorSearchBackend(store, fallback=getattr(retriever, "_vector_search_chunks", None))
 
     async def _vs(self, session, query):
         return await backend._vector_search_chunks(self, session, query)
 
+    async def _pc(self, query, chunks):
+        return await backend._post_compress_chunks(self, query, chunks)
+
     retriever._vector_search_chunks = types.MethodType(_vs, retriever)
+    retriever._post_compress_chunks = types.MethodType(_pc, retriever)
+    retriever._cosine_similarity = backend._cosine_similarity      # static in the reference: called with (vec1, vec2)
+    return backend
+
+
+def install_embedding_utils(target, backend: Optional[EmbeddingUtilsBackend] = None, **kw) -> EmbeddingUtilsBackend:
+    """Rebinds cosine_similarity on the reference's EmbeddingUtils class (or an instance of it)."""
+    backend = backend or EmbeddingUtilsBackend(**kw)
+    fn = backend.cosine_similarity
+    if isinstance(target, type):
+        target.cosine_similarity = staticmethod(fn)
+    else:
+        target.cosine_similarity = fn
     return backend
 
 

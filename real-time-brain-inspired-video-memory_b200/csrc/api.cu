@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <new>
 
 namespace vm {
@@ -48,11 +49,10 @@ int k_pairs_above(int device, const void *x, int dtype, int64_t n, int dim, int 
                   int64_t *out_i, int64_t *out_j, float *out_score, int64_t *out_count, int part, int nparts, int flags,
                   cudaStream_t st);
 
-extern int g_last_tc_stages;
-extern int g_last_tc_variant;
 static constexpr int MAXQ = 64;   // queries per scan pass
 static constexpr int MAXK = 64;   // k and candidate-list bound
 static constexpr int XCTAS = 148; // exact-scan grid
+static constexpr int MAX_DEVICES = 64;
 static constexpr int COLLECT_CAP = 4096;         // rows per query the collect pass may gather
 static constexpr int FLAG_INTERNAL_CAPTURE = 1 << 30;  // set by the CUDA-graph path while capturing
 
@@ -129,6 +129,7 @@ struct vm_store {
         uint64_t version = 0;
         int nq = 0, k = 0, flags = 0, score_mode = 0, sum_mode = 0, q_dtype = 0;
         double min_score = 0.0;
+        int64_t row_offset = 0;  // baked into the captured FinalizeArgs
         vm_topk_stats stats{};
     };
     GraphEntry graphs[4];
@@ -477,10 +478,21 @@ struct TopkCall {
 // Result wait of the synchronous (host-buffer) calls.  cudaStreamSynchronize may park the thread for work longer
 // than ~1 ms and then pays a 0.1-0.2 ms wake-up; a top-k call is latency-critical and short, so poll instead
 // (VIDMEM_SYNC=block restores the blocking wait, e.g. on oversubscribed hosts).
-static cudaError_t wait_stream(cudaStream_t st)
+static cudaError_t wait_stream(cudaStream_t st, const vm_store *s = nullptr)
 {
     static const bool block = [] { const char *e = getenv("VIDMEM_SYNC"); return e && !strcmp(e, "block"); }();
     if (block) return cudaStreamSynchronize(st);
+    if (s) {
+        // a long scan (big shard) is slept through for ~3/4 of its roofline time, so the host core is not
+        // spun for milliseconds; only the last stretch is polled
+        const double est_us = (double)s->size * s->ld * (double)dtype_size(s->dtype) / 6.5e6;  // bytes / (6.5 TB/s)
+        if (est_us > 400.0) {
+            struct timespec ts;
+            const long ns = (long)(est_us * 750.0);
+            ts.tv_sec = ns / 1000000000L; ts.tv_nsec = ns % 1000000000L;
+            nanosleep(&ts, nullptr);
+        }
+    }
     for (;;) {
         const cudaError_t e = cudaStreamQuery(st);
         if (e != cudaErrorNotReady) return e;
@@ -547,7 +559,7 @@ static int topk_batch(const TopkCall &c)
         launches += 2;
         if (c.h_idx) {
             if ((rc = pack_out_enqueue(c)) != VM_OK) return rc;
-            VM_CUDA_CHECK(wait_stream(st));
+            VM_CUDA_CHECK(wait_stream(st, s));
             pack_out_finish(c);
         }
         if (c.stats) { c.stats->scan_kernel = 0; c.stats->scan_launches += launches; }
@@ -563,6 +575,7 @@ static int topk_batch(const TopkCall &c)
     ++launches;
 
     ScanArgs a;
+    ScanInfo sinfo;
     a.rows = s->rows; a.inv_norms = s->inv_norms; a.dtype = s->dtype; a.n = s->size; a.dim = s->dim; a.ld = s->ld;
     a.queries = (const float *)w.q_f32.p; a.nq = c.nq; a.kp = kp; a.cand = (uint64_t *)w.cand.p; a.stream = st;
     const bool timing = (c.flags & VM_FLAG_TIMING) != 0;
@@ -585,7 +598,7 @@ static int topk_batch(const TopkCall &c)
         a.dump = tiles <= s->sm_count && tiles * SCAN_DUMP_TILE <= SCAN_DUMP_MAX_KEYS &&
                  (size_t)tiles * c.nq * SCAN_DUMP_TILE * 8 <= w.cand.bytes &&
                  select_rescore_fits((int)tiles, SCAN_DUMP_TILE, kp, s->dtype, s->dim, s->ld);
-        rc = launch_scan_tc(a, s->dtype == VM_BF16 ? w.q_bf16.p : w.q_f32.p, (uint32_t *)w.seed.p, (int *)w.flags.p + c.nq + 1);
+        rc = launch_scan_tc(a, s->dtype == VM_BF16 ? w.q_bf16.p : w.q_f32.p, (uint32_t *)w.seed.p, (int *)w.flags.p + c.nq + 1, nullptr, &sinfo);
         launches += 1;
     }
     if (rc != VM_OK) return rc;
@@ -633,7 +646,7 @@ static int topk_batch(const TopkCall &c)
     } else {
         VM_CUDA_CHECK(cudaMemcpyAsync(w.h_uncert, uncert, 4, cudaMemcpyDeviceToHost, st));
         if (c.h_idx && (rc = pack_out_enqueue(c)) != VM_OK) return rc;
-        VM_CUDA_CHECK(wait_stream(st));
+        VM_CUDA_CHECK(wait_stream(st, s));
         n_uncert = *w.h_uncert;
         n_full = 0;
         if (n_uncert > 0) {
@@ -642,7 +655,7 @@ static int topk_batch(const TopkCall &c)
                 if ((rc = run_collect()) != VM_OK) return rc;
                 launches += 2;
                 VM_CUDA_CHECK(cudaMemcpyAsync(w.h_uncert, uncert, 4, cudaMemcpyDeviceToHost, st));
-                VM_CUDA_CHECK(wait_stream(st));
+                VM_CUDA_CHECK(wait_stream(st, s));
                 left = *w.h_uncert;
             }
             n_full = left;
@@ -653,7 +666,7 @@ static int topk_batch(const TopkCall &c)
             }
             if (c.h_idx) {
                 if ((rc = pack_out_enqueue(c)) != VM_OK) return rc;
-                VM_CUDA_CHECK(wait_stream(st));
+                VM_CUDA_CHECK(wait_stream(st, s));
             }
         }
         if (c.h_idx) pack_out_finish(c);
@@ -665,8 +678,8 @@ static int topk_batch(const TopkCall &c)
         c.stats->full_rescans = n_full;
         c.stats->candidates = kp;
         c.stats->scan_ctas = a.ctas;
-        c.stats->scan_stages = kernel == 2 ? g_last_tc_stages : 0;
-        c.stats->scan_variant = kernel == 2 ? g_last_tc_variant : 0;
+        c.stats->scan_stages = kernel == 2 ? sinfo.stages : 0;
+        c.stats->scan_variant = kernel == 2 ? sinfo.variant : 0;
     }
     return VM_OK;
 }
@@ -710,7 +723,8 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
         vm_store::GraphEntry *ge = nullptr;
         for (auto &e : s->graphs)
             if (e.exec && e.version == s->version && e.nq == nq && e.k == k && e.flags == flags && e.score_mode == score_mode &&
-                e.sum_mode == sum_mode && e.q_dtype == q_dtype && e.min_score == min_score) { ge = &e; break; }
+                e.sum_mode == sum_mode && e.q_dtype == q_dtype && e.row_offset == row_offset &&
+                memcmp(&e.min_score, &min_score, sizeof(double)) == 0) { ge = &e; break; }  // bitwise: a NaN bound must match itself
         int bq_g = MAXQ;
         if (!(flags & VM_FLAG_FORCE_SIMT)) {
             const int kp_tc = k <= 16 ? 32 : (k <= 48 ? 64 : 0);
@@ -753,11 +767,11 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
                 cudaGraphDestroy(graph);
                 if (ce != cudaSuccess) { ge->exec = nullptr; set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return VM_ERR_CUDA; }
                 ge->version = s->version; ge->nq = nq; ge->k = k; ge->flags = flags; ge->score_mode = score_mode;
-                ge->sum_mode = sum_mode; ge->q_dtype = q_dtype; ge->min_score = min_score; ge->stats = cs;
+                ge->sum_mode = sum_mode; ge->q_dtype = q_dtype; ge->min_score = min_score; ge->row_offset = row_offset; ge->stats = cs;
             }
             memcpy(w.h_q, queries, qbytes);
             VM_CUDA_CHECK(cudaGraphLaunch(ge->exec, s->gstream));
-            VM_CUDA_CHECK(wait_stream(s->gstream));
+            VM_CUDA_CHECK(wait_stream(s->gstream, s));
             if (ge->stats.scan_kernel != 0 && *w.h_uncert > 0) {
                 // some query was not certified: run this batch through the plain path (collect pass / exact scan)
                 TopkCall c{s, queries, q_dtype, VM_MEM_HOST, nq, k, min_score, score_mode, sum_mode, flags, row_offset,
@@ -854,7 +868,7 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
             // merged results sit in the contiguous workspace block [idx | score | count]: one D2H into pinned memory
             const size_t seg = (size_t)nb * k * 8;
             VM_CUDA_CHECK(cudaMemcpyAsync(w.h_pack, ws_idx, 2 * seg + (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-            VM_CUDA_CHECK(wait_stream(st));
+            VM_CUDA_CHECK(wait_stream(st, s));
             memcpy(out_idx + (size_t)q0 * k, w.h_pack, seg);
             memcpy(out_score + (size_t)q0 * k, w.h_pack + seg, seg);
             memcpy(out_count + q0, w.h_pack + 2 * seg, (size_t)nb * 4);
@@ -862,7 +876,7 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
             VM_CUDA_CHECK(cudaMemcpyAsync(out_idx + (size_t)q0 * k, d_idx, (size_t)nb * k * 8, cudaMemcpyDeviceToHost, st));
             VM_CUDA_CHECK(cudaMemcpyAsync(out_score + (size_t)q0 * k, d_score, (size_t)nb * k * 8, cudaMemcpyDeviceToHost, st));
             VM_CUDA_CHECK(cudaMemcpyAsync(out_count + q0, d_count, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-            VM_CUDA_CHECK(wait_stream(st));
+            VM_CUDA_CHECK(wait_stream(st, s));
         }
     }
     return VM_OK;
@@ -897,7 +911,9 @@ extern "C" int vm_merge_topk_lists(int device, const int64_t *idx_dev, const dou
     // trick: launch with per-array strides equalised by passing count through a widened view.
     // Simplest correct path: the kernel takes ONE stride, so gather the counts to that stride.
     size_t stride = (size_t)nq * k * 8;
-    static thread_local Buf cnt_wide;
+    VM_REQUIRE(device >= 0 && device < MAX_DEVICES, VM_ERR_BADARG, "device index %d outside [0, %d)", device, MAX_DEVICES);
+    static thread_local Buf cnt_wide_dev[MAX_DEVICES];  // scratch is device memory: one per device
+    Buf &cnt_wide = cnt_wide_dev[device];
     int rc = cnt_wide.ensure(stride * nlists);
     if (rc != VM_OK) return rc;
     VM_CUDA_CHECK(cudaMemcpy2DAsync(cnt_wide.p, stride, count_dev, (size_t)nq * 4, (size_t)nq * 4, nlists,
@@ -923,13 +939,16 @@ extern "C" int vm_cosine_pairs(int device, const void *a, const void *b, int dty
 {
     VM_REQUIRE(n >= 0 && dim >= 0, VM_ERR_BADARG, "bad shape");
     VM_REQUIRE(dtype == VM_F32 || dtype == VM_F64, VM_ERR_BADARG, "dtype must be VM_F32 or VM_F64");
+    VM_REQUIRE(zero_rule >= 0 && zero_rule <= 2, VM_ERR_BADARG, "zero_rule %d outside [0, 2]", zero_rule);
     if (n == 0) return VM_OK;
     VM_REQUIRE(a && b && out, VM_ERR_BADARG, "NULL buffer");
     int rc = check_arch(device, nullptr);
     if (rc != VM_OK) return rc;
     DeviceGuard g(device);
     cudaStream_t st = (cudaStream_t)stream;
-    static thread_local Buf da, db, dout;
+    VM_REQUIRE(device >= 0 && device < MAX_DEVICES, VM_ERR_BADARG, "device index %d outside [0, %d)", device, MAX_DEVICES);
+    static thread_local Buf scratch[MAX_DEVICES][3];  // scratch is device memory: one set per device
+    Buf &da = scratch[device][0], &db = scratch[device][1], &dout = scratch[device][2];
     size_t bytes = (size_t)n * dim * dtype_size(dtype);
     const void *pa = a, *pb = b;
     if (mem == VM_MEM_HOST) {

@@ -168,8 +168,9 @@ struct ScanCollect {
 };
 // tcgen05 path; seed_tab [ctas][nq_pad] u32 + seed_ctr must be zeroed before the launch (NULL = no seeding);
 // sc != NULL runs the collect pass instead of the top-kp pass
+struct ScanInfo { int stages = 0, variant = 0; };  // what the launch chose (reported in vm_topk_stats): pipeline depth; 0 lists, 1 dump, 2 lists + threshold warp
 int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t *seed_tab, int *seed_ctr,
-                   const ScanCollect *sc = nullptr);
+                   const ScanCollect *sc = nullptr, ScanInfo *info = nullptr);
 bool scan_tc_supported(int dtype, int dim, int nq, int kp);
 
 

@@ -166,7 +166,7 @@ template <bool TF32, bool DUMP, bool TW>
 __global__ void __launch_bounds__(TW ? TC_THREADS_TW : TC_THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const float *__restrict__ inv_norms, int64_t n, int num_tiles, int nq, TcLayout L, uint64_t *__restrict__ cand,
-               uint32_t *__restrict__ seed_tab, int *__restrict__ seed_ctr, int dbg, CollectArgs col, int tw_sleep)
+               uint32_t *__restrict__ seed_tab, int *__restrict__ seed_ctr, CollectArgs col, int tw_sleep)
 {
     const bool collect = !DUMP && col.thr != nullptr;
     if (collect && *col.pending == 0) return;  // nothing left to refine (uniform across the grid)
@@ -255,7 +255,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t b_addr = b0 + (uint32_t)kb * nq_pad * 128;
 #pragma unroll
                     for (int j = 0; j < 4; ++j)  // 4 x 32-byte K slices per 128-byte swizzle row
-                        if (!(dbg & 2) || (kb | j) == 0) umma<TF32>(d_tmem, make_smem_desc_sw128(a_addr + j * 32), make_smem_desc_sw128(b_addr + j * 32), idesc,
+                        umma<TF32>(d_tmem, make_smem_desc_sw128(a_addr + j * 32), make_smem_desc_sw128(b_addr + j * 32), idesc,
                                    (uint32_t)((kb | j) != 0));
                     umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
                     if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -390,7 +390,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const float4 t4 = *reinterpret_cast<const float4 *>(tauf + c + 4 * j4);
                         tf[4 * j4] = t4.x; tf[4 * j4 + 1] = t4.y; tf[4 * j4 + 2] = t4.z; tf[4 * j4 + 3] = t4.w;
                     }
-                    if (valid && !(dbg & 1)) {
+                    if (valid) {
                         uint32_t hits = 0;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) hits |= (__uint_as_float(v[j]) * inv >= tf[j]) ? (1u << j) : 0u;
@@ -532,12 +532,10 @@ bool scan_tc_supported(int dtype, int dim, int nq, int kp)
     return L.stages >= 3;
 }
 
-int g_last_tc_stages = 0;
-int g_last_tc_variant = 0;  // 0 lists, 1 dump, 2 lists + threshold warp (reported in vm_topk_stats)
-
 // queries_store_dtype: the normalised queries [nq_pad][ld] in the STORE dtype (fp32 for the tf32
 // path, bf16 for the bf16 path).
-int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t *seed_tab, int *seed_ctr, const ScanCollect *sc)
+int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t *seed_tab, int *seed_ctr, const ScanCollect *sc,
+                   ScanInfo *info)
 {
     VM_REQUIRE(a.n >= 1 && a.n < 0x7FFFFF00LL, VM_ERR_UNSUPPORTED, "tcgen05 scan: shard rows %lld outside [1, 2^31)", (long long)a.n);
     TcLayout L = make_layout(a.dtype, a.ld, a.nq, a.kp);
@@ -551,11 +549,9 @@ int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t 
     int dev_idx = 0;
     VM_CUDA_CHECK(cudaGetDevice(&dev_idx));
     dev_idx &= 63;
-    static const int dbg = getenv("VIDMEM_TC_DEBUG") ? atoi(getenv("VIDMEM_TC_DEBUG")) : 0;  // perf triage only
-    g_last_tc_stages = L.stages;
     // seeding needs at least kp CTAs (kp first-tile maxima); it pays off even with a single tile per CTA,
     // because a first tile without a threshold costs ~80 us of serial drains (stores below that use dump mode)
-    const bool seed = seed_tab && seed_ctr && a.ctas >= a.kp && a.ctas <= 256 && !(dbg & 4);
+    const bool seed = seed_tab && seed_ctr && a.ctas >= a.kp && a.ctas <= 256;
     if (!seed || sc) { seed_tab = nullptr; seed_ctr = nullptr; }
     CollectArgs col{};
     if (sc) { col.thr = sc->thr; col.buf = sc->buf; col.cnt = sc->cnt; col.cap = sc->cap; col.pending = sc->pending; }
@@ -563,8 +559,7 @@ int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t 
     // of 384 dims stream in 2.2 us; an fp32 tile takes 4.4 us and hides the drains, and measures 3 % slower
     // with the extra warp) -- once a CTA streams enough tiles for the shared bound to matter.  Measured on
     // 64-query batches, bf16: 1M rows 0.247 -> 0.172 ms, 4M rows 0.68 -> 0.49 ms, 12.5M rows 1.68 -> 1.49 ms.
-    static const int tw_min_tiles = getenv("VIDMEM_TC_TW_MIN_TILES") ? atoi(getenv("VIDMEM_TC_TW_MIN_TILES")) : 16;
-    static const int tw_max_tile_kb = getenv("VIDMEM_TC_TW_MAX_TILE_KB") ? atoi(getenv("VIDMEM_TC_TW_MAX_TILE_KB")) : 128;
+    constexpr int tw_min_tiles = 16, tw_max_tile_kb = 128;
     const int tw_sleep = 200;
     // (a single-query scan has no epilogue pressure: C5 bf16 measured 1.11 ms without vs 1.16 ms with it)
     const bool tw = seed_tab != nullptr && !sc && !a.dump && a.nq > 16 && (int64_t)num_tiles >= (int64_t)tw_min_tiles * a.ctas &&
@@ -572,7 +567,7 @@ int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t 
     const bool dump = a.dump && !sc;
     if (dump) VM_REQUIRE(TC_BLOCK_M == SCAN_DUMP_TILE && (int64_t)num_tiles * TC_BLOCK_M <= SCAN_DUMP_MAX_KEYS && a.ctas == num_tiles,
                          VM_ERR_UNSUPPORTED, "tcgen05 scan: dump mode needs one CTA per tile and at most %d rows", SCAN_DUMP_MAX_KEYS);
-    if (!sc) g_last_tc_variant = dump ? 1 : (tw ? 2 : 0);
+    if (info && !sc) { info->stages = L.stages; info->variant = dump ? 1 : (tw ? 2 : 0); }
 #define LAUNCH_TC(TF, DU, TWV)                                                                                                \
     do {                                                                                                                   \
         static bool set[64] = {}; /* the attribute is per device */                                                        \
@@ -581,7 +576,7 @@ int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t 
             set[dev_idx] = true;                                                                                           \
         }                                                                                                                  \
         scan_tc_kernel<TF, DU, TWV><<<a.ctas, TWV ? TC_THREADS_TW : TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, \
-                                                                          seed_tab, seed_ctr, dbg, col, tw_sleep);        \
+                                                                          seed_tab, seed_ctr, col, tw_sleep);             \
     } while (0)
     if (a.dtype == VM_F32) { if (dump) LAUNCH_TC(true, true, false); else if (tw) LAUNCH_TC(true, false, true); else LAUNCH_TC(true, false, false); }
     else { if (dump) LAUNCH_TC(false, true, false); else if (tw) LAUNCH_TC(false, false, true); else LAUNCH_TC(false, false, false); }

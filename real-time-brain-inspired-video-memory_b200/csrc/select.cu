@@ -1015,9 +1015,13 @@ __global__ void cosine_pairs_kernel(const void *__restrict__ a, const void *__re
         aa.add<NEUMAIER>(__dmul_rn(x, x));
         bb.add<NEUMAIER>(__dmul_rn(y, y));
     }
-    double n1 = __dsqrt_rn(aa.result<NEUMAIER>()), n2 = __dsqrt_rn(bb.result<NEUMAIER>());
+    // zero_rule 2 = EmbeddingUtils.cosine_similarity (embedding_utils.py:29-39): magnitudes through `** 0.5`,
+    // i.e. libm pow(x, 0.5) in CPython, here CUDA's pow (<= 2 ulp; not bit-pinned to a particular libm)
+    double n1, n2;
+    if (zero_rule == 2) { n1 = pow(aa.result<NEUMAIER>(), 0.5); n2 = pow(bb.result<NEUMAIER>(), 0.5); }
+    else { n1 = __dsqrt_rn(aa.result<NEUMAIER>()); n2 = __dsqrt_rn(bb.result<NEUMAIER>()); }
     double den = __dmul_rn(n1, n2);
-    bool zero = zero_rule == 0 ? (n1 == 0.0 || n2 == 0.0) : (den == 0.0);
+    bool zero = zero_rule == 1 ? (den == 0.0) : (n1 == 0.0 || n2 == 0.0);
     out[i] = zero ? 0.0 : __ddiv_rn(dot.result<NEUMAIER>(), den);
 }
 

@@ -231,8 +231,22 @@ class EmbeddingStore:
         """Device in / device out on the current stream.  -> (idx, score, count) CUDA tensors."""
         if not queries.is_cuda:
             raise TypeError("queries must be a CUDA tensor")
+        if queries.device != self.device:
+            raise ValueError(f"queries live on {queries.device}, the store on {self.device}")
+        if queries.dim() != 2 or queries.shape[1] != self.dim:
+            raise ValueError(f"expected [nq, {self.dim}] queries, got {tuple(queries.shape)}")
+        if not 1 <= int(k) <= 64:
+            raise ValueError(f"k = {k} outside [1, 64]")
         q = queries.contiguous()
         nq = q.shape[0]
+        if out is not None:
+            want = ((nq, k), torch.int64), ((nq, k), torch.float64), ((nq,), torch.int32)
+            if len(out) != 3:
+                raise ValueError("out must be (idx, score, count)")
+            for t, (shape, dt) in zip(out, want):
+                if (not isinstance(t, torch.Tensor) or t.device != self.device or t.dtype != dt
+                        or tuple(t.shape) != shape or not t.is_contiguous()):
+                    raise ValueError(f"out tensors must be contiguous {want} on {self.device}")
         if out is None:
             out = (torch.empty((nq, k), dtype=torch.int64, device=self.device),
                    torch.empty((nq, k), dtype=torch.float64, device=self.device),
@@ -256,7 +270,8 @@ class EmbeddingStore:
 def cosine_pairs(a, b, zero_rule: int = 0, sum_mode: Optional[int] = None, device: int = 0) -> np.ndarray:
     """n independent cosines, bit-identical to PreLLMInjector._cosine_similarity (zero_rule 0,
     pre_llm_injector.py:374-388) or HybridRetriever._cosine_similarity (zero_rule 1,
-    retriever_hybrid.py:655-664) on equal-length vectors."""
+    retriever_hybrid.py:655-664) on equal-length vectors; zero_rule 2 = EmbeddingUtils.cosine_similarity
+    (embedding_utils.py:29-39, magnitudes through `** 0.5`; a few ulp, see include/vidmem.h)."""
     lib = L.load()
     a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
     b = np.ascontiguousarray(np.asarray(b, dtype=np.float64))

@@ -173,6 +173,28 @@ def test_cosine_pairs_golden(vm, golden_dir):
         a, b = g["a"][i, :la], g["b"][i, :lb]
         assert cosine_pairs(a, b, zero_rule=0, sum_mode=vm.VM_SUM_NEUMAIER)[0] == g["out"][i, 0]
         assert cosine_pairs(a, b, zero_rule=1, sum_mode=vm.VM_SUM_NEUMAIER)[0] == g["out"][i, 1]
+        # a4, EmbeddingUtils.cosine_similarity: `** 0.5` is libm pow in CPython and CUDA's pow here -- the one seam
+        # with a tolerance (a few ulp of binary64; north_star allows 1e-5 relative)
+        got = cosine_pairs(a, b, zero_rule=2, sum_mode=vm.VM_SUM_NEUMAIER)[0]
+        assert got == pytest.approx(g["out"][i, 2], rel=4 * np.finfo(np.float64).eps, abs=0.0), i
+        assert (got == 0.0) == (g["out"][i, 2] == 0.0)
+
+
+def test_cosine_pairs_scratch_is_per_device(vm):
+    """vm_cosine_pairs / vm_merge_topk_lists keep their device scratch per device (round-1 ADVICE: a buffer allocated
+    on device A must not be handed to a kernel on device B); with one GPU this checks the per-device table and the
+    rejection of an out-of-range index."""
+    from vidmem_b200.store import cosine_pairs
+    a, b = np.arange(1.0, 9.0), np.arange(8.0, 0.0, -1.0)
+    want = oracle.cosine(a, b, "injector")
+    for _ in range(3):
+        assert cosine_pairs(a, b, device=0)[0] == want
+    import torch
+    if torch.cuda.device_count() > 1:
+        assert cosine_pairs(a, b, device=1)[0] == want
+        assert cosine_pairs(a, b, device=0)[0] == want
+    with pytest.raises(vm.VidmemError):
+        cosine_pairs(a, b, device=99)
 
 
 def test_merge_max_by_id_golden(vm, golden_dir):
