@@ -181,6 +181,14 @@ int vm_merge_topk_lists(int device, const int64_t *idx_dev, const double *score_
                         int nlists, int nq, int k, int64_t *out_idx_dev, double *out_score_dev,
                         int32_t *out_count_dev, void *stream);
 
+/* The same merge over the PACKED exchange layout vm_topk_sharded all-gathers: `nlists` consecutive blocks of
+ * vm_topk_packed_bytes(nq, k) bytes, each [idx nq*k int64 | score nq*k double | count nq int32, padded to 8 bytes]
+ * (one block per rank, global row indices).  For callers that move the blocks with their own transport, and for
+ * checking the exchange format on a single GPU. */
+size_t vm_topk_packed_bytes(int nq, int k);
+int vm_merge_topk_packed(int device, const void *packed_dev, int nlists, int nq, int k, int64_t *out_idx_dev,
+                         double *out_score_dev, int32_t *out_count_dev, void *stream);
+
 /* Cross-query merge of _parallel_chunk_extraction_with_similarity
  * (src/components/pre_llm_injector.py:235-249): max score per row id over all queries' lists
  * (strict `>` replace), stable sort descending (first-seen order on ties), first k2.
@@ -217,6 +225,20 @@ int vm_cosine_pairs(int device, const void *a, const void *b, int dtype, int mem
 int vm_pairs_above(int device, const void *x_dev, int dtype, int64_t n, int dim, float threshold, int64_t cap,
                    int64_t *out_i_dev, int64_t *out_j_dev, float *out_score_dev, int64_t *out_count_dev, int part,
                    int nparts, int flags, void *stream);
+
+/* Multi-GPU form of vm_pairs_above, collective over `comm` (every rank calls it with the
+ * same n / dim / threshold / cap on its own stream):
+ *   1. the operand x_dev [n][ld] is replicated with ONE ncclBroadcast from rank `root` (root = -1: every
+ *      rank already holds the rows);
+ *   2. the upper-triangular tile grid is dealt cyclically to the ranks (part = rank of vm_pairs_above);
+ *   3. one ncclAllGather of the per-rank hit counts and one ncclAllGather of the hit lists, concatenated in
+ *      rank order on the device -- every rank ends with the same, complete (i, j, score) list in out_* and the
+ *      total in *out_count_dev.  Nothing but the 8-byte counts passes through the host; with VM_FLAG_ASYNC not
+ *      even those (the lists are then gathered at full capacity `cap` per rank).
+ * More than `cap` pairs (in total, or on one rank) -> VM_ERR_OVERFLOW with the total in *out_count_dev. */
+int vm_pairs_above_sharded(vm_comm *comm, void *x_dev, int dtype, int64_t n, int dim, float threshold, int64_t cap,
+                           int64_t *out_i_dev, int64_t *out_j_dev, float *out_score_dev, int64_t *out_count_dev,
+                           int root, int flags, void *stream);
 
 /* ---- multi-GPU plumbing -----------------------------------------------------------------
  * One process per GPU; the 128-byte NCCL unique id is created on rank 0 and shipped to the

@@ -31,7 +31,7 @@ EXPORTS = [
     "vm_store_ld", "vm_store_append", "vm_store_update", "vm_store_invalidate", "vm_store_set_size", "vm_store_clear",
     "vm_store_last_scan_ms",
     "vm_store_avg_scan_ms",
-    "vm_topk", "vm_topk_sharded", "vm_merge_topk_lists", "vm_merge_max_by_id", "vm_cosine_pairs", "vm_pairs_above",
+    "vm_topk", "vm_topk_sharded", "vm_merge_topk_lists", "vm_topk_packed_bytes", "vm_merge_topk_packed", "vm_merge_max_by_id", "vm_cosine_pairs", "vm_pairs_above", "vm_pairs_above_sharded",
     "vm_comm_unique_id", "vm_comm_init_rank", "vm_comm_destroy", "vm_comm_exchange_bytes", "vm_comm_attach_peer_buffers", "vm_comm_nranks", "vm_comm_rank", "vm_synth_fill",
 ]
 
@@ -87,9 +87,12 @@ def load() -> C.CDLL:
         "vm_topk": (ci, [vp, vp, ci, ci, ci, ci, dbl, ci, ci, ci, vp, vp, vp, ci, P(TopkStats), vp]),
         "vm_topk_sharded": (ci, [vp, vp, i64, vp, ci, ci, ci, ci, dbl, ci, ci, ci, vp, vp, vp, ci, P(TopkStats), vp]),
         "vm_merge_topk_lists": (ci, [ci, vp, vp, vp, ci, ci, ci, vp, vp, vp, vp]),
+        "vm_topk_packed_bytes": (sz, [ci, ci]),
+        "vm_merge_topk_packed": (ci, [ci, vp, ci, ci, ci, vp, vp, vp, vp]),
         "vm_merge_max_by_id": (ci, [ci, vp, vp, vp, ci, ci, ci, vp, vp, vp, vp]),
         "vm_cosine_pairs": (ci, [ci, vp, vp, ci, ci, i64, ci, ci, ci, vp, ci, vp]),
         "vm_pairs_above": (ci, [ci, vp, ci, i64, ci, C.c_float, i64, vp, vp, vp, vp, ci, ci, ci, vp]),
+        "vm_pairs_above_sharded": (ci, [vp, vp, ci, i64, ci, C.c_float, i64, vp, vp, vp, vp, ci, ci, vp]),
         "vm_comm_unique_id": (ci, [vp]),
         "vm_comm_init_rank": (ci, [P(vp), ci, ci, ci, vp]),
         "vm_comm_destroy": (ci, [vp]),

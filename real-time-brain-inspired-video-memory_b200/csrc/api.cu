@@ -48,6 +48,8 @@ int k_cosine_pairs(const void *a, const void *b, int dtype, int64_t n, int dim, 
 int k_pairs_above(int device, const void *x, int dtype, int64_t n, int dim, int ld, float threshold, int64_t cap,
                   int64_t *out_i, int64_t *out_j, float *out_score, int64_t *out_count, int part, int nparts, int flags,
                   cudaStream_t st);
+int k_pairs_concat(const void *gathered, size_t per_rank_bytes, int64_t slot, const int64_t *counts, int nranks, int64_t cap,
+                   int64_t *out_i, int64_t *out_j, float *out_score, int64_t *out_count, cudaStream_t st);
 
 static constexpr int MAXQ = 64;   // queries per scan pass
 static constexpr int MAXK = 64;   // k and candidate-list bound
@@ -151,6 +153,9 @@ struct vm_comm {
     void *peer[16] = {};   // peer-mapped exchange buffers (optional, see vm_comm_attach_peer_buffers)
     bool p2p = false;
     unsigned long long gen = 0;
+    // vm_pairs_above_sharded: local hit lists, gathered counts and gathered lists
+    Buf pl_i, pl_j, pl_s, pl_cnt, pg_cnt, pg_send, pg_recv;
+    int64_t *h_counts = nullptr;  // pinned [nranks]
 };
 
 // ---- NCCL, resolved at run time so the library loads on hosts without it --------------------
@@ -161,6 +166,7 @@ struct NcclApi {
     int (*GetUniqueId)(void *) = nullptr;
     int (*CommInitRank)(void **, int, /*ncclUniqueId by value*/ Id128, int) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*CommDestroy)(void *) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
@@ -176,9 +182,10 @@ static int nccl_load()
     g_nccl.GetUniqueId = (int (*)(void *))dlsym(h, "ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(void **, int, Id128, int))dlsym(h, "ncclCommInitRank");
     g_nccl.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(h, "ncclAllGather");
+    g_nccl.Broadcast = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclBroadcast");
     g_nccl.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
-    VM_REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllGather && g_nccl.CommDestroy, VM_ERR_NCCL,
+    VM_REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllGather && g_nccl.Broadcast && g_nccl.CommDestroy, VM_ERR_NCCL,
                "libnccl lacks a required symbol");
     g_nccl.h = h;
     return VM_OK;
@@ -451,6 +458,10 @@ extern "C" int vm_store_clear(vm_store *s)
 }
 
 // ---- top-k ------------------------------------------------------------------------------------
+// One rank's block of the cross-shard exchange: [idx nq*k i64 | score nq*k f64 | count nq i32, padded to 8 bytes]
+static inline size_t packed_bytes(int nq, int k) { return (size_t)nq * k * 16 + (((size_t)nq * 4 + 7) & ~(size_t)7); }
+extern "C" size_t vm_topk_packed_bytes(int nq, int k) { return nq > 0 && k > 0 ? packed_bytes(nq, k) : 0; }
+
 namespace {
 struct TopkCall {
     vm_store *s;
@@ -825,7 +836,7 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
         } else if (sharded) {
             // pack [idx | score | count] contiguously so ONE all-gather moves the batch
             size_t seg = (size_t)nb * k * 8;
-            size_t per_rank = 2 * seg + (((size_t)nb * 4 + 7) & ~(size_t)7);
+            size_t per_rank = packed_bytes(nb, k);
             rc = w.gather_send.ensure(per_rank);
             if (rc == VM_OK) rc = w.gather_recv.ensure(per_rank * comm->nranks);
             if (rc != VM_OK) return rc;
@@ -855,7 +866,7 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
                     rc = k_merge_topk_p2p(comm->peer, comm->nranks, slot_off, XCHG_FLAG_OFF, gen, nb, k, m_idx, m_score, m_count, st);
             } else {
                 size_t seg = (size_t)nb * k * 8;
-                size_t per_rank = 2 * seg + (((size_t)nb * 4 + 7) & ~(size_t)7);
+                size_t per_rank = packed_bytes(nb, k);
                 VM_NCCL_CHECK(g_nccl.AllGather(w.gather_send.p, w.gather_recv.p, per_rank, /*ncclInt8*/ 0, comm->nccl, st));
                 const char *rb = (const char *)w.gather_recv.p;
                 rc = k_merge_topk_lists(rb, rb + seg, rb + 2 * seg, per_rank, comm->nranks, nb, k, m_idx, m_score, m_count, st);
@@ -919,6 +930,18 @@ extern "C" int vm_merge_topk_lists(int device, const int64_t *idx_dev, const dou
     VM_CUDA_CHECK(cudaMemcpy2DAsync(cnt_wide.p, stride, count_dev, (size_t)nq * 4, (size_t)nq * 4, nlists,
                                     cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return k_merge_topk_lists(idx_dev, score_dev, cnt_wide.p, stride, nlists, nq, k, out_idx_dev, out_score_dev,
+                              out_count_dev, (cudaStream_t)stream);
+}
+
+extern "C" int vm_merge_topk_packed(int device, const void *packed_dev, int nlists, int nq, int k, int64_t *out_idx_dev,
+                                    double *out_score_dev, int32_t *out_count_dev, void *stream)
+{
+    VM_REQUIRE(packed_dev && out_idx_dev && out_score_dev && out_count_dev, VM_ERR_BADARG, "NULL buffer");
+    VM_REQUIRE(nlists >= 1 && nq >= 1 && k >= 1, VM_ERR_BADARG, "bad shape");
+    DeviceGuard g(device);
+    const char *rb = (const char *)packed_dev;
+    const size_t seg = (size_t)nq * k * 8;
+    return k_merge_topk_lists(rb, rb + seg, rb + 2 * seg, packed_bytes(nq, k), nlists, nq, k, out_idx_dev, out_score_dev,
                               out_count_dev, (cudaStream_t)stream);
 }
 
@@ -989,6 +1012,65 @@ extern "C" int vm_pairs_above(int device, const void *x_dev, int dtype, int64_t 
                          out_count_dev, part, nparts, flags, (cudaStream_t)stream);
 }
 
+extern "C" int vm_pairs_above_sharded(vm_comm *comm, void *x_dev, int dtype, int64_t n, int dim, float threshold, int64_t cap,
+                                      int64_t *out_i_dev, int64_t *out_j_dev, float *out_score_dev, int64_t *out_count_dev,
+                                      int root, int flags, void *stream)
+{
+    VM_REQUIRE(comm, VM_ERR_BADARG, "comm is NULL");
+    VM_REQUIRE(x_dev && out_count_dev, VM_ERR_BADARG, "NULL buffer");
+    VM_REQUIRE(cap >= 1 && out_i_dev && out_j_dev && out_score_dev, VM_ERR_BADARG, "cap < 1 or NULL output");
+    VM_REQUIRE(dtype == VM_F32 || dtype == VM_BF16, VM_ERR_BADARG, "dtype must be VM_F32 or VM_BF16");
+    VM_REQUIRE(n >= 0 && n < (1LL << 31), VM_ERR_BADARG, "n outside [0, 2^31)");
+    VM_REQUIRE(dim >= 1 && dim <= 4096, VM_ERR_BADARG, "dim outside [1, 4096]");
+    VM_REQUIRE(root >= -1 && root < comm->nranks, VM_ERR_BADARG, "root %d outside [-1, %d)", root, comm->nranks);
+    int rc = check_arch(comm->device, nullptr);
+    if (rc != VM_OK) return rc;
+    DeviceGuard g(comm->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int G = comm->nranks, ld = ld_for_dim(dim);
+    // 1. replicate the operand: ONE broadcast from `root` over NVLink (root < 0: every rank already holds it)
+    if (root >= 0 && G > 1 && n > 0)
+        VM_NCCL_CHECK(g_nccl.Broadcast(x_dev, x_dev, (size_t)n * ld * dtype_size(dtype), /*ncclInt8*/ 0, root, comm->nccl, st));
+    // 2. this rank's share of the upper-triangular tile grid (dealt cyclically) -> local hit lists
+#define ENS(b, bytes) if ((rc = (b).ensure(bytes)) != VM_OK) return rc
+    ENS(comm->pl_i, (size_t)cap * 8); ENS(comm->pl_j, (size_t)cap * 8); ENS(comm->pl_s, (size_t)cap * 4);
+    ENS(comm->pl_cnt, 8); ENS(comm->pg_cnt, (size_t)G * 8);
+    if (!comm->h_counts) VM_CUDA_CHECK(cudaMallocHost((void **)&comm->h_counts, 16 * 8));
+    rc = k_pairs_above(comm->device, x_dev, dtype, n, dim, ld, threshold, cap, (int64_t *)comm->pl_i.p, (int64_t *)comm->pl_j.p,
+                       (float *)comm->pl_s.p, (int64_t *)comm->pl_cnt.p, comm->rank, G, 0, st);
+    if (rc != VM_OK) return rc;
+    // 3. exchange: all-gather of the counts, then ONE all-gather of the lists padded to `slot` entries per rank.
+    //    Default: the counts are read back (8 bytes per rank) so the slot is the largest count -- no padding
+    //    traffic.  VM_FLAG_ASYNC: no host round trip at all, the slot is the full capacity.
+    VM_NCCL_CHECK(g_nccl.AllGather(comm->pl_cnt.p, comm->pg_cnt.p, 8, /*ncclInt8*/ 0, comm->nccl, st));
+    int64_t slot = cap;
+    if (!(flags & VM_FLAG_ASYNC)) {
+        VM_CUDA_CHECK(cudaMemcpyAsync(comm->h_counts, comm->pg_cnt.p, (size_t)G * 8, cudaMemcpyDeviceToHost, st));
+        VM_CUDA_CHECK(cudaStreamSynchronize(st));
+        int64_t mx = 0, total = 0;
+        for (int r = 0; r < G; ++r) { mx = comm->h_counts[r] > mx ? comm->h_counts[r] : mx; total += comm->h_counts[r]; }
+        if (mx > cap || total > cap) {
+            VM_CUDA_CHECK(cudaMemcpyAsync(out_count_dev, &total, 8, cudaMemcpyHostToDevice, st));
+            VM_CUDA_CHECK(cudaStreamSynchronize(st));
+            set_error("%lld pairs above the threshold exceed cap=%lld", (long long)total, (long long)cap);
+            return VM_ERR_OVERFLOW;
+        }
+        slot = mx;
+    }
+    if (slot == 0) { VM_CUDA_CHECK(cudaMemsetAsync(out_count_dev, 0, 8, st)); return VM_OK; }
+    const size_t per_rank = (size_t)slot * 20;  // [i slot*8 | j slot*8 | s slot*4]
+    ENS(comm->pg_send, per_rank); ENS(comm->pg_recv, per_rank * G);
+#undef ENS
+    char *sb = (char *)comm->pg_send.p;
+    VM_CUDA_CHECK(cudaMemcpyAsync(sb, comm->pl_i.p, (size_t)slot * 8, cudaMemcpyDeviceToDevice, st));
+    VM_CUDA_CHECK(cudaMemcpyAsync(sb + (size_t)slot * 8, comm->pl_j.p, (size_t)slot * 8, cudaMemcpyDeviceToDevice, st));
+    VM_CUDA_CHECK(cudaMemcpyAsync(sb + (size_t)slot * 16, comm->pl_s.p, (size_t)slot * 4, cudaMemcpyDeviceToDevice, st));
+    VM_NCCL_CHECK(g_nccl.AllGather(comm->pg_send.p, comm->pg_recv.p, per_rank, /*ncclInt8*/ 0, comm->nccl, st));
+    // 4. concatenate the per-rank lists in rank order on the device (identical on every rank)
+    return k_pairs_concat(comm->pg_recv.p, per_rank, slot, (const int64_t *)comm->pg_cnt.p, G, cap, out_i_dev, out_j_dev,
+                          out_score_dev, out_count_dev, st);
+}
+
 // ---- communicator -----------------------------------------------------------------------------
 extern "C" int vm_comm_unique_id(void *out128)
 {
@@ -1002,7 +1084,7 @@ extern "C" int vm_comm_unique_id(void *out128)
 extern "C" int vm_comm_init_rank(vm_comm **out, int device, int nranks, int rank, const void *id128)
 {
     VM_REQUIRE(out && id128, VM_ERR_BADARG, "NULL argument");
-    VM_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, VM_ERR_BADARG, "bad rank %d / nranks %d", rank, nranks);
+    VM_REQUIRE(nranks >= 1 && nranks <= 16 && rank >= 0 && rank < nranks, VM_ERR_BADARG, "bad rank %d / nranks %d (at most 16 ranks)", rank, nranks);
     int rc = nccl_load();
     if (rc != VM_OK) return rc;
     DeviceGuard g(device);
@@ -1041,6 +1123,12 @@ extern "C" int vm_comm_destroy(vm_comm *c)
 {
     if (!c) return VM_OK;
     if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
+    {
+        DeviceGuard g(c->device);
+        Buf *all[] = {&c->pl_i, &c->pl_j, &c->pl_s, &c->pl_cnt, &c->pg_cnt, &c->pg_send, &c->pg_recv};
+        for (Buf *b : all) b->release();
+        if (c->h_counts) cudaFreeHost(c->h_counts);
+    }
     delete c;
     return VM_OK;
 }

@@ -401,6 +401,34 @@ __global__ void pairs_finalize_kernel(const T *__restrict__ x, int ld, int dim, 
     if (blockIdx.x == 0 && threadIdx.x == 0 && staged > (unsigned long long)st_cap) atomicMax(out_cnt, staged);
 }
 
+// Multi-GPU concatenation: `gathered` holds, per rank r, [i slot*8 | j slot*8 | s slot*4] at r * per_rank_bytes with
+// counts[r] valid entries; they are packed in rank order into out_* (capacity cap) and *out_count = sum of counts.
+__global__ void pairs_concat_kernel(const char *__restrict__ gathered, size_t per_rank_bytes, long long slot,
+                                    const long long *__restrict__ counts, int nranks, long long cap, int64_t *__restrict__ out_i,
+                                    int64_t *__restrict__ out_j, float *__restrict__ out_s, long long *__restrict__ out_count)
+{
+    const int r = blockIdx.y;
+    long long off = 0, total = 0;
+    for (int q = 0; q < nranks; ++q) { if (q < r) off += counts[q]; total += counts[q]; }
+    const long long m = counts[r] < slot ? counts[r] : slot;
+    const char *b = gathered + (size_t)r * per_rank_bytes;
+    const int64_t *gi = reinterpret_cast<const int64_t *>(b), *gj = reinterpret_cast<const int64_t *>(b + (size_t)slot * 8);
+    const float *gs = reinterpret_cast<const float *>(b + (size_t)slot * 16);
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < m; e += (long long)gridDim.x * blockDim.x)
+        if (off + e < cap) { out_i[off + e] = gi[e]; out_j[off + e] = gj[e]; out_s[off + e] = gs[e]; }
+    if (r == 0 && blockIdx.x == 0 && threadIdx.x == 0) *out_count = total;
+}
+
+int k_pairs_concat(const void *gathered, size_t per_rank_bytes, int64_t slot, const int64_t *counts, int nranks, int64_t cap,
+                   int64_t *out_i, int64_t *out_j, float *out_score, int64_t *out_count, cudaStream_t st)
+{
+    dim3 grid((unsigned)imin64((slot + 255) / 256, 256), (unsigned)nranks);
+    pairs_concat_kernel<<<grid, 256, 0, st>>>((const char *)gathered, per_rank_bytes, (long long)slot, (const long long *)counts, nranks,
+                                             (long long)cap, out_i, out_j, out_score, (long long *)out_count);
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
 int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, int *extreme, cudaStream_t st);
 
 namespace {

@@ -43,11 +43,46 @@ def pairs_above(x: torch.Tensor, threshold: float, cap: int = 1 << 20, part: int
     return i[order], j[order], s[order]
 
 
-def pairs_above_sharded(x: torch.Tensor, threshold: float, cap: int = 1 << 20):
-    """Multi-GPU form: the operand is replicated on every rank, the upper-triangular
-    tile grid is dealt cyclically to the ranks (part = rank), and the per-rank hit lists are
-    concatenated with torch.distributed (counts first, then a padded all_gather).  Every rank
-    returns the full, (i, j)-sorted pair set."""
+def _padded(x: torch.Tensor, lib) -> torch.Tensor:
+    n, dim = x.shape
+    ld = lib.vm_ld(dim)
+    if ld != dim or not x.is_contiguous():
+        xp = torch.zeros((n, ld), dtype=x.dtype, device=x.device)
+        xp[:, :dim] = x
+        return xp
+    return x
+
+
+def pairs_above_sharded(x: torch.Tensor, threshold: float, cap: int = 1 << 20, comm=None, root: int = -1):
+    """Multi-GPU form: the upper-triangular tile grid is dealt cyclically to the ranks and every rank
+    returns the full, (i, j)-sorted pair set.
+
+    comm = a sharded.Communicator: ONE call into the C ABI (vm_pairs_above_sharded) -- operand replicated with an
+    ncclBroadcast from `root` (root = -1: `x` is already the same on every rank), per-rank hit lists exchanged with
+    ncclAllGather and concatenated on the device; nothing but the 8-byte counts touches the host.
+    comm = None: the same exchange through torch.distributed (counts first, then a padded all_gather) -- the
+    host-side restatement the gloo tests run on CPU."""
+    if comm is not None:
+        if not x.is_cuda or x.dim() != 2:
+            raise TypeError("x must be a 2-D CUDA tensor")
+        lib = L.load()
+        n, dim = x.shape
+        dt = {torch.float32: L.VM_F32, torch.bfloat16: L.VM_BF16}[x.dtype]
+        xp = _padded(x, lib)
+        dev = x.device
+        oi = torch.empty((cap,), dtype=torch.int64, device=dev)
+        oj = torch.empty((cap,), dtype=torch.int64, device=dev)
+        os_ = torch.empty((cap,), dtype=torch.float32, device=dev)
+        cnt = torch.zeros((1,), dtype=torch.int64, device=dev)
+        L.check(lib.vm_pairs_above_sharded(comm.handle, xp.data_ptr(), dt, n, dim, C.c_float(threshold), cap, oi.data_ptr(),
+                                           oj.data_ptr(), os_.data_ptr(), cnt.data_ptr(), int(root), 0,
+                                           torch.cuda.current_stream(dev).cuda_stream))
+        if root >= 0 and xp is not x:
+            x.copy_(xp[:, :dim])                      # the broadcast landed in the padded copy
+        total = int(cnt.item())
+        i, j, s = oi[:total].cpu().numpy(), oj[:total].cpu().numpy(), os_[:total].cpu().numpy()
+        order = np.lexsort((j, i))
+        return i[order], j[order], s[order]
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
     i, j, s = pairs_above(x, threshold, cap=cap, part=rank, nparts=world)

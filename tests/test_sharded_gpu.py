@@ -76,6 +76,14 @@ def _worker(rank, world, port, out_dir):
     gi, gj, gs = dedup.pairs_above_sharded(x, 0.9)
     oi, oj, _ = oracle.pairs_above(E, 0.9)
     ok = ok and len(oi) > 0 and list(zip(gi.tolist(), gj.tolist())) == list(zip(oi.tolist(), oj.tolist()))
+    # the same through the C ABI alone (vm_pairs_above_sharded): only rank 0 holds the rows, ONE ncclBroadcast
+    # replicates them, ncclAllGather of counts + lists, device concatenation
+    x2 = x.clone() if rank == 0 else torch.zeros_like(x)
+    ci, cj, cs = dedup.pairs_above_sharded(x2, 0.9, comm=comm, root=0)
+    ok = ok and list(zip(ci.tolist(), cj.tolist())) == list(zip(oi.tolist(), oj.tolist())) and torch.equal(x2, x)
+    ok = ok and np.array_equal(cs, gs)
+    ai, aj, _ = dedup.pairs_above_sharded(x, 0.9, comm=comm, cap=4096)          # already replicated (root = -1)
+    ok = ok and list(zip(ai.tolist(), aj.tolist())) == list(zip(oi.tolist(), oj.tolist()))
     # streaming inserts routed over the ranks + one all-gather + vm_merge_topk_lists
     from vidmem_b200.sharded import ShardedChunkStore
     from test_sharded_cpu import _stream_scenario, _stream_expected
