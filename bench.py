@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the embedding-similarity hot path (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c3|c4|c5]
 
 A "step" is one pass of the hot path over one batch: 64 queries, top-10, scored against every
 row of the HBM-resident synthetic store (SURVEY.md 8d generator).
@@ -11,8 +11,16 @@ row of the HBM-resident synthetic store (SURVEY.md 8d generator).
           (strong scaling: the store is fixed, rows per GPU shrink with N).
 One JSON line on stdout (rank 0).  `value` = queries/s with queries and outputs resident in
 HBM; `e2e` = the same metric through the public host-buffer API (pinned host queries in, host
-results out, copies inside the timed region).  `--impl reference` times the reference's CPU
-algorithm (oracle port, all host threads) on a bounded sample of the same workload.
+results out, copies inside the timed region).  The same line carries, at every N:
+  parity      the timed call checked IN THIS RUN: against the binary64 scan of every row (all queries; for N > 1
+              against the host merge of the per-shard binary64 scans, and identical lists on every rank), and
+              against the CPU oracle on rank 0 (>= 8 queries); a mismatch exits non-zero
+  certification  how many timed queries the first pass could not certify and what settled them
+  dedup       config C4 (all-pairs, 1M x 768 bf16, threshold 0.9) on the same N GPUs: pairs/s, TFLOP/s per GPU
+  streaming   config C5 (4096-row inserts interleaved with single-query top-10 over 10M x 384): p50/p99
+  clustered   the main workload on a unit-norm Gaussian-mixture store with non-representable values
+  cpu_baseline  the oracle port on the box's host cores (bounded sample)
+`--impl reference` times the reference's CPU algorithm (oracle port, all host threads) on the same workload.
 """
 from __future__ import annotations
 
@@ -20,7 +28,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -53,6 +60,17 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
+        except Exception:
+            pass
+    return 1400.0, "fallback (B200_PROFILING.md sustained)"
+
+
 class ClockSampler:
     """SM clocks and throttle reasons sampled DURING the timed region (in-process NVML polling,
     ~2 ms period: a subprocess `nvidia-smi -lms` starts too slowly for a region of tens of ms)."""
@@ -81,9 +99,10 @@ class ClockSampler:
             self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
-            return
+            return self
         self.t = threading.Thread(target=self._poll, daemon=True)
         self.t.start()
+        return self
 
     def _poll(self):
         nv = self.nv
@@ -110,19 +129,74 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def _ncu_traffic(cfg: str, scan_kernel: int, rows_local: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel from the committed ncu --set full
-    capture of this workload (profiles/), per launch; None when no capture exists for this shard size."""
-    p = os.path.join(ROOT, "profiles", f"r1_scan_tc_{cfg}_summary.json")
-    if scan_kernel == 2 and os.path.exists(p):
+def _ncu_traffic(dt: str, rows_local: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel, per launch, from the committed
+    `ncu --set full` capture of this dtype and shard size (profiles/*scan*summary.json); None when no
+    capture of exactly this shape exists."""
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        names = sorted(os.listdir(pdir), reverse=True)     # later rounds first
+    except OSError:
+        return None
+    for name in names:
+        if "scan" not in name or not name.endswith("_summary.json"):
+            continue
         try:
-            d = json.load(open(p))
-            if int(d.get("rows", rows_local)) != int(rows_local):
-                return None
-            return d["dram_bytes_read"] + d["dram_bytes_write"]
+            d = json.load(open(os.path.join(pdir, name)))
+            if int(d.get("rows", -1)) == int(rows_local) and str(d.get("store_dtype", dt)) == dt:
+                return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
         except Exception:
-            return None
+            continue
     return None
+
+
+class Ctx:
+    """Process-wide state of one bench run (rank, device, communicator)."""
+
+    def __init__(self, args):
+        import torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.comm = None
+        self.peer_exchange = False
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            from vidmem_b200.sharded import Communicator
+            self.comm = Communicator.from_torch_distributed(self.local_rank)
+            self.peer_exchange = bool(args.peer_exchange and self.comm.enable_peer_exchange())
+
+    def barrier(self):
+        import torch
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        import torch
+        if self.world == 1:
+            return [float(v) for v in values]
+        import torch.distributed as dist
+        t = torch.tensor(list(values), device=self.dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def all_true(self, flag: bool) -> bool:
+        return self.max_over_ranks([0.0 if flag else 1.0])[0] == 0.0
+
+    def close(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            if self.comm is not None:
+                self.comm.close()
+            dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -141,7 +215,7 @@ def cpu_reference_leg(cfg_name: str, steps: int, warmup: int, sample_rows: int):
     Q = synth.synth_queries(qseed, nq, dim, sseed, rows_total).astype(np.float64)
     oracle.lib()
     for _ in range(warmup):
-        oracle.batch_similarities(Q[:8], X[:2000], k)
+        oracle.batch_similarities(Q, X, k)
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
@@ -149,8 +223,8 @@ def cpu_reference_leg(cfg_name: str, steps: int, warmup: int, sample_rows: int):
         times.append(time.perf_counter() - t0)
     per_step = sum(times) / len(times)
     full = per_step * (rows_total / sample_rows)
-    return nq / full, per_step * 1e3, (f"{nq} queries x {sample_rows} rows x {dim} (of {rows_total} rows), "
-                                       f"time scaled linearly in rows to the full store")
+    what = "the full store" if sample_rows == rows_total else f"{sample_rows} of {rows_total} rows, time scaled linearly in rows to the full store"
+    return nq / full, per_step * 1e3, f"{nq} queries x {sample_rows} rows x {dim}: {what}"
 
 
 def cpu_blas_leg(cfg_name: str, sample_rows: int):
@@ -174,22 +248,33 @@ def cpu_blas_leg(cfg_name: str, sample_rows: int):
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU algorithm for this path (the oracle port: the reference is pure
+    Python, there is no C source to compile) with every host thread, on our arm's workload.  --steps / --warmup
+    are honoured; each step scores the 64-query batch against as many rows of the store as keep the whole run
+    inside ~150 s (all of them for C2 on a 16-core box), stated in `sample`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     # torchrun pins OMP_NUM_THREADS=1 in every worker; the reference arm is meant to use every host core
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    cfg = args.config or ("c2" if args.gpus == 1 else "c3")
+    cfg = args.config if args.config in CONFIGS else ("c2" if args.gpus == 1 else "c3")
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample_rows or 100000
-    steps = max(1, min(args.steps, 5))
-    qps, ms, desc = cpu_reference_leg(cfg, steps, min(args.warmup, 1), sample)
     rows_total, dim, dt, nq, k, _, _ = CONFIGS[cfg]
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    if args.cpu_sample_rows:
+        sample = args.cpu_sample_rows
+    else:
+        _q, probe_ms, _d = cpu_reference_leg(cfg, 1, 1, 20000)          # calibrate: ms per 20 000 rows
+        budget_ms = 150e3 / (steps + warmup)
+        sample = int(min(rows_total, max(20000, 20000 * budget_ms / max(probe_ms, 1e-3))))
+        if sample >= rows_total // 2:
+            sample = rows_total
+    qps, ms, desc = cpu_reference_leg(cfg, steps, warmup, sample)
     line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{cfg}: {rows_total}x{dim} {dt} store, {nq}-query batch, top-{k} cosine",
-                       "timed_sample": desc},
+                       "timed_sample": desc, "ms_per_step_is": "one timed step over the sampled rows (value is extrapolated to the full store)"},
             "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -214,45 +299,146 @@ def make_queries(store, n_rows: int, nq: int, dim: int, seed: int, dev, world: i
     return q.cpu()
 
 
+def _hash_normal(ids, dim: int, seed: int):
+    """Standard-normal [len(ids), dim] tensor that is a pure function of (seed, id, column): splitmix-style integer
+    mixing (int64 wrap-around) + Box-Muller, so any rank can produce any row or centre without a shared stream."""
+    import math
+    import torch
+    j = torch.arange(dim, device=ids.device, dtype=torch.int64)
+    z = ids.to(torch.int64)[:, None] * -7046029254386353131 + j[None, :] * -4658895280553007687 + (seed * 2654435761 + 12345)
+    z = (z ^ (z >> 30)) * -4658895280553007687
+    z = (z ^ (z >> 27)) * -7723592293110705685
+    z = z ^ (z >> 31)
+    u1 = ((z & 0xFFFFFF).to(torch.float32) + 0.5) * (1.0 / 16777216.0)
+    u2 = (((z >> 24) & 0xFFFFFF).to(torch.float32) + 0.5) * (1.0 / 16777216.0)
+    return torch.sqrt(-2.0 * torch.log(u1)) * torch.cos((2.0 * math.pi) * u2)
+
+
+def fill_clustered(store, n: int, dim: int, seed: int, per_centre: int, rho: float, row_lo: int = 0):
+    """Unit-norm Gaussian-mixture rows written straight into the store's HBM: centre c = global row // per_centre,
+    row = normalise(unit(centre_c) + rho * g / sqrt(dim)), g ~ N(0, I) -- `per_centre` near-duplicates per centre
+    (cosine between members ~ 1 / (1 + rho^2)); values are NOT representable in bf16 / tf32."""
+    import torch
+    dev = store.device
+    chunk = 1 << 17
+    for r0 in range(0, n, chunk):
+        m = min(chunk, n - r0)
+        rows = torch.arange(row_lo + r0, row_lo + r0 + m, device=dev, dtype=torch.int64)
+        uc, inv = torch.unique(rows // per_centre, return_inverse=True)
+        cvec = _hash_normal(uc, dim, seed * 2 + 1)
+        cvec = cvec / cvec.norm(dim=1, keepdim=True)
+        x = cvec[inv] + (rho / dim ** 0.5) * _hash_normal(rows, dim, seed * 2)
+        x = x / x.norm(dim=1, keepdim=True)
+        store.rows[r0:r0 + m, :dim] = x.to(store.rows.dtype)
+        if store.ld > dim:
+            store.rows[r0:r0 + m, dim:] = 0
+
+
 # ---------------------------------------------------------------------------------------------
-# our arm
+# parity of the timed call, checked inside the run
 # ---------------------------------------------------------------------------------------------
-def run_ours(args):
+def parity_topk(ctx: Ctx, store, q_dev, k: int, row_lo: int, flags_timed: int, exact_queries: int):
+    """(1) the timed call (fast scan + certification, sharded merge for N > 1) against the binary64 scan of every
+    row (VM_FLAG_FORCE_EXACT) of the same store: N = 1 directly; N > 1 against the HOST merge (numpy) of the per-shard
+    binary64 scans, so neither the fast scan nor the NCCL exchange nor the merge kernel is its own witness;
+    (2) N > 1: every rank holds identical lists.  Index lists equal, binary64 scores bit-equal."""
+    import numpy as np
+    import torch
+    import vidmem_b200 as vm
+    from vidmem_b200.sharded import merge_lists_host
+    nq = q_dev.shape[0]
+    got = store.topk_device(q_dev, k, flags=flags_timed & ~vm.VM_FLAG_TIMING, comm=ctx.comm, row_offset=row_lo)
+    torch.cuda.synchronize()
+    g_idx, g_score, g_count = (t.cpu().numpy().copy() for t in got)
+    ne = min(nq, exact_queries)
+    t0 = time.perf_counter()
+    ex = store.topk_device(q_dev[:ne].contiguous(), k, flags=vm.VM_FLAG_FORCE_EXACT)       # local shard, local rows
+    torch.cuda.synchronize()
+    exact_s = time.perf_counter() - t0
+    e_idx, e_score, e_count = (t.cpu().numpy().copy() for t in ex)
+    e_idx = np.where(e_idx >= 0, e_idx + row_lo, e_idx)
+    identical = True
+    if ctx.world > 1:
+        import torch.distributed as dist
+        packs = [None] * ctx.world
+        dist.all_gather_object(packs, (e_idx, e_score, e_count, g_idx, g_score, g_count))
+        e_idx, e_score, e_count = merge_lists_host([(p[0], p[1], p[2]) for p in packs], k)
+        identical = all(np.array_equal(p[3], packs[0][3]) and np.array_equal(p[4].view(np.int64), packs[0][4].view(np.int64))
+                        and np.array_equal(p[5], packs[0][5]) for p in packs)
+    ok = identical and np.array_equal(g_count[:ne], e_count[:ne])
+    for qi in range(ne):
+        c = int(e_count[qi])
+        ok = ok and np.array_equal(g_idx[qi, :c], e_idx[qi, :c]) and np.array_equal(g_score[qi, :c].view(np.int64), e_score[qi, :c].view(np.int64))
+    ok = ctx.all_true(bool(ok))
+    return {"checked": "timed call vs binary64 scan of every row" + (" (host merge of per-shard exact scans) + identical lists on every rank" if ctx.world > 1 else ""),
+            "queries": int(ne), "ok": bool(ok), "identical_across_ranks": bool(identical) if ctx.world > 1 else None,
+            "exact_scan_s": round(exact_s, 3)}, (g_idx, g_score, g_count)
+
+
+def parity_oracle(store, q_host, k: int, n_queries: int, max_rows: int):
+    """Rank 0, after the timed region: the default (fast) path over the first `rows` resident rows against the CPU
+    oracle's blocked tier (float64 BLAS pre-ranking + bit-exact reference rescoring) on the same rows copied back
+    from HBM.  Index lists equal, binary64 scores bit-equal."""
+    import numpy as np
+    import torch
+    from oracle import oracle
+    n = min(len(store), max_rows)
+    view = store.prefix_view(n) if n < len(store) else store
+    try:
+        Q = np.ascontiguousarray(q_host[:n_queries], dtype=np.float32)
+        idx, score, count = view.topk(Q, k)
+        X = store.rows[:n, :store.dim].float().cpu().numpy()
+        t0 = time.perf_counter()
+        oi, os_, oc = oracle.topk_blocked(Q, X, k)
+        dt = time.perf_counter() - t0
+        ok = bool(np.array_equal(count, oc.astype(count.dtype)))
+        for qi in range(len(Q)):
+            c = int(oc[qi])
+            ok = ok and np.array_equal(idx[qi, :c], oi[qi, :c]) and np.array_equal(score[qi, :c].view(np.int64), os_[qi, :c].view(np.int64))
+        return {"checked": "default path vs CPU oracle (blocked tier, bit-exact rescoring)", "queries": int(len(Q)), "rows": int(n),
+                "ok": bool(ok), "oracle_s": round(dt, 2)}
+    finally:
+        if view is not store:
+            view.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# top-k scorer (C1 / C2 / C3, clustered variant)
+# ---------------------------------------------------------------------------------------------
+def bench_topk(ctx: Ctx, args, cfg: str, steps: int, warmup: int, variant: str = "iid", with_e2e: bool = True,
+               with_parity: bool = True, rows_override=None):
     import numpy as np
     import torch
     import vidmem_b200 as vm
     from vidmem_b200.store import EmbeddingStore
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    comm = None
-    peer_exchange = False
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-        from vidmem_b200.sharded import Communicator
-        comm = Communicator.from_torch_distributed(local_rank)
-        peer_exchange = args.peer_exchange and comm.enable_peer_exchange()
-
-    cfg = args.config or ("c2" if world == 1 else "c3")
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
     rows_total, dim, dt, nq, k, sseed, qseed = CONFIGS[cfg]
-    if args.rows:
-        rows_total = args.rows
+    if rows_override:
+        rows_total = rows_override
     row_lo = rows_total * rank // world
     row_hi = rows_total * (rank + 1) // world
     n_local = row_hi - row_lo
     es = 4 if dt == "f32" else 2
 
-    store = EmbeddingStore(dim, n_local, dt, device=local_rank)
-    store.synth_fill(sseed, n_local, row0=row_lo)
-    store.set_size(n_local)
-    torch.cuda.synchronize()
-    q_pinned = make_queries(store, n_local, nq, dim, qseed, dev, world).pin_memory()
+    store = EmbeddingStore(dim, n_local, dt, device=ctx.local_rank)
+    if variant == "iid":
+        store.synth_fill(sseed, n_local, row0=row_lo)
+        store.set_size(n_local)
+        torch.cuda.synchronize()
+        q_pinned = make_queries(store, n_local, nq, dim, qseed, dev, world).pin_memory()
+    else:
+        fill_clustered(store, n_local, dim, sseed, args.cluster_size, args.cluster_rho, row_lo)
+        store.set_size(n_local)
+        torch.cuda.synchronize()
+        # queries: perturbed members of random clusters (so the top-k sits inside a near-duplicate cluster)
+        g = torch.Generator(device="cpu").manual_seed(qseed)
+        ridx = torch.randint(0, max(n_local, 1), (nq,), generator=g)
+        base = store.rows[ridx.to(dev), :dim].float()
+        q = base + (args.cluster_rho / dim ** 0.5) * torch.randn((nq, dim), generator=g).to(dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.broadcast(q, src=0)
+        q_pinned = q.cpu().contiguous().pin_memory()
     Q = q_pinned.numpy()
     q_dev = q_pinned.to(dev)
     out = (torch.empty((nq, k), dtype=torch.int64, device=dev), torch.empty((nq, k), dtype=torch.float64, device=dev),
@@ -260,211 +446,212 @@ def run_ours(args):
     flags_dev = vm.VM_FLAG_ASYNC | vm.VM_FLAG_TIMING | args.flags
 
     def step_device():
-        store.topk_device(q_dev, k, out=out, flags=flags_dev, comm=comm, row_offset=row_lo)
+        store.topk_device(q_dev, k, out=out, flags=flags_dev, comm=ctx.comm, row_offset=row_lo)
 
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
+    parity = None
+    if with_parity:
+        parity, _ = parity_topk(ctx, store, q_dev, k, row_lo, flags_dev, nq if n_local <= 16_000_000 else 8)
 
     # ---- leg 1: inputs resident in HBM ------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
+    warm = max(warmup, 3)
+    for _ in range(warm):
         step_device()
-    barrier()
-    store.avg_scan_ms()  # drop the warm-up steps' event pairs: only the timed region is averaged below
-    sampler = ClockSampler(local_rank)
+    ctx.barrier()
+    store.avg_scan_ms()          # drop the warm-up steps' event pairs: only the timed region is averaged below
+    store.counters(reset=True)   # certification counters of the timed region only
+    sampler = ClockSampler(ctx.local_rank)
     if rank == 0:
         sampler.start()
-    scan_ms = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fits_l2 = n_local * dim * es <= 126e6
-    barrier()
+    ctx.barrier()
     if not fits_l2:
         ev0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             step_device()
         ev1.record()
-        barrier()
+        ctx.barrier()
         dev_ms = ev0.elapsed_time(ev1)
     else:
         # store fits the 126 MB L2: flush it (write a 256 MB buffer) before every step and time the steps one by one
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
         dev_ms = 0.0
-        for _ in range(args.steps):
+        for _ in range(steps):
             flush.zero_()
             ev0.record()
             step_device()
             ev1.record()
             ev1.synchronize()
             dev_ms += ev0.elapsed_time(ev1)
-        barrier()
+        ctx.barrier()
         del flush
-    launches = int(store.last_stats.scan_launches) * args.steps
     stats = store.last_stats
+    launches = int(stats.scan_launches) * steps
+    cert = store.counters(reset=True)
     # scan-kernel time: every timed step above carried its own CUDA event pair on the launching stream
     # (VM_FLAG_TIMING); read them back now -- the average over the last <= 64 steps of the timed region itself
     scan_avg_live, scan_calls = store.avg_scan_ms()
-    scan_ms = [scan_avg_live]
-    barrier()
+    ctx.barrier()
 
     # ---- leg 2: end to end through the host-buffer API ----------------------------------------
-    def step_host():
-        return store.topk(q_pinned.numpy(), k, comm=comm, row_offset=row_lo, flags=args.flags)
+    e2e_ms = float("nan")
+    if with_e2e:
+        def step_host():
+            return store.topk(q_pinned.numpy(), k, comm=ctx.comm, row_offset=row_lo, flags=args.flags)
 
-    for _ in range(3):
-        res = step_host()
-    barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        res = step_host()
-    e1.record()
-    barrier()
-    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max(e0.elapsed_time(e1), e2e_wall_ms)  # host-synchronous API: wall clock is the honest number
+        for _ in range(3):
+            step_host()
+        ctx.barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step_host()
+        e1.record()
+        ctx.barrier()
+        e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+        e2e_ms = max(e0.elapsed_time(e1), e2e_wall_ms)  # host-synchronous API: wall clock is the honest number
     clocks = sampler.stop() if rank == 0 else None
+    dev_ms, e2e_ms, scan_avg = ctx.max_over_ranks([dev_ms, e2e_ms if with_e2e else 0.0, scan_avg_live])
 
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([dev_ms, e2e_ms, float(sum(scan_ms) / max(len(scan_ms), 1))], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms, scan_avg = [float(x) for x in t.tolist()]
-    else:
-        scan_avg = sum(scan_ms) / max(len(scan_ms), 1)
+    oracle_par = None
+    if rank == 0 and with_parity and not args.no_cpu_baseline:
+        oracle_par = parity_oracle(store, Q, k, 8, 2_000_000)
 
+    rec = None
     if rank == 0:
-        ms_per_step = dev_ms / args.steps
-        value = nq / (ms_per_step * 1e-3)
-        e2e_value = nq / (e2e_ms / args.steps * 1e-3)
+        ms_per_step = dev_ms / steps
         peak, peak_src = _peaks()
         alg_bytes = n_local * dim * es + n_local * 4          # store rows once + cached inverse norms
         achieved = alg_bytes / (scan_avg * 1e-3) / 1e9 if scan_avg > 0 else 0.0
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+        n_q = max(int(cert["queries"]), 1)
+        rec = {
+            "metric": METRIC, "value": nq / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None,
             "dtype": "tf32" if (dt == "f32" and stats.scan_kernel == 2) else ("f32" if dt == "f32" else "bf16"),
             "data": "synthetic",
             "config": {"workload": f"{cfg}: {rows_total}x{dim} {dt} store, {nq}-query batch, top-{k} cosine, "
                                    f"{'row-sharded over %d GPUs + NCCL all-gather merge' % world if world > 1 else '1 GPU'}",
+                       "variant": ("iid: counter-hash integers / 128 (SURVEY 8d)" if variant == "iid" else
+                                   f"clustered: unit-norm Gaussian mixture, {args.cluster_size} near-duplicates per centre, "
+                                   f"noise rho={args.cluster_rho} (cosine between members ~{1 / (1 + args.cluster_rho ** 2):.3f}), non-representable values"),
                        "rows_per_gpu": n_local,
                        "l2_policy": ("inputs larger than L2 (%.0f MB store per GPU vs 126 MB L2)" % (n_local * dim * es / 1e6))
-                       if n_local * dim * es > 126e6 else
+                       if not fits_l2 else
                        ("store (%.1f MB) fits L2: L2 flushed (256 MB write) before every timed step, steps timed one by one" % (n_local * dim * es / 1e6)),
                        "scan_kernel": {0: "exact_fp64", 1: "simt", 2: "tcgen05"}[int(stats.scan_kernel)],
+                       "scan_variant": {0: "lists", 1: "dump", 2: "lists+threshold warp"}.get(int(stats.scan_variant), "?"),
                        "scan_ctas": int(stats.scan_ctas), "candidates_per_query": int(stats.candidates),
                        "exact_rescoring": "binary64, reference summation order (Neumaier)", "timing": "cuda events, max over ranks",
-                       "exchange": ("peer memory (symmetric buffers, NVLink pull-merge kernel)" if peer_exchange else
+                       "exchange": ("peer memory (symmetric buffers, NVLink pull-merge kernel)" if ctx.peer_exchange else
                                     "ncclAllGather + merge kernel") if world > 1 else "none"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(Q.nbytes),
-                    "d2h_bytes_per_step": int(nq * k * 16 + nq * 4 + 4), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": _ncu_traffic(cfg, int(stats.scan_kernel), n_local), "kernel": "scan", "kernel_ms": scan_avg, "kernel_ms_samples": scan_calls, "algorithmic_bytes": alg_bytes,
-                         "peak_source": peak_src},
+                         "traffic": _ncu_traffic(dt, n_local), "kernel": "scan_tc_kernel", "kernel_ms": scan_avg,
+                         "kernel_ms_samples": scan_calls, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                         "step_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
+            "certification": {"queries_timed": int(cert["queries"]), "uncertified": int(cert["uncertified"]),
+                              "certified_pct": 100.0 * (1.0 - cert["uncertified"] / n_q),
+                              "band_settled": int(cert["band_settled"]), "collect_settled": int(cert["collect_settled"]),
+                              "full_rescans": int(cert["full_rescans"]),
+                              "note": "rank 0's shard; counted on the device over the timed steps (VM_FLAG_ASYNC)"},
+            "parity": parity,
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            qps, ms, desc = cpu_reference_leg(cfg, 1, 1, args.cpu_sample_rows or 100000)
-            line["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
-            try:
-                line["cpu_baseline"]["sklearn_blas_value"] = cpu_blas_leg(cfg, args.cpu_sample_rows or 100000)
-            except Exception as e:  # pragma: no cover
-                line["cpu_baseline"]["sklearn_blas_value"] = None
+        if with_e2e:
+            rec["e2e"] = {"value": nq / (e2e_ms / steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(Q.nbytes),
+                          "d2h_bytes_per_step": int(nq * k * 16 + nq * 4 + 4), "ms_per_step": e2e_ms / steps}
+        if oracle_par is not None:
+            rec["parity"]["oracle"] = oracle_par
+            rec["parity"]["ok"] = bool(rec["parity"]["ok"] and oracle_par["ok"])
     store.close()
-    if rank == 0:
-        if world == 1 and cfg == "c2" and not args.rows and not args.no_scaling_baseline:
-            # The multi-GPU runs use config C3 (100M x 384 bf16, strong scaling).  Its single-GPU point is
-            # measured here so that the N = 2/4/8 lines have a same-workload N = 1 reference.
-            try:
-                r3, d3, dt3, nq3, k3, ss3, qs3 = CONFIGS["c3"]
-                s3 = EmbeddingStore(d3, r3, dt3, device=local_rank)
-                s3.synth_fill(ss3, r3)
-                s3.set_size(r3)
-                q3 = make_queries(s3, r3, nq3, d3, qs3, dev).to(dev)
-                o3 = (torch.empty((nq3, k3), dtype=torch.int64, device=dev), torch.empty((nq3, k3), dtype=torch.float64, device=dev),
-                      torch.empty((nq3,), dtype=torch.int32, device=dev))
-                for _ in range(3):
-                    s3.topk_device(q3, k3, out=o3, flags=vm.VM_FLAG_ASYNC)
-                torch.cuda.synchronize()
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a0.record()
-                for _ in range(10):
-                    s3.topk_device(q3, k3, out=o3, flags=vm.VM_FLAG_ASYNC)
-                a1.record()
-                torch.cuda.synchronize()
-                ms3 = a0.elapsed_time(a1) / 10
-                line["scaling_baseline"] = {"workload": f"c3: {r3}x{d3} {dt3} store on ONE GPU, {nq3}-query batch, top-{k3}",
-                                            "value": nq3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3,
-                                            "hbm_frac": (r3 * d3 * 2 + r3 * 4) / (ms3 * 1e-3) / 1e9 / _peaks()[0]}
-                s3.close()
-            except Exception as e:  # pragma: no cover - e.g. not enough free HBM
-                line["scaling_baseline"] = {"error": repr(e)}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
+    del store, q_dev, out
+    torch.cuda.empty_cache()
+    return rec
 
 
-def _tensor_peak():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        try:
-            d = json.load(open(p))
-            return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
-        except Exception:
-            pass
-    return 1400.0, "fallback (B200_PROFILING.md sustained)"
+def scaling_baseline(ctx: Ctx):
+    """C3 (the N > 1 workload) on ONE GPU, so that the N = 2/4/8 lines have a same-workload N = 1 reference."""
+    import torch
+    import vidmem_b200 as vm
+    from vidmem_b200.store import EmbeddingStore
+    try:
+        r3, d3, dt3, nq3, k3, ss3, qs3 = CONFIGS["c3"]
+        s3 = EmbeddingStore(d3, r3, dt3, device=ctx.local_rank)
+        s3.synth_fill(ss3, r3)
+        s3.set_size(r3)
+        q3 = make_queries(s3, r3, nq3, d3, qs3, ctx.dev).to(ctx.dev)
+        o3 = (torch.empty((nq3, k3), dtype=torch.int64, device=ctx.dev), torch.empty((nq3, k3), dtype=torch.float64, device=ctx.dev),
+              torch.empty((nq3,), dtype=torch.int32, device=ctx.dev))
+        for _ in range(3):
+            s3.topk_device(q3, k3, out=o3, flags=vm.VM_FLAG_ASYNC)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            s3.topk_device(q3, k3, out=o3, flags=vm.VM_FLAG_ASYNC)
+        a1.record()
+        torch.cuda.synchronize()
+        ms3 = a0.elapsed_time(a1) / 10
+        res = {"workload": f"c3: {r3}x{d3} {dt3} store on ONE GPU, {nq3}-query batch, top-{k3}",
+               "value": nq3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3,
+               "hbm_frac": (r3 * d3 * 2 + r3 * 4) / (ms3 * 1e-3) / 1e9 / _peaks()[0]}
+        s3.close()
+        del s3
+        torch.cuda.empty_cache()
+        return res
+    except Exception as e:  # pragma: no cover - e.g. not enough free HBM
+        return {"error": repr(e)}
 
 
-def run_c4(args):
-    """Config C4: all-pairs dedup, 1M x 768 bf16 vs itself, threshold 0.9 (planted near-duplicates)."""
+# ---------------------------------------------------------------------------------------------
+# all-pairs dedup (C4)
+# ---------------------------------------------------------------------------------------------
+def bench_dedup(ctx: Ctx, args, steps: int, warmup: int, rows_override=None):
+    """Config C4: all-pairs dedup, 1M x 768 bf16 vs itself, threshold 0.9 (planted near-duplicates), on the run's N
+    GPUs.  N > 1 goes through vm_pairs_above_sharded: tile grid dealt cyclically, ncclAllGather of counts and hit
+    lists, every rank ends with the complete list (inside the timed region); the e2e leg additionally starts from
+    rows in rank 0's pinned host memory (H2D + ONE ncclBroadcast) and ends with the pairs on the host."""
+    import ctypes as C
     import numpy as np
     import torch
     import vidmem_b200 as vm
     from vidmem_b200 import dedup
     from vidmem_b200.store import EmbeddingStore
     rows, dim, dt, thr, seed, dup = C4
-    if args.rows:
-        rows = args.rows
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    st = EmbeddingStore(dim, rows, dt, device=local_rank)     # operand replicated on every rank (1.5 GB)
-    st.synth_fill(seed, rows, dup_period=dup)
+    if rows_override:
+        rows = rows_override
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    st = EmbeddingStore(dim, rows, dt, device=ctx.local_rank)
+    st.synth_fill(seed, rows, dup_period=dup)               # every rank synthesises the same operand for the resident leg
     torch.cuda.synchronize()
     x = st.rows[:rows]
     cap = 1 << 22
     lib = vm._lib.load()
-    import ctypes as C
     oi = torch.empty((cap,), dtype=torch.int64, device=dev); oj = torch.empty_like(oi)
     os_ = torch.empty((cap,), dtype=torch.float32, device=dev); cnt = torch.zeros((1,), dtype=torch.int64, device=dev)
 
-    def step():
-        vm._lib.check(lib.vm_pairs_above(local_rank, x.data_ptr(), vm.VM_BF16, rows, dim, C.c_float(thr), cap, oi.data_ptr(),
-                                         oj.data_ptr(), os_.data_ptr(), cnt.data_ptr(), rank, world, 0,
-                                         torch.cuda.current_stream(dev).cuda_stream))
+    def step(xt=x, root=-1):
+        sp = torch.cuda.current_stream(dev).cuda_stream
+        if world == 1:
+            vm._lib.check(lib.vm_pairs_above(ctx.local_rank, xt.data_ptr(), vm.VM_BF16, rows, dim, C.c_float(thr), cap, oi.data_ptr(),
+                                             oj.data_ptr(), os_.data_ptr(), cnt.data_ptr(), 0, 1, 0, sp))
+        else:
+            vm._lib.check(lib.vm_pairs_above_sharded(ctx.comm.handle, xt.data_ptr(), vm.VM_BF16, rows, dim, C.c_float(thr), cap,
+                                                     oi.data_ptr(), oj.data_ptr(), os_.data_ptr(), cnt.data_ptr(), root, 0, sp))
 
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
+    def pair_hash():
+        m = int(cnt.item())
+        h = ((oi[:m] * 1_000_003 + oj[:m]) % 2_147_483_629).sum() if m else torch.zeros((), dtype=torch.int64, device=dev)
+        return m, int(h.item())
 
-    steps = max(1, min(args.steps, 5))
-    for _ in range(max(1, min(args.warmup, 3))):
+    steps = max(1, min(steps, 3))
+    warm = max(1, min(warmup, 1))
+    for _ in range(warm):
         step()
-    barrier()
-    sampler = ClockSampler(local_rank)
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local_rank)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -472,130 +659,240 @@ def run_c4(args):
     for _ in range(steps):
         step()
     e1.record()
-    barrier()
+    ctx.barrier()
     ms = e0.elapsed_time(e1) / steps
-    hits_local = int(cnt.item())
-    # e2e: rows come from pinned host memory every step, pairs go back to the host
-    xh = torch.empty((rows, dim), dtype=torch.bfloat16).pin_memory()
-    xh.copy_(x[:, :dim].cpu())
-    xd = torch.empty_like(x)
-    barrier()
+    hits, hsum = pair_hash()
+    # e2e: rank 0's rows come from pinned host memory every step, pairs go back to the host
+    xh = None
+    if rank == 0:
+        xh = torch.empty((rows, dim), dtype=torch.bfloat16).pin_memory()
+        xh.copy_(x[:, :dim].cpu())
+    xd = torch.zeros_like(x)
+    ctx.barrier()
+    e2e_steps = max(1, min(steps, 2))
     t0 = time.perf_counter()
-    for _ in range(steps):
-        xd[:, :dim].copy_(xh, non_blocking=True)
-        i, j, s = dedup.pairs_above(xd, thr, cap=cap, part=rank, nparts=world)
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    for _ in range(e2e_steps):
+        if rank == 0:
+            xd[:, :dim].copy_(xh, non_blocking=True)
+        step(xd, root=0 if world > 1 else -1)
+        m = int(cnt.item())
+        pi, pj, ps = oi[:m].cpu(), oj[:m].cpu(), os_[:m].cpu()
+    ctx.barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    e2e_hits, e2e_hsum = pair_hash()
     clocks = sampler.stop() if rank == 0 else None
+    ms, e2e_ms = ctx.max_over_ranks([ms, e2e_ms])
+
+    # ---- parity, in this run --------------------------------------------------------------------
+    # (a) N > 1: the sharded pair multiset (count + checksum of i*P+j) == rank 0's own single-GPU pass over the same rows;
+    #     the e2e leg (H2D + broadcast) reproduces it
+    single_hits = single_hsum = None
     if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = [float(v) for v in t.tolist()]
-        h = torch.tensor([hits_local], device=dev, dtype=torch.int64)
-        dist.all_reduce(h)
-        hits = int(h.item())
-    else:
-        hits = hits_local
+        if rank == 0:
+            vm._lib.check(lib.vm_pairs_above(ctx.local_rank, x.data_ptr(), vm.VM_BF16, rows, dim, C.c_float(thr), cap, oi.data_ptr(),
+                                             oj.data_ptr(), os_.data_ptr(), cnt.data_ptr(), 0, 1, 0, torch.cuda.current_stream(dev).cuda_stream))
+            single_hits, single_hsum = pair_hash()
+        ctx.barrier()
+    ok = (hits, hsum) == (e2e_hits, e2e_hsum) and (world == 1 or rank != 0 or (hits, hsum) == (single_hits, single_hsum))
+    # (b) rank 0: exact pair-SET equality against the CPU oracle on the first `ns` rows (also the cpu_baseline sample)
+    sample = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle
+        ns = min(rows, 12288)
+        E = x[:ns, :dim].float().cpu().numpy()
+        t0 = time.perf_counter()
+        ri, rj, _rs = oracle.pairs_above(E, thr)
+        dt_s = time.perf_counter() - t0
+        gi, gj, _gs = dedup.pairs_above(x[:ns].contiguous(), thr, cap=1 << 20)
+        same = len(gi) == len(ri) and np.array_equal(gi, ri) and np.array_equal(gj, rj)
+        ok = ok and bool(same)
+        sample = {"rows": int(ns), "oracle_pairs": int(len(ri)), "gpu_pairs": int(len(gi)), "set_equal": bool(same),
+                  "cpu_pairs_per_s": (ns * (ns - 1) / 2) / dt_s}
+    ok = ctx.all_true(bool(ok))
+
+    rec = None
     if rank == 0:
         pairs = rows * (rows - 1) / 2
         peak, src = _tensor_peak()
         tf = pairs * 2 * dim / (ms * 1e-3) / 1e12 / world      # per GPU
-        line = {"metric": "dedup_unique_pairs_per_sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world,
-                "steps": steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"c4: all-pairs dedup {rows}x{dim} bf16 vs itself, threshold {thr} (strict), "
-                                       f"1/{dup} rows planted near-duplicates, upper triangle split over {world} GPU(s)",
-                           "hits": hits, "l2_policy": "operand %.0f MB > 126 MB L2" % (rows * dim * 2 / 1e6)},
-                "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": rows * dim * 2,
-                        "d2h_bytes_per_step": hits_local * 20 + 8, "ms_per_step": e2e_ms},
-                "gpu_launches": 3 * steps,
-                "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
-                             "traffic": None, "kernel": "pairs_tc_kernel", "peak_source": src,
-                             "flops_counted": "2*D per unordered pair (upper triangle only)"},
-                "clocks": clocks}
-        if world == 1 and not args.no_cpu_baseline:
-            from oracle import oracle, synth
-            ns = 4096
-            E = synth.synth_rows(seed, 0, ns, dim, dup_period=dup)
-            t0 = time.perf_counter()
-            oracle.pairs_above(E, thr)
-            dt_s = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": (ns * (ns - 1) / 2) / dt_s, "unit": "pairs/s", "cores": os.cpu_count() or 1,
-                                    "kind": "port", "sample": f"{ns} x {dim} rows all-pairs (pairs/s is size-independent for the O(N^2 D) loop)"}
-        print(json.dumps(line), flush=True)
+        rec = {"metric": "dedup_unique_pairs_per_sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world,
+               "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+               "scaling": "strong", "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": f"c4: all-pairs dedup {rows}x{dim} bf16 vs itself, threshold {thr} (strict), "
+                                      f"1/{dup} rows planted near-duplicates, upper triangle dealt over {world} GPU(s)"
+                                      + (", ncclAllGather of counts + hit lists inside the timed region" if world > 1 else ""),
+                          "hits": hits, "l2_policy": "operand %.0f MB > 126 MB L2" % (rows * dim * 2 / 1e6)},
+               "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": rows * dim * 2,
+                       "d2h_bytes_per_step": hits * 20 + 8, "ms_per_step": e2e_ms,
+                       "path": "pinned host rows -> H2D" + (" -> ncclBroadcast" if world > 1 else "") + " -> kernel -> pairs D2H"},
+               "gpu_launches": 3 * steps + (1 * steps if world > 1 else 0),
+               "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                            "traffic": None, "kernel": "pairs_tc2_kernel", "kernel_ms": ms, "peak_source": src,
+                            "flops_counted": "2*D per unordered pair (upper triangle only), per GPU",
+                            "frac_of_nominal_2250": tf / 2250.0},
+               "parity": {"ok": bool(ok), "checked": "pair multiset (count + checksum) resident == e2e"
+                                                     + (" == single-GPU pass" if world > 1 else "") + "; exact pair-set equality vs CPU oracle on a row sample",
+                          "pairs": hits, "checksum": hsum, "single_gpu_pairs": single_hits, "oracle_sample": sample},
+               "clocks": clocks}
+        if sample:
+            rec["cpu_baseline"] = {"value": sample["cpu_pairs_per_s"], "unit": "pairs/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                   "sample": f"{sample['rows']} x {dim} rows all-pairs (pairs/s is size-independent for the O(N^2 D) loop)"}
     st.close()
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier(); dist.destroy_process_group()
+    del st, x, xd, oi, oj, os_
+    torch.cuda.empty_cache()
+    return rec
 
 
-def run_c5(args):
+# ---------------------------------------------------------------------------------------------
+# streaming (C5)
+# ---------------------------------------------------------------------------------------------
+def bench_streaming(ctx: Ctx, args, rounds: int, dtype=None, rows_override=None, growable: bool = False):
     """Config C5: streaming mode -- 4096-row inserts interleaved with single-query top-10 lookups over a
-    10M x 384 store on one GPU; reports p50/p99 latencies (host wall clock around synchronous calls)."""
+    10M x 384 store; p50/p99 latencies (host wall clock around synchronous host-buffer calls).
+    N > 1: the store is row-sharded (10M/N rows per rank before the inserts), each 4096-row insert goes to ONE rank
+    (round-robin == least-full), every query is a collective vm_topk_sharded call (local scan, ncclAllGather, merge)."""
     import numpy as np
     import torch
     import vidmem_b200 as vm
     from vidmem_b200.store import EmbeddingStore
     rows_total, dim, dt, nq, k, sseed, qseed = CONFIGS["c5"]
-    if args.rows:
-        rows_total = args.rows
-    dt = args.c5_dtype or dt
-    torch.cuda.set_device(0)
-    dev = torch.device("cuda", 0)
-    rounds = max(8, min(args.steps, 64))
+    if rows_override:
+        rows_total = rows_override
+    dt = dtype or dt
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    rounds = max(8, min(rounds, 64))
     per_round_q = 8
     ins = 4096
-    st = EmbeddingStore(dim, rows_total + rounds * ins, dt, device=0)
-    st.synth_fill(sseed, rows_total)
-    st.set_size(rows_total)
+    n0 = rows_total * (rank + 1) // world - rows_total * rank // world
+    cap_rank = n0 + (rounds // world + 1) * ins
+    row_base = rank * (1 << 32)                       # global row = rank stride + local row (unique, order by rank then age)
+    st = EmbeddingStore(dim, cap_rank, dt, device=ctx.local_rank)
+    st.synth_fill(sseed, n0, row0=rows_total * rank // world)
+    st.set_size(n0)
     torch.cuda.synchronize()
-    qpin = make_queries(st, rows_total, rounds * per_round_q, dim, qseed, dev).pin_memory().numpy()
+    qpin = make_queries(st, n0, rounds * per_round_q, dim, qseed, dev, world).pin_memory().numpy()
     g = torch.Generator(device="cpu").manual_seed(sseed + 1)
     new_rows = (torch.randint(-127, 128, (rounds * ins, dim), generator=g).float() / 128.0).pin_memory()
     for w in range(3):
-        st.topk(qpin[w:w + 1], k)
-    sampler = ClockSampler(0)
-    sampler.start()
+        st.topk(qpin[w:w + 1], k, comm=ctx.comm, row_offset=row_base)
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local_rank)
+    if rank == 0:
+        sampler.start()
     q_lat, i_lat = [], []
     t_all = time.perf_counter()
     for r in range(rounds):
-        t0 = time.perf_counter()
-        st.append(new_rows[r * ins:(r + 1) * ins])          # host -> device, convert, norms; synchronous
-        i_lat.append((time.perf_counter() - t0) * 1e3)
+        if r % world == rank:
+            t0 = time.perf_counter()
+            st.append(new_rows[r * ins:(r + 1) * ins])          # host -> device, convert, norms; synchronous
+            i_lat.append((time.perf_counter() - t0) * 1e3)
         for qi in range(per_round_q):
             t0 = time.perf_counter()
-            st.topk(qpin[r * per_round_q + qi:r * per_round_q + qi + 1], k)
+            st.topk(qpin[r * per_round_q + qi:r * per_round_q + qi + 1], k, comm=ctx.comm, row_offset=row_base)
             q_lat.append((time.perf_counter() - t0) * 1e3)
     wall = time.perf_counter() - t_all
-    clocks = sampler.stop()
+    ctx.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    # the planted row of the last insert must be its own best match (every rank sees the same answer)
+    probe = new_rows[(rounds - 1) * ins + 17:(rounds - 1) * ins + 18].numpy()
+    pi, ps, pc = st.topk(probe, k, comm=ctx.comm, row_offset=row_base)
+    owner = (rounds - 1) % world
+    n_owner_before = (rows_total * (owner + 1) // world - rows_total * owner // world) + ((rounds - 1) // world) * ins
+    ok = int(pc[0]) == k and abs(float(ps[0, 0]) - 1.0) < 1e-12 and int(pi[0, 0]) == owner * (1 << 32) + n_owner_before + 17
+    ok = ctx.all_true(bool(ok))
     scan_ms = []
     for qi in range(5):
         st.topk(qpin[qi:qi + 1], k, flags=vm.VM_FLAG_TIMING)
         scan_ms.append(st.last_scan_ms())
     es = 4 if dt == "f32" else 2
     n_now = len(st)
-    peak, src = _peaks()
-    alg = n_now * dim * es + n_now * 4
-    scan = sum(scan_ms) / len(scan_ms)
-    pct = lambda a, p: float(np.percentile(np.asarray(a), p))
-    line = {"metric": "streaming_queries_per_sec_top10_384d", "value": len(q_lat) / (sum(q_lat) * 1e-3), "unit": "queries/s",
-            "n_gpus": 1, "steps": rounds, "warmup": 3, "ms_per_step": wall * 1e3 / rounds, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if dt == "f32" else "bf16", "data": "synthetic",
-            "config": {"workload": f"c5: streaming, {rows_total}x{dim} {dt} store, {ins}-row inserts interleaved with "
-                                   f"{per_round_q} single-query top-{k} lookups per insert, host buffers, synchronous calls",
-                       "scan_kernel": {0: "exact_fp64", 1: "simt", 2: "tcgen05"}[int(st.last_stats.scan_kernel)]},
-            "latency_ms": {"query_p50": pct(q_lat, 50), "query_p99": pct(q_lat, 99), "insert_p50": pct(i_lat, 50),
-                           "insert_p99": pct(i_lat, 99)},
-            "e2e": {"value": len(q_lat) / (sum(q_lat) * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": ins * dim * 4 + per_round_q * dim * 4,
-                    "d2h_bytes_per_step": per_round_q * (k * 16 + 8)},
-            "gpu_launches": int(st.last_stats.scan_launches) * len(q_lat) + 2 * rounds,
-            "roofline": {"bound": "hbm", "achieved": alg / (scan * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (scan * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "scan", "kernel_ms": scan,
-                         "algorithmic_bytes": alg, "peak_source": src},
-            "clocks": clocks}
-    print(json.dumps(line), flush=True)
+    q50, q99, scan = ctx.max_over_ranks([float(np.percentile(q_lat, 50)), float(np.percentile(q_lat, 99)), sum(scan_ms) / len(scan_ms)])
+    ins_all = None
+    if world > 1:
+        import torch.distributed as dist
+        packs = [None] * world
+        dist.all_gather_object(packs, i_lat)
+        ins_all = [v for p in packs for v in p]
+    else:
+        ins_all = i_lat
+    rec = None
+    if rank == 0:
+        peak, src = _peaks()
+        alg = n_now * dim * es + n_now * 4
+        rec = {"metric": "streaming_queries_per_sec_top10_384d", "value": len(q_lat) / (sum(q_lat) * 1e-3), "unit": "queries/s",
+               "n_gpus": world, "steps": rounds, "warmup": 3, "ms_per_step": wall * 1e3 / rounds, "higher_is_better": True,
+               "scaling": "strong", "dtype": "tf32" if dt == "f32" else "bf16", "data": "synthetic",
+               "config": {"workload": f"c5: streaming, {rows_total}x{dim} {dt} store" + (f" row-sharded over {world} GPUs" if world > 1 else "")
+                                      + f", {ins}-row inserts interleaved with {per_round_q} single-query top-{k} lookups per insert, "
+                                        "host buffers, synchronous calls",
+                          "scan_kernel": {0: "exact_fp64", 1: "simt", 2: "tcgen05"}[int(st.last_stats.scan_kernel)],
+                          "l2_policy": "inputs larger than L2 (%.0f MB per GPU)" % (n_now * dim * es / 1e6)},
+               "latency_ms": {"query_p50": q50, "query_p99": q99, "insert_p50": float(np.percentile(ins_all, 50)),
+                              "insert_p99": float(np.percentile(ins_all, 99)), "inserts": len(ins_all), "queries": len(q_lat)},
+               "e2e": {"value": len(q_lat) / (sum(q_lat) * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": ins * dim * 4 + per_round_q * dim * 4,
+                       "d2h_bytes_per_step": per_round_q * (k * 16 + 8)},
+               "gpu_launches": int(st.last_stats.scan_launches) * len(q_lat) + 2 * len(i_lat),
+               "roofline": {"bound": "hbm", "achieved": alg / (scan * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": alg / (scan * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "scan_tc_kernel", "kernel_ms": scan,
+                            "algorithmic_bytes": alg, "peak_source": src},
+               "parity": {"ok": bool(ok), "checked": "a row of the last insert is its own exact top-1 (score 1.0, expected global row) on every rank"},
+               "clocks": clocks}
     st.close()
+    del st
+    torch.cuda.empty_cache()
+    return rec
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    ctx = Ctx(args)
+    rank, world = ctx.rank, ctx.world
+    cfg = args.config or ("c2" if world == 1 else "c3")
+    failed = []
+
+    def note(name, rec):
+        if rec is not None and rec.get("parity") and rec["parity"].get("ok") is False:
+            failed.append(name)
+        return rec
+
+    if cfg == "c4":
+        line = note("dedup", bench_dedup(ctx, args, args.steps, args.warmup, args.rows))
+    elif cfg == "c5":
+        line = note("streaming", bench_streaming(ctx, args, args.steps, args.c5_dtype, args.rows))
+    else:
+        line = note("topk", bench_topk(ctx, args, cfg, args.steps, args.warmup, variant=args.variant, rows_override=args.rows))
+        full = cfg in ("c2", "c3") and not args.rows and not args.only_main
+        if rank == 0 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            os.environ["OMP_NUM_THREADS"] = str(cores)      # torchrun pins it to 1 in every worker
+            qps, ms, desc = cpu_reference_leg(cfg, 1, 1, args.cpu_sample_rows or 100000)
+            line["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+            try:
+                line["cpu_baseline"]["sklearn_blas_value"] = cpu_blas_leg(cfg, args.cpu_sample_rows or 100000)
+            except Exception:  # pragma: no cover
+                line["cpu_baseline"]["sklearn_blas_value"] = None
+        if full:
+            clustered = note("clustered", bench_topk(ctx, args, cfg, min(args.steps, 20), 3, variant="clustered", with_e2e=False,
+                                                     rows_override=None if world > 1 else None))
+            dd = note("dedup", bench_dedup(ctx, args, args.steps, args.warmup))
+            stream = note("streaming", bench_streaming(ctx, args, args.steps))
+            if rank == 0:
+                line["clustered"] = {key: clustered[key] for key in ("value", "unit", "ms_per_step", "config", "roofline", "certification", "parity", "clocks")}
+                line["clustered"]["vs_iid"] = clustered["value"] / line["value"]
+                line["dedup"] = dd
+                line["streaming"] = stream
+            if world == 1 and cfg == "c2" and not args.no_scaling_baseline:
+                line["scaling_baseline"] = scaling_baseline(ctx)
+    if rank == 0:
+        line["vs_baseline"] = None
+        if failed:
+            line["parity_failed"] = failed
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if failed:
+        sys.stderr.write("bench.py: PARITY FAILED in " + ", ".join(failed) + "\n")
+        sys.exit(3)
 
 
 def torchrun_argv(gpus: int, argv, port: int):
@@ -611,10 +908,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS) + ["c4"])
+    ap.add_argument("--variant", default="iid", choices=["iid", "clustered"], help="store contents of the main top-k measurement")
+    ap.add_argument("--cluster-size", type=int, default=64, help="clustered variant: near-duplicates per centre")
+    ap.add_argument("--cluster-rho", type=float, default=0.2, help="clustered variant: noise norm relative to the centre")
     ap.add_argument("--rows", type=int, default=None, help="override the total row count (debug)")
     ap.add_argument("--flags", type=int, default=0, help="extra VM_FLAG_* bits (debug: 4 = force SIMT, 8 = force tcgen05)")
     ap.add_argument("--cpu-sample-rows", type=int, default=None)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip every CPU leg (oracle timing and oracle parity)")
+    ap.add_argument("--only-main", action="store_true", help="skip the clustered / dedup / streaming sub-records")
     ap.add_argument("--peer-exchange", action="store_true",
                     help="multi-GPU: replace ncclAllGather + merge by the peer-memory pull-merge kernel (symmetric memory)")
     ap.add_argument("--no-scaling-baseline", action="store_true", help="skip the extra C3-on-one-GPU measurement of the N=1 run")
@@ -629,10 +930,6 @@ def main():
         os.execv(sys.executable, torchrun_argv(args.gpus, sys.argv[1:], port))
     if args.impl == "reference":
         run_reference(args)
-    elif args.config == "c4":
-        run_c4(args)
-    elif args.config == "c5":
-        run_c5(args)
     else:
         run_ours(args)
 

@@ -141,6 +141,20 @@ int vm_store_last_scan_ms(vm_store *s, float *ms);
  * until this call, so a back-to-back timed loop is measured as it ran.  *calls (optional) = how many. */
 int vm_store_avg_scan_ms(vm_store *s, float *ms, int *calls);
 
+/* Certification counters over the store's lifetime (or since the last reset), kept on the device by the
+ * rescoring kernels so that they also cover VM_FLAG_ASYNC calls and graph replays, whose per-call stats
+ * cannot report them.  queries = uncertified + (queries certified by the first pass); every uncertified query
+ * is settled exactly by one of the three fallbacks.  Synchronises with the device. */
+typedef struct vm_store_counters {
+    int64_t batches;          /* scan passes (<= 64 queries each) */
+    int64_t queries;          /* queries scored */
+    int64_t uncertified;      /* queries whose first candidate list could not be certified */
+    int64_t band_settled;     /* ... settled inside the same pass from the complete near-tie band (no second scan) */
+    int64_t collect_settled;  /* ... settled by the collect pass (one more streaming scan) */
+    int64_t full_rescans;     /* ... redone by the binary64 scan of every row */
+} vm_store_counters;
+int vm_store_read_counters(vm_store *s, vm_store_counters *out, int reset);
+
 /* ---- top-k scorer ---------------------------------------------------------------------
  * Replaces the hot loop of PreLLMInjector._calculate_batch_similarities
  * (src/components/pre_llm_injector.py:356-370: every query x every stored row through

@@ -30,7 +30,7 @@ EXPORTS = [
     "vm_store_create", "vm_store_attach", "vm_store_destroy", "vm_store_size", "vm_store_capacity", "vm_store_dim",
     "vm_store_ld", "vm_store_append", "vm_store_update", "vm_store_invalidate", "vm_store_set_size", "vm_store_clear",
     "vm_store_last_scan_ms",
-    "vm_store_avg_scan_ms",
+    "vm_store_avg_scan_ms", "vm_store_read_counters",
     "vm_topk", "vm_topk_sharded", "vm_merge_topk_lists", "vm_topk_packed_bytes", "vm_merge_topk_packed", "vm_merge_max_by_id", "vm_cosine_pairs", "vm_pairs_above", "vm_pairs_above_sharded",
     "vm_comm_unique_id", "vm_comm_init_rank", "vm_comm_destroy", "vm_comm_exchange_bytes", "vm_comm_attach_peer_buffers", "vm_comm_nranks", "vm_comm_rank", "vm_synth_fill",
 ]
@@ -39,6 +39,13 @@ EXPORTS = [
 class TopkStats(C.Structure):
     _fields_ = [("scan_kernel", C.c_int32), ("scan_launches", C.c_int32), ("uncertified", C.c_int32),
                 ("candidates", C.c_int32), ("scan_ctas", C.c_int32), ("scan_stages", C.c_int32), ("full_rescans", C.c_int32), ("scan_variant", C.c_int32)]
+
+
+class StoreCounters(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("batches", "queries", "uncertified", "band_settled", "collect_settled", "full_rescans")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
 class VidmemError(RuntimeError):
@@ -84,6 +91,7 @@ def load() -> C.CDLL:
         "vm_store_clear": (ci, [vp]),
         "vm_store_last_scan_ms": (ci, [vp, P(C.c_float)]),
         "vm_store_avg_scan_ms": (ci, [vp, P(C.c_float), P(C.c_int)]),
+        "vm_store_read_counters": (ci, [vp, P(StoreCounters), ci]),
         "vm_topk": (ci, [vp, vp, ci, ci, ci, ci, dbl, ci, ci, ci, vp, vp, vp, ci, P(TopkStats), vp]),
         "vm_topk_sharded": (ci, [vp, vp, i64, vp, ci, ci, ci, ci, dbl, ci, ci, ci, vp, vp, vp, ci, P(TopkStats), vp]),
         "vm_merge_topk_lists": (ci, [ci, vp, vp, vp, ci, ci, ci, vp, vp, vp, vp]),

@@ -116,6 +116,8 @@ struct vm_store {
     float *inv_norms = nullptr;
     bool owns = false;
     int *extreme = nullptr;  // device counter: rows outside the fast scans' numeric range
+    unsigned long long *cum = nullptr;  // device, [4]: lifetime certification counters (RescoreArgs::cum)
+    int64_t n_batches = 0, n_queries = 0;  // host side of vm_store_read_counters
     Buf stage, stage_idx;
     Workspace ws;
     // VM_FLAG_TIMING: a ring of event pairs, one per timed call, so a whole timed loop can be read back afterwards
@@ -283,7 +285,8 @@ static int store_new(vm_store **out, int device, int dim, int dtype, int64_t cap
     s->device = device; s->dim = dim; s->ld = ld_for_dim(dim); s->dtype = dtype; s->capacity = capacity; s->sm_count = sms;
     {
         DeviceGuard g(device);
-        if (cudaMalloc((void **)&s->extreme, 4) != cudaSuccess || cudaMemset(s->extreme, 0, 4) != cudaSuccess) {
+        if (cudaMalloc((void **)&s->extreme, 4) != cudaSuccess || cudaMemset(s->extreme, 0, 4) != cudaSuccess ||
+            cudaMalloc((void **)&s->cum, 32) != cudaSuccess || cudaMemset(s->cum, 0, 32) != cudaSuccess) {
             set_error("store allocation failed");
             delete s;
             return VM_ERR_OOM;
@@ -334,6 +337,7 @@ extern "C" int vm_store_destroy(vm_store *s)
     cudaDeviceSynchronize();
     if (s->owns) { cudaFree(s->rows); cudaFree(s->inv_norms); }
     if (s->extreme) cudaFree(s->extreme);
+    if (s->cum) cudaFree(s->cum);
     s->stage.release(); s->stage_idx.release();
     s->ws.release();
     for (auto &pr : s->evr) { if (pr[0]) cudaEventDestroy(pr[0]); if (pr[1]) cudaEventDestroy(pr[1]); }
@@ -447,6 +451,22 @@ extern "C" int vm_store_avg_scan_ms(vm_store *s, float *ms, int *calls)
     return VM_OK;
 }
 
+extern "C" int vm_store_read_counters(vm_store *s, vm_store_counters *out, int reset)
+{
+    VM_REQUIRE(s && out, VM_ERR_BADARG, "NULL argument");
+    DeviceGuard g(s->device);
+    unsigned long long h[4] = {0, 0, 0, 0};
+    VM_CUDA_CHECK(cudaMemcpy(h, s->cum, sizeof(h), cudaMemcpyDeviceToHost));  // synchronises with the work enqueued so far
+    out->batches = s->n_batches; out->queries = s->n_queries;
+    out->uncertified = (int64_t)h[0]; out->band_settled = (int64_t)h[1]; out->collect_settled = (int64_t)h[2];
+    out->full_rescans = (int64_t)h[3];
+    if (reset) {
+        VM_CUDA_CHECK(cudaMemset(s->cum, 0, sizeof(h)));
+        s->n_batches = 0; s->n_queries = 0;
+    }
+    return VM_OK;
+}
+
 extern "C" int vm_store_clear(vm_store *s)
 {
     VM_REQUIRE(s, VM_ERR_BADARG, "store is NULL");
@@ -545,7 +565,8 @@ static int topk_batch(const TopkCall &c)
     }
     FinalizeArgs fin{c.k, c.min_score, c.score_mode, c.row_offset, c.d_idx, c.d_score, c.d_count};
     ExactArgs ex{s->rows, s->inv_norms, s->dtype, s->ld, s->dim, s->size, q_dev, c.q_dtype, c.nq, c.k, c.sum_mode,
-                 nullptr, (double *)w.xs.p, (uint32_t *)w.xr.p, (int32_t *)w.xc.p, (uint8_t *)w.taken.p, XCTAS, fin};
+                 nullptr, (double *)w.xs.p, (uint32_t *)w.xr.p, (int32_t *)w.xc.p, (uint8_t *)w.taken.p, XCTAS, fin, s->cum};
+    if (!(c.flags & FLAG_INTERNAL_CAPTURE)) { ++s->n_batches; s->n_queries += c.nq; }
     int launches = 0;
     if (c.stats) { c.stats->uncertified = 0; c.stats->candidates = 0; c.stats->scan_ctas = 0; }
 
@@ -619,7 +640,7 @@ static int topk_batch(const TopkCall &c)
     int32_t *uncert = flags + c.nq;  // counter sits right after the nq flags (zeroed by the normalise kernel)
     RescoreArgs rs{(const uint64_t *)w.merged.p, kp, s->rows, s->inv_norms, s->dtype, s->ld, s->dim, s->size, q_dev,
                    c.q_dtype, c.nq, scan_eps(kernel, s->dtype, s->dim), c.sum_mode, fin, flags, uncert, s->extreme,
-                   kernel == 2 ? (float *)w.col_thr.p : nullptr};
+                   kernel == 2 ? (float *)w.col_thr.p : nullptr, s->cum};
     rc = k_select_rescore(a.cand, a.ctas, a.dump ? SCAN_DUMP_TILE : kp, rs, st);  // fused merge + exact rescoring
     if (rc == VM_ERR_UNSUPPORTED && !a.dump) {                 // rows too large for shared memory: two kernels
         rc = k_merge_candidates(a.cand, a.ctas, c.nq, kp, (uint64_t *)w.merged.p, st);
@@ -781,6 +802,7 @@ static int topk_common(vm_store *s, vm_comm *comm, int64_t row_offset, const voi
                 ge->sum_mode = sum_mode; ge->q_dtype = q_dtype; ge->min_score = min_score; ge->row_offset = row_offset; ge->stats = cs;
             }
             memcpy(w.h_q, queries, qbytes);
+            ++s->n_batches; s->n_queries += nq;
             VM_CUDA_CHECK(cudaGraphLaunch(ge->exec, s->gstream));
             VM_CUDA_CHECK(wait_stream(s->gstream, s));
             if (ge->stats.scan_kernel != 0 && *w.h_uncert > 0) {

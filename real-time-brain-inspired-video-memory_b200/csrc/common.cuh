@@ -199,6 +199,8 @@ struct RescoreArgs {
     int32_t *flags, *uncertified_count;
     const int *extreme;  // store-level count of rows outside the scans' numeric range (forces the exact pass)
     float *collect_thr;  // [nq] out: threshold of the collect pass for uncertified queries (+inf otherwise); may be NULL
+    unsigned long long *cum = nullptr;  // store-lifetime counters (vm_store_read_counters): [0] uncertified, [1] settled from the
+                                        // band, [2] settled by the collect pass, [3] redone by the binary64 scan of every row
 };
 struct ExactArgs {
     const void *rows;
@@ -214,6 +216,7 @@ struct ExactArgs {
     uint8_t *taken;        // [nq][ctas*k]
     int ctas;
     FinalizeArgs fin;
+    unsigned long long *cum = nullptr;  // see RescoreArgs::cum
 };
 
 }  // namespace vm

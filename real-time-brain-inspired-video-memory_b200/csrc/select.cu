@@ -248,7 +248,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rescore_kernel(const uint64_t *
                                                             const void *__restrict__ queries, int q_dtype, double eps,
                                                             FinalizeArgs f, int32_t *__restrict__ flags,
                                                             int32_t *__restrict__ uncertified_count, int chunk,
-                                                            const int *__restrict__ extreme, float *__restrict__ collect_thr)
+                                                            const int *__restrict__ extreme, float *__restrict__ collect_thr,
+                                                            unsigned long long *__restrict__ cum)
 {
     constexpr int VEC = 16 / (int)sizeof(T);      // elements per 16-byte load
     extern __shared__ double rs_smem[];
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rescore_kernel(const uint64_t *
             t = nextafterf(nextafterf(t, -INFINITY), -INFINITY);  // the cast may have rounded up
             collect_thr[q] = (!cert && bound_ok) ? t : INFINITY;
         }
-        if (!cert) atomicAdd(uncertified_count, 1);
+        if (!cert) { atomicAdd(uncertified_count, 1); if (cum) atomicAdd(cum, 1ull); }
     }
     if (ncand == 0 && j == 0) { flags[q] = 0; if (collect_thr) collect_thr[q] = INFINITY; }
     if (j == 0) f.out_count[q] = s_cnt;
@@ -400,7 +401,8 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uin
                                                                    const void *__restrict__ queries, int q_dtype, double eps,
                                                                    FinalizeArgs f, int32_t *__restrict__ flags,
                                                                    int32_t *__restrict__ uncertified_count,
-                                                                   const int *__restrict__ extreme, float *__restrict__ collect_thr)
+                                                                   const int *__restrict__ extreme, float *__restrict__ collect_thr,
+                                                                   unsigned long long *__restrict__ cum)
 {
     extern __shared__ __align__(16) unsigned char sr_smem[];
     const int total = lists * list_len;  // list_len == kp for per-CTA top-kp lists, 128 for dumped tiles
@@ -590,7 +592,7 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uin
             t = nextafterf(nextafterf(t, -INFINITY), -INFINITY);
             collect_thr[q] = (!cert && bound_ok) ? t : INFINITY;
         }
-        if (!cert) atomicAdd(uncertified_count, 1);
+        if (!cert) { atomicAdd(uncertified_count, 1); if (cum) atomicAdd(cum, 1ull); }
     }
     if (ncand == 0 && tid == 0) { flags[q] = 0; if (collect_thr) collect_thr[q] = INFINITY; }
     if (tid == 0) f.out_count[q] = s_cnt;
@@ -616,7 +618,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) collect_rescore_kernel(const ui
                                                                        const T *__restrict__ rows, int ld, int dim,
                                                                        const void *__restrict__ queries, int q_dtype, FinalizeArgs f,
                                                                        int32_t *__restrict__ flags, int32_t *__restrict__ uncertified_count,
-                                                                       int nq)
+                                                                       int nq, unsigned long long *__restrict__ cum)
 {
     extern __shared__ __align__(16) unsigned char cr_smem[];
     double *sq = reinterpret_cast<double *>(cr_smem);               // [dim]
@@ -686,6 +688,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) collect_rescore_kernel(const ui
         f.out_count[q] = cntv;
         flags[q] = 0;
         atomicSub(uncertified_count, 1);
+        if (cum) atomicAdd(cum + 2, 1ull);
     }
     for (int t = cntv + tid; t < f.k; t += CR_THREADS) {
         f.out_idx[(int64_t)q * f.k + t] = -1;
@@ -706,10 +709,11 @@ __global__ void __launch_bounds__(128) exact_scan_kernel(const T *__restrict__ r
                                                         int64_t n, int ld, int dim, const void *__restrict__ queries,
                                                         int q_dtype, int nq, const int32_t *__restrict__ flags, int k,
                                                         double *__restrict__ xlist_score, uint32_t *__restrict__ xlist_row,
-                                                        int32_t *__restrict__ xlist_cnt)
+                                                        int32_t *__restrict__ xlist_cnt, unsigned long long *__restrict__ cum)
 {
     // flags[nq] is the uncertified-query counter written by rescore_kernel: nothing to do when 0
     if (flags && flags[nq] == 0) return;
+    if (flags && cum && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(cum + 3, (unsigned long long)flags[nq]);
     extern __shared__ double sq[];  // [dim] query as doubles
     __shared__ double l_score[XK], n_score[XK];
     __shared__ uint32_t l_row[XK], n_row[XK];
@@ -1052,7 +1056,7 @@ int k_rescore(const RescoreArgs &a, cudaStream_t st)
         }                                                                                                              \
         rescore_kernel<NEU, T><<<a.nq, RS_THREADS, smem, st>>>(a.merged, a.kp, (const T *)a.rows, a.inv_norms, a.ld, a.dim, \
                                                                a.n_rows, a.queries, a.q_dtype, a.eps, a.fin, a.flags,    \
-                                                               a.uncertified_count, chunk, a.extreme, a.collect_thr);                             \
+                                                               a.uncertified_count, chunk, a.extreme, a.collect_thr, a.cum);                      \
     } while (0)
     // column chunk: whole rows when kp rows fit in RS_SMEM_ROW_BYTES, else a multiple of 8 columns
     int chunk = RS_SMEM_ROW_BYTES / (4 * a.kp) - 1;
@@ -1096,7 +1100,7 @@ int k_select_rescore(const uint64_t *cand, int lists, int list_len, const Rescor
         }                                                                                                              \
         select_rescore_kernel<NEU, T><<<a.nq, SR_THREADS, smem, st>>>(cand, lists, list_len, a.nq, a.kp, (const T *)a.rows, a.ld, a.dim, \
                                                                       a.n_rows, a.queries, a.q_dtype, a.eps, a.fin, a.flags,  \
-                                                                      a.uncertified_count, a.extreme, a.collect_thr);             \
+                                                                      a.uncertified_count, a.extreme, a.collect_thr, a.cum);      \
     } while (0)
     const bool neu = a.sum_mode == VM_SUM_NEUMAIER;
     if (a.dtype == VM_F32) { if (neu) LAUNCH_SR(true, float); else LAUNCH_SR(false, float); }
@@ -1120,7 +1124,7 @@ int k_collect_rescore(const uint64_t *buf, const int *cnt, int cap, const Rescor
             attr_set_dev[dev_idx_ & 63] = true;                                                                         \
         }                                                                                                               \
         collect_rescore_kernel<NEU, T><<<a.nq, CR_THREADS, smem, st>>>(buf, cnt, cap, (const T *)a.rows, a.ld, a.dim, a.queries, \
-                                                                       a.q_dtype, a.fin, a.flags, a.uncertified_count, a.nq);    \
+                                                                       a.q_dtype, a.fin, a.flags, a.uncertified_count, a.nq, a.cum); \
     } while (0)
     const bool neu = a.sum_mode == VM_SUM_NEUMAIER;
     if (a.dtype == VM_F32) { if (neu) LAUNCH_CR(true, float); else LAUNCH_CR(false, float); }
@@ -1137,7 +1141,7 @@ int k_exact(const ExactArgs &a, cudaStream_t st)
 #define LAUNCH_EX(NEU, T)                                                                                               \
     exact_scan_kernel<NEU, T><<<a.ctas, 128, smem, st>>>((const T *)a.rows, a.inv_norms, a.n, a.ld, a.dim, a.queries, \
                                                          a.q_dtype, a.nq, a.flags, a.k, a.xlist_score, a.xlist_row,  \
-                                                         a.xlist_cnt)
+                                                         a.xlist_cnt, a.cum)
     bool neu = a.sum_mode == VM_SUM_NEUMAIER;
     if (a.dtype == VM_F32) { if (neu) LAUNCH_EX(true, float); else LAUNCH_EX(false, float); }
     else { if (neu) LAUNCH_EX(true, __nv_bfloat16); else LAUNCH_EX(false, __nv_bfloat16); }

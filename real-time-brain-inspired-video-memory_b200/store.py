@@ -52,7 +52,7 @@ class EmbeddingStore:
     """Row-major embedding shard on one GPU.  Row index == append order (the reference's dict
     insertion order)."""
 
-    def __init__(self, dim: int, capacity: int, dtype: str = "f32", device: int = 0):
+    def __init__(self, dim: int, capacity: int, dtype: str = "f32", device: int = 0, _buffers=None):
         if not torch.cuda.is_available():
             raise RuntimeError("EmbeddingStore needs a CUDA device (sm_100); there is no CPU fallback")
         self.lib = L.load()
@@ -61,14 +61,28 @@ class EmbeddingStore:
         self.device = torch.device("cuda", device)
         self.ld = self.lib.vm_ld(self.dim)
         # PyTorch owns the HBM; the library attaches to it
-        self.rows = torch.empty((self.capacity, self.ld), dtype=_TORCH_DT[self.dtype_code], device=self.device)
-        self.inv_norms = torch.empty((self.capacity,), dtype=torch.float32, device=self.device)
+        if _buffers is None:
+            self.rows = torch.empty((self.capacity, self.ld), dtype=_TORCH_DT[self.dtype_code], device=self.device)
+            self.inv_norms = torch.empty((self.capacity,), dtype=torch.float32, device=self.device)
+        else:
+            self.rows, self.inv_norms = _buffers
         h = C.c_void_p()
         L.check(self.lib.vm_store_attach(C.byref(h), device, self.dim, self.dtype_code, self.capacity,
                                          self.rows.data_ptr(), self.inv_norms.data_ptr()))
         self._h = h
         self.last_stats = L.TopkStats()
         self._stats_ref = C.byref(self.last_stats)
+
+    def prefix_view(self, n: int) -> "EmbeddingStore":
+        """A second handle over the FIRST n resident rows (same HBM, same cached inverse norms): what a store
+        holding only those rows would answer.  Read-only use; close it before the parent."""
+        n = int(n)
+        if not 1 <= n <= len(self):
+            raise ValueError(f"prefix of {n} rows outside [1, {len(self)}]")
+        dt = "bf16" if self.dtype_code == L.VM_BF16 else "f32"
+        v = EmbeddingStore(self.dim, n, dt, self.device.index, _buffers=(self.rows[:n], self.inv_norms[:n]))
+        L.check(self.lib.vm_store_set_size(v._h, n, n, _stream_ptr(self.device)))   # norms are already cached
+        return v
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self) -> None:
@@ -142,6 +156,13 @@ class EmbeddingStore:
         ms, n = C.c_float(0.0), C.c_int(0)
         L.check(self.lib.vm_store_avg_scan_ms(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
+
+    def counters(self, reset: bool = False) -> dict:
+        """Certification counters since creation / the last reset (also cover VM_FLAG_ASYNC calls): batches, queries,
+        uncertified, band_settled, collect_settled, full_rescans.  Synchronises with the device."""
+        c = L.StoreCounters()
+        L.check(self.lib.vm_store_read_counters(self._h, C.byref(c), 1 if reset else 0))
+        return c.as_dict()
 
     def clear(self) -> None:
         L.check(self.lib.vm_store_clear(self._h))
