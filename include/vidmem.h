@@ -71,7 +71,9 @@ enum {
     VM_FLAG_FORCE_EXACT = 2, /* skip the fast scan: binary64 scan of every row (slow, always exact) */
     VM_FLAG_FORCE_SIMT = 4,  /* use the CUDA-core scan kernel even where the tcgen05 kernel applies */
     VM_FLAG_FORCE_TC = 8,    /* use the tcgen05/TMA scan kernel even for small query batches */
-    VM_FLAG_TIMING = 16      /* bracket the scan kernel with CUDA events on `stream` (see vm_store_last_scan_ms) */
+    VM_FLAG_TIMING = 16,     /* bracket the scan kernel with CUDA events on `stream` (see vm_store_last_scan_ms);
+                                also launches the call's kernels without programmatic overlap */
+    VM_FLAG_NO_SPLIT = 32    /* bf16 store: feed the query as ONE bf16 term (error bound 2^-8 instead of ~2^-16): A/B only */
 };
 
 typedef struct vm_store vm_store; /* a row-major embedding store resident in HBM (one shard) */
@@ -152,6 +154,9 @@ typedef struct vm_store_counters {
     int64_t band_settled;     /* ... settled inside the same pass from the complete near-tie band (no second scan) */
     int64_t collect_settled;  /* ... settled by the collect pass (one more streaming scan) */
     int64_t full_rescans;     /* ... redone by the binary64 scan of every row */
+    int64_t bound_violations; /* queries in which a rescored candidate's approximate score was further from its exact
+                                 score than the scan's error bound (audited on every candidate; such a query is always
+                                 redone by the binary64 scan).  Expected: 0. */
 } vm_store_counters;
 int vm_store_read_counters(vm_store *s, vm_store_counters *out, int reset);
 

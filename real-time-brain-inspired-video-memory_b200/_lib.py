@@ -20,7 +20,7 @@ VM_F32, VM_BF16, VM_F64 = 0, 1, 2
 VM_MEM_HOST, VM_MEM_DEVICE = 0, 1
 VM_SCORE_RAW, VM_SCORE_NEO4J = 0, 1
 VM_SUM_NAIVE, VM_SUM_NEUMAIER = 0, 1
-VM_FLAG_ASYNC, VM_FLAG_FORCE_EXACT, VM_FLAG_FORCE_SIMT, VM_FLAG_FORCE_TC, VM_FLAG_TIMING = 1, 2, 4, 8, 16
+VM_FLAG_ASYNC, VM_FLAG_FORCE_EXACT, VM_FLAG_FORCE_SIMT, VM_FLAG_FORCE_TC, VM_FLAG_TIMING, VM_FLAG_NO_SPLIT = 1, 2, 4, 8, 16, 32
 
 #: summation order CPython's builtin sum() uses in THIS interpreter (what the reference would compute here)
 DEFAULT_SUM_MODE = VM_SUM_NEUMAIER if sys.version_info >= (3, 12) else VM_SUM_NAIVE
@@ -42,7 +42,7 @@ class TopkStats(C.Structure):
 
 
 class StoreCounters(C.Structure):
-    _fields_ = [(n, C.c_int64) for n in ("batches", "queries", "uncertified", "band_settled", "collect_settled", "full_rescans")]
+    _fields_ = [(n, C.c_int64) for n in ("batches", "queries", "uncertified", "band_settled", "collect_settled", "full_rescans", "bound_violations")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

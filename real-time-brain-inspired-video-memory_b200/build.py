@@ -38,7 +38,20 @@ def _digest(paths) -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str = None, objdir: str = None) -> str:
+    """extra_flags / out / objdir: A/B builds (e.g. -DVIDMEM_TRIAGE_KERNELS) into another .so, selected at run time
+    with VIDMEM_LIB=<path>; the shipped library is always the default build."""
+    global OBJ, LIB, NVCC_FLAGS
+    saved = (OBJ, LIB, NVCC_FLAGS)
+    if out:
+        OBJ, LIB, NVCC_FLAGS = objdir or (out + ".obj"), out, NVCC_FLAGS + list(extra_flags)
+    try:
+        return _build(force, verbose)
+    finally:
+        OBJ, LIB, NVCC_FLAGS = saved
+
+
+def _build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "vidmem.h"))
@@ -74,4 +87,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, extra_flags=defs, out=outs[0] if outs else None))

@@ -26,16 +26,17 @@ int k_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype, int
 int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, int *extreme, cudaStream_t st);
 int k_invalidate_rows(float *inv_norms, const int64_t *rows_dev, int64_t n, int64_t size, cudaStream_t st);
 int k_normalize_queries(const void *q, int q_dtype, int nq, int nq_pad, int dim, int ld, float *out_f32, void *out_bf16,
-                        int32_t *zero_me, uint32_t *zero_tab, int zero_tab_n, cudaStream_t st);
+                        int32_t *zero_me, uint32_t *zero_tab, int zero_tab_n, int tf32_round, int split, bool pdl, cudaStream_t st);
 int k_synth_fill(void *rows, int dtype, uint64_t seed, int64_t row0, int64_t n, int dim, int ld, uint64_t dup_period,
                  cudaStream_t st);
 int k_merge_candidates(const uint64_t *cand, int lists, int nq, int kp, uint64_t *merged, cudaStream_t st);
 
-int k_rescore(const RescoreArgs &a, cudaStream_t st);
-int k_select_rescore(const uint64_t *cand, int lists, int list_len, const RescoreArgs &a, cudaStream_t st);
+int k_slab_top(const SelectArgs &sa, int nq, int kp, uint64_t *merged, int *incomplete, cudaStream_t st);
+int k_rescore(const RescoreArgs &a, cudaStream_t st, const int *incomplete);
+int k_select_rescore(const SelectArgs &sa, const RescoreArgs &a, cudaStream_t st, bool pdl);
 bool select_rescore_fits(int lists, int list_len, int kp, int dtype, int dim, int ld);
 int k_collect_rescore(const uint64_t *buf, const int *cnt, int cap, const RescoreArgs &a, cudaStream_t st);
-int k_exact(const ExactArgs &a, cudaStream_t st);
+int k_exact(const ExactArgs &a, cudaStream_t st, bool pdl);
 int k_merge_topk_lists(const void *idx, const void *score, const void *count, size_t stride_bytes, int lists, int nq, int k,
                        int64_t *out_idx, double *out_score, int32_t *out_count, cudaStream_t st);
 int k_p2p_publish(void *flag, unsigned long long gen, cudaStream_t st);
@@ -88,14 +89,14 @@ struct Buf {
 struct Workspace {
     bool ready = false;
     int lists_max = 0;
-    Buf q_raw, q_f32, q_bf16, seed, cand, merged, o_idx, flags, col_thr, col_cnt, col_buf, xs, xr, xc, taken, gather_send, gather_recv, misc;
+    Buf q_raw, q_f32, q_bf16, seed, cand, merged, o_idx, flags, col_thr, col_cnt, col_buf, xs, xr, xc, taken, gather_send, gather_recv, misc, ubuf, done, scnt, sel_inc;
     int32_t *h_uncert = nullptr;  // pinned
     unsigned char *h_pack = nullptr;  // pinned: packed [idx | score | count] of one batch
     unsigned char *h_q = nullptr;     // pinned: host queries of one batch
     void release()
     {
         Buf *all[] = {&q_raw, &q_f32, &q_bf16, &seed, &cand, &merged, &o_idx, &flags, &col_thr, &col_cnt, &col_buf, &xs, &xr, &xc, &taken,
-                      &gather_send, &gather_recv, &misc};
+                      &gather_send, &gather_recv, &misc, &ubuf, &done, &scnt, &sel_inc};
         for (Buf *b : all) b->release();
         if (h_uncert) cudaFreeHost(h_uncert);
         if (h_pack) cudaFreeHost(h_pack);
@@ -222,13 +223,20 @@ static int ws_prepare(vm_store *s)
 #define ENS(b, bytes) if ((rc = (b).ensure(bytes)) != VM_OK) return rc
     ENS(w.q_raw, (size_t)MAXQ * s->dim * 8);
     ENS(w.q_f32, (size_t)MAXQ * s->ld * 4);
-    ENS(w.q_bf16, (size_t)MAXQ * s->ld * 2);
+    ENS(w.q_bf16, (size_t)2 * MAXQ * s->ld * 2);  // hi terms, then lo terms (split query)
     ENS(w.cand, (size_t)lists * MAXQ * MAXK * 8);
     ENS(w.merged, (size_t)MAXQ * MAXK * 8);
     // one contiguous block [idx | score | count] so a host caller gets its results with ONE copy
     ENS(w.o_idx, (size_t)MAXQ * MAXK * 16 + (size_t)MAXQ * 4 + 64);
     ENS(w.flags, (size_t)(MAXQ + 2) * 4);
-    ENS(w.seed, (size_t)(256 * MAXQ + 2 * MAXQ) * 4);  // per-CTA maxima + published per-query bounds + their counter (scan_tc.cu)
+    // per-CTA maxima [256][64] + published per-query bounds [64] + their counter [64] + union-buffer counters [64] (scan_tc.cu);
+    // zeroed as one block by the normalise kernel
+    ENS(w.seed, (size_t)(SEED_TAB_WORDS + 3 * MAXQ) * 4);
+    ENS(w.ubuf, (size_t)MAXQ * SCAN_UNION_CAP * 8);
+    ENS(w.done, 64);
+    ENS(w.scnt, (size_t)256 * MAXQ * 4);
+    ENS(w.sel_inc, (size_t)MAXQ * 4);
+    VM_CUDA_CHECK(cudaMemset(w.done.p, 0, 64));
     ENS(w.col_thr, (size_t)MAXQ * 4);
     ENS(w.col_cnt, (size_t)MAXQ * 4);
     ENS(w.col_buf, (size_t)MAXQ * COLLECT_CAP * 8);
@@ -244,13 +252,18 @@ static int ws_prepare(vm_store *s)
     return VM_OK;
 }
 
-static double scan_eps(int kernel, int store_dtype, int dim)
+static double scan_eps(int kernel, int store_dtype, int dim, int split)
 {
-    // Bound on |approximate cosine - exact cosine| (DESIGN.md "certification").
-    double fp32_acc = (double)(dim + 16) * 1.1920928955078125e-07;  // (D+16) * 2^-23
-    if (kernel == 1) return fp32_acc;                                  // CUDA-core fp32 scan
-    if (store_dtype == VM_F32) return 1.953125e-3 + fp32_acc;          // tf32: both operands truncated, 2 * 2^-10
-    return 3.90625e-3 + fp32_acc;                                      // bf16 store, query rounded to bf16: 2^-8
+    // Bound on |approximate cosine - exact cosine| (DESIGN.md "certification"), in cosine units (Cauchy-Schwarz).
+    const double u = 1.1920928955078125e-07;                         // 2^-23
+    const double fp32_acc = (double)(dim + 16) * u;                  // fp32 accumulation + normalisation of query and row
+    if (kernel == 1) return fp32_acc;                                // CUDA-core fp32 scan
+    if (store_dtype == VM_F32)                                       // tf32: rows truncated (2^-10), query pre-rounded to nearest (2^-11)
+        return 9.765625e-4 + 4.8828125e-4 + 1e-6 + fp32_acc;
+    if (!split) return 3.90625e-3 + fp32_acc;                        // bf16 store (exact operand), query rounded to bf16: 2^-8
+    // bf16 store, query = hi + lo: residual 2^-16; the lo products are 2^-8 of the hi ones, their MMAs add one
+    // accumulator rounding each (dim/16 of them) -- counted generously as dim/8 + 16 extra terms
+    return 1.52587890625e-5 * 1.01 + (double)(dim + dim / 8 + 32) * u;
 }
 
 // ---- library --------------------------------------------------------------------------------
@@ -286,7 +299,7 @@ static int store_new(vm_store **out, int device, int dim, int dtype, int64_t cap
     {
         DeviceGuard g(device);
         if (cudaMalloc((void **)&s->extreme, 4) != cudaSuccess || cudaMemset(s->extreme, 0, 4) != cudaSuccess ||
-            cudaMalloc((void **)&s->cum, 32) != cudaSuccess || cudaMemset(s->cum, 0, 32) != cudaSuccess) {
+            cudaMalloc((void **)&s->cum, 64) != cudaSuccess || cudaMemset(s->cum, 0, 64) != cudaSuccess) {
             set_error("store allocation failed");
             delete s;
             return VM_ERR_OOM;
@@ -455,11 +468,12 @@ extern "C" int vm_store_read_counters(vm_store *s, vm_store_counters *out, int r
 {
     VM_REQUIRE(s && out, VM_ERR_BADARG, "NULL argument");
     DeviceGuard g(s->device);
-    unsigned long long h[4] = {0, 0, 0, 0};
+    unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     VM_CUDA_CHECK(cudaMemcpy(h, s->cum, sizeof(h), cudaMemcpyDeviceToHost));  // synchronises with the work enqueued so far
     out->batches = s->n_batches; out->queries = s->n_queries;
     out->uncertified = (int64_t)h[0]; out->band_settled = (int64_t)h[1]; out->collect_settled = (int64_t)h[2];
     out->full_rescans = (int64_t)h[3];
+    out->bound_violations = (int64_t)h[4];
     if (reset) {
         VM_CUDA_CHECK(cudaMemset(s->cum, 0, sizeof(h)));
         s->n_batches = 0; s->n_queries = 0;
@@ -565,7 +579,8 @@ static int topk_batch(const TopkCall &c)
     }
     FinalizeArgs fin{c.k, c.min_score, c.score_mode, c.row_offset, c.d_idx, c.d_score, c.d_count};
     ExactArgs ex{s->rows, s->inv_norms, s->dtype, s->ld, s->dim, s->size, q_dev, c.q_dtype, c.nq, c.k, c.sum_mode,
-                 nullptr, (double *)w.xs.p, (uint32_t *)w.xr.p, (int32_t *)w.xc.p, (uint8_t *)w.taken.p, XCTAS, fin, s->cum};
+                 nullptr, (double *)w.xs.p, (uint32_t *)w.xr.p, (int32_t *)w.xc.p, (uint8_t *)w.taken.p, XCTAS, fin, s->cum,
+                 (int *)w.done.p};
     if (!(c.flags & FLAG_INTERNAL_CAPTURE)) { ++s->n_batches; s->n_queries += c.nq; }
     int launches = 0;
     if (c.stats) { c.stats->uncertified = 0; c.stats->candidates = 0; c.stats->scan_ctas = 0; }
@@ -586,7 +601,7 @@ static int topk_batch(const TopkCall &c)
         else if (tc_ok) { kernel = 2; kp = kp_tc; }
     }
     if (kernel == 0) {
-        int rc = k_exact(ex, st);
+        int rc = k_exact(ex, st, false);
         if (rc != VM_OK) return rc;
         launches += 2;
         if (c.h_idx) {
@@ -599,17 +614,27 @@ static int topk_batch(const TopkCall &c)
     }
 
     int nq_pad = kernel == 2 ? ((c.nq + 15) & ~15) : c.nq;
+    // bf16 store: feed the query as hi + lo bf16 terms (two MMAs per K slice) whenever that layout fits shared memory
+    const int split = (kernel == 2 && s->dtype == VM_BF16 && !(c.flags & VM_FLAG_NO_SPLIT) &&
+                       scan_tc_supported(s->dtype, s->dim, c.nq, kp, 1)) ? 1 : 0;
+    // The kernels of one call are chained with programmatic dependent launch (common.cuh): each one's launch and
+    // prologue overlap its predecessor's drain.  Off while events bracket the scan (VM_FLAG_TIMING) or a graph is captured.
+    const bool pdl = !(c.flags & (VM_FLAG_TIMING | FLAG_INTERNAL_CAPTURE));
     int rc = k_normalize_queries(q_dev, c.q_dtype, c.nq, nq_pad, s->dim, s->ld, (float *)w.q_f32.p,
                                  (kernel == 2 && s->dtype == VM_BF16) ? w.q_bf16.p : nullptr,
                                  (int32_t *)w.flags.p + c.nq, kernel == 2 ? (uint32_t *)w.seed.p : nullptr,
-                                 kernel == 2 ? (int)(w.seed.bytes / 4) : 0, st);
+                                 kernel == 2 ? (int)(w.seed.bytes / 4) : 0, kernel == 2 && s->dtype == VM_F32, split, pdl, st);
     if (rc != VM_OK) return rc;
     ++launches;
+    const double eps = scan_eps(kernel, s->dtype, s->dim, split);
 
     ScanArgs a;
     ScanInfo sinfo;
     a.rows = s->rows; a.inv_norms = s->inv_norms; a.dtype = s->dtype; a.n = s->size; a.dim = s->dim; a.ld = s->ld;
     a.queries = (const float *)w.q_f32.p; a.nq = c.nq; a.kp = kp; a.cand = (uint64_t *)w.cand.p; a.stream = st;
+    a.slab = (uint64_t *)w.cand.p; a.scnt = (int *)w.scnt.p;
+    a.ubuf = (uint64_t *)w.ubuf.p; a.ucnt = (int *)w.seed.p + SEED_TAB_WORDS + 2 * MAXQ; a.ucap = SCAN_UNION_CAP;
+    a.band = nextafterf((float)(2.0 * eps), INFINITY); a.ksel = c.k; a.split = split; a.pdl = pdl;
     const bool timing = (c.flags & VM_FLAG_TIMING) != 0;
     if (timing) {
         s->ev_cur = s->ev_next;
@@ -639,13 +664,22 @@ static int topk_batch(const TopkCall &c)
     int32_t *flags = (int32_t *)w.flags.p;
     int32_t *uncert = flags + c.nq;  // counter sits right after the nq flags (zeroed by the normalise kernel)
     RescoreArgs rs{(const uint64_t *)w.merged.p, kp, s->rows, s->inv_norms, s->dtype, s->ld, s->dim, s->size, q_dev,
-                   c.q_dtype, c.nq, scan_eps(kernel, s->dtype, s->dim), c.sum_mode, fin, flags, uncert, s->extreme,
+                   c.q_dtype, c.nq, eps, c.sum_mode, fin, flags, uncert, s->extreme,
                    kernel == 2 ? (float *)w.col_thr.p : nullptr, s->cum};
-    rc = k_select_rescore(a.cand, a.ctas, a.dump ? SCAN_DUMP_TILE : kp, rs, st);  // fused merge + exact rescoring
-    if (rc == VM_ERR_UNSUPPORTED && !a.dump) {                 // rows too large for shared memory: two kernels
-        rc = k_merge_candidates(a.cand, a.ctas, c.nq, kp, (uint64_t *)w.merged.p, st);
+    // where the candidates are: the union buffer of the tcgen05 scan (complete band), its dumped tiles (every row),
+    // or the per-CTA top-kp lists of the CUDA-core scan
+    SelectArgs sel;
+    const bool union_src = kernel == 2 && !a.dump;
+    if (union_src) {
+        sel.slab = a.slab; sel.scnt = a.scnt; sel.ctas = a.ctas; sel.ubuf = a.ubuf; sel.ucnt = a.ucnt; sel.ucap = a.ucap;
+        sel.seed_tab = a.ctas <= 256 ? (const uint32_t *)w.seed.p : nullptr; sel.nq_pad = nq_pad; sel.ksel = c.k; sel.band = a.band;
+    } else { sel.cand = a.cand; sel.lists = a.ctas; sel.list_len = a.dump ? SCAN_DUMP_TILE : kp; sel.complete = a.dump ? 1 : 0; }
+    rc = k_select_rescore(sel, rs, st, pdl);   // fused selection + exact rescoring + band settlement
+    if (rc == VM_ERR_UNSUPPORTED && !a.dump) {  // rows too large for shared memory: two kernels
+        if (union_src) rc = k_slab_top(sel, c.nq, kp, (uint64_t *)w.merged.p, (int *)w.sel_inc.p, st);
+        else rc = k_merge_candidates(a.cand, a.ctas, c.nq, kp, (uint64_t *)w.merged.p, st);
         if (rc != VM_OK) return rc;
-        rc = k_rescore(rs, st);
+        rc = k_rescore(rs, st, union_src ? (const int *)w.sel_inc.p : nullptr);
         ++launches;
     }
     if (rc != VM_OK) return rc;
@@ -670,9 +704,9 @@ static int topk_batch(const TopkCall &c)
             // re-runs the batch through the plain path in the rare case it is non-zero
             VM_CUDA_CHECK(cudaMemcpyAsync(w.h_uncert, uncert, 4, cudaMemcpyDeviceToHost, st));
         } else {
-            rc = k_exact(ex, st);  // device-side conditional: returns immediately when nothing is flagged
+            rc = k_exact(ex, st, pdl);  // ONE conditional launch: exits at once when nothing is flagged
             if (rc != VM_OK) return rc;
-            launches += 2;
+            launches += 1;
         }
         n_uncert = -1;
     } else {
@@ -692,9 +726,9 @@ static int topk_batch(const TopkCall &c)
             }
             n_full = left;
             if (left > 0) {
-                rc = k_exact(ex, st);
+                rc = k_exact(ex, st, false);
                 if (rc != VM_OK) return rc;
-                launches += 2;
+                launches += 1;
             }
             if (c.h_idx) {
                 if ((rc = pack_out_enqueue(c)) != VM_OK) return rc;

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
+#include <utility>
 #include "../../include/vidmem.h"
 
 namespace vm {
@@ -26,6 +27,30 @@ void set_error(const char *fmt, ...);
             return (code);                   \
         }                                    \
     } while (0)
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------
+// The kernels of one top-k call are launched back to back with cudaLaunchAttributeProgrammaticStreamSerialization
+// (launch_pdl below): kernel N+1 may be scheduled -- and run its prologue: shared-memory carve-up, barrier init,
+// TMEM allocation, work that only depends on its own arguments -- while kernel N drains; pdl_wait() blocks until
+// kernel N has COMPLETED and its writes are visible.  Every kernel of the chain calls pdl_wait() before it touches
+// global memory another kernel of the chain writes or reads, so the chain is transitively ordered.  Without the
+// launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                     Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- candidate keys --------------------------------------------------------------------
 // A candidate is one u64: high word = order-preserving image of the fp32 score, low word =
@@ -58,6 +83,46 @@ __host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t row)
 }
 __host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) { return 0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFu); }
 __host__ __device__ __forceinline__ float key_score(uint64_t k) { return f32_from_ordered((uint32_t)(k >> 32)); }
+
+static constexpr int SEED_TAB_WORDS = 256 * 64;  // scan table: per-CTA maxima [<= 256 CTAs][<= 64 queries]; [64] published bounds,
+                                                 // [64] publication counter, [64] spill counters follow
+#ifdef __CUDACC__
+// k-th largest of the per-CTA maxima of query q (one warp, G <= 256 CTAs): a lower bound on the shard's k-th best
+// score, because k distinct rows (one per CTA) reach it.  16 radix bits; truncation rounds down.
+__device__ __forceinline__ float seed_select(const uint32_t *seed_tab, int G, int nq_pad, int q, int k, int lane)
+{
+    uint32_t vals[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int i = lane + 32 * t;
+        vals[t] = i < G ? __ldcg(seed_tab + (size_t)i * nq_pad + q) : 0u;
+    }
+    uint32_t prefix = 0;
+    int need = k;
+    for (int bit = 31; bit >= 16; --bit) {
+        const uint32_t hi = bit == 31 ? 0u : (0xFFFFFFFFu << (bit + 1));
+        int cnt = 0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) cnt += ((vals[t] & hi) == prefix && ((vals[t] >> bit) & 1u)) ? 1 : 0;
+        const int tot = __reduce_add_sync(0xffffffffu, cnt);
+        if (tot >= need) prefix |= 1u << bit;
+        else need -= tot;
+    }
+    float sd = f32_from_ordered(prefix);
+    if (!(sd > -INFINITY) || G < k) sd = -INFINITY;  // also catches NaN patterns
+    return sd;
+}
+
+// band threshold for a lower bound L on the k-th best approximate score: L - band, rounded DOWN (a lower threshold
+// only keeps more rows)
+__device__ __forceinline__ float band_floor(float L, float band)
+{
+    if (!(L > -INFINITY)) return -INFINITY;
+    const float t = __fsub_rd(L, band);
+    return nextafterf(t, -INFINITY);
+}
+
+#endif
 
 // ---- binary64 reference arithmetic -----------------------------------------------------
 // Python's builtin sum() over float products (see oracle/vm_oracle.c): the first item enters
@@ -153,7 +218,20 @@ struct ScanArgs {
     int ctas;                // number of CTAs to launch (lists produced)
     cudaStream_t stream;
     int dump = 0;            // tcgen05 scan only: small store -- emit EVERY row's key, cand = [tiles][nq][128] (see scan_tc.cu)
+    // tcgen05 scan, band scheme (scan_tc.cu): every key with approximate score >= (bound on the k-th best) - band
+    uint64_t *slab = nullptr;  // [ctas][nq][SCAN_SLAB] per-CTA append buffers
+    int *scnt = nullptr;       // [ctas][nq] keys appended per slab (> SCAN_SLAB: the rest was spilled)
+    uint64_t *ubuf = nullptr;  // [nq][ucap] shared spill buffer
+    int *ucnt = nullptr;       // [nq] keys spilled, zeroed before the launch (> ucap: overflow)
+    int ucap = 0;
+    float band = 0.0f;         // 2 eps, rounded up
+    int ksel = 0;              // k
+    int split = 0;             // bf16 store: queries given as hi + lo bf16 terms, [2][nq_pad][ld]
+    bool pdl = false;          // launch with programmatic stream serialization
 };
+static constexpr int SCAN_UNION_CAP = 16384; // shared spill-buffer entries per query (filtered with the final bound before staging)
+static constexpr int SCAN_SLAB = 64;          // keys per (CTA, query) slab
+static constexpr int SELECT_KEY_CAP = 4096;   // band keys the rescoring kernel stages per query after the final filter
 static constexpr int SCAN_DUMP_TILE = 128;     // rows (= keys per query) per dumped tile
 static constexpr int SCAN_DUMP_MAX_KEYS = 9472;  // per query: what the fused select kernel ranks in shared memory (148 x 64)
 int launch_scan_simt(const ScanArgs &a);
@@ -171,7 +249,7 @@ struct ScanCollect {
 struct ScanInfo { int stages = 0, variant = 0; };  // what the launch chose (reported in vm_topk_stats): pipeline depth; 0 lists, 1 dump, 2 lists + threshold warp
 int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t *seed_tab, int *seed_ctr,
                    const ScanCollect *sc = nullptr, ScanInfo *info = nullptr);
-bool scan_tc_supported(int dtype, int dim, int nq, int kp);
+bool scan_tc_supported(int dtype, int dim, int nq, int kp, int split = 0);
 
 
 // ---- argument blocks shared by api.cu and select.cu ------------------------------------
@@ -200,7 +278,23 @@ struct RescoreArgs {
     const int *extreme;  // store-level count of rows outside the scans' numeric range (forces the exact pass)
     float *collect_thr;  // [nq] out: threshold of the collect pass for uncertified queries (+inf otherwise); may be NULL
     unsigned long long *cum = nullptr;  // store-lifetime counters (vm_store_read_counters): [0] uncertified, [1] settled from the
-                                        // band, [2] settled by the collect pass, [3] redone by the binary64 scan of every row
+                                        // band, [2] settled by the collect pass, [3] redone by the binary64 scan of every row, [4] error-bound violations
+};
+// where the fused select + rescore kernel takes a query's candidate keys from
+struct SelectArgs {
+    const uint64_t *cand = nullptr;  // list mode: [lists][nq][list_len] (CUDA-core scan lists, or dumped tiles)
+    int lists = 0, list_len = 0;
+    int complete = 0;                // list mode: the lists hold EVERY row of the shard (dump mode)
+    // slab mode (tcgen05 scan): per-CTA slabs + shared spill buffer + the table of per-CTA maxima / published bounds
+    const uint64_t *slab = nullptr;  // [ctas][nq][SCAN_SLAB]
+    const int *scnt = nullptr;       // [ctas][nq]
+    int ctas = 0;
+    const uint64_t *ubuf = nullptr;  // [nq][ucap]
+    const int *ucnt = nullptr;
+    int ucap = 0;
+    const uint32_t *seed_tab = nullptr;  // [ctas][nq_pad] final per-CTA maxima, then [64] published bounds (may be NULL)
+    int nq_pad = 0, ksel = 0;
+    float band = 0.0f;
 };
 struct ExactArgs {
     const void *rows;
@@ -209,7 +303,7 @@ struct ExactArgs {
     int64_t n;
     const void *queries;
     int q_dtype, nq, k, sum_mode;
-    const int32_t *flags;  // NULL = all queries
+    int32_t *flags;        // NULL = all queries
     double *xlist_score;   // [ctas][nq][k]
     uint32_t *xlist_row;
     int32_t *xlist_cnt;    // [ctas][nq]
@@ -217,6 +311,7 @@ struct ExactArgs {
     int ctas;
     FinalizeArgs fin;
     unsigned long long *cum = nullptr;  // see RescoreArgs::cum
+    int *done_ctr = nullptr;            // conditional form: ticket counter (zero between calls) -> in-kernel merge by the last CTA
 };
 
 }  // namespace vm

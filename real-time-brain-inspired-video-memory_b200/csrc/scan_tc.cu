@@ -1,6 +1,6 @@
 // scan_tc.cu -- tcgen05 / TMA streaming scorer: the bandwidth-bound scan for query batches.
 //
-// One persistent CTA per SM, warp-specialised (192 threads; 288 with the threshold warp, see below):
+// One persistent CTA per SM, warp-specialised (288 threads; 192 in dump mode):
 //   warp 0   TMA producer   streams the store as 128-row x 128-byte boxes (SWIZZLE_128B) through a
 //                           ring of 16 KB shared-memory stages, L2 evict-first; loads the
 //                           normalised queries once (evict-last) -- no thread ever touches a row
@@ -9,40 +9,38 @@
 //                           in TMEM (8 stages x nq columns), tcgen05.commit frees stages / publishes D
 //   warps 2-5 epilogue      tcgen05.ld their 32-lane TMEM quadrant (lane = store row, column = query),
 //                           multiply by the cached 1/||row|| (fused normalisation), compare with the
-//                           per-query running threshold, push the rare survivors into per-query
-//                           queues; thread q then folds them into query q's unsorted top-kp set in
-//                           shared memory (replace the minimum, rescan with pipelined loads).  While a
-//                           tile overflows a queue its accumulator simply stays in TMEM and is re-read
-//                           after the drain.
-// Threshold seeding: each CTA starts without a threshold, so for its first tiles every score would
-// be a "survivor".  Instead every CTA first publishes, per query, the maximum score of its first
-// tile; the kp-th largest of those per-CTA maxima is a valid lower bound on the shard's kp-th best
-// score (kp distinct rows reach it), and with ~148 CTAs it is as tight as the kp-th best of the
-// first 19 K rows.  All CTAs adopt it as their initial threshold (bounded wait, no grid barrier
-// semantics needed: a late CTA only makes the bound looser), while TMA/MMA keep streaming into the
-// 8 TMEM stages.  This removes the per-CTA warm-up flood that otherwise dominates small shards.
-// Threshold warp (template TW, narrow tiles): a CTA's own kp-th best is a weak filter -- it has seen
-// 1/148 of the shard -- so ~every tile still produced a survivor and paid the two-barrier drain, and the
-// epilogue, not HBM, paced bf16 scans.  With TW the drains keep each CTA's RUNNING maximum per query
-// current in the seed table and one extra warp per CTA runs a distributed bound service: the CTA that
-// owns query q (q mod G) keeps re-deriving the exact kp-th largest of all CTAs' maxima (same proof as the
-// first seed: kp distinct rows reach it) and publishes it with an atomic max; every CTA adopts the
-// published bounds of all queries with a CAS-max on its shared-memory thresholds.  The bound then follows
-// the shard-wide top-kp (~40th best of everything scanned so far), survivors become rare, and the epilogue
-// drops off the critical path.  The first seed is derived the same way (one select per owner CTA, a second
-// short bounded wait) instead of 64 selects in every CTA.
-// HBM traffic = the store bytes exactly once per batch of <= 64 queries; the per-CTA lists are
-// merged and exactly rescored by select.cu.
-// Collect mode (second pass for queries the first pass could not certify): thresholds are fixed per
+//                           per-query band threshold; a survivor is APPENDED, lock-free, to this CTA's
+//                           private slab of the query (a shared-memory counter hands out the slot, the key
+//                           goes to global memory with a fire-and-forget store).  No queues, no CTA-wide
+//                           barriers, no serial drain: the four warps run independently, tile after tile.
+//   warp 8   bound service  keeps the thresholds current (see below); sleeps between rounds
+//
+// What the scan keeps -- the COMPLETE NEAR-TIE BAND, not a top-kp list.  Let a_(k) be the k-th best approximate
+// score of the shard and eps the scan's error bound.  A row can only be in the exact top-k if its approximate score
+// reaches a_(k) - 2 eps (its exact score must reach the k-th exact score, which is >= a_(k) - eps).  Every CTA filters
+// with the band threshold B = L - 2 eps, where L <= a_(k) is a lower bound that only grows:
+//   * seed: each CTA publishes, per query, the maximum of its first tile; the k-th largest of those <= 148 maxima is
+//     reached by k distinct rows, so it is <= a_(k).  Derived once by the CTA that owns the query (q mod G),
+//     published with an atomic max, adopted by all CTAs (bounded waits; a late CTA only loosens the bound);
+//   * bound service (one warp per CTA, off the critical path): publishes this CTA's RUNNING maximum per query, the
+//     owner CTA of a query keeps re-deriving the k-th largest of all CTAs' maxima -- the bound follows the
+//     shard-wide top-k --, a CTA whose own slab fills up publishes its own k-th best (k of its own rows reach it:
+//     what finds a tight cluster that lives in ONE CTA, e.g. the 64 consecutive near-duplicate chunks of a static
+//     scene), and every CTA adopts whatever has been published.
+// A slab holds 64 keys per (CTA, query); beyond that keys go to the query's shared spill buffer (global atomic; rare
+// once the own-k-th bound is in place).  Slabs + spill therefore hold EVERY row with approximate score >= the final
+// threshold: select.cu filters them once more with the final bound, rescores the best kp in binary64, and if more
+// than those lie within eps of the k-th exact score it rescores that whole band from the same keys -- no second
+// scan.  Only a spill overflow (thousands of near-ties: duplicates, a zero query) falls back to the collect pass.
+// bf16 stores, split query (ScanArgs::split): the normalised fp32 query is fed as q_hi + q_lo (two bf16 terms, 16
+// mantissa bits), two MMAs per K slice into the same accumulator, so eps drops from 2^-8 to ~2^-16 + (D+16) 2^-23.
+// HBM traffic = the store bytes exactly once per batch of <= 64 queries.
+// Collect mode (second pass for queries the first pass could not settle): thresholds are fixed per
 // query (exact k-th candidate score - 2 eps; +inf for queries that need nothing) and every row at or
-// above its query's threshold is appended to that query's global buffer -- no lists, no drains.
-// Dump mode (template DUMP, stores of <= 9472 rows): with one or two tiles per CTA there is no
-// threshold to filter with -- every row of a first tile is a "survivor" and the serial per-query
-// drain dominates (measured 82 us for 5000 rows x 30 queries).  Instead the epilogue writes the
-// key of EVERY row, [tile][query][128], and select.cu ranks all of them per query; nothing is
-// dropped before the exact rescoring, so the certification bound is the kp-th best approximate score.
+// above its query's threshold is appended to that query's global buffer.
+// Dump mode (template DUMP, stores of <= 9472 rows): with one tile per CTA there is nothing to filter with.
+// The epilogue writes the key of EVERY row, [tile][query][128], and select.cu ranks all of them per query.
 #include "tc_common.cuh"
-#include <stdlib.h>
 
 namespace vm {
 using namespace tc;
@@ -50,16 +48,12 @@ using namespace tc;
 static constexpr int TC_BLOCK_M = 128;
 static constexpr int TC_STAGE_BYTES = TC_BLOCK_M * 128;
 static constexpr int TC_ACC = 8;      // accumulator stages in TMEM (8 x 64 columns = all 512)
-static constexpr int TC_QCAP = 32;
-static constexpr int TC_THREADS_TW = 288;  // with the threshold warp (TW)
-static constexpr int TC_THREADS = 192;     // without: TMA warp, MMA warp, 4 epilogue warps
-// 288:  // TMA warp, MMA warp, 4 epilogue warps, (2 idle), threshold warp 8 -> scheduler 0,
-                                         // away from the schedulers of the warps that run the drains (2 and 3)
+static constexpr int TC_THREADS_SVC = 288;  // TMA warp, MMA warp, 4 epilogue warps, (2 idle), bound-service warp 8
+static constexpr int TC_THREADS = 192;      // dump mode: no service warp
 static constexpr int TC_TMEM_COLS = 512;
 static constexpr int TC_MAX_STAGES = 8;
-static constexpr int SEED_TAB_WORDS = 256 * 64;  // per-CTA maxima [<= 256 CTAs][<= 64 queries]; the published bounds follow
 
-// second-pass ("collect") arguments; thr == nullptr selects the normal top-kp mode
+// second-pass ("collect") arguments; thr == nullptr selects the normal mode
 struct CollectArgs {
     const float *thr;      // [nq] per-query score threshold (+inf: ignore the query)
     uint64_t *buf;         // [nq][cap] collected keys
@@ -68,108 +62,89 @@ struct CollectArgs {
     const int *pending;    // device counter of uncertified queries: 0 -> the kernel exits at once
 };
 
-struct TcLayout {
-    int nq_pad, KB, stages, kp;
-    uint32_t off_b, off_a, off_list, off_queue, off_tauk, off_tauf, off_seedf, off_qcnt, off_flags, off_bars, off_tmem, total;
+// where the survivors go (normal mode)
+struct BandArgs {
+    uint64_t *slab;   // [ctas][nq][SCAN_SLAB] private append buffers
+    int *scnt;        // [ctas][nq] keys appended to each slab (may exceed SCAN_SLAB: the rest went to the spill buffer)
+    uint64_t *ubuf;   // [nq][ucap] shared spill buffer
+    int *ucnt;        // [nq] keys spilled (may exceed ucap: overflow, the query goes to the collect pass)
+    int ucap;
+    float band;       // 2 eps, rounded up
+    int ksel;         // k: the bound is the k-th largest per-CTA maximum
+    int use_seed;     // first-tile seeding + owner selects (needs ksel <= ctas <= 256)
 };
 
-static TcLayout make_layout(int dtype, int ld, int nq, int kp)
+struct TcLayout {
+    int nq_pad, KB, stages, split;
+    uint32_t off_b, off_a, off_tauf, off_lcnt, off_cmax, off_wmax, off_flags, off_bars, off_tmem, total;
+};
+
+static TcLayout make_layout(int dtype, int ld, int nq, int split = 0)
 {
     TcLayout L{};
     const int es = dtype == VM_F32 ? 4 : 2;
     L.nq_pad = (nq + 15) & ~15;
     L.KB = (ld * es + 127) / 128;
-    L.kp = kp;
+    L.split = (split && dtype == VM_BF16) ? 1 : 0;
     uint32_t o = 0;
-    L.off_b = o; o += (uint32_t)L.KB * L.nq_pad * 128;
-    uint32_t epi = (uint32_t)kp * L.nq_pad * 8 + (uint32_t)TC_QCAP * L.nq_pad * 8 + (uint32_t)L.nq_pad * (8 + 4 + 4 + 4) + 64 + 512;
-    int64_t room = 227 * 1024 - 1024 - (int64_t)o - epi;
+    L.off_b = o; o += (uint32_t)L.KB * L.nq_pad * 128 * (L.split ? 2 : 1);
+    const uint32_t epi = (uint32_t)L.nq_pad * (4 + 4 + 4 + 16) + 64 + 8 * (2 * TC_MAX_STAGES + 1 + 2 * TC_ACC) + 16;
+    int64_t room = 227 * 1024 - 2048 - (int64_t)o - epi;
     L.stages = (int)(room / TC_STAGE_BYTES);
     if (L.stages > TC_MAX_STAGES) L.stages = TC_MAX_STAGES;
     if (L.stages < 0) L.stages = 0;
     L.off_a = o; o += (uint32_t)L.stages * TC_STAGE_BYTES;
-    L.off_list = o; o += (uint32_t)kp * L.nq_pad * 8;
-    L.off_queue = o; o += (uint32_t)TC_QCAP * L.nq_pad * 8;
-    L.off_tauk = o; o += (uint32_t)L.nq_pad * 8;
-    L.off_tauf = o; o += (uint32_t)L.nq_pad * 4;
-    L.off_seedf = o; o += (uint32_t)L.nq_pad * 4;
-    L.off_qcnt = o; o += (uint32_t)L.nq_pad * 4;
+    L.off_tauf = o; o += (uint32_t)L.nq_pad * 4;   // 16-byte aligned: everything above is a multiple of 128
+    L.off_lcnt = o; o += (uint32_t)L.nq_pad * 4;
+    L.off_cmax = o; o += (uint32_t)L.nq_pad * 4;
+    L.off_wmax = o; o += (uint32_t)L.nq_pad * 16;  // [4][nq_pad] seeding scratch
     L.off_flags = o; o += 64;
     L.off_bars = o; o += 8 * (2 * TC_MAX_STAGES + 1 + 2 * TC_ACC);
     L.off_tmem = o; o += 16;
     L.total = o + 1024;  // slack for the 1024-byte alignment of the swizzled tiles
+#ifdef VIDMEM_AB_SMEMPAD
+    if (L.total < 220 * 1024) L.total = 220 * 1024;
+#endif
     return L;
 }
 
-
-// monotone update of a shared-memory float (several writers, values only grow)
-__device__ __forceinline__ void smem_fmax(float *addr, float v)
+// k-th largest score (ordered bits) among the n keys of one slab (global memory; a slot whose store has not landed
+// yet reads as 0 and is ignored): a lower bound on the shard's k-th best, because k rows of this CTA reach it.
+// One thread; rare (once per slab that fills up).
+__device__ __noinline__ uint32_t own_kth_score(const uint64_t *slab, int n, int k)
 {
-    uint32_t *a = reinterpret_cast<uint32_t *>(addr);
-    uint32_t old = *reinterpret_cast<volatile uint32_t *>(a);
-    while (!(__uint_as_float(old) >= v)) {
-        const uint32_t prev = atomicCAS(a, old, __float_as_uint(v));
-        if (prev == old) break;
-        old = prev;
+    uint32_t upper = 0xFFFFFFFFu;  // exclusive upper bound of the next pick
+    int picked = 0;
+    uint32_t cur = 0;
+    while (picked < k) {
+        uint32_t best = 0;
+        int mult = 0;
+        for (int j = 0; j < n; ++j) {
+            const uint32_t h = (uint32_t)(__ldcg(slab + j) >> 32);
+            if (h < upper) { if (h > best) { best = h; mult = 1; } else if (h == best) ++mult; }
+        }
+        if (mult == 0 || best == 0u) return 0u;
+        cur = best;
+        picked += mult;
+        upper = best;
     }
+    return cur;
 }
 
-// Cheap lower bound on the kp-th largest of the per-CTA maxima of query q (one warp, kp <= 64 <= G <= 256... or
-// kp <= 32 <= G): lane l holds the entries of CTAs l, l+32, ...; the minimum over the lanes of each lane's
-// largest (kp <= 32) or second largest (kp <= 64) entry is reached by at least kp distinct CTAs.  ~40 cycles
-// after the loads instead of ~1000 for the exact select; typically the ~2*kp-th largest instead of the kp-th.
-__device__ __forceinline__ uint32_t seed_bound_fast(const uint32_t *seed_tab, int G, int nq_pad, int q, int kp, int lane)
-{
-    uint32_t m1 = 0, m2 = 0;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const int i = lane + 32 * t;
-        const uint32_t x = i < G ? __ldcg(seed_tab + (size_t)i * nq_pad + q) : 0u;
-        m2 = max(m2, min(m1, x));
-        m1 = max(m1, x);
-    }
-    return __reduce_min_sync(0xffffffffu, kp > 32 ? m2 : m1);
-}
-__device__ __forceinline__ float seed_from_ordered(uint32_t o)
-{
-    const float sd = f32_from_ordered(o);
-    return sd > -INFINITY ? sd : -INFINITY;  // 0 (an empty slot) maps to a NaN pattern
-}
-
-// kp-th largest of the per-CTA maxima of query q (one warp, G <= 256 CTAs): a lower bound on the shard's
-// kp-th best score, because kp distinct rows (one per CTA) reach it.  16 radix bits; truncation rounds down.
-__device__ __forceinline__ float seed_select(const uint32_t *seed_tab, int G, int nq_pad, int q, int kp, int lane)
-{
-    uint32_t vals[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const int i = lane + 32 * t;
-        vals[t] = i < G ? __ldcg(seed_tab + (size_t)i * nq_pad + q) : 0u;
-    }
-    uint32_t prefix = 0;
-    int need = kp;
-    for (int bit = 31; bit >= 16; --bit) {
-        const uint32_t hi = bit == 31 ? 0u : (0xFFFFFFFFu << (bit + 1));
-        int cnt = 0;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) cnt += ((vals[t] & hi) == prefix && ((vals[t] >> bit) & 1u)) ? 1 : 0;
-        const int tot = __reduce_add_sync(0xffffffffu, cnt);
-        if (tot >= need) prefix |= 1u << bit;
-        else need -= tot;
-    }
-    float sd = f32_from_ordered(prefix);
-    if (!(sd > -INFINITY) || G < kp) sd = -INFINITY;  // also catches NaN patterns
-    return sd;
-}
-
-template <bool TF32, bool DUMP, bool TW>
-__global__ void __launch_bounds__(TW ? TC_THREADS_TW : TC_THREADS, 1)
+template <bool TF32, bool DUMP>
+__global__ void __launch_bounds__(DUMP ? TC_THREADS : TC_THREADS_SVC, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const float *__restrict__ inv_norms, int64_t n, int num_tiles, int nq, TcLayout L, uint64_t *__restrict__ cand,
-               uint32_t *__restrict__ seed_tab, int *__restrict__ seed_ctr, CollectArgs col, int tw_sleep)
+               const float *__restrict__ inv_norms, int64_t n, int num_tiles, int nq, TcLayout L, uint64_t *__restrict__ dump_keys,
+               uint32_t *__restrict__ seed_tab, int *__restrict__ seed_ctr, CollectArgs col, BandArgs ub, int svc_sleep)
 {
     const bool collect = !DUMP && col.thr != nullptr;
-    if (collect && *col.pending == 0) return;  // nothing left to refine (uniform across the grid)
+#ifndef VIDMEM_AB_NOPDL
+    pdl_launch_dependents();  // the next kernel of the stream may be scheduled as SMs free up (it waits for our completion)
+#endif
+    if (collect) {
+        pdl_wait();
+        if (*col.pending == 0) return;  // nothing left to refine (uniform across the grid)
+    }
 
     extern __shared__ __align__(16) uint8_t smem_raw[];
     // align to 1024 B with pointer arithmetic on the __shared__ array (an integer round trip would
@@ -177,15 +152,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *sB = base + L.off_b;
     uint8_t *sA = base + L.off_a;
-    uint64_t *list = (uint64_t *)(base + L.off_list);    // [kp][nq_pad] unsorted top-kp set per query
-    uint64_t *queue = (uint64_t *)(base + L.off_queue);  // [QCAP][nq_pad]
-    uint64_t *tauk = (uint64_t *)(base + L.off_tauk);
-    float *tauf = (float *)(base + L.off_tauf);
-    float *seedf = (float *)(base + L.off_seedf);         // [nq_pad] seeded lower bound per query (only grows)
-    int *qcnt = (int *)(base + L.off_qcnt);
-    volatile int *s_hit = (volatile int *)(base + L.off_flags);  // [2]
-    volatile int *s_ovf = s_hit + 2;                             // [2]
-    volatile int *s_done = s_hit + 4;                            // epilogue finished (stops the threshold warp)
+    float *tauf = (float *)(base + L.off_tauf);            // [nq_pad] band threshold per query (only grows)
+    int *lcnt = (int *)(base + L.off_lcnt);                // [nq_pad] keys appended to this CTA's slab of the query
+    uint32_t *cmax = (uint32_t *)(base + L.off_cmax);      // [nq_pad] best score (ordered bits) this CTA has seen
+    uint32_t *wmax = (uint32_t *)(base + L.off_wmax);      // [4][nq_pad] seeding scratch
+    volatile int *s_done = (volatile int *)(base + L.off_flags);  // [0] epilogue warps finished, [1] seed phase over
     uint64_t *bars = (uint64_t *)(base + L.off_bars);
     uint64_t *full = bars, *empty = bars + TC_MAX_STAGES, *qfull = bars + 2 * TC_MAX_STAGES;
     uint64_t *tfull = qfull + 1, *tempty = tfull + TC_ACC;
@@ -193,7 +164,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
-    const int nq_pad = L.nq_pad, KB = L.KB, stages = L.stages, kp = L.kp;
+    const int nq_pad = L.nq_pad, KB = L.KB, stages = L.stages, split = L.split;
     constexpr int ELEMS = TF32 ? 32 : 64;  // elements per 128-byte K block
 
     if (warp == 0 && lane == 0) {
@@ -205,25 +176,31 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TC_TMEM_COLS);
-    if (warp >= 2) {
+#ifndef VIDMEM_AB_NOPDL
+    if (!collect) pdl_wait();  // everything above overlapped the previous kernel; from here on we read what it wrote
+#endif
+    if (warp >= 2 && warp < 6) {
         const int e = threadIdx.x - 64;
         if (e < nq_pad) {
-            for (int j = 0; j < kp; ++j) list[j * nq_pad + e] = 0;
-            tauk[e] = 0; qcnt[e] = 0; seedf[e] = -INFINITY;
-            tauf[e] = collect ? (e < nq ? col.thr[e] : INFINITY) : -INFINITY;
+            lcnt[e] = 0;
+            cmax[e] = 0u;
+            tauf[e] = collect ? (e < nq ? col.thr[e] : INFINITY) : (e < nq ? -INFINITY : INFINITY);
         }
-        if (e < 5) s_hit[e] = 0;  // s_hit[0..1], s_ovf[0..1], s_done
+        if (e < 2) s_done[e] = 0;
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    uint32_t *gbound = seed_tab ? seed_tab + SEED_TAB_WORDS : nullptr;  // [64] published lower bounds on a_(k), ordered bits
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
-            mbar_arrive_expect_tx(qfull, (uint32_t)KB * nq_pad * 128);
-            for (int kb = 0; kb < KB; ++kb) tma_load_2d(&tmB, qfull, sB + (size_t)kb * nq_pad * 128, kb * ELEMS, 0, L2_EVICT_LAST);
+            const int kbq = KB * (split ? 2 : 1);  // query blocks: hi part, then (split) lo part = rows [nq_pad, 2 nq_pad) of tmB
+            mbar_arrive_expect_tx(qfull, (uint32_t)kbq * nq_pad * 128);
+            for (int kb = 0; kb < kbq; ++kb)
+                tma_load_2d(&tmB, qfull, sB + (size_t)kb * nq_pad * 128, (kb % KB) * ELEMS, (kb / KB) * nq_pad, L2_EVICT_LAST);
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -244,6 +221,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+            const uint32_t lo_off = (uint32_t)KB * nq_pad * 128;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -254,9 +232,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t a_addr = a0 + (uint32_t)stage * TC_STAGE_BYTES;
                     const uint32_t b_addr = b0 + (uint32_t)kb * nq_pad * 128;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)  // 4 x 32-byte K slices per 128-byte swizzle row
-                        umma<TF32>(d_tmem, make_smem_desc_sw128(a_addr + j * 32), make_smem_desc_sw128(b_addr + j * 32), idesc,
-                                   (uint32_t)((kb | j) != 0));
+                    for (int j = 0; j < 4; ++j) {  // 4 x 32-byte K slices per 128-byte swizzle row
+                        const uint64_t da = make_smem_desc_sw128(a_addr + j * 32);
+                        umma<TF32>(d_tmem, da, make_smem_desc_sw128(b_addr + j * 32), idesc, (uint32_t)((kb | j) != 0));
+#ifndef VIDMEM_AB_NOSPLITCODE
+                        if (!TF32 && split) umma<TF32>(d_tmem, da, make_smem_desc_sw128(b_addr + lo_off + j * 32), idesc, 1u);
+#endif
+                    }
                     umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
@@ -269,10 +251,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int e = threadIdx.x - 64;   // 0..127
         const int quad = warp & 3;        // TMEM lane quadrant this warp may read
         const int row_in_tile = quad * 32 + lane;
-        uint64_t my_tau = 0;              // threshold key (= minimum of the set) of query e (threads e < nq_pad)
-        int my_min = 0;                   // its position in the set
-        uint32_t my_max = 0;              // best score (ordered bits) in query e's set == this CTA's entry in seed_tab
-        int acc = 0, par = 0;
+        int acc = 0;
         uint32_t acc_phase = 0;
         if constexpr (DUMP) {
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -281,7 +260,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * nq_pad);
-                uint64_t *out = cand + (int64_t)tile * nq * TC_BLOCK_M + row_in_tile;
+                uint64_t *out = dump_keys + (int64_t)tile * nq * TC_BLOCK_M + row_in_tile;
                 for (int c = 0; c < nq_pad; c += 16) {
                     uint32_t v[16];
                     tmem_ld16(taddr + c, v);
@@ -297,9 +276,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1; }
             }
         } else {
-        if (seed_tab != nullptr && !collect) {
-            // ---- cooperative threshold seeding from the first tile (see file header) ----
-            uint32_t *wmax = reinterpret_cast<uint32_t *>(queue);  // [4][nq_pad] scratch (queue is idle now)
+        if (ub.use_seed && !collect) {
+            // ---- cooperative bound seeding from the first tile (see file header) ----
             const int64_t row0 = (int64_t)blockIdx.x * TC_BLOCK_M + row_in_tile;
             const float inv0 = row0 < n ? __ldg(inv_norms + row0) : -1.0f;
             mbar_wait(&tfull[0], 0);
@@ -322,7 +300,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int w = 1; w < 4; ++w) m = max(m, wmax[w * nq_pad + e]);
                 seed_tab[(size_t)blockIdx.x * nq_pad + e] = m;
-                my_max = m;
+                cmax[e] = m;  // the running maximum starts from the first tile's (a real row's score, survivor or not)
             }
             __threadfence();
             named_bar_sync(1, 128);
@@ -337,11 +315,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // The bound of query q is derived once, by the CTA that owns it (q mod G), and published; a second,
             // short bounded wait lets every CTA adopt all nq bounds (64 exact selects in every CTA cost ~15 us).
             const int G = (int)gridDim.x;
-            uint32_t *gbound = seed_tab + SEED_TAB_WORDS;
             int *pub_ctr = reinterpret_cast<int *>(gbound + 64);
             if (warp == 2) {
                 for (int q = blockIdx.x; q < nq; q += G) {
-                    const float sd = seed_select(seed_tab, G, nq_pad, q, kp, lane);
+                    const float sd = seed_select(seed_tab, G, nq_pad, q, ub.ksel, lane);
                     if (lane == 0) {
                         if (sd > -INFINITY) atomicMax(gbound + q, f32_ordered(sd));
                         __threadfence();
@@ -358,14 +335,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             named_bar_sync(1, 128);
             if (e < nq) {
                 const uint32_t o = __ldcg(gbound + e);
-                if (o != 0u) {
-                    const float f = f32_from_ordered(o);
-                    smem_fmax(&seedf[e], f);
-                    smem_fmax(&tauf[e], f);
-                }
+                if (o != 0u) tauf[e] = band_floor(f32_from_ordered(o), ub.band);  // the service warp takes over after the go-ahead below
             }
             named_bar_sync(1, 128);
         }
+        if (!collect && e == 0) s_done[1] = 1;  // go-ahead for the bound service: the seed is in place
+        uint64_t *my_slab = collect ? nullptr : ub.slab + (size_t)blockIdx.x * nq * SCAN_SLAB;
         int64_t row = (int64_t)blockIdx.x * TC_BLOCK_M + row_in_tile;
         float inv = row < n ? __ldg(inv_norms + row) : -1.0f;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -376,99 +351,70 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * nq_pad);
-            uint64_t pushed = 0;
-            for (;;) {
-                bool hit_any = false, ovf = false;
-                // 16 queries (TMEM columns) at a time; the load of chunk c+1 is issued before chunk c is
-                // processed so its TMEM latency hides behind the compares
-                auto process = [&](const uint32_t (&v)[16], int c) {
-                    // thresholds of these 16 queries, loaded up front (a stale, lower value only lets an
-                    // extra candidate through to the drain, which re-checks against the live key)
-                    float tf[16];
+            // 16 queries (TMEM columns) at a time; the load of chunk c+1 is issued before chunk c is
+            // processed so its TMEM latency hides behind the compares
+            auto process = [&](const uint32_t (&v)[16], int c) {
+                // thresholds of these 16 queries (a stale, lower value only lets an extra key through)
+                float tf[16];
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        const float4 t4 = *reinterpret_cast<const float4 *>(tauf + c + 4 * j4);
-                        tf[4 * j4] = t4.x; tf[4 * j4 + 1] = t4.y; tf[4 * j4 + 2] = t4.z; tf[4 * j4 + 3] = t4.w;
-                    }
-                    if (valid) {
-                        uint32_t hits = 0;
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 t4 = *reinterpret_cast<const float4 *>(tauf + c + 4 * j4);
+                    tf[4 * j4] = t4.x; tf[4 * j4 + 1] = t4.y; tf[4 * j4 + 2] = t4.z; tf[4 * j4 + 3] = t4.w;
+                }
+                if (valid) {
+                    uint32_t hits = 0;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) hits |= (__uint_as_float(v[j]) * inv >= tf[j]) ? (1u << j) : 0u;
-                        hits &= ~(uint32_t)(pushed >> c) & (nq - c >= 16 ? 0xFFFFu : ((1u << (nq - c > 0 ? nq - c : 0)) - 1u));
-                        while (hits) {  // rare path
-                            const int j = __ffs(hits) - 1;
-                            hits &= hits - 1;
-                            const int q = c + j;
-                            float s = 0.0f;
+                    for (int j = 0; j < 16; ++j) hits |= (__uint_as_float(v[j]) * inv >= tf[j]) ? (1u << j) : 0u;
+                    hits &= nq - c >= 16 ? 0xFFFFu : ((1u << (nq - c > 0 ? nq - c : 0)) - 1u);
+                    while (hits) {  // rare path
+                        const int j = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        const int q = c + j;
+                        float s = 0.0f;
 #pragma unroll
-                            for (int jj = 0; jj < 16; ++jj) s = (jj == j) ? __uint_as_float(v[jj]) * inv : s;
-                            const uint64_t key = make_key(s, (uint32_t)row);
-                            if (collect) {
-                                const int pos = atomicAdd(col.cnt + q, 1);
-                                if (pos < col.cap) col.buf[(size_t)q * col.cap + pos] = key;
-                            } else if (key > tauk[q]) {
-                                hit_any = true;
-                                const int pos = atomicAdd(&qcnt[q], 1);
-                                if (pos < TC_QCAP) { queue[pos * nq_pad + q] = key; pushed |= 1ull << q; }
-                                else ovf = true;
+                        for (int jj = 0; jj < 16; ++jj) s = (jj == j) ? __uint_as_float(v[jj]) * inv : s;
+                        const uint64_t key = make_key(s, (uint32_t)row);
+                        if (collect) {
+                            const int pos = atomicAdd(col.cnt + q, 1);
+                            if (pos < col.cap) col.buf[(size_t)q * col.cap + pos] = key;
+                        } else {
+#ifdef VIDMEM_AB_NORARE
+                            if (key == 1) tauf[q] = 0.0f;
+                            continue;
+#endif
+                            const int pos = atomicAdd(&lcnt[q], 1);           // shared-memory counter hands out the slot
+                            atomicMax(&cmax[q], (uint32_t)(key >> 32));
+                            if (pos < SCAN_SLAB) __stcg(my_slab + (size_t)q * SCAN_SLAB + pos, key);   // fire and forget
+                            else {
+                                const int p = atomicAdd(ub.ucnt + q, 1);     // slab full: the query's shared spill buffer
+                                if (p < ub.ucap) __stcg(ub.ubuf + (size_t)q * ub.ucap + p, key);
+                                else tauf[q] = INFINITY;  // spill overflow: the query is re-done anyway, stop collecting
                             }
                         }
                     }
-                };
-                uint32_t va[16], vb[16];
-                tmem_ld16(taddr, va);
-                for (int c = 0; c < nq_pad; c += 32) {
+                }
+            };
+            uint32_t va[16], vb[16];
+#ifdef VIDMEM_AB_NOEPI
+            if (tile < 0)
+#endif
+            tmem_ld16(taddr, va);
+#ifdef VIDMEM_AB_NOEPI
+            if (tile < 0)
+#endif
+            for (int c = 0; c < nq_pad; c += 32) {
+                tmem_ld_wait();
+                if (c + 16 < nq_pad) tmem_ld16(taddr + c + 16, vb);
+                process(va, c);
+                if (c + 16 < nq_pad) {
                     tmem_ld_wait();
-                    if (c + 16 < nq_pad) tmem_ld16(taddr + c + 16, vb);
-                    process(va, c);
-                    if (c + 16 < nq_pad) {
-                        tmem_ld_wait();
-                        if (c + 32 < nq_pad) tmem_ld16(taddr + c + 32, va);
-                        process(vb, c + 16);
-                    }
+                    if (c + 32 < nq_pad) tmem_ld16(taddr + c + 32, va);
+                    process(vb, c + 16);
                 }
-                if (hit_any) s_hit[par] = 1;
-                if (ovf) s_ovf[par] = 1;
-                if (e == 0) { s_hit[par ^ 1] = 0; s_ovf[par ^ 1] = 0; }  // arm the next round's flags
-                named_bar_sync(1, 128);
-                const int h = s_hit[par], o = s_ovf[par];
-                par ^= 1;
-                if (!h) break;
-                if (e < nq_pad) {
-                    // drain query e's queue: replace the current minimum of the (unsorted) top-kp set,
-                    // then rescan for the new minimum with independent, pipelined loads
-                    int cnt = qcnt[e];
-                    cnt = cnt < TC_QCAP ? cnt : TC_QCAP;
-                    const uint32_t max_before = my_max;
-                    for (int i = 0; i < cnt; ++i) {
-                        const uint64_t key = queue[i * nq_pad + e];
-                        if (key > my_tau) {
-                            if (TW) my_max = max(my_max, (uint32_t)(key >> 32));
-                            list[my_min * nq_pad + e] = key;
-                            uint64_t m = ~0ull;
-                            int p = 0;
-#pragma unroll 8
-                            for (int j = 0; j < kp; ++j) {
-                                const uint64_t x = list[j * nq_pad + e];
-                                if (x < m) { m = x; p = j; }
-                            }
-                            my_tau = m;
-                            my_min = p;
-                        }
-                    }
-                    qcnt[e] = 0;
-                    tauk[e] = my_tau;
-                    const float sd = seedf[e];
-                    if (TW) {
-                        smem_fmax(&tauf[e], my_tau ? fmaxf(key_score(my_tau), sd) : sd);
-                        if (seed_tab != nullptr && my_max != max_before) __stcg(seed_tab + (size_t)blockIdx.x * nq_pad + e, my_max);
-                    } else {
-                        tauf[e] = my_tau ? fmaxf(key_score(my_tau), sd) : sd;
-                    }
-                }
-                named_bar_sync(1, 128);
-                if (!o) break;
             }
+#ifdef VIDMEM_AB_TILEBAR
+            named_bar_sync(1, 128);
+#endif
             // release the accumulator stage to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -477,41 +423,74 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             row = row_next;
             inv = inv_next;
         }
-        named_bar_sync(1, 128);
-        for (int i = e; i < nq * kp && !collect; i += 128) {
-            const int q = i / kp, j = i - q * kp;
-            cand[((int64_t)blockIdx.x * nq + q) * kp + j] = list[j * nq_pad + q];
+        if (!collect) {
+            named_bar_sync(1, 128);  // all four warps have appended their last keys
+            if (e < nq) {
+                ub.scnt[(size_t)blockIdx.x * nq + e] = lcnt[e];
+                // final running maximum of this CTA: select.cu derives the final bound from the table
+                if (seed_tab != nullptr) __stcg(seed_tab + (size_t)blockIdx.x * nq_pad + e, cmax[e]);
+            }
         }
         }  // !DUMP
-        if (e == 0) *s_done = 1;
+        __syncwarp();
+        if (lane == 0) atomicAdd((int *)s_done, 1);
     } else {
-        // ================================ threshold warp ================================
-        // Keeps re-deriving, query by query, the kp-th largest of all CTAs' RUNNING maxima (seed_tab, kept
-        // current by the drains) and raises the query's threshold to it: the bound then follows the
-        // shard-wide top-kp instead of this CTA's own, so survivors -- and the per-tile drains they cause --
-        // become rare.  Off the epilogue's critical path; a stale table entry only loosens the bound.
-        if (TW && !DUMP && warp == 8 && seed_tab != nullptr && !collect) {
-            // A distributed bound service: CTA b owns queries b, b+G, ... (at most one with G >= nq), keeps
-            // re-deriving their exact kp-th largest running maximum and publishes it with an atomic max; every
-            // CTA adopts the published bounds of all queries.  One table column per owner per round instead of
-            // every column in every CTA keeps the shared 38 KB table from becoming an L2 hot spot.
+        // ================================ bound service ================================
+        // Off the critical path (one warp, sleeps between rounds); a stale bound only keeps a few more rows.
+#ifdef VIDMEM_AB_NOSVC
+        if (false) {
+#else
+        if (!DUMP && warp == 8 && seed_tab != nullptr && !collect) {
+#endif
             const int G = (int)gridDim.x;
-            uint32_t *gbound = seed_tab + SEED_TAB_WORDS;
+            while (s_done[1] == 0 && s_done[0] < 4) __nanosleep(100);   // wait for the seed phase (it writes tauf)
+            uint32_t pub0 = 0xFFFFFFFFu, pub1 = 0xFFFFFFFFu;            // running maxima last written to the table (lanes q, q+32)
+            uint32_t kth_done = 0;                                       // bit 0 / 1: own k-th already published for q / q+32
+            const uint64_t *my_slab = ub.slab + (size_t)blockIdx.x * nq * SCAN_SLAB;
             // the exit test is a warp vote: a lane that lags behind must not leave the loop while the others
             // are already inside the next round's warp reductions
-            while (!__any_sync(0xffffffffu, *s_done != 0)) {
-                for (int q = blockIdx.x; q < nq; q += G) {
-                    const float sd = seed_select(seed_tab, G, nq_pad, q, kp, lane);
-                    if (lane == 0 && sd > -INFINITY) atomicMax(gbound + q, f32_ordered(sd));
-                }
-                for (int q = lane; q < nq; q += 32) {
-                    const uint32_t o = __ldcg(gbound + q);
-                    if (o != 0u) {
-                        const float f = f32_from_ordered(o);
-                        if (f > seedf[q]) { smem_fmax(&seedf[q], f); smem_fmax(&tauf[q], f); }
+            while (!__any_sync(0xffffffffu, s_done[0] >= 4)) {
+                // 1. this CTA's running maxima -> the table
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int q = lane + 32 * h;
+                    if (q < nq) {
+                        const uint32_t c = *(volatile uint32_t *)(cmax + q);
+                        uint32_t &pub = h ? pub1 : pub0;
+                        if (c != pub && c != 0u) { __stcg(seed_tab + (size_t)blockIdx.x * nq_pad + q, c); pub = c; }
                     }
                 }
-                __nanosleep(tw_sleep);
+                __syncwarp();
+                // 2. queries this CTA owns: k-th largest of all CTAs' maxima (warp-collective)
+                if (G >= ub.ksel)
+                    for (int q = blockIdx.x; q < nq; q += G) {
+                        const float sd = seed_select(seed_tab, G, nq_pad, q, ub.ksel, lane);
+                        if (lane == 0 && sd > -INFINITY) atomicMax(gbound + q, f32_ordered(sd));
+                    }
+                __syncwarp();
+                // 3. a slab that has filled up: this CTA's own k-th best is a valid bound too (k of its rows reach it)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int q = lane + 32 * h;
+                    if (q < nq && !((kth_done >> h) & 1u) && *(volatile int *)(lcnt + q) >= SCAN_SLAB) {
+                        const uint32_t ok = own_kth_score(my_slab + (size_t)q * SCAN_SLAB, SCAN_SLAB, ub.ksel);
+                        if (ok != 0u) { atomicMax(gbound + q, ok); kth_done |= 1u << h; }
+                    }
+                }
+                __syncwarp();
+                // 4. adopt whatever has been published
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int q = lane + 32 * h;
+                    if (q < nq) {
+                        const uint32_t o = __ldcg(gbound + q);
+                        if (o != 0u) {
+                            const float f = band_floor(f32_from_ordered(o), ub.band);
+                            if (f > tauf[q]) *(volatile float *)(tauf + q) = f;   // only this warp writes tauf from here on
+                        }
+                    }
+                }
+                __nanosleep(svc_sleep);
             }
         }
     }
@@ -524,63 +503,73 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
-bool scan_tc_supported(int dtype, int dim, int nq, int kp)
+bool scan_tc_supported(int dtype, int dim, int nq, int kp, int split)
 {
+    (void)kp;
     if (dtype != VM_F32 && dtype != VM_BF16) return false;
-    if (nq < 1 || nq > 64 || kp < 1 || kp > 64) return false;
-    TcLayout L = make_layout(dtype, ld_for_dim(dim), nq, kp);
+    if (nq < 1 || nq > 64) return false;
+    TcLayout L = make_layout(dtype, ld_for_dim(dim), nq, split);
     return L.stages >= 3;
 }
 
-// queries_store_dtype: the normalised queries [nq_pad][ld] in the STORE dtype (fp32 for the tf32
-// path, bf16 for the bf16 path).
+// queries_store_dtype: the normalised queries in the STORE dtype: fp32 [nq_pad][ld] (tf32 path), bf16 [nq_pad][ld],
+// or bf16 [2][nq_pad][ld] (hi terms, then lo terms) with a.split.
 int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t *seed_tab, int *seed_ctr, const ScanCollect *sc,
                    ScanInfo *info)
 {
     VM_REQUIRE(a.n >= 1 && a.n < 0x7FFFFF00LL, VM_ERR_UNSUPPORTED, "tcgen05 scan: shard rows %lld outside [1, 2^31)", (long long)a.n);
-    TcLayout L = make_layout(a.dtype, a.ld, a.nq, a.kp);
+    TcLayout L = make_layout(a.dtype, a.ld, a.nq, a.split);
     VM_REQUIRE(L.stages >= 3, VM_ERR_UNSUPPORTED, "tcgen05 scan: dim %d x %d queries does not fit shared memory", a.dim, a.nq);
     CUtensorMap tmA, tmB;
     int rc = make_tmap_2d_cached(&tmA, a.rows, a.dtype, (uint64_t)a.n, (uint64_t)a.ld, (uint64_t)a.ld, TC_BLOCK_M);
     if (rc != VM_OK) return rc;
-    rc = make_tmap_2d_cached(&tmB, queries_store_dtype, a.dtype, (uint64_t)L.nq_pad, (uint64_t)a.ld, (uint64_t)a.ld, (uint32_t)L.nq_pad);
+    rc = make_tmap_2d_cached(&tmB, queries_store_dtype, a.dtype, (uint64_t)L.nq_pad * (L.split ? 2 : 1), (uint64_t)a.ld, (uint64_t)a.ld,
+                             (uint32_t)L.nq_pad);
     if (rc != VM_OK) return rc;
     const int num_tiles = (int)((a.n + TC_BLOCK_M - 1) / TC_BLOCK_M);
     int dev_idx = 0;
     VM_CUDA_CHECK(cudaGetDevice(&dev_idx));
     dev_idx &= 63;
-    // seeding needs at least kp CTAs (kp first-tile maxima); it pays off even with a single tile per CTA,
-    // because a first tile without a threshold costs ~80 us of serial drains (stores below that use dump mode)
-    const bool seed = seed_tab && seed_ctr && a.ctas >= a.kp && a.ctas <= 256;
-    if (!seed || sc) { seed_tab = nullptr; seed_ctr = nullptr; }
+    const bool dump = a.dump && !sc;
+    if (sc || dump || a.ctas > 256) { seed_tab = nullptr; seed_ctr = nullptr; }
     CollectArgs col{};
     if (sc) { col.thr = sc->thr; col.buf = sc->buf; col.cnt = sc->cnt; col.cap = sc->cap; col.pending = sc->pending; }
-    // Threshold warp: pays off where the epilogue, not HBM, paces the scan -- tiles of <= 128 KB (bf16 rows
-    // of 384 dims stream in 2.2 us; an fp32 tile takes 4.4 us and hides the drains, and measures 3 % slower
-    // with the extra warp) -- once a CTA streams enough tiles for the shared bound to matter.  Measured on
-    // 64-query batches, bf16: 1M rows 0.247 -> 0.172 ms, 4M rows 0.68 -> 0.49 ms, 12.5M rows 1.68 -> 1.49 ms.
-    constexpr int tw_min_tiles = 16, tw_max_tile_kb = 128;
-    const int tw_sleep = 200;
-    // (a single-query scan has no epilogue pressure: C5 bf16 measured 1.11 ms without vs 1.16 ms with it)
-    const bool tw = seed_tab != nullptr && !sc && !a.dump && a.nq > 16 && (int64_t)num_tiles >= (int64_t)tw_min_tiles * a.ctas &&
-                    (int64_t)TC_BLOCK_M * a.ld * (a.dtype == VM_F32 ? 4 : 2) <= (int64_t)tw_max_tile_kb * 1024;
-    const bool dump = a.dump && !sc;
+    BandArgs ub{a.slab, a.scnt, a.ubuf, a.ucnt, a.ucap, a.band, a.ksel, 0};
+    // first-tile seeding needs at least k CTAs (k first-tile maxima); without it the scan still works -- every row
+    // is a survivor until a slab fills up and the CTA's own k-th best takes over
+    ub.use_seed = (seed_tab && seed_ctr && a.ksel >= 1 && a.ctas >= a.ksel) ? 1 : 0;
+    if (!sc && !dump)
+        VM_REQUIRE(ub.slab && ub.scnt && ub.ubuf && ub.ucnt && ub.ucap > 0 && ub.ksel >= 1, VM_ERR_BADARG, "tcgen05 scan: slab / spill buffers missing");
     if (dump) VM_REQUIRE(TC_BLOCK_M == SCAN_DUMP_TILE && (int64_t)num_tiles * TC_BLOCK_M <= SCAN_DUMP_MAX_KEYS && a.ctas == num_tiles,
                          VM_ERR_UNSUPPORTED, "tcgen05 scan: dump mode needs one CTA per tile and at most %d rows", SCAN_DUMP_MAX_KEYS);
-    if (info && !sc) { info->stages = L.stages; info->variant = dump ? 1 : (tw ? 2 : 0); }
-#define LAUNCH_TC(TF, DU, TWV)                                                                                                \
+    // The bound service polls faster where the epilogue, not HBM, paces the scan (bf16 tiles stream in 2.2 us) and
+    // lazily where an fp32 tile (4.4 us) hides everything anyway.
+#ifdef VIDMEM_AB_SVCSLEEP
+    const int svc_sleep = VIDMEM_AB_SVCSLEEP;
+#else
+    const int svc_sleep = a.dtype == VM_F32 ? 1000 : 200;
+#endif
+    if (info && !sc) { info->stages = L.stages; info->variant = dump ? 1 : 2; }
+    const bool pdl = a.pdl && !sc;
+#ifdef VIDMEM_AB_CLASSIC_LAUNCH
+#define LAUNCH_IMPL(TF, DU) scan_tc_kernel<TF, DU><<<a.ctas, DU ? TC_THREADS : TC_THREADS_SVC, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, seed_tab, seed_ctr, col, ub, svc_sleep)
+#else
+#define LAUNCH_IMPL(TF, DU) VM_CUDA_CHECK(launch_pdl(scan_tc_kernel<TF, DU>, dim3(a.ctas), dim3(DU ? TC_THREADS : TC_THREADS_SVC), L.total, a.stream, pdl, \
+                                 tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, seed_tab, seed_ctr, col, ub, svc_sleep))
+#endif
+#define LAUNCH_TC(TF, DU)                                                                                                  \
     do {                                                                                                                   \
         static bool set[64] = {}; /* the attribute is per device */                                                        \
         if (!set[dev_idx]) {                                                                                               \
-            VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<TF, DU, TWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<TF, DU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
             set[dev_idx] = true;                                                                                           \
         }                                                                                                                  \
-        scan_tc_kernel<TF, DU, TWV><<<a.ctas, TWV ? TC_THREADS_TW : TC_THREADS, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, \
-                                                                          seed_tab, seed_ctr, col, tw_sleep);             \
+        LAUNCH_IMPL(TF, DU);                                                                                             \
     } while (0)
-    if (a.dtype == VM_F32) { if (dump) LAUNCH_TC(true, true, false); else if (tw) LAUNCH_TC(true, false, true); else LAUNCH_TC(true, false, false); }
-    else { if (dump) LAUNCH_TC(false, true, false); else if (tw) LAUNCH_TC(false, false, true); else LAUNCH_TC(false, false, false); }
+    if (a.dtype == VM_F32) { if (dump) LAUNCH_TC(true, true); else LAUNCH_TC(true, false); }
+    else { if (dump) LAUNCH_TC(false, true); else LAUNCH_TC(false, false); }
 #undef LAUNCH_TC
+#undef LAUNCH_IMPL
     VM_CUDA_CHECK(cudaGetLastError());
     return VM_OK;
 }

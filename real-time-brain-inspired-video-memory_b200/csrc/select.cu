@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rescore_kernel(const uint64_t *
                                                             FinalizeArgs f, int32_t *__restrict__ flags,
                                                             int32_t *__restrict__ uncertified_count, int chunk,
                                                             const int *__restrict__ extreme, float *__restrict__ collect_thr,
-                                                            unsigned long long *__restrict__ cum)
+                                                            unsigned long long *__restrict__ cum, const int *__restrict__ incomplete)
 {
     constexpr int VEC = 16 / (int)sizeof(T);      // elements per 16-byte load
     extern __shared__ double rs_smem[];
@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rescore_kernel(const uint64_t *
             float worst = key_score(merged[(int64_t)q * kp + kp - 1]);
             cert = ((double)worst + eps) < sc;
         }
+        if (incomplete && incomplete[q]) cert = false;  // the slabs / spill buffer this list was taken from overflowed: rows are missing
         // flag 1: a collect pass (all rows within 2 eps of this score) can settle the query;
         // flag 2: the error bound does not hold for this store -> binary64 scan of every row
         const bool bound_ok = !(extreme && *extreme != 0);
@@ -377,16 +378,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rescore_kernel(const uint64_t *
 }
 
 // =========================================================================================
-// 2b. fused candidate selection + exact rescoring (the normal path: one launch instead of two)
+// 2b. fused candidate selection + exact rescoring + band settlement (the normal path: ONE launch)
 // =========================================================================================
-// One CTA (512 threads) per query:
-//   A. the per-CTA candidate sets are loaded into shared memory and thinned with the list-maxima
-//      bound (see merge_candidates_kernel); survivors are ranked -> the kp best keys, descending;
-//   B. the kp candidate rows are pulled into shared memory with cp.async (16-byte, L2-cached) in three
-//      column chunks, the query is converted to doubles;
-//   C. the reference recurrences (dot per candidate, ||row||^2 per candidate, ||q||^2) run as
-//      independent sequential chains on 2kp+1 threads, chunk c overlapping the loads of chunk c+1;
-//   D. rank, emit, certify (as rescore_kernel).
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -395,8 +388,175 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 static constexpr int SR_THREADS = 512;
+static constexpr int BAND_CAP = 1024;  // rows of one query's near-tie band the kernel rescores itself
+
+// Exact top-k among m gathered rows (block-wide): every row is scored with the reference recurrence by one thread
+// (one sequential chain pair per row), then k rounds of block-wide arg-best by (score desc, row asc) emit the list.
+// s_sc / s_row / s_taken: [m] scratch; w_*: one slot per warp.  Returns the number of entries emitted (uniform).
+template <bool NEUMAIER, typename T, int THREADS>
+__device__ int band_topk(const T *__restrict__ rows, int ld, int dim, const double *sq, double n1, int m, double *s_sc, uint32_t *s_row,
+                         unsigned char *s_taken, double *w_s, uint32_t *w_r, int *w_p, int *s_out, const FinalizeArgs &f, int q)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) *s_out = 0;
+    for (int e = tid; e < m; e += THREADS) {
+        s_sc[e] = exact_cosine_sq<NEUMAIER, T>(sq, n1, rows + (int64_t)s_row[e] * ld, dim);
+        s_taken[e] = 0;
+    }
+    __syncthreads();
+    for (int r = 0; r < f.k; ++r) {
+        double bs = 0.0; uint32_t br = 0; int bp = -1;
+        for (int e = tid; e < m; e += THREADS)
+            if (!s_taken[e] && (bp < 0 || better(s_sc[e], s_row[e], bs, br))) { bs = s_sc[e]; br = s_row[e]; bp = e; }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ts = __shfl_xor_sync(0xffffffffu, bs, o);
+            const uint32_t tr = __shfl_xor_sync(0xffffffffu, br, o);
+            const int tp = __shfl_xor_sync(0xffffffffu, bp, o);
+            if (tp >= 0 && (bp < 0 || better(ts, tr, bs, br))) { bs = ts; br = tr; bp = tp; }
+        }
+        if (lane == 0) { w_s[warp] = bs; w_r[warp] = br; w_p[warp] = bp; }
+        __syncthreads();
+        bs = w_s[0]; br = w_r[0]; bp = w_p[0];
+        for (int w = 1; w < THREADS / 32; ++w)
+            if (w_p[w] >= 0 && (bp < 0 || better(w_s[w], w_r[w], bs, br))) { bs = w_s[w]; br = w_r[w]; bp = w_p[w]; }
+        if (bp < 0) break;  // uniform
+        if (tid == 0) {
+            s_taken[bp] = 1;
+            const double outv = convert_score(bs, f.score_mode);
+            if (outv > f.min_score) {
+                f.out_idx[(int64_t)q * f.k + r] = (int64_t)br + f.row_offset;
+                f.out_score[(int64_t)q * f.k + r] = outv;
+                *s_out = r + 1;
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    const int cntv = *s_out;
+    if (tid == 0) f.out_count[q] = cntv;
+    for (int t = cntv + tid; t < f.k; t += THREADS) {
+        f.out_idx[(int64_t)q * f.k + t] = -1;
+        f.out_score[(int64_t)q * f.k + t] = 0.0;
+    }
+    return cntv;
+}
+
+// Where one query's candidate keys come from.
+struct SelectSrc {
+    const uint64_t *cand;  // list mode: [lists][nq][list_len] (per-CTA lists of the CUDA-core scan, or dumped tiles)
+    int lists, list_len;
+    int complete;          // list mode: 1 = the lists hold EVERY row of the shard (dump mode)
+    // slab mode (tcgen05 scan): per-CTA slabs + the shared spill buffer hold every key at or above the scan's final
+    // band threshold; seed_tab = the final per-CTA maxima and the published bounds (NULL: no table)
+    const uint64_t *slab;  // [ctas][nq][SCAN_SLAB]
+    const int *scnt;       // [ctas][nq]
+    int ctas;
+    const uint64_t *ubuf;  // [nq][ucap]
+    const int *ucnt;       // [nq] keys spilled (> ucap: overflow -> keys are missing)
+    int ucap;
+    const uint32_t *seed_tab;
+    int nq_pad, ksel;
+    float band;
+    int key_cap;           // keys one CTA stages in shared memory
+};
+
+// Slab mode: stages query q's keys in shared memory, filtered once more with the FINAL bound -- the k-th largest of the
+// CTAs' final maxima or a published bound, whichever is larger, minus the band: both are lower bounds on the k-th best
+// approximate score, so nothing below can matter, whereas the slabs were filled under the looser bounds in force while
+// the scan ran (typically ~1000 keys per query come in, a few dozen stay).  Block-wide; returns the number of keys
+// staged (uniform) and sets *incomplete when keys are missing (spill or staging overflow).
+template <int THREADS>
+__device__ int load_slab_keys(const SelectSrc &src, int q, int nq, uint64_t *skeys, int *s_cnts, int *s_total, float *s_bf, bool *incomplete)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) {
+        float Lb = -INFINITY;
+        if (src.seed_tab != nullptr) {
+            if (src.ctas >= src.ksel) Lb = seed_select(src.seed_tab, src.ctas, src.nq_pad, q, src.ksel, lane);
+            const uint32_t o = __ldcg(src.seed_tab + SEED_TAB_WORDS + q);
+            if (o != 0u) Lb = fmaxf(Lb, f32_from_ordered(o));
+        }
+        if (lane == 0) { *s_bf = band_floor(Lb, src.band); *s_total = 0; }
+    }
+    for (int c = tid; c < src.ctas; c += THREADS) s_cnts[c] = min(src.scnt[(size_t)c * nq + q], SCAN_SLAB);
+    __syncthreads();
+    const float bf = *s_bf;
+    for (int idx = tid; idx < src.ctas * SCAN_SLAB; idx += THREADS) {
+        const int c = idx / SCAN_SLAB, j = idx - c * SCAN_SLAB;
+        if (j < s_cnts[c]) {
+            const uint64_t k = __ldcg(src.slab + ((size_t)c * nq + q) * SCAN_SLAB + j);
+            if (k != 0 && key_score(k) >= bf) {
+                const int p = atomicAdd(s_total, 1);
+                if (p < src.key_cap) skeys[p] = k;
+            }
+        }
+    }
+    const int spilled = src.ucnt[q];
+    const int ns = min(spilled, src.ucap);
+    for (int e = tid; e < ns; e += THREADS) {
+        const uint64_t k = __ldcg(src.ubuf + (size_t)q * src.ucap + e);
+        if (k != 0 && key_score(k) >= bf) {
+            const int p = atomicAdd(s_total, 1);
+            if (p < src.key_cap) skeys[p] = k;
+        }
+    }
+    __syncthreads();
+    const int got = *s_total;
+    *incomplete = spilled > src.ucap || got > src.key_cap;
+    return min(got, src.key_cap);
+}
+
+// Slab-mode form of the merge for rows too large for the fused kernel's shared memory: the query's filtered keys ->
+// its kp best in descending order, zero padded; incomplete[q] = keys were missing.  One CTA per query.
+__global__ void __launch_bounds__(SR_THREADS) slab_top_kernel(SelectSrc src, int nq, int kp, uint64_t *__restrict__ merged,
+                                                             int *__restrict__ incomplete)
+{
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    uint64_t *skeys = reinterpret_cast<uint64_t *>(st_smem);  // [key_cap]
+    __shared__ int s_cnts[256];
+    __shared__ int s_total, s_bin, s_need, s_m;
+    __shared__ int hist[256];
+    __shared__ float s_bf;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    bool inc = false;
+    const int total = load_slab_keys<SR_THREADS>(src, q, nq, skeys, s_cnts, &s_total, &s_bf, &inc);
+    for (int e = tid; e < kp; e += SR_THREADS) merged[(int64_t)q * kp + e] = 0;
+    if (tid == 0) { incomplete[q] = inc ? 1 : 0; s_m = 0; }
+    __syncthreads();
+    if (total <= MERGE_SURV) {
+        for (int e = tid; e < total; e += SR_THREADS) {
+            const uint64_t k = skeys[e];
+            int rank = 0;
+            for (int i = 0; i < total; ++i) rank += skeys[i] > k ? 1 : 0;
+            if (rank < kp) merged[(int64_t)q * kp + rank] = k;
+        }
+        return;
+    }
+    const uint64_t Tk = radix_select_kth(skeys, total, kp, hist, &s_bin, &s_need);
+    for (int e = tid; e < total; e += SR_THREADS) {
+        const uint64_t k = skeys[e];
+        if (k > Tk) merged[(int64_t)q * kp + atomicAdd(&s_m, 1)] = k;
+        else if (k == Tk) merged[(int64_t)q * kp + kp - 1] = k;  // the worst candidate goes last
+    }
+}
+
+// One CTA (512 threads) per query:
+//   A. the query's candidate keys are loaded into shared memory (union buffer: typically a few dozen keys; dumped
+//      tiles / per-CTA lists: thinned with the list-maxima bound, see merge_candidates_kernel) and the kp best by
+//      approximate score are ranked;
+//   B. their rows are pulled into shared memory with cp.async (16-byte, L2-cached) in three column chunks;
+//   C. the reference recurrences (dot per candidate, ||row||^2 per candidate, ||q||^2) run as independent
+//      sequential chains on 2kp+1 threads, chunk c overlapping the loads of chunk c+1;
+//   D. rank, emit, certify: with s_k the k-th exact score, only rows whose approximate score reaches s_k - eps can
+//      still matter.  When the source is complete they are all in shared memory already: if they are all among the
+//      rescored kp the list is final, otherwise
+//   E. the whole band (<= BAND_CAP rows) is rescored with the reference recurrence right here and the exact top-k
+//      of it is emitted -- no second scan.  Only an incomplete source (union-buffer overflow, CUDA-core lists) or a
+//      band beyond BAND_CAP flags the query for the collect pass / the binary64 scan of every row.
+// Every rescored candidate also audits the scan's error bound: |approximate - exact| > eps flags the query for the
+// binary64 scan (and is counted), so a wrong bound cannot silently produce a wrong list.
 template <bool NEUMAIER, typename T>
-__global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uint64_t *__restrict__ cand, int lists, int list_len, int nq, int kp,
+__global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(SelectSrc src, int nq, int kp,
                                                                    const T *__restrict__ rows, int ld, int dim, int64_t n_rows,
                                                                    const void *__restrict__ queries, int q_dtype, double eps,
                                                                    FinalizeArgs f, int32_t *__restrict__ flags,
@@ -405,39 +565,65 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uin
                                                                    unsigned long long *__restrict__ cum)
 {
     extern __shared__ __align__(16) unsigned char sr_smem[];
-    const int total = lists * list_len;  // list_len == kp for per-CTA top-kp lists, 128 for dumped tiles
-    uint64_t *skeys = reinterpret_cast<uint64_t *>(sr_smem);                       // [total]
-    uint32_t *lmax = reinterpret_cast<uint32_t *>(skeys + total);                  // [lists] (+pad)
-    double *sq = reinterpret_cast<double *>(lmax + ((lists + 3) & ~3));            // [dim]
+    uint64_t *skeys = reinterpret_cast<uint64_t *>(sr_smem);                       // [key_cap]
+    uint32_t *lmax = reinterpret_cast<uint32_t *>(skeys + src.key_cap);            // [lists] (+pad)
+    double *sq = reinterpret_cast<double *>(lmax + ((src.lists + 3) & ~3));        // [dim]
     const int pitch = ld * (int)sizeof(T) + 16;                                    // bytes, 16-B aligned rows
-    unsigned char *srow = reinterpret_cast<unsigned char *>(sq + ((dim + 1) & ~1)); // [kp][pitch]
+    unsigned char *srow = reinterpret_cast<unsigned char *>(sq + ((dim + 1) & ~1)); // [kp][pitch], later the band scratch
     __shared__ uint64_t s_top[64];
     __shared__ uint64_t surv[MERGE_SURV];
     __shared__ int hist[256];
-    __shared__ int s_bin, s_need, s_m, s_nz, s_cnt;
+    __shared__ int s_bin, s_need, s_m, s_nz, s_cnt, s_band, s_viol, s_out, s_total;
+    __shared__ int s_cnts[256];
     __shared__ uint32_t s_L;
+    __shared__ float s_thr, s_bf;
     __shared__ double s_dot[64], s_rr[64], s_qq, s_score[64];
+    __shared__ double w_s[SR_THREADS / 32];
+    __shared__ uint32_t w_r[SR_THREADS / 32];
+    __shared__ int w_p[SR_THREADS / 32];
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // ---------------- A. candidate selection ----------------
-    if (tid == 0) { s_m = 0; s_nz = 0; s_cnt = 0; }
+    pdl_launch_dependents();
+    if (tid == 0) { s_m = 0; s_nz = 0; s_cnt = 0; s_band = 0; s_viol = 0; s_thr = -INFINITY; }
     if (tid < 64) s_top[tid] = 0;
+    pdl_wait();  // the scan has completed: its keys are visible
     __syncthreads();
+
+    // ---------------- A. candidate selection ----------------
+    const bool union_mode = src.slab != nullptr;
+    int total, lists = src.lists, list_len = src.list_len;
+    bool overflow = false;
     int nz = 0;
+    if (union_mode) {
+        total = load_slab_keys<SR_THREADS>(src, q, nq, skeys, s_cnts, &s_total, &s_bf, &overflow);
+        lists = 0;
+        if (tid == 0) nz = total;  // staged keys are non-zero by construction
+    } else {
+        total = lists * list_len;
 #pragma unroll 10
-    for (int e = tid; e < total; e += SR_THREADS) {
-        const int l = e / list_len, j = e - l * list_len;
-        const uint64_t k = cand[((int64_t)l * nq + q) * list_len + j];
-        skeys[e] = k;
-        nz += k != 0;
+        for (int e = tid; e < total; e += SR_THREADS) {
+            const int l = e / list_len, j = e - l * list_len;
+            const uint64_t k = src.cand[((int64_t)l * nq + q) * list_len + j];
+            skeys[e] = k;
+            nz += k != 0;
+        }
     }
-    // the query does not depend on the selection: convert it now
     for (int i = tid; i < dim; i += SR_THREADS) sq[i] = load_as_double(queries, q_dtype, (int64_t)q * dim + i);
     if (nz) atomicAdd(&s_nz, nz);
     __syncthreads();
     const int nonzero = s_nz;
     bool done = false;
-    if (nonzero >= kp && lists >= kp && lists <= 256) {
+    if (total <= MERGE_SURV) {
+        // few keys (the union buffer's normal case): rank them directly (keys are unique)
+        for (int e = tid; e < total; e += SR_THREADS) {
+            const uint64_t k = skeys[e];
+            if (k == 0) continue;
+            int rank = 0;
+            for (int i = 0; i < total; ++i) rank += skeys[i] > k ? 1 : 0;
+            if (rank < kp) s_top[rank] = k;
+        }
+        done = true;
+    } else if (nonzero >= kp && lists >= kp && lists <= 256) {
         for (int l = warp; l < lists; l += SR_THREADS / 32) {
             uint32_t m = 0;
             for (int j = lane; j < list_len; j += 32) m = max(m, (uint32_t)(skeys[l * list_len + j] >> 32));
@@ -485,16 +671,16 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uin
             }
         }
     }
-    if (!done) {  // uniform across the block: exact radix select (few lists, heavy duplication)
+    if (!done) {  // uniform across the block: exact radix select (few lists, heavy duplication, a large union)
         __syncthreads();
-        uint64_t T = 1;
-        if (nonzero >= kp) T = radix_select_kth(skeys, total, kp, hist, &s_bin, &s_need);
+        uint64_t Tk = 1;
+        if (nonzero >= kp) Tk = radix_select_kth(skeys, total, kp, hist, &s_bin, &s_need);
         if (tid == 0) s_m = 0;
         __syncthreads();
         for (int e = tid; e < total; e += SR_THREADS) {
             const uint64_t k = skeys[e];
-            if (k >= T && k != 0) {
-                if (nonzero >= kp && k == T) s_top[kp - 1] = k;  // the worst candidate goes last
+            if (k >= Tk && k != 0) {
+                if (nonzero >= kp && k == Tk) s_top[kp - 1] = k;  // the worst candidate goes last
                 else s_top[atomicAdd(&s_m, 1)] = k;
             }
         }
@@ -557,10 +743,12 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uin
     // ---------------- D. rank, emit, certify ----------------
     double sc = 0.0;
     const uint32_t row = cand_valid ? key_row(mykey) : 0;
+    const double n1 = __dsqrt_rn(s_qq);
     if (cand_valid) {
-        const double n1 = __dsqrt_rn(s_qq);
         const double n2 = __dsqrt_rn(s_rr[j]);
         sc = (n1 == 0.0 || n2 == 0.0) ? 0.0 : __ddiv_rn(s_dot[j], __dmul_rn(n1, n2));
+        // audit of the scan's error bound on every rescored candidate
+        if (fabs((double)key_score(mykey) - sc) > eps) atomicAdd(&s_viol, 1);
     }
     if (j < 64) s_score[j] = sc;
     __syncthreads();
@@ -577,25 +765,78 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uin
         f.out_score[(int64_t)q * f.k + rank] = outv;
         atomicAdd(&s_cnt, 1);
     }
-    __syncthreads();
-    if (cand_valid && rank == min(f.k, ncand) - 1) {
-        bool cert = true;
-        if (ncand >= kp && (int64_t)ncand < n_rows) {
-            const float worst = key_score(s_top[kp - 1]);  // smallest approximate score among the candidates
-            cert = ((double)worst + eps) < sc;
-        }
-        const bool bound_ok = !(extreme && *extreme != 0);
-        if (!bound_ok && (int64_t)ncand < n_rows) cert = false;
-        flags[q] = cert ? 0 : (bound_ok ? 1 : 2);  // 1: collect pass can settle it, 2: needs the full binary64 scan
-        if (collect_thr) {
-            float t = (float)(sc - 2.0 * eps);
-            t = nextafterf(nextafterf(t, -INFINITY), -INFINITY);
-            collect_thr[q] = (!cert && bound_ok) ? t : INFINITY;
-        }
-        if (!cert) { atomicAdd(uncertified_count, 1); if (cum) atomicAdd(cum, 1ull); }
+    // the k-th exact score decides which other rows could still matter: approximate score >= s_k - eps
+    if (cand_valid && ncand >= f.k && rank == f.k - 1) {
+        float t = (float)(sc - eps);
+        t = nextafterf(nextafterf(t, -INFINITY), -INFINITY);  // the cast may have rounded up
+        s_thr = t;
     }
-    if (ncand == 0 && tid == 0) { flags[q] = 0; if (collect_thr) collect_thr[q] = INFINITY; }
-    if (tid == 0) f.out_count[q] = s_cnt;
+    __syncthreads();
+    const float thr = s_thr;  // -inf when there are fewer than k candidates (then every key is in the band)
+    {
+        int inb = 0;
+        for (int e = tid; e < total; e += SR_THREADS) {
+            const uint64_t k = skeys[e];
+            inb += (k != 0 && key_score(k) >= thr) ? 1 : 0;
+        }
+        if (inb) atomicAdd(&s_band, inb);
+    }
+    __syncthreads();
+    const int band = s_band;
+    const bool bound_ok = !(extreme && *extreme != 0) && s_viol == 0;
+    const bool src_complete = union_mode ? !overflow : (src.complete != 0);
+    bool cert;
+    if (src_complete) cert = band <= ncand;            // every band row is among the rescored candidates
+    else if (union_mode) cert = false;                 // overflowed union buffer: rows are missing
+    else cert = ncand < kp || band < kp;               // per-CTA top-kp lists: outside rows are bounded by the kp-th key only
+    if (!bound_ok && (int64_t)ncand < n_rows) cert = false;
+    if (ncand == 0) cert = true;
+    if (cert) {
+        if (tid == 0) {
+            flags[q] = 0;
+            if (collect_thr) collect_thr[q] = INFINITY;
+            f.out_count[q] = s_cnt;
+        }
+        const int cnt = s_cnt;
+        for (int t = cnt + tid; t < f.k; t += SR_THREADS) {
+            f.out_idx[(int64_t)q * f.k + t] = -1;
+            f.out_score[(int64_t)q * f.k + t] = 0.0;
+        }
+        return;
+    }
+    if (tid == 0 && cum) { atomicAdd(cum, 1ull); if (s_viol) atomicAdd(cum + 4, 1ull); }
+    if (bound_ok && src_complete && band <= BAND_CAP) {
+        // ---------------- E. settle from the band ----------------
+        double *b_sc = reinterpret_cast<double *>(srow);
+        uint32_t *b_row = reinterpret_cast<uint32_t *>(b_sc + BAND_CAP);
+        unsigned char *b_taken = reinterpret_cast<unsigned char *>(b_row + BAND_CAP);
+        if (tid == 0) s_m = 0;
+        __syncthreads();
+        for (int e = tid; e < total; e += SR_THREADS) {
+            const uint64_t k = skeys[e];
+            if (k != 0 && key_score(k) >= thr) b_row[atomicAdd(&s_m, 1)] = key_row(k);
+        }
+        __syncthreads();
+        band_topk<NEUMAIER, T, SR_THREADS>(rows, ld, dim, sq, n1, band, b_sc, b_row, b_taken, w_s, w_r, w_p, &s_out, f, q);
+        if (tid == 0) {
+            flags[q] = 0;
+            if (collect_thr) collect_thr[q] = INFINITY;
+            if (cum) atomicAdd(cum + 1, 1ull);
+        }
+        return;
+    }
+    // the collect pass (one more streaming scan gathering every row >= s_k - 2 eps) or, when the bound itself is
+    // in doubt, the binary64 scan of every row settles the query; the provisional list stays in place until then
+    if (tid == 0) {
+        flags[q] = bound_ok ? 1 : 2;
+        if (collect_thr) {
+            float t = thr > -INFINITY ? (float)((double)thr - eps) : -INFINITY;
+            t = nextafterf(t, -INFINITY);
+            collect_thr[q] = bound_ok ? t : INFINITY;
+        }
+        atomicAdd(uncertified_count, 1);
+        f.out_count[q] = s_cnt;
+    }
     const int cnt = s_cnt;
     for (int t = cnt + tid; t < f.k; t += SR_THREADS) {
         f.out_idx[(int64_t)q * f.k + t] = -1;
@@ -609,9 +850,8 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(const uin
 // One CTA (512 threads) per query with flag 1.  The collect scan stored every row whose approximate
 // score reached (exact k-th candidate score - 2 eps): that set contains the reference's top-k (a row
 // outside it is more than eps below the k-th candidate).  All gathered rows are scored with the
-// reference recurrence (one sequential chain pair per thread and row) and the best k by (score desc,
-// row asc) are emitted; the query's flag is cleared.  If the buffer overflowed the flag becomes 2 and
-// the binary64 scan of every row takes over.
+// reference recurrence (band_topk) and the best k by (score desc, row asc) are emitted; the query's flag is
+// cleared.  If the buffer overflowed the flag becomes 2 and the binary64 scan of every row takes over.
 static constexpr int CR_THREADS = 512;
 template <bool NEUMAIER, typename T>
 __global__ void __launch_bounds__(CR_THREADS, 1) collect_rescore_kernel(const uint64_t *__restrict__ buf, const int *__restrict__ cnt, int cap,
@@ -630,7 +870,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) collect_rescore_kernel(const ui
     __shared__ int w_p[CR_THREADS / 32];
     __shared__ double s_n1;
     __shared__ int s_out;
-    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = blockIdx.x, tid = threadIdx.x;
     if (flags[nq] == 0 || flags[q] != 1) return;
     const int m = cnt[q];
     if (m > cap) {  // too many rows inside the band: leave it to the full binary64 scan
@@ -638,7 +878,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) collect_rescore_kernel(const ui
         return;
     }
     for (int i = tid; i < dim; i += CR_THREADS) sq[i] = load_as_double(queries, q_dtype, (int64_t)q * dim + i);
-    if (tid == 0) s_out = 0;
+    for (int e = tid; e < m; e += CR_THREADS) s_row[e] = key_row(buf[(size_t)q * cap + e]);
     __syncthreads();
     if (tid == 0) {
         RefSum qq; qq.init();
@@ -646,53 +886,11 @@ __global__ void __launch_bounds__(CR_THREADS, 1) collect_rescore_kernel(const ui
         s_n1 = __dsqrt_rn(qq.result<NEUMAIER>());
     }
     __syncthreads();
-    const double n1 = s_n1;
-    for (int e = tid; e < m; e += CR_THREADS) {
-        const uint32_t r = key_row(buf[(size_t)q * cap + e]);
-        s_row[e] = r;
-        s_sc[e] = exact_cosine_sq<NEUMAIER, T>(sq, n1, rows + (int64_t)r * ld, dim);
-        s_taken[e] = 0;
-    }
-    __syncthreads();
-    // k rounds of block-wide arg-best over the m scored rows
-    for (int r = 0; r < f.k; ++r) {
-        double bs = 0.0; uint32_t br = 0; int bp = -1;
-        for (int e = tid; e < m; e += CR_THREADS)
-            if (!s_taken[e] && (bp < 0 || better(s_sc[e], s_row[e], bs, br))) { bs = s_sc[e]; br = s_row[e]; bp = e; }
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ts = __shfl_xor_sync(0xffffffffu, bs, o);
-            const uint32_t tr = __shfl_xor_sync(0xffffffffu, br, o);
-            const int tp = __shfl_xor_sync(0xffffffffu, bp, o);
-            if (tp >= 0 && (bp < 0 || better(ts, tr, bs, br))) { bs = ts; br = tr; bp = tp; }
-        }
-        if (lane == 0) { w_s[warp] = bs; w_r[warp] = br; w_p[warp] = bp; }
-        __syncthreads();
-        bs = w_s[0]; br = w_r[0]; bp = w_p[0];
-        for (int w = 1; w < CR_THREADS / 32; ++w)
-            if (w_p[w] >= 0 && (bp < 0 || better(w_s[w], w_r[w], bs, br))) { bs = w_s[w]; br = w_r[w]; bp = w_p[w]; }
-        if (bp < 0) break;  // uniform
-        if (tid == 0) {
-            s_taken[bp] = 1;
-            const double outv = convert_score(bs, f.score_mode);
-            if (outv > f.min_score) {
-                f.out_idx[(int64_t)q * f.k + r] = (int64_t)br + f.row_offset;
-                f.out_score[(int64_t)q * f.k + r] = outv;
-                s_out = r + 1;
-            }
-        }
-        __syncthreads();
-    }
-    __syncthreads();
-    const int cntv = s_out;
+    band_topk<NEUMAIER, T, CR_THREADS>(rows, ld, dim, sq, s_n1, m, s_sc, s_row, s_taken, w_s, w_r, w_p, &s_out, f, q);
     if (tid == 0) {
-        f.out_count[q] = cntv;
         flags[q] = 0;
         atomicSub(uncertified_count, 1);
         if (cum) atomicAdd(cum + 2, 1ull);
-    }
-    for (int t = cntv + tid; t < f.k; t += CR_THREADS) {
-        f.out_idx[(int64_t)q * f.k + t] = -1;
-        f.out_score[(int64_t)q * f.k + t] = 0.0;
     }
 }
 
@@ -701,17 +899,84 @@ __global__ void __launch_bounds__(CR_THREADS, 1) collect_rescore_kernel(const ui
 // =========================================================================================
 // Grid-stride over 128-row tiles; thread t scores row tile*128+t against one flagged query at a
 // time.  Per-CTA exact top-k list in shared memory, updated by parallel rank-merge whenever a
-// tile produced a row that beats the current k-th entry.  Lists go to
-// xlist_*[cta][q][k]; exact_merge_kernel reduces them.
+// tile produced a row that beats the current k-th entry.  Lists go to xlist_*[cta][q][k]; they are reduced by
+// exact_merge_kernel (VM_FLAG_FORCE_EXACT: every query) or -- in the conditional form that follows every fast
+// pass, which exits at once when nothing is flagged -- by the last CTA to finish (ticket), so the rare fix-up is
+// ONE launch.
 #define XK 64
+
+// k rounds of block arg-best over lists*k (score,row) pairs that stay in global/L2 -> best k of query q.
+template <int THREADS>
+__device__ void exact_merge_query(const double *__restrict__ xlist_score, const uint32_t *__restrict__ xlist_row,
+                                  const int32_t *__restrict__ xlist_cnt, int lists, int nq, int k, int q, const FinalizeArgs &f,
+                                  uint8_t *__restrict__ taken, double *w_s, uint32_t *w_r, int *w_p, int *s_out)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total = lists * k;
+    uint8_t *tk = taken + (int64_t)q * total;
+    for (int e = tid; e < total; e += THREADS) tk[e] = 0;
+    if (tid == 0) *s_out = 0;
+    __syncthreads();
+    auto scan_local = [&](double &bs, uint32_t &br, int &bp) {
+        bp = -1; bs = 0.0; br = 0;
+        for (int e = tid; e < total; e += THREADS) {
+            int l = e / k, j = e - l * k;
+            if (tk[e] || j >= xlist_cnt[(int64_t)l * nq + q]) continue;
+            int64_t g = ((int64_t)l * nq + q) * k + j;
+            double s = xlist_score[g];
+            uint32_t r = xlist_row[g];
+            if (bp < 0 || better(s, r, bs, br)) { bs = s; br = r; bp = e; }
+        }
+    };
+    double bs; uint32_t br; int bp;
+    scan_local(bs, br, bp);
+    for (int r = 0; r < f.k; ++r) {
+        double ms = bs; uint32_t mr = br; int mp = bp;
+        for (int o = 16; o > 0; o >>= 1) {
+            double ts = __shfl_xor_sync(0xffffffffu, ms, o);
+            uint32_t tr = __shfl_xor_sync(0xffffffffu, mr, o);
+            int tp = __shfl_xor_sync(0xffffffffu, mp, o);
+            if (tp >= 0 && (mp < 0 || better(ts, tr, ms, mr))) { ms = ts; mr = tr; mp = tp; }
+        }
+        if (lane == 0) { w_s[warp] = ms; w_r[warp] = mr; w_p[warp] = mp; }
+        __syncthreads();
+        ms = w_s[0]; mr = w_r[0]; mp = w_p[0];
+        for (int w = 1; w < THREADS / 32; ++w)
+            if (w_p[w] >= 0 && (mp < 0 || better(w_s[w], w_r[w], ms, mr))) { ms = w_s[w]; mr = w_r[w]; mp = w_p[w]; }
+        if (mp < 0) break;  // uniform
+        double outv = convert_score(ms, f.score_mode);
+        if (tid == 0 && outv > f.min_score) {
+            f.out_idx[(int64_t)q * f.k + r] = (int64_t)mr + f.row_offset;
+            f.out_score[(int64_t)q * f.k + r] = outv;
+            *s_out = r + 1;
+        }
+        if (mp == bp) {
+            tk[bp] = 1;
+            scan_local(bs, br, bp);
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    int cnt = *s_out;
+    if (tid == 0) f.out_count[q] = cnt;
+    for (int t = cnt + tid; t < f.k; t += THREADS) {
+        f.out_idx[(int64_t)q * f.k + t] = -1;
+        f.out_score[(int64_t)q * f.k + t] = 0.0;
+    }
+    __syncthreads();
+}
+
 template <bool NEUMAIER, typename T>
 __global__ void __launch_bounds__(128) exact_scan_kernel(const T *__restrict__ rows, const float *__restrict__ inv_norms,
                                                         int64_t n, int ld, int dim, const void *__restrict__ queries,
-                                                        int q_dtype, int nq, const int32_t *__restrict__ flags, int k,
+                                                        int q_dtype, int nq, int32_t *__restrict__ flags, int k,
                                                         double *__restrict__ xlist_score, uint32_t *__restrict__ xlist_row,
-                                                        int32_t *__restrict__ xlist_cnt, unsigned long long *__restrict__ cum)
+                                                        int32_t *__restrict__ xlist_cnt, unsigned long long *__restrict__ cum,
+                                                        int *__restrict__ done_ctr, FinalizeArgs f, uint8_t *__restrict__ taken)
 {
-    // flags[nq] is the uncertified-query counter written by rescore_kernel: nothing to do when 0
+    pdl_launch_dependents();
+    pdl_wait();
+    // flags[nq] is the uncertified-query counter written by the rescoring kernel: nothing to do when 0
     if (flags && flags[nq] == 0) return;
     if (flags && cum && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(cum + 3, (unsigned long long)flags[nq]);
     extern __shared__ double sq[];  // [dim] query as doubles
@@ -779,10 +1044,27 @@ __global__ void __launch_bounds__(128) exact_scan_kernel(const T *__restrict__ r
         for (int e = tid; e < lc; e += 128) { xlist_score[base + e] = l_score[e]; xlist_row[base + e] = l_row[e]; }
         if (tid == 0) xlist_cnt[(int64_t)blockIdx.x * nq + q] = lc;
     }
+    if (done_ctr == nullptr) return;
+    // conditional form: the last CTA to finish reduces the per-CTA lists of every flagged query
+    __shared__ int s_last, s_out;
+    __shared__ double w_s[4];
+    __shared__ uint32_t w_r[4];
+    __shared__ int w_p[4];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(done_ctr, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int q = 0; q < nq; ++q) {
+        if (flags[q] == 0) continue;
+        exact_merge_query<128>(xlist_score, xlist_row, xlist_cnt, (int)gridDim.x, nq, k, q, f, taken, w_s, w_r, w_p, &s_out);
+        if (tid == 0) flags[q] = 0;
+    }
+    if (tid == 0) { *done_ctr = 0; flags[nq] = 0; }
 }
 
-// One CTA (256 threads) per query: k rounds of block arg-best over lists*k (score,row) pairs
-// that stay in global/L2.  Skips queries whose flag is 0.
+// One CTA (256 threads) per query; skips queries whose flag is 0.
 __global__ void __launch_bounds__(256) exact_merge_kernel(const double *__restrict__ xlist_score, const uint32_t *__restrict__ xlist_row,
                                                          const int32_t *__restrict__ xlist_cnt, int lists, int nq, int k,
                                                          const int32_t *__restrict__ flags, FinalizeArgs f, uint8_t *__restrict__ taken)
@@ -791,59 +1073,9 @@ __global__ void __launch_bounds__(256) exact_merge_kernel(const double *__restri
     __shared__ uint32_t w_r[8];
     __shared__ int w_p[8];
     __shared__ int s_out;
-    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = blockIdx.x;
     if (flags && (flags[nq] == 0 || flags[q] == 0)) return;
-    const int total = lists * k;
-    uint8_t *tk = taken + (int64_t)q * total;
-    for (int e = tid; e < total; e += 256) tk[e] = 0;
-    if (tid == 0) s_out = 0;
-    __syncthreads();
-    auto scan_local = [&](double &bs, uint32_t &br, int &bp) {
-        bp = -1; bs = 0.0; br = 0;
-        for (int e = tid; e < total; e += 256) {
-            int l = e / k, j = e - l * k;
-            if (tk[e] || j >= xlist_cnt[(int64_t)l * nq + q]) continue;
-            int64_t g = ((int64_t)l * nq + q) * k + j;
-            double s = xlist_score[g];
-            uint32_t r = xlist_row[g];
-            if (bp < 0 || better(s, r, bs, br)) { bs = s; br = r; bp = e; }
-        }
-    };
-    double bs; uint32_t br; int bp;
-    scan_local(bs, br, bp);
-    for (int r = 0; r < f.k; ++r) {
-        double ms = bs; uint32_t mr = br; int mp = bp;
-        for (int o = 16; o > 0; o >>= 1) {
-            double ts = __shfl_xor_sync(0xffffffffu, ms, o);
-            uint32_t tr = __shfl_xor_sync(0xffffffffu, mr, o);
-            int tp = __shfl_xor_sync(0xffffffffu, mp, o);
-            if (tp >= 0 && (mp < 0 || better(ts, tr, ms, mr))) { ms = ts; mr = tr; mp = tp; }
-        }
-        if (lane == 0) { w_s[warp] = ms; w_r[warp] = mr; w_p[warp] = mp; }
-        __syncthreads();
-        ms = w_s[0]; mr = w_r[0]; mp = w_p[0];
-        for (int w = 1; w < 8; ++w)
-            if (w_p[w] >= 0 && (mp < 0 || better(w_s[w], w_r[w], ms, mr))) { ms = w_s[w]; mr = w_r[w]; mp = w_p[w]; }
-        if (mp < 0) break;  // uniform
-        double outv = convert_score(ms, f.score_mode);
-        if (tid == 0 && outv > f.min_score) {
-            f.out_idx[(int64_t)q * f.k + r] = (int64_t)mr + f.row_offset;
-            f.out_score[(int64_t)q * f.k + r] = outv;
-            s_out = r + 1;
-        }
-        if (mp == bp) {
-            tk[bp] = 1;
-            scan_local(bs, br, bp);
-        }
-        __syncthreads();
-    }
-    __syncthreads();
-    int cnt = s_out;
-    if (tid == 0) f.out_count[q] = cnt;
-    for (int t = cnt + tid; t < f.k; t += 256) {
-        f.out_idx[(int64_t)q * f.k + t] = -1;
-        f.out_score[(int64_t)q * f.k + t] = 0.0;
-    }
+    exact_merge_query<256>(xlist_score, xlist_row, xlist_cnt, lists, nq, k, q, f, taken, w_s, w_r, w_p, &s_out);
 }
 
 // =========================================================================================
@@ -1045,7 +1277,7 @@ int k_merge_candidates(const uint64_t *cand, int lists, int nq, int kp, uint64_t
 }
 
 
-int k_rescore(const RescoreArgs &a, cudaStream_t st)
+int k_rescore(const RescoreArgs &a, cudaStream_t st, const int *incomplete)
 {
 #define LAUNCH_RS(NEU, T)                                                                                              \
     do {                                                                                                               \
@@ -1056,7 +1288,7 @@ int k_rescore(const RescoreArgs &a, cudaStream_t st)
         }                                                                                                              \
         rescore_kernel<NEU, T><<<a.nq, RS_THREADS, smem, st>>>(a.merged, a.kp, (const T *)a.rows, a.inv_norms, a.ld, a.dim, \
                                                                a.n_rows, a.queries, a.q_dtype, a.eps, a.fin, a.flags,    \
-                                                               a.uncertified_count, chunk, a.extreme, a.collect_thr, a.cum);                      \
+                                                               a.uncertified_count, chunk, a.extreme, a.collect_thr, a.cum, incomplete);         \
     } while (0)
     // column chunk: whole rows when kp rows fit in RS_SMEM_ROW_BYTES, else a multiple of 8 columns
     int chunk = RS_SMEM_ROW_BYTES / (4 * a.kp) - 1;
@@ -1075,20 +1307,35 @@ int k_rescore(const RescoreArgs &a, cudaStream_t st)
 // Fused path when the candidate keys + kp whole rows fit in shared memory; otherwise the caller falls
 // back to k_merge_candidates + k_rescore.  Returns VM_ERR_UNSUPPORTED (without setting an error the
 // caller must report) when it does not apply.
-bool select_rescore_fits(int lists, int list_len, int kp, int dtype, int dim, int ld)
+static size_t select_rescore_smem(int key_cap, int lists, int kp, int dtype, int dim, int ld)
 {
     const int es = dtype == VM_F32 ? 4 : 2;
-    const size_t smem = (size_t)lists * list_len * 8 + (size_t)((lists + 3) & ~3) * 4 + (size_t)((dim + 1) & ~1) * 8 +
-                        (size_t)kp * ((size_t)ld * es + 16) + 32;
-    return smem <= 180 * 1024 && kp <= 64 && 2 * kp + 1 <= SR_THREADS;
+    size_t rows_area = (size_t)kp * ((size_t)ld * es + 16);
+    const size_t band_area = (size_t)BAND_CAP * (8 + 4 + 1) + 16;
+    if (rows_area < band_area) rows_area = band_area;
+    return (size_t)key_cap * 8 + (size_t)((lists + 3) & ~3) * 4 + (size_t)((dim + 1) & ~1) * 8 + rows_area + 32;
+}
+// lists == 0: slab mode (tcgen05 scan); else list mode with lists x list_len keys per query
+bool select_rescore_fits(int lists, int list_len, int kp, int dtype, int dim, int ld)
+{
+    const int key_cap = lists > 0 ? lists * list_len : SELECT_KEY_CAP;
+    return select_rescore_smem(key_cap, lists, kp, dtype, dim, ld) <= 180 * 1024 && kp <= 64 && 2 * kp + 1 <= SR_THREADS;
 }
 
-int k_select_rescore(const uint64_t *cand, int lists, int list_len, const RescoreArgs &a, cudaStream_t st)
+static SelectSrc make_src(const SelectArgs &sa)
 {
-    const int es = a.dtype == VM_F32 ? 4 : 2;
-    const size_t smem = (size_t)lists * list_len * 8 + (size_t)((lists + 3) & ~3) * 4 + (size_t)((a.dim + 1) & ~1) * 8 +
-                        (size_t)a.kp * ((size_t)a.ld * es + 16) + 32;
-    if (!select_rescore_fits(lists, list_len, a.kp, a.dtype, a.dim, a.ld)) return VM_ERR_UNSUPPORTED;
+    const bool slab_mode = sa.slab != nullptr;
+    const int lists = slab_mode ? 0 : sa.lists;
+    return SelectSrc{sa.cand, lists, sa.list_len, sa.complete, sa.slab, sa.scnt, sa.ctas, sa.ubuf, sa.ucnt, sa.ucap, sa.seed_tab,
+                     sa.nq_pad, sa.ksel, sa.band, slab_mode ? SELECT_KEY_CAP : lists * sa.list_len};
+}
+
+int k_select_rescore(const SelectArgs &sa, const RescoreArgs &a, cudaStream_t st, bool pdl)
+{
+    const SelectSrc src = make_src(sa);
+    VM_REQUIRE(src.slab == nullptr || src.ctas <= 256, VM_ERR_UNSUPPORTED, "select: %d scan CTAs exceed 256", src.ctas);
+    if (!select_rescore_fits(src.lists, src.list_len, a.kp, a.dtype, a.dim, a.ld)) return VM_ERR_UNSUPPORTED;
+    const size_t smem = select_rescore_smem(src.key_cap, src.lists, a.kp, a.dtype, a.dim, a.ld);
 #define LAUNCH_SR(NEU, T)                                                                                              \
     do {                                                                                                               \
         static bool attr_set_dev[64] = {};                                                                             \
@@ -1098,14 +1345,24 @@ int k_select_rescore(const uint64_t *cand, int lists, int list_len, const Rescor
             VM_CUDA_CHECK(cudaFuncSetAttribute(select_rescore_kernel<NEU, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024)); \
             attr_set_dev[dev_idx_ & 63] = true;                                                                        \
         }                                                                                                              \
-        select_rescore_kernel<NEU, T><<<a.nq, SR_THREADS, smem, st>>>(cand, lists, list_len, a.nq, a.kp, (const T *)a.rows, a.ld, a.dim, \
-                                                                      a.n_rows, a.queries, a.q_dtype, a.eps, a.fin, a.flags,  \
-                                                                      a.uncertified_count, a.extreme, a.collect_thr, a.cum);      \
+        VM_CUDA_CHECK(launch_pdl(select_rescore_kernel<NEU, T>, dim3(a.nq), dim3(SR_THREADS), smem, st, pdl, src, a.nq, a.kp, \
+                                 (const T *)a.rows, a.ld, a.dim, a.n_rows, a.queries, a.q_dtype, a.eps, a.fin, a.flags,      \
+                                 a.uncertified_count, a.extreme, a.collect_thr, a.cum));                                     \
     } while (0)
     const bool neu = a.sum_mode == VM_SUM_NEUMAIER;
     if (a.dtype == VM_F32) { if (neu) LAUNCH_SR(true, float); else LAUNCH_SR(false, float); }
     else { if (neu) LAUNCH_SR(true, __nv_bfloat16); else LAUNCH_SR(false, __nv_bfloat16); }
 #undef LAUNCH_SR
+    VM_CUDA_CHECK(cudaGetLastError());
+    return VM_OK;
+}
+
+// slab-mode selection alone (rows too large for the fused kernel): merged [nq][kp], incomplete [nq]
+int k_slab_top(const SelectArgs &sa, int nq, int kp, uint64_t *merged, int *incomplete, cudaStream_t st)
+{
+    const SelectSrc src = make_src(sa);
+    VM_REQUIRE(src.slab != nullptr && src.ctas <= 256, VM_ERR_UNSUPPORTED, "slab selection: bad source");
+    slab_top_kernel<<<nq, SR_THREADS, (size_t)src.key_cap * 8, st>>>(src, nq, kp, merged, incomplete);
     VM_CUDA_CHECK(cudaGetLastError());
     return VM_OK;
 }
@@ -1134,21 +1391,27 @@ int k_collect_rescore(const uint64_t *buf, const int *cnt, int cap, const Rescor
     return VM_OK;
 }
 
-int k_exact(const ExactArgs &a, cudaStream_t st)
+// a.flags == NULL: every query (VM_FLAG_FORCE_EXACT), scan + merge kernel.  a.flags != NULL: the conditional fix-up
+// after a fast pass -- ONE launch (exits at once when nothing is flagged; otherwise the last CTA merges), optionally
+// programmatically chained to the rescoring kernel.
+int k_exact(const ExactArgs &a, cudaStream_t st, bool pdl)
 {
     size_t smem = (size_t)a.dim * sizeof(double);
     VM_REQUIRE(smem <= 40 * 1024, VM_ERR_UNSUPPORTED, "exact scan: dim %d too large", a.dim);
+    const bool conditional = a.flags != nullptr && a.done_ctr != nullptr;
 #define LAUNCH_EX(NEU, T)                                                                                               \
-    exact_scan_kernel<NEU, T><<<a.ctas, 128, smem, st>>>((const T *)a.rows, a.inv_norms, a.n, a.ld, a.dim, a.queries, \
-                                                         a.q_dtype, a.nq, a.flags, a.k, a.xlist_score, a.xlist_row,  \
-                                                         a.xlist_cnt, a.cum)
+    VM_CUDA_CHECK(launch_pdl(exact_scan_kernel<NEU, T>, dim3(a.ctas), dim3(128), smem, st, pdl && conditional, (const T *)a.rows, \
+                             a.inv_norms, a.n, a.ld, a.dim, a.queries, a.q_dtype, a.nq, a.flags, a.k, a.xlist_score, a.xlist_row, \
+                             a.xlist_cnt, a.cum, conditional ? a.done_ctr : (int *)nullptr, a.fin, a.taken))
     bool neu = a.sum_mode == VM_SUM_NEUMAIER;
     if (a.dtype == VM_F32) { if (neu) LAUNCH_EX(true, float); else LAUNCH_EX(false, float); }
     else { if (neu) LAUNCH_EX(true, __nv_bfloat16); else LAUNCH_EX(false, __nv_bfloat16); }
 #undef LAUNCH_EX
     VM_CUDA_CHECK(cudaGetLastError());
-    exact_merge_kernel<<<a.nq, 256, 0, st>>>(a.xlist_score, a.xlist_row, a.xlist_cnt, a.ctas, a.nq, a.k, a.flags, a.fin, a.taken);
-    VM_CUDA_CHECK(cudaGetLastError());
+    if (!conditional) {
+        exact_merge_kernel<<<a.nq, 256, 0, st>>>(a.xlist_score, a.xlist_row, a.xlist_cnt, a.ctas, a.nq, a.k, a.flags, a.fin, a.taken);
+        VM_CUDA_CHECK(cudaGetLastError());
+    }
     return VM_OK;
 }
 

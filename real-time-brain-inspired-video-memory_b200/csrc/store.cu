@@ -67,12 +67,18 @@ __global__ void invalidate_rows_kernel(float *inv_norms, const int64_t *rows, in
 
 // Queries (any dtype) -> fp32 [nq_pad][ld], each scaled by 1/||q|| (binary64 norm, zero query
 // stays zero), plus an optional bf16 copy for the tcgen05 bf16 path.  One warp per query.
+//   tf32_round: the fp32 copy is rounded to nearest tf32 (10 mantissa bits) -- the tensor core would otherwise
+//               truncate it, and rounding halves the query's share of the scan's error bound;
+//   split:      the bf16 copy is [2][nq_pad][ld]: hi = bf16(v), lo = bf16(v - hi) -- 16 mantissa bits in two terms.
 __global__ void normalize_queries_kernel(const void *__restrict__ q, int q_dtype, int nq, int nq_pad, int dim, int ld,
                                          float *__restrict__ out_f32, __nv_bfloat16 *__restrict__ out_bf16,
-                                         int32_t *__restrict__ zero_me, uint32_t *__restrict__ zero_tab, int zero_tab_n)
+                                         int32_t *__restrict__ zero_me, uint32_t *__restrict__ zero_tab, int zero_tab_n,
+                                         int tf32_round, int split)
 {
+    pdl_launch_dependents();
+    pdl_wait();  // first kernel of the chain: the previous call's kernels may still be reading what is zeroed below
     // per-batch device state: zero_me[0] = uncertified-query counter, zero_me[1] = seed counter,
-    // zero_tab = the threshold-seeding table of the tcgen05 scan
+    // zero_tab = the threshold-seeding table, published bounds and union-buffer counters of the tcgen05 scan
     if (zero_me && blockIdx.x == 0 && threadIdx.x < 2) zero_me[threadIdx.x] = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < zero_tab_n; i += gridDim.x * blockDim.x) zero_tab[i] = 0u;
     int lane = threadIdx.x & 31;
@@ -89,8 +95,14 @@ __global__ void normalize_queries_kernel(const void *__restrict__ q, int q_dtype
     for (int c = lane; c < ld; c += 32) {
         float v = 0.0f;
         if (w < nq && c < dim) v = (float)(load_as_double(q, q_dtype, (int64_t)w * dim + c) * inv);
-        out_f32[(int64_t)w * ld + c] = v;
-        if (out_bf16) out_bf16[(int64_t)w * ld + c] = __float2bfloat16_rn(v);
+        float vf = v;
+        if (tf32_round) vf = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+        out_f32[(int64_t)w * ld + c] = vf;
+        if (out_bf16) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            out_bf16[(int64_t)w * ld + c] = hi;
+            if (split) out_bf16[((int64_t)nq_pad + w) * ld + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        }
     }
 }
 
@@ -163,11 +175,13 @@ int k_invalidate_rows(float *inv_norms, const int64_t *rows_dev, int64_t n, int6
 }
 
 int k_normalize_queries(const void *q, int q_dtype, int nq, int nq_pad, int dim, int ld, float *out_f32,
-                        void *out_bf16, int32_t *zero_me, uint32_t *zero_tab, int zero_tab_n, cudaStream_t st)
+                        void *out_bf16, int32_t *zero_me, uint32_t *zero_tab, int zero_tab_n, int tf32_round, int split, bool pdl,
+                        cudaStream_t st)
 {
     int threads = 128;
     int grid = (nq_pad * 32 + threads - 1) / threads;
-    normalize_queries_kernel<<<grid, threads, 0, st>>>(q, q_dtype, nq, nq_pad, dim, ld, out_f32, (__nv_bfloat16 *)out_bf16, zero_me, zero_tab, zero_tab_n);
+    VM_CUDA_CHECK(launch_pdl(normalize_queries_kernel, dim3(grid), dim3(threads), 0, st, pdl, q, q_dtype, nq, nq_pad, dim, ld, out_f32,
+                             (__nv_bfloat16 *)out_bf16, zero_me, zero_tab, zero_tab_n, tf32_round, split));
     VM_CUDA_CHECK(cudaGetLastError());
     return VM_OK;
 }

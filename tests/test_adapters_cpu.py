@@ -125,7 +125,8 @@ def test_ragged_rows_follow_the_length_mismatch_rule(monkeypatch):
         store = {f"u_{i}": list(r) for i, r in enumerate(row_list)}
         want = ref_import.run_batch_similarities(queries, store, k)
         res = adapters.ResidentChunkStore(initial_capacity=4)
-        for i in range(0, len(row_list), batch):
+        res.upsert([("u_0", row_list[0])])                                       # ... which arrives first
+        for i in range(1, len(row_list), batch):
             res.upsert([(f"u_{j}", row_list[j]) for j in range(i, min(i + batch, len(row_list)))])
         assert res.topk(queries, k) == want
 

@@ -99,7 +99,8 @@ def test_simt_vs_oracle(vm, dtype, n, d, nq, k):
 
 
 def test_many_duplicates_fall_back_to_exact(vm):
-    # more exact ties at the top than the candidate list holds -> uncertified -> exact re-scan
+    # more exact ties at the top than the candidate list holds -> the whole tie band is rescored (300 duplicates) or,
+    # for the zero query (every row ties at 0.0), the binary64 scan of every row takes over
     d, n, k = 64, 5000, 10
     rng = np.random.default_rng(5)
     X = rng.standard_normal((n, d)).astype(np.float32)
@@ -108,7 +109,8 @@ def test_many_duplicates_fall_back_to_exact(vm):
     st = vm.EmbeddingStore(d, n, "f32")
     st.append(X)
     idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)
-    assert st.last_stats.uncertified >= 1
+    c = st.counters()
+    assert c["uncertified"] >= 2 and c["band_settled"] >= 1 and c["full_rescans"] >= 1 and c["bound_violations"] == 0
     _check(idx, score, count, oracle.batch_similarities(Q, X, k), k)
     assert list(idx[0]) == list(range(100, 110))
     assert list(idx[2]) == list(range(10)) and (score[2] == 0.0).all()   # zero query: store order
@@ -430,10 +432,10 @@ def test_boundaries_empty_store_large_k_no_queries(vm):
 
 
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
-def test_near_duplicate_cluster_uses_collect_pass(vm, dtype):
+def test_near_duplicate_cluster_is_settled_from_the_band(vm, dtype):
     """A cluster of near-identical rows (video chunks of a static scene) puts more rows inside the scan's
-    error band than the candidate list holds: the query is uncertified, and the collect pass -- not the
-    binary64 scan of every row -- settles it exactly."""
+    error band than the rescoring kernel takes at first: the scan has kept the COMPLETE band in the query's union
+    buffer, so the same kernel rescores all of it -- no second scan, no binary64 scan of every row."""
     import torch
     d, n, k = 384, 120000, 10
     rng = np.random.default_rng(23)
@@ -448,18 +450,67 @@ def test_near_duplicate_cluster_uses_collect_pass(vm, dtype):
     with torch.cuda.stream(torch.cuda.Stream()):                      # non-default stream: plain (non-graph) sync path, stats are read back
         idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)
     assert np.array_equal(idx, ref[0]) and np.array_equal(score, ref[1])
-    assert st.last_stats.scan_kernel == 2 and st.last_stats.uncertified >= 1
-    assert st.last_stats.full_rescans == 0                            # settled by the collect pass
-    idx2, score2, _ = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)      # default stream: CUDA-graph replay, same answer
+    c = st.counters(reset=True)
+    assert st.last_stats.scan_kernel == 2 and st.last_stats.uncertified == 0      # nothing was left for a fallback pass
+    assert c["band_settled"] >= 1 and c["collect_settled"] == 0 and c["full_rescans"] == 0 and c["bound_violations"] == 0
+    for _ in range(20):                                               # default stream: CUDA-graph replay after 16 calls, same answer
+        idx2, score2, _ = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)
     assert np.array_equal(idx2, idx) and np.array_equal(score2, score)
-    # more near-ties than the collect buffer holds -> the binary64 scan takes over, still exact
+    qd = torch.from_numpy(Q).cuda()                                   # device path, no host round trip at all
+    i4, s4, _ = st.topk_device(qd, k, sum_mode=vm.VM_SUM_NEUMAIER, flags=vm.VM_FLAG_ASYNC)
+    torch.cuda.synchronize()
+    assert np.array_equal(i4.cpu().numpy(), idx) and np.array_equal(s4.cpu().numpy(), score)
+    # a band of 1500 rows: beyond what the rescoring kernel takes itself (1024), within the collect pass (4096)
+    X1 = X.copy(); X1[30000:31200] = X1[5000:5001] + 0.0
+    st1 = vm.EmbeddingStore(d, n, dtype); st1.append(X1)
+    ref1 = oracle.topk_blocked(Q[:1], X1, k, slack=2000)
+    with torch.cuda.stream(torch.cuda.Stream()):
+        i5, s5, _ = st1.topk(Q[:1], k, sum_mode=vm.VM_SUM_NEUMAIER)
+    c1 = st1.counters()
+    assert np.array_equal(i5, ref1[0]) and np.array_equal(s5, ref1[1])
+    assert c1["collect_settled"] == 1 and c1["full_rescans"] == 0 and st1.last_stats.uncertified == 1
+    i6, s6, _ = st1.topk_device(qd[:1].contiguous(), k, sum_mode=vm.VM_SUM_NEUMAIER, flags=vm.VM_FLAG_ASYNC)   # async: straight to the exact scan
+    torch.cuda.synchronize()
+    assert np.array_equal(i6.cpu().numpy(), ref1[0]) and np.array_equal(s6.cpu().numpy(), ref1[1])
+    assert st1.counters()["full_rescans"] == 1
+    # more near-ties than the union and collect buffers hold -> the binary64 scan takes over, still exact
     X2 = X.copy(); X2[20000:25000] = X2[5000]
     st2 = vm.EmbeddingStore(d, n, dtype); st2.append(X2)
     ref2 = oracle.topk_blocked(Q[:1], X2, k, slack=6000)
     with torch.cuda.stream(torch.cuda.Stream()):
         i3, s3, _ = st2.topk(Q[:1], k, sum_mode=vm.VM_SUM_NEUMAIER)
     assert np.array_equal(i3, ref2[0]) and np.array_equal(s3, ref2[1]) and st2.last_stats.full_rescans == 1
-    st.close(); st2.close()
+    st.close(); st1.close(); st2.close()
+
+
+@pytest.mark.parametrize("dtype,flags", [("f32", 0), ("bf16", 0), ("bf16", 32)])
+def test_clustered_store_single_pass(vm, dtype, flags):
+    """Unit-norm Gaussian-mixture store (64 near-duplicates per centre, stored consecutively like the chunks of one
+    scene; values not representable in bf16 / tf32) and queries that are perturbed members: every top-10 sits inside a
+    near-duplicate cluster.  Exact against the oracle, settled in ONE scan, and the scan's error bound holds on every
+    rescored candidate.  flags=32 (VM_FLAG_NO_SPLIT): the single-term bf16 query, whose band is 60x wider."""
+    import torch
+    d, n, nq, k, per, rho = 384, 131072 + 777, 64, 10, 64, 0.2
+    rng = np.random.default_rng(99)
+    cent = rng.standard_normal((n // per + 1, d)).astype(np.float32)
+    cent /= np.linalg.norm(cent, axis=1, keepdims=True)
+    X = cent[np.arange(n) // per] + (rho / np.sqrt(d)) * rng.standard_normal((n, d)).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    X = _quantise(X.astype(np.float32), dtype)
+    pick = rng.integers(0, n, nq)
+    Q = (X[pick] + (rho / np.sqrt(d)) * rng.standard_normal((nq, d))).astype(np.float32)
+    st = vm.EmbeddingStore(d, n, dtype)
+    st.append(X)
+    ref = oracle.topk_blocked(Q, X, k, slack=120)
+    idx, score, count = st.topk_device(torch.from_numpy(Q).cuda(), k, sum_mode=vm.VM_SUM_NEUMAIER, flags=vm.VM_FLAG_ASYNC | flags)
+    torch.cuda.synchronize()
+    assert np.array_equal(idx.cpu().numpy(), ref[0]) and np.array_equal(score.cpu().numpy(), ref[1])
+    c = st.counters()
+    assert c["queries"] == nq and c["bound_violations"] == 0 and c["full_rescans"] == 0 and c["collect_settled"] == 0
+    assert c["uncertified"] == c["band_settled"]
+    if dtype == "bf16" and flags == 0:
+        assert c["uncertified"] <= 2                                  # split query: the band is ~1e-4 wide
+    st.close()
 
 
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
@@ -485,9 +536,9 @@ def test_small_store_dump_mode_boundaries(vm, dtype, n):
     st.close()
 
 
-def test_small_store_near_ties_collect_after_dump(vm):
-    """More near-identical rows than the candidate list holds, in a store small enough for dump mode: the
-    query is uncertified and the (list-mode) collect pass settles it exactly."""
+def test_small_store_near_ties_band_after_dump(vm):
+    """More near-identical rows than the candidate list holds, in a store small enough for dump mode: every row's
+    key is in the dump, so the rescoring kernel settles the query from the band itself."""
     import torch
     d, n, k = 384, 6000, 10
     rng = np.random.default_rng(5)
@@ -501,7 +552,9 @@ def test_small_store_near_ties_collect_after_dump(vm):
     with torch.cuda.stream(torch.cuda.Stream()):
         idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)
     _check(idx, score, count, ref, k)
-    assert st.last_stats.scan_kernel == 2 and st.last_stats.uncertified >= 1 and st.last_stats.full_rescans == 0
+    c = st.counters()
+    assert st.last_stats.scan_kernel == 2 and st.last_stats.scan_variant == 1 and st.last_stats.uncertified == 0
+    assert c["band_settled"] >= 1 and c["collect_settled"] == 0 and c["full_rescans"] == 0
     st.close()
 
 
