@@ -73,7 +73,10 @@ enum {
     VM_FLAG_FORCE_TC = 8,    /* use the tcgen05/TMA scan kernel even for small query batches */
     VM_FLAG_TIMING = 16,     /* bracket the scan kernel with CUDA events on `stream` (see vm_store_last_scan_ms);
                                 also launches the call's kernels without programmatic overlap */
-    VM_FLAG_NO_SPLIT = 32    /* bf16 store: feed the query as ONE bf16 term (error bound 2^-8 instead of ~2^-16): A/B only */
+    VM_FLAG_NO_SPLIT = 32,   /* bf16 store: feed the query as ONE bf16 term (scan error bound 2^-8) */
+    VM_FLAG_SPLIT = 64       /* bf16 store: feed the query as hi + lo bf16 terms, two MMAs per K slice (scan error bound
+                                ~2^-16 + (D+16) 2^-23 < 1e-4 at 384-d).  Default: split for batches of <= 48 queries,
+                                where it is free; single term above (the complete near-tie band is rescored either way). */
 };
 
 typedef struct vm_store vm_store; /* a row-major embedding store resident in HBM (one shard) */
@@ -109,6 +112,34 @@ int vm_store_create(vm_store **out, int device, int dim, int dtype, int64_t capa
  * capacity * vm_ld(dim) elements of `dtype`, inv_norms_dev holds capacity floats. */
 int vm_store_attach(vm_store **out, int device, int dim, int dtype, int64_t capacity, void *rows_dev,
                     float *inv_norms_dev);
+/* BINARY64 store: the rows are kept exactly as given (the reference scores Python float lists, i.e. binary64:
+ * pre_llm_injector.py:382-388), [capacity][ld] doubles, next to a rounded SHADOW copy in `shadow_dtype` (VM_F32 or
+ * VM_BF16) that only the streaming scan reads.  Candidate selection runs on the shadow with an error bound widened
+ * by the shadow's rounding (2^-24 / 2^-9 in cosine units); every exact step -- rescoring, near-tie band, collect pass,
+ * binary64 scan -- reads the binary64 rows.  Returned scores and order are therefore those of the reference formula on
+ * the ORIGINAL values, whatever their representability in fp32 / bf16.  HBM per row: ld * (8 + sizeof(shadow)) + 4
+ * bytes; scan traffic is that of the shadow alone.  vm_store_attach_exact: rows_exact_dev holds capacity * vm_ld(dim)
+ * doubles (16-byte aligned).  Rows whose elements overflow the shadow type, or that vanish in it, stay scorable: they
+ * are counted as out of range and every query then also takes the binary64 pass (exact, slower). */
+int vm_store_create_exact(vm_store **out, int device, int dim, int shadow_dtype, int64_t capacity);
+int vm_store_attach_exact(vm_store **out, int device, int dim, int shadow_dtype, int64_t capacity, void *rows_dev,
+                          float *inv_norms_dev, double *rows_exact_dev);
+/* GROWABLE store (the reference's store only ever grows, one SET c.embedding per new chunk,
+ * neo4j_handler.py:221-253).  The library reserves a VIRTUAL address range for max_capacity rows and backs it with
+ * physical HBM from its start as rows arrive (CUDA virtual memory management): vm_store_append grows the backed part on
+ * demand (+25 % each time, capped at max_capacity), vm_store_reserve grows it explicitly.  Base addresses never change and
+ * resident rows are never copied -- no second allocation, no device-to-device copy, HBM in use = the backed rows.
+ * exact != 0: a binary64 store as vm_store_create_exact (dtype = the shadow type). */
+int vm_store_create_growable(vm_store **out, int device, int dim, int dtype, int exact, int64_t initial_capacity,
+                             int64_t max_capacity);
+int vm_store_reserve(vm_store *s, int64_t capacity);    /* no-op when capacity <= vm_store_capacity(s) */
+int64_t vm_store_max_capacity(const vm_store *s);       /* == capacity for a store over fixed buffers */
+size_t vm_store_resident_bytes(const vm_store *s);      /* physical HBM behind rows + inverse norms (+ binary64 rows) */
+/* device addresses of the store's buffers (valid for the store's lifetime; rows beyond vm_store_capacity() of a
+ * growable store are not backed) */
+void *vm_store_rows_ptr(const vm_store *s);
+float *vm_store_inv_norms_ptr(const vm_store *s);
+double *vm_store_rows_exact_ptr(const vm_store *s);     /* NULL unless a binary64 store */
 int vm_store_destroy(vm_store *s);
 int64_t vm_store_size(const vm_store *s);
 int64_t vm_store_capacity(const vm_store *s);
@@ -171,7 +202,8 @@ int vm_store_read_counters(vm_store *s, vm_store_counters *out, int reset);
  *  min_score  strict lower bound on the returned score (use -INFINITY for none)
  *  out_idx    [nq][k] int64 row indices, best first; ties -> lowest row
  *  out_score  [nq][k] binary64 scores, BIT-IDENTICAL to the reference formula evaluated on the
- *             stored (dtype-rounded) row values and the given query values
+ *             stored row values (fp32 / bf16 store: rounded once at append; binary64 store: the
+ *             original values) and the given query values
  *  out_count  [nq] number of valid entries (rows may be fewer than k: no padding, :370)
  *  out_mem    where the three outputs live
  *

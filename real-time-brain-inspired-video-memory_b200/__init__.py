@@ -7,7 +7,7 @@ root; the directory name carries the reference's hyphenated name).
 """
 from . import _lib
 from ._lib import (VM_F32, VM_BF16, VM_F64, VM_SCORE_RAW, VM_SCORE_NEO4J, VM_SUM_NAIVE, VM_SUM_NEUMAIER,
-                   VM_FLAG_ASYNC, VM_FLAG_FORCE_EXACT, VM_FLAG_FORCE_SIMT, VM_FLAG_FORCE_TC, VM_FLAG_TIMING, VM_FLAG_NO_SPLIT, VidmemError)
+                   VM_FLAG_ASYNC, VM_FLAG_FORCE_EXACT, VM_FLAG_FORCE_SIMT, VM_FLAG_FORCE_TC, VM_FLAG_TIMING, VM_FLAG_NO_SPLIT, VM_FLAG_SPLIT, VidmemError)
 
 __all__ = ["_lib", "EmbeddingStore", "cosine_pairs", "VidmemError"]
 

@@ -20,14 +20,15 @@ VM_F32, VM_BF16, VM_F64 = 0, 1, 2
 VM_MEM_HOST, VM_MEM_DEVICE = 0, 1
 VM_SCORE_RAW, VM_SCORE_NEO4J = 0, 1
 VM_SUM_NAIVE, VM_SUM_NEUMAIER = 0, 1
-VM_FLAG_ASYNC, VM_FLAG_FORCE_EXACT, VM_FLAG_FORCE_SIMT, VM_FLAG_FORCE_TC, VM_FLAG_TIMING, VM_FLAG_NO_SPLIT = 1, 2, 4, 8, 16, 32
+VM_FLAG_ASYNC, VM_FLAG_FORCE_EXACT, VM_FLAG_FORCE_SIMT, VM_FLAG_FORCE_TC, VM_FLAG_TIMING, VM_FLAG_NO_SPLIT, VM_FLAG_SPLIT = 1, 2, 4, 8, 16, 32, 64
 
 #: summation order CPython's builtin sum() uses in THIS interpreter (what the reference would compute here)
 DEFAULT_SUM_MODE = VM_SUM_NEUMAIER if sys.version_info >= (3, 12) else VM_SUM_NAIVE
 
 EXPORTS = [
     "vm_version", "vm_last_error", "vm_device_info", "vm_ld",
-    "vm_store_create", "vm_store_attach", "vm_store_destroy", "vm_store_size", "vm_store_capacity", "vm_store_dim",
+    "vm_store_create", "vm_store_attach", "vm_store_create_exact", "vm_store_attach_exact", "vm_store_create_growable", "vm_store_reserve",
+    "vm_store_max_capacity", "vm_store_resident_bytes", "vm_store_rows_ptr", "vm_store_inv_norms_ptr", "vm_store_rows_exact_ptr", "vm_store_destroy", "vm_store_size", "vm_store_capacity", "vm_store_dim",
     "vm_store_ld", "vm_store_append", "vm_store_update", "vm_store_invalidate", "vm_store_set_size", "vm_store_clear",
     "vm_store_last_scan_ms",
     "vm_store_avg_scan_ms", "vm_store_read_counters",
@@ -79,6 +80,15 @@ def load() -> C.CDLL:
         "vm_ld": (ci, [ci]),
         "vm_store_create": (ci, [P(vp), ci, ci, ci, i64]),
         "vm_store_attach": (ci, [P(vp), ci, ci, ci, i64, vp, vp]),
+        "vm_store_create_exact": (ci, [P(vp), ci, ci, ci, i64]),
+        "vm_store_attach_exact": (ci, [P(vp), ci, ci, ci, i64, vp, vp, vp]),
+        "vm_store_create_growable": (ci, [P(vp), ci, ci, ci, ci, i64, i64]),
+        "vm_store_reserve": (ci, [vp, i64]),
+        "vm_store_max_capacity": (i64, [vp]),
+        "vm_store_resident_bytes": (sz, [vp]),
+        "vm_store_rows_ptr": (vp, [vp]),
+        "vm_store_inv_norms_ptr": (vp, [vp]),
+        "vm_store_rows_exact_ptr": (vp, [vp]),
         "vm_store_destroy": (ci, [vp]),
         "vm_store_size": (i64, [vp]),
         "vm_store_capacity": (i64, [vp]),

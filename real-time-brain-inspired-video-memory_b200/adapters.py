@@ -25,15 +25,19 @@ def _falsy_embedding(emb) -> bool:
 
 
 class ResidentChunkStore:
-    """Host-side id table + one HBM-resident EmbeddingStore that grows by doubling.
+    """Host-side id table + one HBM-resident EmbeddingStore that grows IN PLACE: the store reserves virtual
+    addresses for `max_capacity` rows (default: what the GPU's memory could hold) and backs them with HBM as chunks
+    arrive -- resident rows are never copied, there is no second allocation.
 
     Replaces the dict returned by PreLLMInjector._get_chunk_embeddings
     (src/components/pre_llm_injector.py:390-412) and is fed by the insert hook S6
     (src/components/neo4j_handler.py:221-253)."""
 
-    def __init__(self, dtype: str = "f32", device: int = 0, initial_capacity: int = 8192):
+    def __init__(self, dtype: str = "f32", device: int = 0, initial_capacity: int = 8192,
+                 max_capacity: Optional[int] = None):
         self.dtype, self.device = dtype, device
         self.initial_capacity = int(initial_capacity)
+        self.max_capacity = max_capacity
         self.store = None                      # created lazily: the dimension is whatever the embedder returns
         self.dim: Optional[int] = None
         self.ids: List[str] = []               # row -> chunk id
@@ -55,22 +59,24 @@ class ResidentChunkStore:
         if self.store is None:
             self.dim = int(dim)
             cap = max(self.initial_capacity, 2 * extra)
-            self.store = EmbeddingStore(self.dim, cap, self.dtype, self.device)
+            top = self.max_capacity if self.max_capacity is not None else self._device_row_limit(self.dim)
+            self.store = EmbeddingStore(self.dim, cap, self.dtype, self.device, max_capacity=max(int(top), cap))
             return
         if dim != self.dim:
             raise ValueError(f"embedding dimension changed from {self.dim} to {dim}")
         need = len(self.ids) + extra
         if need > self.store.capacity:
-            old = self.store
-            new = EmbeddingStore(self.dim, max(2 * old.capacity, need), self.dtype, self.device)
-            n = len(old)
-            if n:
-                new.append(old.rows[:n, :self.dim].float().contiguous())      # device -> device, exact for f32/bf16
-                bad = (old.inv_norms[:n] < 0).nonzero().flatten().cpu().numpy()
-                if len(bad):
-                    new.invalidate(bad)
-            old.close()
-            self.store = new
+            if need > self.store.max_capacity:
+                raise MemoryError(f"{need} rows exceed the store's reserved maximum of {self.store.max_capacity}")
+            # back more of the reserved range: no reallocation, no copy, row addresses unchanged
+            self.store.reserve(min(max(2 * self.store.capacity, need), self.store.max_capacity))
+
+    def _device_row_limit(self, dim: int) -> int:
+        """Rows the device's memory could hold at most (virtual addresses are reserved for that many)."""
+        import torch
+        per_row = ((dim + 7) & ~7) * {"f32": 4, "bf16": 2, "f64": 12, "f64+bf16": 10}.get(self.dtype, 12) + 4
+        total = torch.cuda.get_device_properties(self.device).total_memory if torch.cuda.is_available() else 1 << 34
+        return max(1, min(total // per_row, (1 << 31) - 512))
 
     def clear(self) -> None:
         if self.store is not None:
@@ -184,7 +190,7 @@ class ResidentChunkStore:
         import json
         from .store import EmbeddingStore
         st, ids, extra = EmbeddingStore.load(path, capacity=None, device=device, with_extra=True, min_capacity=initial_capacity)
-        self = cls("bf16" if st.dtype_code == L.VM_BF16 else "f32", device, initial_capacity)
+        self = cls(st.dtype, device, initial_capacity)
         self.store, self.dim = st, st.dim
         if len(ids) != len(st):
             raise ValueError(f"sidecar holds {len(st)} rows but {len(ids)} ids")

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libvidmem.so")
-SOURCES = ["api.cu", "store.cu", "select.cu", "scan_simt.cu", "scan_tc.cu", "pairs.cu"]
+SOURCES = ["api.cu", "store.cu", "select.cu", "scan_simt.cu", "scan_tc.cu", "pairs.cu", "arena.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -23,7 +23,8 @@ void set_error(const char *fmt, ...)
 
 // ---- kernels implemented in the other translation units -----------------------------------
 int k_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype, int64_t n, int dim, int ld, cudaStream_t st);
-int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, int *extreme, cudaStream_t st);
+int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, int *extreme, cudaStream_t st,
+                    const double *exact = nullptr);
 int k_invalidate_rows(float *inv_norms, const int64_t *rows_dev, int64_t n, int64_t size, cudaStream_t st);
 int k_normalize_queries(const void *q, int q_dtype, int nq, int nq_pad, int dim, int ld, float *out_f32, void *out_bf16,
                         int32_t *zero_me, uint32_t *zero_tab, int zero_tab_n, int tf32_round, int split, bool pdl, cudaStream_t st);
@@ -51,6 +52,14 @@ int k_pairs_above(int device, const void *x, int dtype, int64_t n, int dim, int 
                   cudaStream_t st);
 int k_pairs_concat(const void *gathered, size_t per_rank_bytes, int64_t slot, const int64_t *counts, int nranks, int64_t cap,
                    int64_t *out_i, int64_t *out_j, float *out_score, int64_t *out_count, cudaStream_t st);
+
+// growable device ranges (arena.cu): a reserved virtual range, physically backed from its start as the store grows
+struct Arena;
+int arena_create(Arena **out, int device, size_t max_bytes);
+int arena_grow(Arena *a, size_t bytes);
+void arena_destroy(Arena *a);
+void *arena_base(const Arena *a);
+size_t arena_mapped(const Arena *a);
 
 static constexpr int MAXQ = 64;   // queries per scan pass
 static constexpr int MAXK = 64;   // k and candidate-list bound
@@ -115,7 +124,17 @@ struct vm_store {
     int64_t capacity = 0, size = 0;
     void *rows = nullptr;
     float *inv_norms = nullptr;
+    // binary64 store (vm_store_create_exact / vm_store_attach_exact): the rows as the caller gave them, [capacity][ld]
+    // doubles.  `rows` is then their rounded SHADOW in `dtype`, which only the scan reads; every exact pass
+    // (rescoring, band, collect, binary64 scan) reads rows_exact, so scores and order are those of the originals.
+    double *rows_exact = nullptr;
     bool owns = false;
+    // growable store (vm_store_create_growable): the three buffers live in reserved virtual ranges that are backed
+    // with physical memory as `capacity` grows towards max_capacity; base addresses never move (arena.cu)
+    Arena *ar_rows = nullptr, *ar_inv = nullptr, *ar_exact = nullptr;
+    int64_t max_capacity = 0;
+    const void *exact_rows() const { return rows_exact ? (const void *)rows_exact : (const void *)rows; }
+    int exact_dtype() const { return rows_exact ? (int)VM_F64 : dtype; }
     int *extreme = nullptr;  // device counter: rows outside the fast scans' numeric range
     unsigned long long *cum = nullptr;  // device, [4]: lifetime certification counters (RescoreArgs::cum)
     int64_t n_batches = 0, n_queries = 0;  // host side of vm_store_read_counters
@@ -224,7 +243,7 @@ static int ws_prepare(vm_store *s)
     ENS(w.q_raw, (size_t)MAXQ * s->dim * 8);
     ENS(w.q_f32, (size_t)MAXQ * s->ld * 4);
     ENS(w.q_bf16, (size_t)2 * MAXQ * s->ld * 2);  // hi terms, then lo terms (split query)
-    ENS(w.cand, (size_t)lists * MAXQ * MAXK * 8);
+    ENS(w.cand, (size_t)lists * MAXQ * (MAXK > SCAN_SLAB ? MAXK : SCAN_SLAB) * 8);  // per-CTA lists / dumped tiles / slabs
     ENS(w.merged, (size_t)MAXQ * MAXK * 8);
     // one contiguous block [idx | score | count] so a host caller gets its results with ONE copy
     ENS(w.o_idx, (size_t)MAXQ * MAXK * 16 + (size_t)MAXQ * 4 + 64);
@@ -252,7 +271,17 @@ static int ws_prepare(vm_store *s)
     return VM_OK;
 }
 
-static double scan_eps(int kernel, int store_dtype, int dim, int split)
+static double scan_eps_stored(int kernel, int store_dtype, int dim, int split);
+// shadow: the store keeps binary64 originals and the scan reads their rounded copy.  Rounding a row moves its
+// direction by an angle of at most asin(u) (u = unit roundoff of the shadow type, relative per element, hence relative
+// in norm), and a cosine moves by at most the angle: + 2^-24 (fp32 shadow) or + 2^-9 (bf16 shadow), taken with margin.
+static double scan_eps(int kernel, int store_dtype, int dim, int split, bool shadow = false)
+{
+    const double base = scan_eps_stored(kernel, store_dtype, dim, split);
+    if (!shadow) return base;
+    return base + (store_dtype == VM_F32 ? 1.1920928955078125e-07 : 1.953125e-3 * 1.01);
+}
+static double scan_eps_stored(int kernel, int store_dtype, int dim, int split)
 {
     // Bound on |approximate cosine - exact cosine| (DESIGN.md "certification"), in cosine units (Cauchy-Schwarz).
     const double u = 1.1920928955078125e-07;                         // 2^-23
@@ -330,6 +359,88 @@ extern "C" int vm_store_create(vm_store **out, int device, int dim, int dtype, i
     return VM_OK;
 }
 
+extern "C" int vm_store_create_exact(vm_store **out, int device, int dim, int shadow_dtype, int64_t capacity)
+{
+    int rc = vm_store_create(out, device, dim, shadow_dtype, capacity);
+    if (rc != VM_OK) return rc;
+    vm_store *s = *out;
+    DeviceGuard g(device);
+    const size_t bytes = (size_t)capacity * s->ld * 8;
+    cudaError_t e = cudaMalloc((void **)&s->rows_exact, bytes);
+    if (e != cudaSuccess) {
+        set_error("store allocation of %zu bytes (binary64 rows) failed: %s", bytes, cudaGetErrorString(e));
+        vm_store_destroy(s);
+        *out = nullptr;
+        return VM_ERR_OOM;
+    }
+    return VM_OK;
+}
+
+// back the first `capacity` rows of a growable store
+static int store_back(vm_store *s, int64_t capacity)
+{
+    int rc = arena_grow(s->ar_rows, (size_t)capacity * s->ld * dtype_size(s->dtype));
+    if (rc == VM_OK) rc = arena_grow(s->ar_inv, (size_t)capacity * 4);
+    if (rc == VM_OK && s->ar_exact) rc = arena_grow(s->ar_exact, (size_t)capacity * s->ld * 8);
+    return rc;
+}
+
+extern "C" int vm_store_create_growable(vm_store **out, int device, int dim, int dtype, int exact, int64_t initial_capacity,
+                                        int64_t max_capacity)
+{
+    VM_REQUIRE(initial_capacity >= 1 && max_capacity >= initial_capacity, VM_ERR_BADARG, "need 1 <= initial_capacity <= max_capacity");
+    int rc = store_new(out, device, dim, dtype, max_capacity);   // validates dim / dtype / the row-count limit
+    if (rc != VM_OK) return rc;
+    vm_store *s = *out;
+    DeviceGuard g(device);
+    s->max_capacity = max_capacity;
+    s->capacity = initial_capacity;
+    rc = arena_create(&s->ar_rows, device, (size_t)max_capacity * s->ld * dtype_size(dtype));
+    if (rc == VM_OK) rc = arena_create(&s->ar_inv, device, (size_t)max_capacity * 4);
+    if (rc == VM_OK && exact) rc = arena_create(&s->ar_exact, device, (size_t)max_capacity * s->ld * 8);
+    if (rc == VM_OK) rc = store_back(s, initial_capacity);
+    if (rc != VM_OK) { vm_store_destroy(s); *out = nullptr; return rc; }
+    s->rows = arena_base(s->ar_rows);
+    s->inv_norms = (float *)arena_base(s->ar_inv);
+    if (exact) s->rows_exact = (double *)arena_base(s->ar_exact);
+    return VM_OK;
+}
+
+extern "C" int vm_store_reserve(vm_store *s, int64_t capacity)
+{
+    VM_REQUIRE(s, VM_ERR_BADARG, "store is NULL");
+    if (capacity <= s->capacity) return VM_OK;
+    VM_REQUIRE(s->ar_rows, VM_ERR_STATE, "store is not growable (created over fixed buffers of %lld rows)", (long long)s->capacity);
+    VM_REQUIRE(capacity <= s->max_capacity, VM_ERR_OVERFLOW, "capacity %lld exceeds the reserved maximum %lld", (long long)capacity,
+               (long long)s->max_capacity);
+    DeviceGuard g(s->device);
+    int rc = store_back(s, capacity);   // maps new physical chunks behind the resident rows; nothing is copied or moved
+    if (rc != VM_OK) return rc;
+    s->capacity = capacity;
+    return VM_OK;
+}
+
+extern "C" int64_t vm_store_max_capacity(const vm_store *s) { return s ? (s->ar_rows ? s->max_capacity : s->capacity) : -1; }
+extern "C" void *vm_store_rows_ptr(const vm_store *s) { return s ? s->rows : nullptr; }
+extern "C" float *vm_store_inv_norms_ptr(const vm_store *s) { return s ? s->inv_norms : nullptr; }
+extern "C" double *vm_store_rows_exact_ptr(const vm_store *s) { return s ? s->rows_exact : nullptr; }
+extern "C" size_t vm_store_resident_bytes(const vm_store *s)
+{
+    if (!s) return 0;
+    if (s->ar_rows) return arena_mapped(s->ar_rows) + arena_mapped(s->ar_inv) + (s->ar_exact ? arena_mapped(s->ar_exact) : 0);
+    return (size_t)s->capacity * ((size_t)s->ld * (dtype_size(s->dtype) + (s->rows_exact ? 8 : 0)) + 4);
+}
+
+extern "C" int vm_store_attach_exact(vm_store **out, int device, int dim, int shadow_dtype, int64_t capacity, void *rows_dev,
+                                     float *inv_norms_dev, double *rows_exact_dev)
+{
+    VM_REQUIRE(rows_exact_dev && ((uintptr_t)rows_exact_dev & 15) == 0, VM_ERR_BADARG, "binary64 rows buffer must be 16-byte aligned");
+    int rc = vm_store_attach(out, device, dim, shadow_dtype, capacity, rows_dev, inv_norms_dev);
+    if (rc != VM_OK) return rc;
+    (*out)->rows_exact = rows_exact_dev;
+    return VM_OK;
+}
+
 extern "C" int vm_store_attach(vm_store **out, int device, int dim, int dtype, int64_t capacity, void *rows_dev,
                                float *inv_norms_dev)
 {
@@ -348,7 +459,8 @@ extern "C" int vm_store_destroy(vm_store *s)
     if (!s) return VM_OK;
     DeviceGuard g(s->device);
     cudaDeviceSynchronize();
-    if (s->owns) { cudaFree(s->rows); cudaFree(s->inv_norms); }
+    if (s->owns) { cudaFree(s->rows); cudaFree(s->inv_norms); if (s->rows_exact) cudaFree(s->rows_exact); }
+    arena_destroy(s->ar_rows); arena_destroy(s->ar_inv); arena_destroy(s->ar_exact);
     if (s->extreme) cudaFree(s->extreme);
     if (s->cum) cudaFree(s->cum);
     s->stage.release(); s->stage_idx.release();
@@ -382,7 +494,11 @@ static int store_write(vm_store *s, int64_t row0, const void *rows, int src_dtyp
     char *dst = (char *)s->rows + (size_t)row0 * s->ld * dtype_size(s->dtype);
     int rc = k_convert_rows(src, src_dtype, dst, s->dtype, n, s->dim, s->ld, st);
     if (rc != VM_OK) return rc;
-    return k_row_inv_norms(s->rows, s->dtype, s->inv_norms, row0, row0 + n, s->ld, s->extreme, st);
+    if (s->rows_exact) {  // the originals, widened exactly (or copied) into the binary64 rows
+        rc = k_convert_rows(src, src_dtype, s->rows_exact + (size_t)row0 * s->ld, VM_F64, n, s->dim, s->ld, st);
+        if (rc != VM_OK) return rc;
+    }
+    return k_row_inv_norms(s->rows, s->dtype, s->inv_norms, row0, row0 + n, s->ld, s->extreme, st, s->rows_exact);
 }
 
 extern "C" int vm_store_append(vm_store *s, const void *rows, int src_dtype, int src_mem, int64_t n, int64_t *first_row,
@@ -390,6 +506,17 @@ extern "C" int vm_store_append(vm_store *s, const void *rows, int src_dtype, int
 {
     VM_REQUIRE(s, VM_ERR_BADARG, "store is NULL");
     VM_REQUIRE(n >= 0, VM_ERR_BADARG, "n < 0");
+    if (s->ar_rows && s->size + n > s->capacity) {
+        // growable store: back more of the reserved range (+25 %, capped at the maximum: mapping costs time and HBM in
+        // proportion to the NEW rows only, so a small factor keeps the slack small); resident rows stay put
+        int64_t want = s->capacity + s->capacity / 4 > s->size + n ? s->capacity + s->capacity / 4 : s->size + n;
+        if (want > s->max_capacity) want = s->max_capacity;
+        if (want >= s->size + n) {
+            int rc = vm_store_reserve(s, want);
+            if (rc != VM_OK && want > s->size + n) rc = vm_store_reserve(s, s->size + n);   // out of memory for the slack: take what is needed
+            if (rc != VM_OK) return rc;
+        }
+    }
     VM_REQUIRE(s->size + n <= s->capacity, VM_ERR_OVERFLOW, "append of %lld rows exceeds capacity %lld (size %lld)",
                (long long)n, (long long)s->capacity, (long long)s->size);
     int rc = store_write(s, s->size, rows, src_dtype, src_mem, n, (cudaStream_t)stream);
@@ -429,8 +556,17 @@ extern "C" int vm_store_set_size(vm_store *s, int64_t n, int64_t recompute_from_
     DeviceGuard g(s->device);
     s->size = n;
     ++s->version;
-    if (recompute_from_row >= 0 && recompute_from_row < n)
-        return k_row_inv_norms(s->rows, s->dtype, s->inv_norms, recompute_from_row, n, s->ld, s->extreme, (cudaStream_t)stream);
+    if (recompute_from_row >= 0 && recompute_from_row < n) {
+        if (s->rows_exact) {
+            // rows filled in place are shadow values (vm_synth_fill): their binary64 originals are those values, widened.
+            // The shadow is [n][ld] with leading dimension ld, so it converts as a dense [n][ld] source.
+            const int64_t r0 = recompute_from_row;
+            int rc = k_convert_rows((const char *)s->rows + (size_t)r0 * s->ld * dtype_size(s->dtype), s->dtype,
+                                    s->rows_exact + (size_t)r0 * s->ld, VM_F64, n - r0, s->ld, s->ld, (cudaStream_t)stream);
+            if (rc != VM_OK) return rc;
+        }
+        return k_row_inv_norms(s->rows, s->dtype, s->inv_norms, recompute_from_row, n, s->ld, s->extreme, (cudaStream_t)stream, s->rows_exact);
+    }
     return VM_OK;
 }
 
@@ -578,7 +714,7 @@ static int topk_batch(const TopkCall &c)
         q_dev = w.q_raw.p;
     }
     FinalizeArgs fin{c.k, c.min_score, c.score_mode, c.row_offset, c.d_idx, c.d_score, c.d_count};
-    ExactArgs ex{s->rows, s->inv_norms, s->dtype, s->ld, s->dim, s->size, q_dev, c.q_dtype, c.nq, c.k, c.sum_mode,
+    ExactArgs ex{s->exact_rows(), s->inv_norms, s->exact_dtype(), s->ld, s->dim, s->size, q_dev, c.q_dtype, c.nq, c.k, c.sum_mode,
                  nullptr, (double *)w.xs.p, (uint32_t *)w.xr.p, (int32_t *)w.xc.p, (uint8_t *)w.taken.p, XCTAS, fin, s->cum,
                  (int *)w.done.p};
     if (!(c.flags & FLAG_INTERNAL_CAPTURE)) { ++s->n_batches; s->n_queries += c.nq; }
@@ -615,8 +751,11 @@ static int topk_batch(const TopkCall &c)
 
     int nq_pad = kernel == 2 ? ((c.nq + 15) & ~15) : c.nq;
     // bf16 store: feed the query as hi + lo bf16 terms (two MMAs per K slice) whenever that layout fits shared memory
+    // -- free up to 48 queries per pass (measured, 12.5 M x 384: 1.34 ms either way); at 64 the doubled MMA count makes
+    // the tensor pipe the pacing unit (+4..10 %), and since a wide band is settled inside the rescoring kernel anyway
+    // the single-term query is the default there (VM_FLAG_SPLIT forces the split, VM_FLAG_NO_SPLIT forbids it)
     const int split = (kernel == 2 && s->dtype == VM_BF16 && !(c.flags & VM_FLAG_NO_SPLIT) &&
-                       scan_tc_supported(s->dtype, s->dim, c.nq, kp, 1)) ? 1 : 0;
+                       (c.nq <= 48 || (c.flags & VM_FLAG_SPLIT)) && scan_tc_supported(s->dtype, s->dim, c.nq, kp, 1)) ? 1 : 0;
     // The kernels of one call are chained with programmatic dependent launch (common.cuh): each one's launch and
     // prologue overlap its predecessor's drain.  Off while events bracket the scan (VM_FLAG_TIMING) or a graph is captured.
     const bool pdl = !(c.flags & (VM_FLAG_TIMING | FLAG_INTERNAL_CAPTURE));
@@ -626,7 +765,7 @@ static int topk_batch(const TopkCall &c)
                                  kernel == 2 ? (int)(w.seed.bytes / 4) : 0, kernel == 2 && s->dtype == VM_F32, split, pdl, st);
     if (rc != VM_OK) return rc;
     ++launches;
-    const double eps = scan_eps(kernel, s->dtype, s->dim, split);
+    const double eps = scan_eps(kernel, s->dtype, s->dim, split, s->rows_exact != nullptr);
 
     ScanArgs a;
     ScanInfo sinfo;
@@ -654,7 +793,7 @@ static int topk_batch(const TopkCall &c)
         // small store: too few tiles per CTA for a threshold to form -> rank every row's key instead
         a.dump = tiles <= s->sm_count && tiles * SCAN_DUMP_TILE <= SCAN_DUMP_MAX_KEYS &&
                  (size_t)tiles * c.nq * SCAN_DUMP_TILE * 8 <= w.cand.bytes &&
-                 select_rescore_fits((int)tiles, SCAN_DUMP_TILE, kp, s->dtype, s->dim, s->ld);
+                 select_rescore_fits((int)tiles, SCAN_DUMP_TILE, kp, s->exact_dtype(), s->dim, s->ld);
         rc = launch_scan_tc(a, s->dtype == VM_BF16 ? w.q_bf16.p : w.q_f32.p, (uint32_t *)w.seed.p, (int *)w.flags.p + c.nq + 1, nullptr, &sinfo);
         launches += 1;
     }
@@ -663,7 +802,7 @@ static int topk_batch(const TopkCall &c)
 
     int32_t *flags = (int32_t *)w.flags.p;
     int32_t *uncert = flags + c.nq;  // counter sits right after the nq flags (zeroed by the normalise kernel)
-    RescoreArgs rs{(const uint64_t *)w.merged.p, kp, s->rows, s->inv_norms, s->dtype, s->ld, s->dim, s->size, q_dev,
+    RescoreArgs rs{(const uint64_t *)w.merged.p, kp, s->exact_rows(), s->inv_norms, s->exact_dtype(), s->ld, s->dim, s->size, q_dev,
                    c.q_dtype, c.nq, eps, c.sum_mode, fin, flags, uncert, s->extreme,
                    kernel == 2 ? (float *)w.col_thr.p : nullptr, s->cum};
     // where the candidates are: the union buffer of the tcgen05 scan (complete band), its dumped tiles (every row),

@@ -193,6 +193,10 @@ __device__ __forceinline__ void ref_sum_range(RefSum &acc, int lo, int hi, F pro
 
 __device__ __forceinline__ float load_as_float(const float *p, int64_t i) { return p[i]; }
 __device__ __forceinline__ float load_as_float(const __nv_bfloat16 *p, int64_t i) { return __bfloat162float(p[i]); }
+// one row element as a double (exact widening), by the row's storage type
+__device__ __forceinline__ double load_elem(const float *p, int64_t i) { return (double)p[i]; }
+__device__ __forceinline__ double load_elem(const __nv_bfloat16 *p, int64_t i) { return (double)__bfloat162float(p[i]); }
+__device__ __forceinline__ double load_elem(const double *p, int64_t i) { return p[i]; }
 __device__ __forceinline__ double load_as_double(const void *p, int dtype, int64_t i)
 {
     if (dtype == VM_F32) return (double)((const float *)p)[i];
@@ -230,7 +234,7 @@ struct ScanArgs {
     bool pdl = false;          // launch with programmatic stream serialization
 };
 static constexpr int SCAN_UNION_CAP = 16384; // shared spill-buffer entries per query (filtered with the final bound before staging)
-static constexpr int SCAN_SLAB = 64;          // keys per (CTA, query) slab
+static constexpr int SCAN_SLAB = 128;         // keys per (CTA, query) slab
 static constexpr int SELECT_KEY_CAP = 4096;   // band keys the rescoring kernel stages per query after the final filter
 static constexpr int SCAN_DUMP_TILE = 128;     // rows (= keys per query) per dumped tile
 static constexpr int SCAN_DUMP_MAX_KEYS = 9472;  // per query: what the fused select kernel ranks in shared memory (148 x 64)

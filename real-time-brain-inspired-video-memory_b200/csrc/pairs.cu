@@ -429,7 +429,8 @@ int k_pairs_concat(const void *gathered, size_t per_rank_bytes, int64_t slot, co
     return VM_OK;
 }
 
-int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, int *extreme, cudaStream_t st);
+int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, int *extreme, cudaStream_t st,
+                    const double *exact = nullptr);
 
 namespace {
 struct PairsWs {

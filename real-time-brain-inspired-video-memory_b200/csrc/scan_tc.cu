@@ -108,11 +108,29 @@ static TcLayout make_layout(int dtype, int ld, int nq, int split = 0)
     return L;
 }
 
-// k-th largest score (ordered bits) among the n keys of one slab (global memory; a slot whose store has not landed
-// yet reads as 0 and is ignored): a lower bound on the shard's k-th best, because k rows of this CTA reach it.
-// One thread; rare (once per slab that fills up).
+// k-th largest score (ordered bits) among the first n keys of one slab (global memory; a slot whose store has not
+// landed yet reads as 0 and is ignored): a lower bound on the shard's k-th best, because k rows of this CTA reach it.
+// One thread; rare (twice per slab at most).  k <= 16: one pass with the running top-k in registers.
 __device__ __noinline__ uint32_t own_kth_score(const uint64_t *slab, int n, int k)
 {
+    if (k <= 16) {
+        uint32_t top[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) top[i] = 0u;   // descending
+        for (int j = 0; j < n; ++j) {
+            uint32_t h = (uint32_t)(__ldcg(slab + j) >> 32);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {            // insertion by compare-exchange down the array
+                const uint32_t hi = max(top[i], h);
+                h = min(top[i], h);
+                top[i] = hi;
+            }
+        }
+        uint32_t r = 0u;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r = (i == k - 1) ? top[i] : r;
+        return r;
+    }
     uint32_t upper = 0xFFFFFFFFu;  // exclusive upper bound of the next pick
     int picked = 0;
     uint32_t cur = 0;
@@ -131,7 +149,7 @@ __device__ __noinline__ uint32_t own_kth_score(const uint64_t *slab, int n, int 
     return cur;
 }
 
-template <bool TF32, bool DUMP>
+template <bool TF32, bool DUMP, bool SPLIT>
 __global__ void __launch_bounds__(DUMP ? TC_THREADS : TC_THREADS_SVC, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const float *__restrict__ inv_norms, int64_t n, int num_tiles, int nq, TcLayout L, uint64_t *__restrict__ dump_keys,
@@ -164,7 +182,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
-    const int nq_pad = L.nq_pad, KB = L.KB, stages = L.stages, split = L.split;
+    const int nq_pad = L.nq_pad, KB = L.KB, stages = L.stages;
     constexpr int ELEMS = TF32 ? 32 : 64;  // elements per 128-byte K block
 
     if (warp == 0 && lane == 0) {
@@ -196,55 +214,63 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
-            const int kbq = KB * (split ? 2 : 1);  // query blocks: hi part, then (split) lo part = rows [nq_pad, 2 nq_pad) of tmB
-            mbar_arrive_expect_tx(qfull, (uint32_t)kbq * nq_pad * 128);
-            for (int kb = 0; kb < kbq; ++kb)
-                tma_load_2d(&tmB, qfull, sB + (size_t)kb * nq_pad * 128, (kb % KB) * ELEMS, (kb / KB) * nq_pad, L2_EVICT_LAST);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                for (int kb = 0; kb < KB; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+        // The whole warp runs the loop converged and ONE elected lane issues (elect.sync): the compiler then keeps the
+        // loop state in uniform registers instead of wrapping every issue in a per-lane loop.  The issue thread's
+        // instruction count per 16 KB block is what bounds a bf16 scan (2.2 us per tile), so it is kept minimal.
+        if (elect_one()) {
+            constexpr int QPARTS = SPLIT ? 2 : 1;  // query blocks: hi part, then (split) lo part = rows [nq_pad, 2 nq_pad) of tmB
+            mbar_arrive_expect_tx(qfull, (uint32_t)(KB * QPARTS) * nq_pad * 128);
+            for (int part = 0; part < QPARTS; ++part)
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_2d(&tmB, qfull, sB + (size_t)(part * KB + kb) * nq_pad * 128, kb * ELEMS, part * nq_pad, L2_EVICT_LAST);
+        }
+        __syncwarp();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
                     tma_load_2d(&tmA, &full[stage], sA + (size_t)stage * TC_STAGE_BYTES, kb * ELEMS, tile * TC_BLOCK_M, L2_EVICT_FIRST);
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, TC_BLOCK_M, (uint32_t)nq_pad);
-            mbar_wait(qfull, 0);
+        // Same scheme: converged warp, one elected lane issues the MMAs of a block and its commit.  Descriptors are
+        // the stage-0 descriptor plus an offset in the 14-bit start-address field (units of 16 bytes).
+        const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, TC_BLOCK_M, (uint32_t)nq_pad);
+        mbar_wait(qfull, 0);
+        tc_fence_after();
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        const uint64_t da0 = make_smem_desc_sw128(smem_u32(sA)), db0 = make_smem_desc_sw128(smem_u32(sB));
+        const uint32_t kb_step = (uint32_t)(nq_pad * 128) >> 4, lo_step = (uint32_t)(KB * nq_pad * 128) >> 4;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
             tc_fence_after();
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-            const uint32_t lo_off = (uint32_t)KB * nq_pad * 128;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * nq_pad);
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * nq_pad);
-                for (int kb = 0; kb < KB; ++kb) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = a0 + (uint32_t)stage * TC_STAGE_BYTES;
-                    const uint32_t b_addr = b0 + (uint32_t)kb * nq_pad * 128;
+                if (elect_one()) {
+                    const uint64_t da = da0 + (uint64_t)((uint32_t)stage * (TC_STAGE_BYTES >> 4));
+                    const uint64_t db = db0 + (uint64_t)((uint32_t)kb * kb_step);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {  // 4 x 32-byte K slices per 128-byte swizzle row
-                        const uint64_t da = make_smem_desc_sw128(a_addr + j * 32);
-                        umma<TF32>(d_tmem, da, make_smem_desc_sw128(b_addr + j * 32), idesc, (uint32_t)((kb | j) != 0));
-#ifndef VIDMEM_AB_NOSPLITCODE
-                        if (!TF32 && split) umma<TF32>(d_tmem, da, make_smem_desc_sw128(b_addr + lo_off + j * 32), idesc, 1u);
-#endif
+                        umma<TF32>(d_tmem, da + 2 * j, db + 2 * j, idesc, (uint32_t)((kb | j) != 0));
+                        if constexpr (SPLIT) umma<TF32>(d_tmem, da + 2 * j, db + lo_step + 2 * j, idesc, 1u);
                     }
-                    umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                    umma_commit(&empty[stage]);               // stage reusable once these MMAs have read it
+                    if (kb == KB - 1) umma_commit(&tfull[acc]);  // ... and the accumulator is complete
                 }
-                umma_commit(&tfull[acc]);  // accumulator complete
-                if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == stages) { stage = 0; phase ^= 1; }
             }
+            if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp < 6) {
         // ================================ epilogue =====================================
@@ -445,7 +471,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int G = (int)gridDim.x;
             while (s_done[1] == 0 && s_done[0] < 4) __nanosleep(100);   // wait for the seed phase (it writes tauf)
             uint32_t pub0 = 0xFFFFFFFFu, pub1 = 0xFFFFFFFFu;            // running maxima last written to the table (lanes q, q+32)
-            uint32_t kth_done = 0;                                       // bit 0 / 1: own k-th already published for q / q+32
+            uint32_t kth_done = 0;                                       // 2 bits per owned query (q, q+32): own k-th published at half / full slab
             const uint64_t *my_slab = ub.slab + (size_t)blockIdx.x * nq * SCAN_SLAB;
             // the exit test is a warp vote: a lane that lags behind must not leave the loop while the others
             // are already inside the next round's warp reductions
@@ -468,13 +494,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (lane == 0 && sd > -INFINITY) atomicMax(gbound + q, f32_ordered(sd));
                     }
                 __syncwarp();
-                // 3. a slab that has filled up: this CTA's own k-th best is a valid bound too (k of its rows reach it)
+                // 3. a slab that is half full / full: this CTA's own k-th best is a valid bound too (k of its rows reach it)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int q = lane + 32 * h;
-                    if (q < nq && !((kth_done >> h) & 1u) && *(volatile int *)(lcnt + q) >= SCAN_SLAB) {
-                        const uint32_t ok = own_kth_score(my_slab + (size_t)q * SCAN_SLAB, SCAN_SLAB, ub.ksel);
-                        if (ok != 0u) { atomicMax(gbound + q, ok); kth_done |= 1u << h; }
+                    if (q < nq) {
+                        const int have = *(volatile int *)(lcnt + q);
+                        const int level = have >= SCAN_SLAB ? 2 : (have >= SCAN_SLAB / 2 ? 1 : 0);
+                        const int done = (int)((kth_done >> (2 * h)) & 3u);
+                        if (level > done) {
+                            const uint32_t ok = own_kth_score(my_slab + (size_t)q * SCAN_SLAB, level == 2 ? SCAN_SLAB : SCAN_SLAB / 2, ub.ksel);
+                            if (ok != 0u) { atomicMax(gbound + q, ok); kth_done = (kth_done & ~(3u << (2 * h))) | ((uint32_t)level << (2 * h)); }
+                        }
                     }
                 }
                 __syncwarp();
@@ -547,27 +578,28 @@ int launch_scan_tc(const ScanArgs &a, const void *queries_store_dtype, uint32_t 
 #ifdef VIDMEM_AB_SVCSLEEP
     const int svc_sleep = VIDMEM_AB_SVCSLEEP;
 #else
-    const int svc_sleep = a.dtype == VM_F32 ? 1000 : 200;
+    const int svc_sleep = a.dtype == VM_F32 ? 500 : 200;
 #endif
     if (info && !sc) { info->stages = L.stages; info->variant = dump ? 1 : 2; }
     const bool pdl = a.pdl && !sc;
 #ifdef VIDMEM_AB_CLASSIC_LAUNCH
-#define LAUNCH_IMPL(TF, DU) scan_tc_kernel<TF, DU><<<a.ctas, DU ? TC_THREADS : TC_THREADS_SVC, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, seed_tab, seed_ctr, col, ub, svc_sleep)
+#define LAUNCH_IMPL(TF, DU, SP) scan_tc_kernel<TF, DU, SP><<<a.ctas, DU ? TC_THREADS : TC_THREADS_SVC, L.total, a.stream>>>(tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, seed_tab, seed_ctr, col, ub, svc_sleep)
 #else
-#define LAUNCH_IMPL(TF, DU) VM_CUDA_CHECK(launch_pdl(scan_tc_kernel<TF, DU>, dim3(a.ctas), dim3(DU ? TC_THREADS : TC_THREADS_SVC), L.total, a.stream, pdl, \
+#define LAUNCH_IMPL(TF, DU, SP) VM_CUDA_CHECK(launch_pdl(scan_tc_kernel<TF, DU, SP>, dim3(a.ctas), dim3(DU ? TC_THREADS : TC_THREADS_SVC), L.total, a.stream, pdl, \
                                  tmA, tmB, a.inv_norms, a.n, num_tiles, a.nq, L, a.cand, seed_tab, seed_ctr, col, ub, svc_sleep))
 #endif
-#define LAUNCH_TC(TF, DU)                                                                                                  \
+#define LAUNCH_TC(TF, DU, SP)                                                                                                \
     do {                                                                                                                   \
         static bool set[64] = {}; /* the attribute is per device */                                                        \
         if (!set[dev_idx]) {                                                                                               \
-            VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<TF, DU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            VM_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<TF, DU, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
             set[dev_idx] = true;                                                                                           \
         }                                                                                                                  \
-        LAUNCH_IMPL(TF, DU);                                                                                             \
+        LAUNCH_IMPL(TF, DU, SP);                                                                                           \
     } while (0)
-    if (a.dtype == VM_F32) { if (dump) LAUNCH_TC(true, true); else LAUNCH_TC(true, false); }
-    else { if (dump) LAUNCH_TC(false, true); else LAUNCH_TC(false, false); }
+    if (a.dtype == VM_F32) { if (dump) LAUNCH_TC(true, true, false); else LAUNCH_TC(true, false, false); }
+    else if (L.split) { if (dump) LAUNCH_TC(false, true, true); else LAUNCH_TC(false, false, true); }
+    else { if (dump) LAUNCH_TC(false, true, false); else LAUNCH_TC(false, false, false); }
 #undef LAUNCH_TC
 #undef LAUNCH_IMPL
     VM_CUDA_CHECK(cudaGetLastError());

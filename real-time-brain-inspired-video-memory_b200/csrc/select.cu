@@ -187,7 +187,7 @@ __device__ double exact_cosine(const void *q, int q_dtype, int64_t qoff, const T
     dot.init(); qq.init(); rr.init();
     for (int i = 0; i < dim; ++i) {
         double x = load_as_double(q, q_dtype, qoff + i);
-        double y = (double)load_as_float(row, i);
+        double y = load_elem(row, i);
         dot.add<NEUMAIER>(__dmul_rn(x, y));
         qq.add<NEUMAIER>(__dmul_rn(x, x));
         rr.add<NEUMAIER>(__dmul_rn(y, y));
@@ -204,8 +204,8 @@ __device__ double exact_cosine_sq(const double *sq, double n1, const T *row, int
 {
     RefSum dot, rr;
     dot.init(); rr.init();
-    ref_sum_range<NEUMAIER>(dot, 0, dim, [&](int i) { return __dmul_rn(sq[i], (double)load_as_float(row, i)); });
-    ref_sum_range<NEUMAIER>(rr, 0, dim, [&](int i) { const double y = (double)load_as_float(row, i); return __dmul_rn(y, y); });
+    ref_sum_range<NEUMAIER>(dot, 0, dim, [&](int i) { return __dmul_rn(sq[i], load_elem(row, i)); });
+    ref_sum_range<NEUMAIER>(rr, 0, dim, [&](int i) { const double y = load_elem(row, i); return __dmul_rn(y, y); });
     double n2 = __dsqrt_rn(rr.result<NEUMAIER>());
     if (n1 == 0.0 || n2 == 0.0) return 0.0;
     return __ddiv_rn(dot.result<NEUMAIER>(), __dmul_rn(n1, n2));
@@ -242,6 +242,15 @@ __device__ __forceinline__ void load_vec16(const __nv_bfloat16 *p, float *o)
     o[6] = __uint_as_float(u.w << 16); o[7] = __uint_as_float(u.w & 0xffff0000u);
 }
 
+__device__ __forceinline__ void load_vec16(const double *p, double *o)
+{
+    const double2 t = *reinterpret_cast<const double2 *>(p);
+    o[0] = t.x; o[1] = t.y;
+}
+// what a staged row element is held as in shared memory: float is exact for fp32 / bf16 rows, binary64 rows stay binary64
+template <typename T> struct StageOf { using type = float; };
+template <> struct StageOf<double> { using type = double; };
+
 template <bool NEUMAIER, typename T>
 __global__ void __launch_bounds__(RS_THREADS, 1) rescore_kernel(const uint64_t *__restrict__ merged, int kp, const T *__restrict__ rows,
                                                             const float *__restrict__ inv_norms, int ld, int dim, int64_t n_rows,
@@ -254,7 +263,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rescore_kernel(const uint64_t *
     constexpr int VEC = 16 / (int)sizeof(T);      // elements per 16-byte load
     extern __shared__ double rs_smem[];
     double *sq = rs_smem;                          // [chunk] query as doubles
-    float *srow = reinterpret_cast<float *>(rs_smem + chunk);  // [kp][chunk + 1] candidate rows (odd pitch)
+    using S = typename StageOf<T>::type;
+    S *srow = reinterpret_cast<S *>(rs_smem + chunk);  // [kp][chunk + 1] candidate rows (odd pitch)
     const int pitch = chunk + 1;
     __shared__ double s_dot[64], s_rr[64], s_qq;
     __shared__ double s_score[64];
@@ -282,7 +292,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rescore_kernel(const uint64_t *
         // stage the candidate rows: batches of 4 independent 16-byte loads per thread
         const int groups = kp * vlen;
         for (int g0 = j; g0 < groups; g0 += 4 * RS_THREADS) {
-            float buf[4][VEC];
+            S buf[4][VEC];
             int rr_[4], cc_[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -292,7 +302,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rescore_kernel(const uint64_t *
                 if (rr_[u] >= 0 && s_valid[rr_[u]]) load_vec16(rows + (int64_t)s_row[rr_[u]] * ld + c0 + cc_[u], buf[u]);
                 else
 #pragma unroll
-                    for (int x = 0; x < VEC; ++x) buf[u][x] = 0.0f;
+                    for (int x = 0; x < VEC; ++x) buf[u][x] = (S)0;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
@@ -303,7 +313,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rescore_kernel(const uint64_t *
         }
         __syncthreads();
         if (active) {
-            const float *mine = srow + cand * pitch;
+            const S *mine = srow + cand * pitch;
             if (kind == 0)
                 ref_sum_range<NEUMAIER>(acc, 0, len, [&](int i) { return __dmul_rn(sq[i], (double)mine[i]); });
             else if (kind == 1)
@@ -390,46 +400,55 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 static constexpr int SR_THREADS = 512;
 static constexpr int BAND_CAP = 1024;  // rows of one query's near-tie band the kernel rescores itself
 
-// Exact top-k among m gathered rows (block-wide): every row is scored with the reference recurrence by one thread
-// (one sequential chain pair per row), then k rounds of block-wide arg-best by (score desc, row asc) emit the list.
-// s_sc / s_row / s_taken: [m] scratch; w_*: one slot per warp.  Returns the number of entries emitted (uniform).
+// Exact top-k among m gathered rows (block-wide).  The rows sit in DRAM (the scan streams them through L2 with
+// evict-first), so all their 128-byte lines are first pulled into L2 by the whole block at once -- a thread walking
+// its row would otherwise pay one serial DRAM miss per line.  Then 2m independent sequential chains (dot and
+// ||row||^2 per row: the reference recurrences, in index order) run on 2m threads, every row is ranked by counting
+// the rows that beat it (score desc, row asc: keys are unique, so ranks are) and the first k are emitted.
+// s_sc / s_rr / s_row: [m] scratch.  Returns the number of entries emitted (uniform).
 template <bool NEUMAIER, typename T, int THREADS>
-__device__ int band_topk(const T *__restrict__ rows, int ld, int dim, const double *sq, double n1, int m, double *s_sc, uint32_t *s_row,
-                         unsigned char *s_taken, double *w_s, uint32_t *w_r, int *w_p, int *s_out, const FinalizeArgs &f, int q)
+__device__ int band_topk(const T *__restrict__ rows, int ld, int dim, const double *sq, double n1, int m, double *s_sc, double *s_rr,
+                         uint32_t *s_row, int *s_out, const FinalizeArgs &f, int q)
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     if (tid == 0) *s_out = 0;
-    for (int e = tid; e < m; e += THREADS) {
-        s_sc[e] = exact_cosine_sq<NEUMAIER, T>(sq, n1, rows + (int64_t)s_row[e] * ld, dim);
-        s_taken[e] = 0;
+    const int lines = (ld * (int)sizeof(T) + 127) / 128;
+    for (int e = tid; e < m * lines; e += THREADS) {
+        const int r = e / lines, l = e - r * lines;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(rows + (int64_t)s_row[r] * ld) + (size_t)l * 128));
+    }
+    for (int t = tid; t < 2 * m; t += THREADS) {
+        const int e = t >> 1;
+        const T *row = rows + (int64_t)s_row[e] * ld;
+        RefSum acc;
+        acc.init();
+        if (t & 1) {
+            ref_sum_range<NEUMAIER>(acc, 0, dim, [&](int i) { const double y = load_elem(row, i); return __dmul_rn(y, y); });
+            s_rr[e] = acc.result<NEUMAIER>();
+        } else {
+            ref_sum_range<NEUMAIER>(acc, 0, dim, [&](int i) { return __dmul_rn(sq[i], load_elem(row, i)); });
+            s_sc[e] = acc.result<NEUMAIER>();
+        }
     }
     __syncthreads();
-    for (int r = 0; r < f.k; ++r) {
-        double bs = 0.0; uint32_t br = 0; int bp = -1;
-        for (int e = tid; e < m; e += THREADS)
-            if (!s_taken[e] && (bp < 0 || better(s_sc[e], s_row[e], bs, br))) { bs = s_sc[e]; br = s_row[e]; bp = e; }
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ts = __shfl_xor_sync(0xffffffffu, bs, o);
-            const uint32_t tr = __shfl_xor_sync(0xffffffffu, br, o);
-            const int tp = __shfl_xor_sync(0xffffffffu, bp, o);
-            if (tp >= 0 && (bp < 0 || better(ts, tr, bs, br))) { bs = ts; br = tr; bp = tp; }
-        }
-        if (lane == 0) { w_s[warp] = bs; w_r[warp] = br; w_p[warp] = bp; }
-        __syncthreads();
-        bs = w_s[0]; br = w_r[0]; bp = w_p[0];
-        for (int w = 1; w < THREADS / 32; ++w)
-            if (w_p[w] >= 0 && (bp < 0 || better(w_s[w], w_r[w], bs, br))) { bs = w_s[w]; br = w_r[w]; bp = w_p[w]; }
-        if (bp < 0) break;  // uniform
-        if (tid == 0) {
-            s_taken[bp] = 1;
-            const double outv = convert_score(bs, f.score_mode);
-            if (outv > f.min_score) {
-                f.out_idx[(int64_t)q * f.k + r] = (int64_t)br + f.row_offset;
-                f.out_score[(int64_t)q * f.k + r] = outv;
-                *s_out = r + 1;
+    for (int e = tid; e < m; e += THREADS) {
+        const double n2 = __dsqrt_rn(s_rr[e]);
+        s_sc[e] = (n1 == 0.0 || n2 == 0.0) ? 0.0 : __ddiv_rn(s_sc[e], __dmul_rn(n1, n2));
+    }
+    __syncthreads();
+    for (int e = tid; e < m; e += THREADS) {
+        const double sc = s_sc[e];
+        const uint32_t row = s_row[e];
+        int rank = 0;
+        for (int i = 0; i < m && rank < f.k; ++i) rank += better(s_sc[i], s_row[i], sc, row) ? 1 : 0;  // k better rows: out
+        if (rank < f.k) {
+            const double outv = convert_score(sc, f.score_mode);
+            if (outv > f.min_score) {   // scores descend with the rank, so the emitted entries are a prefix
+                f.out_idx[(int64_t)q * f.k + rank] = (int64_t)row + f.row_offset;
+                f.out_score[(int64_t)q * f.k + rank] = outv;
+                atomicMax(s_out, rank + 1);
             }
         }
-        __syncthreads();
     }
     __syncthreads();
     const int cntv = *s_out;
@@ -481,15 +500,28 @@ __device__ int load_slab_keys(const SelectSrc &src, int q, int nq, uint64_t *ske
     for (int c = tid; c < src.ctas; c += THREADS) s_cnts[c] = min(src.scnt[(size_t)c * nq + q], SCAN_SLAB);
     __syncthreads();
     const float bf = *s_bf;
-    for (int idx = tid; idx < src.ctas * SCAN_SLAB; idx += THREADS) {
-        const int c = idx / SCAN_SLAB, j = idx - c * SCAN_SLAB;
-        if (j < s_cnts[c]) {
-            const uint64_t k = __ldcg(src.slab + ((size_t)c * nq + q) * SCAN_SLAB + j);
-            if (k != 0 && key_score(k) >= bf) {
-                const int p = atomicAdd(s_total, 1);
-                if (p < src.key_cap) skeys[p] = k;
-            }
+    // one warp per slab, lanes over its (contiguous) keys; the loads of four slabs are issued before any is consumed
+    constexpr int WARPS = THREADS / 32, PER = SCAN_SLAB / 32, BATCH = 4;
+    for (int c0 = warp; c0 < src.ctas; c0 += WARPS * BATCH) {
+        uint64_t kk[BATCH][PER];
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+            const int c = c0 + b * WARPS;
+            const int cnt = c < src.ctas ? s_cnts[c] : 0;
+#pragma unroll
+            for (int t = 0; t < PER; ++t)
+                kk[b][t] = (lane + 32 * t < cnt) ? __ldcg(src.slab + ((size_t)c * nq + q) * SCAN_SLAB + lane + 32 * t) : 0ull;
         }
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b)
+#pragma unroll
+            for (int t = 0; t < PER; ++t) {
+                const uint64_t k = kk[b][t];
+                if (k != 0 && key_score(k) >= bf) {
+                    const int p = atomicAdd(s_total, 1);
+                    if (p < src.key_cap) skeys[p] = k;
+                }
+            }
     }
     const int spilled = src.ucnt[q];
     const int ns = min(spilled, src.ucap);
@@ -578,9 +610,6 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(SelectSrc
     __shared__ uint32_t s_L;
     __shared__ float s_thr, s_bf;
     __shared__ double s_dot[64], s_rr[64], s_qq, s_score[64];
-    __shared__ double w_s[SR_THREADS / 32];
-    __shared__ uint32_t w_r[SR_THREADS / 32];
-    __shared__ int w_p[SR_THREADS / 32];
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     pdl_launch_dependents();
@@ -725,9 +754,9 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(SelectSrc
         const int i_lo = g_lo * EPG, i_hi = min(g_hi * EPG, dim);
         if (active) {
             if (kind == 0)
-                ref_sum_range<NEUMAIER>(acc, i_lo, i_hi, [&](int i) { return __dmul_rn(sq[i], (double)load_as_float(mine, i)); });
+                ref_sum_range<NEUMAIER>(acc, i_lo, i_hi, [&](int i) { return __dmul_rn(sq[i], load_elem(mine, i)); });
             else if (kind == 1)
-                ref_sum_range<NEUMAIER>(acc, i_lo, i_hi, [&](int i) { const double y = (double)load_as_float(mine, i); return __dmul_rn(y, y); });
+                ref_sum_range<NEUMAIER>(acc, i_lo, i_hi, [&](int i) { const double y = load_elem(mine, i); return __dmul_rn(y, y); });
             else
                 ref_sum_range<NEUMAIER>(acc, i_lo, i_hi, [&](int i) { const double x = sq[i]; return __dmul_rn(x, x); });
         }
@@ -808,8 +837,8 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(SelectSrc
     if (bound_ok && src_complete && band <= BAND_CAP) {
         // ---------------- E. settle from the band ----------------
         double *b_sc = reinterpret_cast<double *>(srow);
-        uint32_t *b_row = reinterpret_cast<uint32_t *>(b_sc + BAND_CAP);
-        unsigned char *b_taken = reinterpret_cast<unsigned char *>(b_row + BAND_CAP);
+        double *b_rr = b_sc + BAND_CAP;
+        uint32_t *b_row = reinterpret_cast<uint32_t *>(b_rr + BAND_CAP);
         if (tid == 0) s_m = 0;
         __syncthreads();
         for (int e = tid; e < total; e += SR_THREADS) {
@@ -817,7 +846,7 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(SelectSrc
             if (k != 0 && key_score(k) >= thr) b_row[atomicAdd(&s_m, 1)] = key_row(k);
         }
         __syncthreads();
-        band_topk<NEUMAIER, T, SR_THREADS>(rows, ld, dim, sq, n1, band, b_sc, b_row, b_taken, w_s, w_r, w_p, &s_out, f, q);
+        band_topk<NEUMAIER, T, SR_THREADS>(rows, ld, dim, sq, n1, band, b_sc, b_rr, b_row, &s_out, f, q);
         if (tid == 0) {
             flags[q] = 0;
             if (collect_thr) collect_thr[q] = INFINITY;
@@ -863,11 +892,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) collect_rescore_kernel(const ui
     extern __shared__ __align__(16) unsigned char cr_smem[];
     double *sq = reinterpret_cast<double *>(cr_smem);               // [dim]
     double *s_sc = sq + ((dim + 1) & ~1);                           // [cap]
-    uint32_t *s_row = reinterpret_cast<uint32_t *>(s_sc + cap);     // [cap]
-    unsigned char *s_taken = reinterpret_cast<unsigned char *>(s_row + cap);  // [cap]
-    __shared__ double w_s[CR_THREADS / 32];
-    __shared__ uint32_t w_r[CR_THREADS / 32];
-    __shared__ int w_p[CR_THREADS / 32];
+    double *s_rr = s_sc + cap;                                      // [cap]
+    uint32_t *s_row = reinterpret_cast<uint32_t *>(s_rr + cap);     // [cap]
     __shared__ double s_n1;
     __shared__ int s_out;
     const int q = blockIdx.x, tid = threadIdx.x;
@@ -886,7 +912,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) collect_rescore_kernel(const ui
         s_n1 = __dsqrt_rn(qq.result<NEUMAIER>());
     }
     __syncthreads();
-    band_topk<NEUMAIER, T, CR_THREADS>(rows, ld, dim, sq, s_n1, m, s_sc, s_row, s_taken, w_s, w_r, w_p, &s_out, f, q);
+    band_topk<NEUMAIER, T, CR_THREADS>(rows, ld, dim, sq, s_n1, m, s_sc, s_rr, s_row, &s_out, f, q);
     if (tid == 0) {
         flags[q] = 0;
         atomicSub(uncertified_count, 1);
@@ -1291,12 +1317,14 @@ int k_rescore(const RescoreArgs &a, cudaStream_t st, const int *incomplete)
                                                                a.uncertified_count, chunk, a.extreme, a.collect_thr, a.cum, incomplete);         \
     } while (0)
     // column chunk: whole rows when kp rows fit in RS_SMEM_ROW_BYTES, else a multiple of 8 columns
-    int chunk = RS_SMEM_ROW_BYTES / (4 * a.kp) - 1;
+    const int ssz = a.dtype == VM_F64 ? 8 : 4;  // staged element size (StageOf)
+    int chunk = RS_SMEM_ROW_BYTES / (ssz * a.kp) - 1;
     chunk &= ~7;
     if (chunk > a.ld) chunk = a.ld;
-    const size_t smem = (size_t)chunk * sizeof(double) + (size_t)a.kp * (chunk + 1) * sizeof(float) + 16;
+    const size_t smem = (size_t)chunk * sizeof(double) + (size_t)a.kp * (chunk + 1) * ssz + 16;
     bool neu = a.sum_mode == VM_SUM_NEUMAIER;
     if (a.dtype == VM_F32) { if (neu) LAUNCH_RS(true, float); else LAUNCH_RS(false, float); }
+    else if (a.dtype == VM_F64) { if (neu) LAUNCH_RS(true, double); else LAUNCH_RS(false, double); }
     else { if (neu) LAUNCH_RS(true, __nv_bfloat16); else LAUNCH_RS(false, __nv_bfloat16); }
 #undef LAUNCH_RS
     VM_CUDA_CHECK(cudaGetLastError());
@@ -1309,9 +1337,9 @@ int k_rescore(const RescoreArgs &a, cudaStream_t st, const int *incomplete)
 // caller must report) when it does not apply.
 static size_t select_rescore_smem(int key_cap, int lists, int kp, int dtype, int dim, int ld)
 {
-    const int es = dtype == VM_F32 ? 4 : 2;
+    const int es = (int)dtype_size(dtype);
     size_t rows_area = (size_t)kp * ((size_t)ld * es + 16);
-    const size_t band_area = (size_t)BAND_CAP * (8 + 4 + 1) + 16;
+    const size_t band_area = (size_t)BAND_CAP * (8 + 8 + 4) + 16;
     if (rows_area < band_area) rows_area = band_area;
     return (size_t)key_cap * 8 + (size_t)((lists + 3) & ~3) * 4 + (size_t)((dim + 1) & ~1) * 8 + rows_area + 32;
 }
@@ -1351,6 +1379,7 @@ int k_select_rescore(const SelectArgs &sa, const RescoreArgs &a, cudaStream_t st
     } while (0)
     const bool neu = a.sum_mode == VM_SUM_NEUMAIER;
     if (a.dtype == VM_F32) { if (neu) LAUNCH_SR(true, float); else LAUNCH_SR(false, float); }
+    else if (a.dtype == VM_F64) { if (neu) LAUNCH_SR(true, double); else LAUNCH_SR(false, double); }
     else { if (neu) LAUNCH_SR(true, __nv_bfloat16); else LAUNCH_SR(false, __nv_bfloat16); }
 #undef LAUNCH_SR
     VM_CUDA_CHECK(cudaGetLastError());
@@ -1369,7 +1398,7 @@ int k_slab_top(const SelectArgs &sa, int nq, int kp, uint64_t *merged, int *inco
 
 int k_collect_rescore(const uint64_t *buf, const int *cnt, int cap, const RescoreArgs &a, cudaStream_t st)
 {
-    const size_t smem = (size_t)((a.dim + 1) & ~1) * 8 + (size_t)cap * (8 + 4 + 1) + 32;
+    const size_t smem = (size_t)((a.dim + 1) & ~1) * 8 + (size_t)cap * (8 + 8 + 4) + 32;
     VM_REQUIRE(smem <= 200 * 1024, VM_ERR_UNSUPPORTED, "collect pass: buffer of %d rows exceeds shared memory", cap);
 #define LAUNCH_CR(NEU, T)                                                                                               \
     do {                                                                                                                \
@@ -1385,6 +1414,7 @@ int k_collect_rescore(const uint64_t *buf, const int *cnt, int cap, const Rescor
     } while (0)
     const bool neu = a.sum_mode == VM_SUM_NEUMAIER;
     if (a.dtype == VM_F32) { if (neu) LAUNCH_CR(true, float); else LAUNCH_CR(false, float); }
+    else if (a.dtype == VM_F64) { if (neu) LAUNCH_CR(true, double); else LAUNCH_CR(false, double); }
     else { if (neu) LAUNCH_CR(true, __nv_bfloat16); else LAUNCH_CR(false, __nv_bfloat16); }
 #undef LAUNCH_CR
     VM_CUDA_CHECK(cudaGetLastError());
@@ -1405,6 +1435,7 @@ int k_exact(const ExactArgs &a, cudaStream_t st, bool pdl)
                              a.xlist_cnt, a.cum, conditional ? a.done_ctr : (int *)nullptr, a.fin, a.taken))
     bool neu = a.sum_mode == VM_SUM_NEUMAIER;
     if (a.dtype == VM_F32) { if (neu) LAUNCH_EX(true, float); else LAUNCH_EX(false, float); }
+    else if (a.dtype == VM_F64) { if (neu) LAUNCH_EX(true, double); else LAUNCH_EX(false, double); }
     else { if (neu) LAUNCH_EX(true, __nv_bfloat16); else LAUNCH_EX(false, __nv_bfloat16); }
 #undef LAUNCH_EX
     VM_CUDA_CHECK(cudaGetLastError());

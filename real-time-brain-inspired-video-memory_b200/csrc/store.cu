@@ -5,7 +5,8 @@
 
 namespace vm {
 
-// src [n][dim] (f32/bf16/f64) -> dst [n][ld] (f32/bf16), zero padded columns [dim, ld).
+// src [n][dim] (f32/bf16/f64) -> dst [n][ld] (f32/bf16, or f64: the exact copy of a binary64 store), zero padded
+// columns [dim, ld).
 template <typename DST>
 __global__ void convert_rows_kernel(const void *__restrict__ src, int src_dtype, DST *__restrict__ dst, int64_t n,
                                     int dim, int ld)
@@ -14,15 +15,14 @@ __global__ void convert_rows_kernel(const void *__restrict__ src, int src_dtype,
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = e / ld;
         int c = (int)(e - r * ld);
-        float v = 0.0f;
-        if (c < dim) {
-            int64_t si = r * dim + c;
-            if (src_dtype == VM_F32) v = ((const float *)src)[si];
-            else if (src_dtype == VM_BF16) v = __bfloat162float(((const __nv_bfloat16 *)src)[si]);
-            else v = (float)((const double *)src)[si];  // binary64 -> binary32, round to nearest
+        double dv = 0.0;
+        if (c < dim) dv = load_as_double(src, src_dtype, r * dim + c);
+        if constexpr (sizeof(DST) == 8) dst[e] = dv;  // widening is exact
+        else {
+            const float v = (float)dv;                // binary64 -> binary32, round to nearest
+            if constexpr (sizeof(DST) == 4) dst[e] = v;
+            else dst[e] = __float2bfloat16_rn(v);
         }
-        if constexpr (sizeof(DST) == 4) dst[e] = v;
-        else dst[e] = __float2bfloat16_rn(v);
     }
 }
 
@@ -32,9 +32,13 @@ __global__ void convert_rows_kernel(const void *__restrict__ src, int src_dtype,
 // error bound assumes normal-range arithmetic (tensor cores flush fp32 denormals, huge rows overflow the
 // fp32 accumulator), so any such row makes the exact pass re-do every query of this store.
 // Rows with a non-finite norm (NaN / Inf elements) are marked skipped.
+// exact (binary64 store only, else NULL): the binary64 originals of the rows.  The scan works on `rows`, their rounded
+// shadow: a row whose shadow lost it (all elements flushed to zero, or pushed to infinity, by the rounding) while the
+// original is an ordinary vector is counted as extreme as well, and keeps inverse norm 0 instead of "skipped" -- the
+// binary64 pass then scores it from the original.
 template <typename T>
 __global__ void row_inv_norms_kernel(const T *__restrict__ rows, float *__restrict__ inv_norms, int64_t row0,
-                                     int64_t n, int ld, int *__restrict__ extreme)
+                                     int64_t n, int ld, int *__restrict__ extreme, const double *__restrict__ exact)
 {
     int lane = threadIdx.x & 31;
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -47,12 +51,24 @@ __global__ void row_inv_norms_kernel(const T *__restrict__ rows, float *__restri
             ss += v * v;
         }
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        double se = 0.0;   // exact rows: scaled squared norm of the original (scaled so that it cannot overflow)
+        if (exact != nullptr) {
+            for (int c = lane; c < ld; c += 32) {
+                const double v = exact[r * (int64_t)ld + c] * 0x1p-600;
+                se += v * v;
+            }
+            for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+        }
         if (lane == 0) {
             float inv = 0.0f;
-            if (!isfinite(ss)) inv = -1.0f;
-            else if (ss > 0.0) {
+            if (!isfinite(ss)) {
+                inv = -1.0f;
+                if (exact != nullptr && isfinite(se)) { inv = 0.0f; if (extreme) atomicAdd(extreme, 1); }  // finite original
+            } else if (ss > 0.0) {
                 inv = (float)(1.0 / sqrt(ss));
                 if (extreme && (ss < 7.52316384526264e-37 || ss > 1.329227995784916e+36)) atomicAdd(extreme, 1);
+            } else if (exact != nullptr && se != 0.0) {
+                if (extreme) atomicAdd(extreme, 1);                                                     // shadow flushed to zero
             }
             inv_norms[r] = inv;
         }
@@ -150,18 +166,20 @@ int k_convert_rows(const void *src, int src_dtype, void *dst, int dst_dtype, int
     int64_t total = n * (int64_t)ld;
     int grid = (int)vm::imin64((total + 255) / 256, 148 * 16);
     if (dst_dtype == VM_F32) convert_rows_kernel<float><<<grid, 256, 0, st>>>(src, src_dtype, (float *)dst, n, dim, ld);
+    else if (dst_dtype == VM_F64) convert_rows_kernel<double><<<grid, 256, 0, st>>>(src, src_dtype, (double *)dst, n, dim, ld);
     else convert_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, src_dtype, (__nv_bfloat16 *)dst, n, dim, ld);
     VM_CUDA_CHECK(cudaGetLastError());
     return VM_OK;
 }
 
-int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, int *extreme, cudaStream_t st)
+int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0, int64_t n, int ld, int *extreme, cudaStream_t st,
+                    const double *exact)
 {
     if (n <= row0) return VM_OK;
     int64_t warps = n - row0;
     int grid = (int)vm::imin64((warps * 32 + 255) / 256, 148 * 16);
-    if (dtype == VM_F32) row_inv_norms_kernel<float><<<grid, 256, 0, st>>>((const float *)rows, inv_norms, row0, n, ld, extreme);
-    else row_inv_norms_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)rows, inv_norms, row0, n, ld, extreme);
+    if (dtype == VM_F32) row_inv_norms_kernel<float><<<grid, 256, 0, st>>>((const float *)rows, inv_norms, row0, n, ld, extreme, exact);
+    else row_inv_norms_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)rows, inv_norms, row0, n, ld, extreme, exact);
     VM_CUDA_CHECK(cudaGetLastError());
     return VM_OK;
 }

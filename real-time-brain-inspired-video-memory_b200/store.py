@@ -17,6 +17,9 @@ import torch
 from . import _lib as L
 
 _DT = {"f32": L.VM_F32, "fp32": L.VM_F32, "float32": L.VM_F32, "bf16": L.VM_BF16, "bfloat16": L.VM_BF16}
+#: binary64 stores: the rows are kept as given (what the reference scores: Python floats), the scan reads a rounded
+#: shadow copy -- "f64" with an fp32 shadow, "f64+bf16" with a bf16 shadow (half the scan traffic, a wider near-tie band)
+_DT_EXACT = {"f64": L.VM_F32, "fp64": L.VM_F32, "float64": L.VM_F32, "f64+f32": L.VM_F32, "f64+bf16": L.VM_BF16}
 _TORCH_DT = {L.VM_F32: torch.float32, L.VM_BF16: torch.bfloat16}
 
 
@@ -48,30 +51,93 @@ def _stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class _DeviceRange:
+    """A library-owned device range as a __cuda_array_interface__ object (torch.as_tensor wraps it without a copy)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
 class EmbeddingStore:
     """Row-major embedding shard on one GPU.  Row index == append order (the reference's dict
-    insertion order)."""
+    insertion order).
 
-    def __init__(self, dim: int, capacity: int, dtype: str = "f32", device: int = 0, _buffers=None):
+    max_capacity=None: a store over fixed torch buffers of `capacity` rows.  max_capacity=N: a GROWABLE store -- the
+    library reserves virtual addresses for N rows and backs them with HBM as rows arrive (`append` grows on demand,
+    `reserve` explicitly); resident rows are never copied and `rows` / `inv_norms` keep their addresses."""
+
+    def __init__(self, dim: int, capacity: int, dtype: str = "f32", device: int = 0, _buffers=None,
+                 max_capacity: Optional[int] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("EmbeddingStore needs a CUDA device (sm_100); there is no CPU fallback")
         self.lib = L.load()
         self.dim, self.capacity = int(dim), int(capacity)
-        self.dtype_code = _DT[dtype]
+        self.growable = max_capacity is not None
+        self.dtype = str(dtype)
+        self.exact = dtype in _DT_EXACT
+        self.dtype_code = _DT_EXACT[dtype] if self.exact else _DT[dtype]   # what the scan reads (`rows`)
         self.device = torch.device("cuda", device)
         self.ld = self.lib.vm_ld(self.dim)
         # PyTorch owns the HBM; the library attaches to it
+        self.rows_exact = None
+        if self.growable:
+            h = C.c_void_p()
+            with torch.cuda.device(self.device):
+                L.check(self.lib.vm_store_create_growable(C.byref(h), device, self.dim, self.dtype_code, 1 if self.exact else 0,
+                                                          self.capacity, max(int(max_capacity), self.capacity)))
+            self._h = h
+            self.max_capacity = int(self.lib.vm_store_max_capacity(h))
+            self._refresh_views()
+            self.last_stats = L.TopkStats()
+            self._stats_ref = C.byref(self.last_stats)
+            return
+        self.max_capacity = self.capacity
         if _buffers is None:
             self.rows = torch.empty((self.capacity, self.ld), dtype=_TORCH_DT[self.dtype_code], device=self.device)
             self.inv_norms = torch.empty((self.capacity,), dtype=torch.float32, device=self.device)
+            if self.exact:
+                self.rows_exact = torch.empty((self.capacity, self.ld), dtype=torch.float64, device=self.device)
+        elif self.exact:
+            self.rows, self.inv_norms, self.rows_exact = _buffers
         else:
             self.rows, self.inv_norms = _buffers
         h = C.c_void_p()
-        L.check(self.lib.vm_store_attach(C.byref(h), device, self.dim, self.dtype_code, self.capacity,
-                                         self.rows.data_ptr(), self.inv_norms.data_ptr()))
+        if self.exact:
+            L.check(self.lib.vm_store_attach_exact(C.byref(h), device, self.dim, self.dtype_code, self.capacity,
+                                                   self.rows.data_ptr(), self.inv_norms.data_ptr(), self.rows_exact.data_ptr()))
+        else:
+            L.check(self.lib.vm_store_attach(C.byref(h), device, self.dim, self.dtype_code, self.capacity,
+                                             self.rows.data_ptr(), self.inv_norms.data_ptr()))
         self._h = h
         self.last_stats = L.TopkStats()
         self._stats_ref = C.byref(self.last_stats)
+
+    def _refresh_views(self) -> None:
+        """(growable store) torch views of the library-owned ranges, over the rows backed right now."""
+        self.capacity = cap = int(self.lib.vm_store_capacity(self._h))
+        dev = self.device
+        if self.dtype_code == L.VM_BF16:
+            r = torch.as_tensor(_DeviceRange(self.lib.vm_store_rows_ptr(self._h), (cap, self.ld), "<i2"), device=dev).view(torch.bfloat16)
+        else:
+            r = torch.as_tensor(_DeviceRange(self.lib.vm_store_rows_ptr(self._h), (cap, self.ld), "<f4"), device=dev)
+        self.rows = r
+        self.inv_norms = torch.as_tensor(_DeviceRange(self.lib.vm_store_inv_norms_ptr(self._h), (cap,), "<f4"), device=dev)
+        if self.exact:
+            self.rows_exact = torch.as_tensor(_DeviceRange(self.lib.vm_store_rows_exact_ptr(self._h), (cap, self.ld), "<f8"), device=dev)
+
+    def reserve(self, capacity: int) -> None:
+        """Back at least `capacity` rows (growable stores; no-op when already backed).  Nothing is copied."""
+        if int(capacity) <= self.capacity:
+            return
+        if not self.growable:
+            raise ValueError(f"store over fixed buffers of {self.capacity} rows cannot grow; create it with max_capacity")
+        L.check(self.lib.vm_store_reserve(self._h, int(capacity)))
+        self._refresh_views()
+
+    def resident_bytes(self) -> int:
+        """Physical HBM behind the store's rows, inverse norms and (binary64 store) original rows."""
+        return int(self.lib.vm_store_resident_bytes(self._h))
 
     def prefix_view(self, n: int) -> "EmbeddingStore":
         """A second handle over the FIRST n resident rows (same HBM, same cached inverse norms): what a store
@@ -79,14 +145,16 @@ class EmbeddingStore:
         n = int(n)
         if not 1 <= n <= len(self):
             raise ValueError(f"prefix of {n} rows outside [1, {len(self)}]")
-        dt = "bf16" if self.dtype_code == L.VM_BF16 else "f32"
-        v = EmbeddingStore(self.dim, n, dt, self.device.index, _buffers=(self.rows[:n], self.inv_norms[:n]))
+        bufs = (self.rows[:n], self.inv_norms[:n]) + ((self.rows_exact[:n],) if self.exact else ())
+        v = EmbeddingStore(self.dim, n, self.dtype, self.device.index, _buffers=bufs)
         L.check(self.lib.vm_store_set_size(v._h, n, n, _stream_ptr(self.device)))   # norms are already cached
         return v
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self) -> None:
         if getattr(self, "_h", None):
+            if self.growable:
+                self.rows = self.inv_norms = self.rows_exact = None   # views of memory the library is about to unmap
             self.lib.vm_store_destroy(self._h)
             self._h = None
 
@@ -125,6 +193,8 @@ class EmbeddingStore:
         ptr, dt, mem, n, keep = self._src(rows)
         first = C.c_int64(-1)
         L.check(self.lib.vm_store_append(self._h, ptr, dt, mem, n, C.byref(first), _stream_ptr(self.device)))
+        if self.growable and int(first.value) + n > self.capacity:
+            self._refresh_views()                                 # the library backed more rows
         if mem == L.VM_MEM_HOST:
             torch.cuda.current_stream(self.device).synchronize()  # host buffer may be released after return
         return int(first.value)
@@ -182,10 +252,14 @@ class EmbeddingStore:
         src/components/graph_exporter.py:81-108 stores embeddings as float lists; this is the same
         information without float parsing.  Plain arrays only -- nothing in the file is pickled."""
         n = len(self)
-        rows = self.rows[:n, :self.dim].contiguous()
-        raw = rows.view(torch.int16).cpu().numpy().view(np.uint16) if self.dtype_code == L.VM_BF16 else rows.cpu().numpy()
+        if self.exact:      # binary64 originals; the shadow is re-derived on load
+            raw = self.rows_exact[:n, :self.dim].contiguous().cpu().numpy()
+        else:
+            rows = self.rows[:n, :self.dim].contiguous()
+            raw = rows.view(torch.int16).cpu().numpy().view(np.uint16) if self.dtype_code == L.VM_BF16 else rows.cpu().numpy()
         skipped = (self.inv_norms[:n] < 0).cpu().numpy()
         arrays = {"rows": raw, "skipped": skipped, "dim": np.int64(self.dim), "dtype": np.int64(self.dtype_code),
+                  "exact": np.int64(1 if self.exact else 0),
                   "ids": np.asarray([str(x) for x in ids] if ids is not None else [], dtype=np.str_)}
         for name, text in (extra or {}).items():
             arrays["extra_" + name] = np.frombuffer(str(text).encode("utf-8"), dtype=np.uint8)
@@ -193,15 +267,17 @@ class EmbeddingStore:
 
     @classmethod
     def load(cls, path: str, capacity: Optional[int] = None, device: int = 0, with_extra: bool = False,
-             min_capacity: int = 1):
+             min_capacity: int = 1, max_capacity: Optional[int] = None):
         """-> (store, ids) or (store, ids, extra).  Bit-identical rows, same skipped rows, same order."""
         z = np.load(path if path.endswith(".npz") else path + ".npz", allow_pickle=False)
         dim, code = int(z["dim"]), int(z["dtype"])
         raw = z["rows"]
         n = raw.shape[0]
-        st = cls(dim, max(int(capacity or n), int(min_capacity), 1), "bf16" if code == L.VM_BF16 else "f32", device)
+        exact = "exact" in z.files and int(z["exact"]) == 1
+        name = ("f64+bf16" if code == L.VM_BF16 else "f64") if exact else ("bf16" if code == L.VM_BF16 else "f32")
+        st = cls(dim, max(int(capacity or n), int(min_capacity), 1), name, device, max_capacity=max_capacity)
         if n:
-            if code == L.VM_BF16:
+            if code == L.VM_BF16 and not exact:
                 t = torch.from_numpy(raw.view(np.int16).copy()).view(torch.bfloat16)
                 st.append(t.to(st.device))
             else:

@@ -15,3 +15,4 @@ timeout 300 python bench.py --steps 20 --config c5 --c5-dtype bf16 > $O/bench_c5
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/launches_c2.csv \
     python bench.py --steps 2 --warmup 1 --only-main --no-cpu-baseline --no-scaling-baseline > $O/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
 tail -c 400 $O/*.err
+for nq in 16 32 48; do for fl in 0 32; do timeout 120 python scripts/ab_scan.py real-time-brain-inspired-video-memory_b200/libvidmem.so 12500000 bf16 $nq $fl 20 2>&1 | tail -1; done; done | tee $O/ab_split_nq.txt

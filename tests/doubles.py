@@ -7,13 +7,22 @@ from oracle import oracle
 class OracleBackedStore:
     """Stands in for vidmem_b200.store.EmbeddingStore inside ResidentChunkStore (tests only)."""
 
-    def __init__(self, dim, capacity, dtype="f32", device=0):
+    exact = False
+    growable = True
+
+    def __init__(self, dim, capacity, dtype="f32", device=0, max_capacity=None):
         self.dim, self.capacity = dim, capacity
+        self.max_capacity = max_capacity if max_capacity is not None else capacity
+        self.dtype = dtype
         self.X = np.zeros((0, dim))
         self.ok = np.zeros(0, np.uint8)
 
     def __len__(self):
         return len(self.X)
+
+    def reserve(self, capacity):
+        assert capacity <= self.max_capacity
+        self.capacity = max(self.capacity, capacity)
 
     # what ResidentChunkStore reads directly from the real store (torch tensors there)
     @property
@@ -28,6 +37,7 @@ class OracleBackedStore:
 
     def append(self, rows):
         first = len(self.X)
+        assert first + len(rows) <= self.capacity, "append beyond the backed capacity"
         rows = np.asarray(rows, np.float64).astype(np.float32).astype(np.float64)   # fp32 store rounding
         self.X = np.concatenate([self.X, rows]); self.ok = np.concatenate([self.ok, np.ones(len(rows), np.uint8)])
         return first

@@ -483,12 +483,13 @@ def test_near_duplicate_cluster_is_settled_from_the_band(vm, dtype):
     st.close(); st1.close(); st2.close()
 
 
-@pytest.mark.parametrize("dtype,flags", [("f32", 0), ("bf16", 0), ("bf16", 32)])
+@pytest.mark.parametrize("dtype,flags", [("f32", 0), ("bf16", 0), ("bf16", 32), ("bf16", 64)])
 def test_clustered_store_single_pass(vm, dtype, flags):
     """Unit-norm Gaussian-mixture store (64 near-duplicates per centre, stored consecutively like the chunks of one
     scene; values not representable in bf16 / tf32) and queries that are perturbed members: every top-10 sits inside a
     near-duplicate cluster.  Exact against the oracle, settled in ONE scan, and the scan's error bound holds on every
-    rescored candidate.  flags=32 (VM_FLAG_NO_SPLIT): the single-term bf16 query, whose band is 60x wider."""
+    rescored candidate.  flags=32 (VM_FLAG_NO_SPLIT): the single-term bf16 query, whose band is 60x wider than that of
+    flags=64 (VM_FLAG_SPLIT: hi + lo query terms; the default up to 48 queries per batch)."""
     import torch
     d, n, nq, k, per, rho = 384, 131072 + 777, 64, 10, 64, 0.2
     rng = np.random.default_rng(99)
@@ -508,8 +509,12 @@ def test_clustered_store_single_pass(vm, dtype, flags):
     c = st.counters()
     assert c["queries"] == nq and c["bound_violations"] == 0 and c["full_rescans"] == 0 and c["collect_settled"] == 0
     assert c["uncertified"] == c["band_settled"]
-    if dtype == "bf16" and flags == 0:
+    if flags == 64:
         assert c["uncertified"] <= 2                                  # split query: the band is ~1e-4 wide
+    if dtype == "bf16":                                               # batches of <= 48 queries take the split path by default
+        i2, s2, _ = st.topk_device(torch.from_numpy(Q[:40]).cuda(), k, sum_mode=vm.VM_SUM_NEUMAIER, flags=vm.VM_FLAG_ASYNC)
+        torch.cuda.synchronize()
+        assert np.array_equal(i2.cpu().numpy(), ref[0][:40]) and np.array_equal(s2.cpu().numpy(), ref[1][:40])
     st.close()
 
 
