@@ -215,3 +215,50 @@ def topk_blocked(queries_f32, store_f32, top_k: int, slack: int = 24, block: int
         os_[i, :m] = ex[order[:m]]
         oc[i] = m
     return oi, os_, oc
+
+
+def topk_streamed(queries_f32, n: int, block_fn, rows_fn, top_k: int, slack: int = 54, block: int = 262144,
+                  sum_mode: int = SUM_NEUMAIER):
+    """The blocked tier for stores too large to hold on the host as one array (C3's 12.5 M-row shard and beyond).
+    block_fn(b0, b1) -> float32 rows [b0, b1); rows_fn(sorted row indices) -> float32 rows.  Pre-ranking is a float32
+    BLAS matmul per block (|error| <= PRE_TOL = (d + 8) 2^-24 in cosine units), the best top_k + slack rows per
+    query are rescored with the bit-exact reference formula, and the result is only returned if it is PROVEN complete:
+    every row that was not rescored has a pre-ranking score more than 2 * PRE_TOL below the k-th exact score (else
+    AssertionError -- raise `slack`).  Returns (idx [q, top_k] int64, score [q, top_k] float64, count [q])."""
+    qf = np.ascontiguousarray(queries_f32, np.float32)
+    q, d = qf.shape
+    PRE_TOL = (d + 8) * 2.0 ** -24 * 1.01      # float32 dot product + normalisations, Cauchy-Schwarz, cosine units
+    keep = min(n, top_k + slack)
+    qn = np.sqrt(np.einsum("ij,ij->i", qf, qf, dtype=np.float64))
+    qn[qn == 0] = 1.0
+    qs = (qf / qn[:, None]).astype(np.float32)
+    cand_s = np.full((q, 0), -np.inf, np.float32)
+    cand_i = np.zeros((q, 0), np.int64)
+    for b0 in range(0, n, block):
+        xb = np.ascontiguousarray(block_fn(b0, min(n, b0 + block)), np.float32)
+        nb = np.sqrt(np.einsum("ij,ij->i", xb, xb, dtype=np.float64))
+        nb[nb == 0] = 1.0
+        s = (qs @ xb.T) / nb[None, :].astype(np.float32)
+        cs = np.concatenate([cand_s, s], axis=1)
+        ci = np.concatenate([cand_i, np.broadcast_to(np.arange(b0, b0 + xb.shape[0]), s.shape)], axis=1)
+        if cs.shape[1] > keep:
+            part = np.argpartition(-cs, keep - 1, axis=1)[:, :keep]
+            cs = np.take_along_axis(cs, part, 1)
+            ci = np.take_along_axis(ci, part, 1)
+        cand_s, cand_i = cs, ci
+    oi = np.zeros((q, top_k), np.int64)
+    os_ = np.zeros((q, top_k), np.float64)
+    oc = np.zeros(q, np.int64)
+    for i in range(q):
+        rows = np.sort(cand_i[i])
+        vals = np.ascontiguousarray(rows_fn(rows), np.float32)
+        ex = rescore_rows(qf[i], vals, np.arange(len(rows)), sum_mode)
+        order = np.lexsort((rows, -ex))
+        m = min(top_k, len(rows))
+        oi[i, :m] = rows[order[:m]]
+        os_[i, :m] = ex[order[:m]]
+        oc[i] = m
+        if len(rows) < n and m == top_k:      # rows outside the candidate set: pre-ranking score <= the set's minimum
+            assert float(cand_s[i].min()) + 2 * PRE_TOL < os_[i, m - 1], "oracle.topk_streamed: candidate set not provably complete"
+    return oi, os_, oc
+

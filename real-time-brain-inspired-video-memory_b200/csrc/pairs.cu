@@ -499,7 +499,11 @@ int k_pairs_above(int device, const void *x, int dtype, int64_t n, int dim, int 
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const int dev_idx = device & 63;
-    static const bool one_cta = getenv("VIDMEM_PAIRS_1CTA") != nullptr;  // perf triage: force the 1-CTA kernel
+#ifdef VIDMEM_TRIAGE_KERNELS
+    static const bool one_cta = getenv("VIDMEM_PAIRS_1CTA") != nullptr;  // perf triage builds only: force the 1-CTA kernel
+#else
+    constexpr bool one_cta = false;  // the shipped library has no environment switch that changes what a kernel computes
+#endif
     if (!one_cta) {
         // ---- CTA-pair kernel: 256 x 256 tiles ----
         const long long nb = (n + 255) / 256, groups = (nb + P_GJ - 1) / P_GJ;

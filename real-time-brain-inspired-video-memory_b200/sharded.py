@@ -123,7 +123,7 @@ class ShardedChunkStore:
     Exposes the ResidentChunkStore surface the adapters use (upsert / sync_from_dict / topk / ids /
     row_of / meta / device), so it plugs into ChunkSimilarityBackend and VectorSearchBackend."""
 
-    def __init__(self, dtype: str = "f32", device: int = 0, rank: int = None, world: int = None, group=None,
+    def __init__(self, dtype: str = "f64", device: int = 0, rank: int = None, world: int = None, group=None,
                  initial_capacity: int = 8192):
         import torch.distributed as dist
         from .adapters import ResidentChunkStore

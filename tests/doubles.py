@@ -20,6 +20,11 @@ class OracleBackedStore:
     def __len__(self):
         return len(self.X)
 
+    def _stored(self, rows):
+        """what the store holds: a binary64 store ("f64...") keeps the values as given, the others round once"""
+        rows = np.asarray(rows, np.float64)
+        return rows if str(self.dtype).startswith("f64") else rows.astype(np.float32).astype(np.float64)
+
     def reserve(self, capacity):
         assert capacity <= self.max_capacity
         self.capacity = max(self.capacity, capacity)
@@ -38,12 +43,12 @@ class OracleBackedStore:
     def append(self, rows):
         first = len(self.X)
         assert first + len(rows) <= self.capacity, "append beyond the backed capacity"
-        rows = np.asarray(rows, np.float64).astype(np.float32).astype(np.float64)   # fp32 store rounding
+        rows = self._stored(rows)
         self.X = np.concatenate([self.X, rows]); self.ok = np.concatenate([self.ok, np.ones(len(rows), np.uint8)])
         return first
 
     def update(self, row0, rows):
-        self.X[row0:row0 + len(rows)] = np.asarray(rows, np.float64).astype(np.float32); self.ok[row0:row0 + len(rows)] = 1
+        self.X[row0:row0 + len(rows)] = self._stored(rows); self.ok[row0:row0 + len(rows)] = 1
 
     def invalidate(self, rows):
         self.ok[list(rows)] = 0

@@ -101,7 +101,7 @@ def test_load_export_takes_chunk_nodes_in_file_order(monkeypatch, tmp_path):
     st = adapters.ResidentChunkStore()
     assert st.load_export(str(path)) == 6
     assert st.ids == [f"c{i}" for i in range(6)] and st.meta["c3"]["content"] == "t3"
-    assert np.array_equal(st.store.X, X.astype(np.float32).astype(np.float64))
+    assert np.array_equal(st.store.X, X)                                    # default store dtype: binary64, values as given
 
 
 def test_s3_vector_search_adapter_shape_threshold_and_error_convention(monkeypatch):
@@ -127,7 +127,7 @@ def test_s3_vector_search_adapter_shape_threshold_and_error_convention(monkeypat
     retriever = types.SimpleNamespace(neo4j_handler=types.SimpleNamespace(embedder=Embedder()), config=types.SimpleNamespace(top_k_chunks=5))
     vs = adapters.install_retriever(retriever, backend.store)
     got = asyncio.run(retriever._vector_search_chunks(None, "what happened?"))
-    want = oracle.vector_search(np.array(q), X.astype(np.float32).astype(np.float64), 5, min_score=0.3)
+    want = oracle.vector_search(np.array(q), X, 5, min_score=0.3)
     assert [g["id"] for g in got] == [f"u_{r}" for r, _ in want] and [g["score"] for g in got] == [s for _, s in want]
     assert got[0]["id"] == "u_7" and got[0]["score"] == 1.0 and got[0]["content"] == "text 7" and got[0]["time"] == "00:07"
     assert all(set(g) == {"id", "time", "content", "score", "source"} and g["source"] == "vector" and g["score"] > 0.3 for g in got)

@@ -64,3 +64,19 @@ def test_topk_matches_python_sort(n, d, q, k, seed):
         sims = [(i, float(py_injector(list(Q[qi]), list(X[i])))) for i in range(n)]
         sims.sort(key=lambda x: x[1], reverse=True)                    # stable, like the reference (:369)
         assert got[qi] == sims[:k]
+
+
+def test_streamed_tier_equals_blocked_tier():
+    """oracle.topk_streamed (float32 pre-ranking + completeness proof, rows fetched block by block) == oracle.topk_blocked
+    (float64 pre-ranking over one array) == the plain reference loop, on the same rows."""
+    n, d, k = 20_000, 96, 7
+    X = oracle.synth_rows_c(9, 0, n, d)
+    Q = np.random.default_rng(4).standard_normal((5, d)).astype(np.float32)
+    Q[0] = X[777]
+    a = oracle.topk_blocked(Q, X, k)
+    b = oracle.topk_streamed(Q, n, lambda b0, b1: X[b0:b1], lambda r: X[r], k, block=3000)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    ref = oracle.batch_similarities(Q, X, k)
+    assert [[r for r, _ in lst] for lst in ref] == b[0].tolist()
+    assert [[s for _, s in lst] for lst in ref] == b[1].tolist()
+
