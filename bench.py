@@ -402,11 +402,38 @@ def parity_oracle(store, q_host, k: int, n_queries: int, max_rows: int):
             view.close()
 
 
+def parity_oracle_f64(store, q_host, k: int, n_queries: int, max_rows: int):
+    """Binary64 store: the default path over the first `rows` resident rows against the CPU oracle's plain reference
+    loop (vo_batch_similarities: every query x every row, reference summation order) on the float64 ORIGINALS copied
+    back from HBM.  Index lists equal, binary64 scores bit-equal."""
+    import numpy as np
+    from oracle import oracle
+    n = min(len(store), max_rows)
+    view = store.prefix_view(n) if n < len(store) else store
+    try:
+        Q = np.ascontiguousarray(q_host[:n_queries], dtype=np.float64)
+        idx, score, count = view.topk(Q, k)
+        X = store.rows_exact[:n, :store.dim].cpu().numpy()
+        t0 = time.perf_counter()
+        ref = oracle.batch_similarities(Q, X, k)
+        dt = time.perf_counter() - t0
+        ok = all(int(count[qi]) == len(lst) and [int(v) for v in idx[qi, :len(lst)]] == [r for r, _ in lst]
+                 and [float(v) for v in score[qi, :len(lst)]] == [sc for _, sc in lst] for qi, lst in enumerate(ref))
+        return {"checked": "default path vs CPU oracle (plain reference loop on the float64 originals)", "queries": int(len(Q)),
+                "rows": int(n), "ok": bool(ok), "oracle_s": round(dt, 2)}
+    finally:
+        if view is not store:
+            view.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # top-k scorer (C1 / C2 / C3, clustered variant)
 # ---------------------------------------------------------------------------------------------
 def bench_topk(ctx: Ctx, args, cfg: str, steps: int, warmup: int, variant: str = "iid", with_e2e: bool = True,
-               with_parity: bool = True, rows_override=None):
+               with_parity: bool = True, rows_override=None, store_dtype=None):
+    """store_dtype "f64" / "f64+bf16": the same workload on a BINARY64 store -- rows kept as float64 originals (here the
+    synthetic values times (1 + 1e-9 g), g ~ N(0,1): not representable in fp32 / bf16), the scan streams their rounded
+    fp32 / bf16 shadow, every exact step reads the originals; queries are float64 too."""
     import numpy as np
     import torch
     import vidmem_b200 as vm
@@ -418,14 +445,26 @@ def bench_topk(ctx: Ctx, args, cfg: str, steps: int, warmup: int, variant: str =
     row_lo = rows_total * rank // world
     row_hi = rows_total * (rank + 1) // world
     n_local = row_hi - row_lo
+    exact_store = store_dtype in ("f64", "f64+bf16")
+    if store_dtype:
+        dt = "bf16" if store_dtype in ("bf16", "f64+bf16") else "f32"      # what the scan streams
     es = 4 if dt == "f32" else 2
 
-    store = EmbeddingStore(dim, n_local, dt, device=ctx.local_rank)
+    store = EmbeddingStore(dim, n_local, store_dtype or dt, device=ctx.local_rank)
     if variant == "iid":
         store.synth_fill(sseed, n_local, row0=row_lo)
-        store.set_size(n_local)
+        store.set_size(n_local)            # binary64 store: the originals start as the widened shadow values
         torch.cuda.synchronize()
-        q_pinned = make_queries(store, n_local, nq, dim, qseed, dev, world).pin_memory()
+        q_pinned = make_queries(store, n_local, nq, dim, qseed, dev, world)
+        if exact_store:
+            # originals off the fp32 / bf16 grid: relative 1e-9 is far below half an ulp of either shadow type, so the
+            # shadow (and its cached norms) IS the rounding of these originals
+            for r0 in range(0, n_local, 1 << 17):
+                m = min(1 << 17, n_local - r0)
+                ids = torch.arange(row_lo + r0, row_lo + r0 + m, device=dev, dtype=torch.int64)
+                store.rows_exact[r0:r0 + m, :dim] *= (1.0 + 1e-9 * _hash_normal(ids, dim, sseed + 77).double())
+            q_pinned = q_pinned.double() * (1.0 + 1e-9 * torch.randn(q_pinned.shape, generator=torch.Generator().manual_seed(qseed), dtype=torch.float64))
+        q_pinned = q_pinned.pin_memory()
     else:
         fill_clustered(store, n_local, dim, sseed, args.cluster_size, args.cluster_rho, row_lo)
         store.set_size(n_local)
@@ -528,7 +567,7 @@ def bench_topk(ctx: Ctx, args, cfg: str, steps: int, warmup: int, variant: str =
 
     oracle_par = None
     if rank == 0 and with_parity and not args.no_cpu_baseline:
-        oracle_par = parity_oracle(store, Q, k, 8, 2_000_000)
+        oracle_par = parity_oracle_f64(store, Q, k, 8, 150_000) if exact_store else parity_oracle(store, Q, k, 8, 2_000_000)
 
     rec = None
     if rank == 0:
@@ -543,7 +582,8 @@ def bench_topk(ctx: Ctx, args, cfg: str, steps: int, warmup: int, variant: str =
             "scaling": "strong", "vs_baseline": None,
             "dtype": "tf32" if (dt == "f32" and stats.scan_kernel == 2) else ("f32" if dt == "f32" else "bf16"),
             "data": "synthetic",
-            "config": {"workload": f"{cfg}: {rows_total}x{dim} {dt} store, {nq}-query batch, top-{k} cosine, "
+            "config": {"workload": f"{cfg}: {rows_total}x{dim} {store_dtype or dt} store" + (f" (binary64 rows + {dt} shadow)" if exact_store else "")
+                                   + f", {nq}-query batch, top-{k} cosine, "
                                    f"{'row-sharded over %d GPUs + NCCL all-gather merge' % world if world > 1 else '1 GPU'}",
                        "variant": ("iid: counter-hash integers / 128 (SURVEY 8d)" if variant == "iid" else
                                    f"clustered: unit-norm Gaussian mixture, {args.cluster_size} near-duplicates per centre, "
@@ -882,7 +922,8 @@ def run_ours(args):
     elif cfg == "c5":
         line = note("streaming", bench_streaming(ctx, args, args.steps, args.c5_dtype, args.rows))
     else:
-        line = note("topk", bench_topk(ctx, args, cfg, args.steps, args.warmup, variant=args.variant, rows_override=args.rows))
+        line = note("topk", bench_topk(ctx, args, cfg, args.steps, args.warmup, variant=args.variant, rows_override=args.rows,
+                                       store_dtype=args.store_dtype))
         full = cfg in ("c2", "c3") and not args.rows and not args.only_main
         if rank == 0 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -896,11 +937,18 @@ def run_ours(args):
         if full:
             clustered = note("clustered", bench_topk(ctx, args, cfg, min(args.steps, 20), 3, variant="clustered", with_e2e=False,
                                                      rows_override=None if world > 1 else None))
+            b64 = None
+            if world == 1 and cfg == "c2":
+                b64 = {sd: note("binary64_" + sd, bench_topk(ctx, args, cfg, min(args.steps, 20), 3, with_e2e=True, store_dtype=sd))
+                       for sd in ("f64", "f64+bf16")}
             dd = note("dedup", bench_dedup(ctx, args, args.steps, args.warmup))
             stream = note("streaming", bench_streaming(ctx, args, args.steps))
             if rank == 0:
                 line["clustered"] = {key: clustered[key] for key in ("value", "unit", "ms_per_step", "config", "roofline", "certification", "parity", "clocks")}
                 line["clustered"]["vs_iid"] = clustered["value"] / line["value"]
+                if b64:
+                    line["binary64_store"] = {sd: {key: r[key] for key in ("value", "unit", "ms_per_step", "config", "roofline", "certification", "parity", "e2e")}
+                                              for sd, r in b64.items()}
                 line["dedup"] = dd
                 line["streaming"] = stream
             if world == 1 and cfg == "c2" and not args.no_scaling_baseline:
@@ -941,6 +989,8 @@ def main():
                     help="multi-GPU: replace ncclAllGather + merge by the peer-memory pull-merge kernel (symmetric memory)")
     ap.add_argument("--no-scaling-baseline", action="store_true", help="skip the extra C3-on-one-GPU measurement of the N=1 run")
     ap.add_argument("--c5-dtype", default=None, choices=["f32", "bf16"])
+    ap.add_argument("--store-dtype", default=None, choices=["f32", "bf16", "f64", "f64+bf16"],
+                    help="store dtype override for the top-k configs (f64 / f64+bf16: binary64 store, see DESIGN.md 2)")
     args = ap.parse_args()
     if args.gpus > 1 and args.impl == "ours" and "WORLD_SIZE" not in os.environ:
         # started as plain `python bench.py --gpus N`: re-launch under torchrun, one rank per GPU

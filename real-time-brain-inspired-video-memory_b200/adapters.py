@@ -76,10 +76,8 @@ class ResidentChunkStore:
 
     def _device_row_limit(self, dim: int) -> int:
         """Rows the device's memory could hold at most (virtual addresses are reserved for that many)."""
-        import torch
-        per_row = ((dim + 7) & ~7) * {"f32": 4, "bf16": 2, "f64": 12, "f64+bf16": 10}.get(self.dtype, 12) + 4
-        total = torch.cuda.get_device_properties(self.device).total_memory if torch.cuda.is_available() else 1 << 34
-        return max(1, min(total // per_row, (1 << 31) - 512))
+        from .store import device_row_limit
+        return device_row_limit(dim, self.dtype, self.device)
 
     def clear(self) -> None:
         if self.store is not None:
@@ -192,7 +190,8 @@ class ResidentChunkStore:
         """Re-hydrates the HBM store from a sidecar: bit-identical rows, same row order, same ids."""
         import json
         from .store import EmbeddingStore
-        st, ids, extra = EmbeddingStore.load(path, capacity=None, device=device, with_extra=True, min_capacity=initial_capacity)
+        st, ids, extra = EmbeddingStore.load(path, capacity=None, device=device, with_extra=True, min_capacity=initial_capacity,
+                                             max_capacity="auto")
         self = cls(st.dtype, device, initial_capacity)
         self.store, self.dim = st, st.dim
         if len(ids) != len(st):

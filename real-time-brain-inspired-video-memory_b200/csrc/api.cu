@@ -758,7 +758,11 @@ static int topk_batch(const TopkCall &c)
                        (c.nq <= 48 || (c.flags & VM_FLAG_SPLIT)) && scan_tc_supported(s->dtype, s->dim, c.nq, kp, 1)) ? 1 : 0;
     // The kernels of one call are chained with programmatic dependent launch (common.cuh): each one's launch and
     // prologue overlap its predecessor's drain.  Off while events bracket the scan (VM_FLAG_TIMING) or a graph is captured.
+#ifdef VIDMEM_GRAPH_PDL
+    const bool pdl = !(c.flags & VM_FLAG_TIMING);   // A/B build: programmatic edges inside the captured graph too
+#else
     const bool pdl = !(c.flags & (VM_FLAG_TIMING | FLAG_INTERNAL_CAPTURE));
+#endif
     int rc = k_normalize_queries(q_dev, c.q_dtype, c.nq, nq_pad, s->dim, s->ld, (float *)w.q_f32.p,
                                  (kernel == 2 && s->dtype == VM_BF16) ? w.q_bf16.p : nullptr,
                                  (int32_t *)w.flags.p + c.nq, kernel == 2 ? (uint32_t *)w.seed.p : nullptr,

@@ -400,18 +400,16 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 static constexpr int SR_THREADS = 512;
 static constexpr int BAND_CAP = 1024;  // rows of one query's near-tie band the kernel rescores itself
 
-// Exact top-k among m gathered rows (block-wide).  The rows sit in DRAM (the scan streams them through L2 with
-// evict-first), so all their 128-byte lines are first pulled into L2 by the whole block at once -- a thread walking
-// its row would otherwise pay one serial DRAM miss per line.  Then 2m independent sequential chains (dot and
-// ||row||^2 per row: the reference recurrences, in index order) run on 2m threads, every row is ranked by counting
-// the rows that beat it (score desc, row asc: keys are unique, so ranks are) and the first k are emitted.
-// s_sc / s_rr / s_row: [m] scratch.  Returns the number of entries emitted (uniform).
+// Exact scores of m gathered rows straight from global memory (block-wide; the collect pass, whose row sets do not fit
+// shared memory).  The rows sit in DRAM (the scan streams them through L2 with evict-first), so all their 128-byte lines
+// are first pulled into L2 by the whole block at once -- a thread walking its row would otherwise pay one serial DRAM
+// miss per line.  Then 2m independent sequential chains (dot and ||row||^2 per row: the reference recurrences, in index
+// order) run on 2m threads.  s_sc / s_rr / s_row: [m]; on return s_sc holds the reference scores.
 template <bool NEUMAIER, typename T, int THREADS>
-__device__ int band_topk(const T *__restrict__ rows, int ld, int dim, const double *sq, double n1, int m, double *s_sc, double *s_rr,
-                         uint32_t *s_row, int *s_out, const FinalizeArgs &f, int q)
+__device__ void band_score_global(const T *__restrict__ rows, int ld, int dim, const double *sq, double n1, int m, double *s_sc, double *s_rr,
+                                  const uint32_t *s_row)
 {
     const int tid = threadIdx.x;
-    if (tid == 0) *s_out = 0;
     const int lines = (ld * (int)sizeof(T) + 127) / 128;
     for (int e = tid; e < m * lines; e += THREADS) {
         const int r = e / lines, l = e - r * lines;
@@ -436,6 +434,17 @@ __device__ int band_topk(const T *__restrict__ rows, int ld, int dim, const doub
         s_sc[e] = (n1 == 0.0 || n2 == 0.0) ? 0.0 : __ddiv_rn(s_sc[e], __dmul_rn(n1, n2));
     }
     __syncthreads();
+}
+
+// Exact top-k among m rows with reference scores s_sc (block-wide): every row is ranked by counting the rows that beat it
+// (score desc, row asc: rows are distinct, so ranks are) and the first k are emitted.  Returns the number of entries
+// emitted (uniform).
+template <int THREADS>
+__device__ int band_emit(int m, const double *s_sc, const uint32_t *s_row, int *s_out, const FinalizeArgs &f, int q)
+{
+    const int tid = threadIdx.x;
+    if (tid == 0) *s_out = 0;
+    __syncthreads();
     for (int e = tid; e < m; e += THREADS) {
         const double sc = s_sc[e];
         const uint32_t row = s_row[e];
@@ -458,6 +467,66 @@ __device__ int band_topk(const T *__restrict__ rows, int ld, int dim, const doub
         f.out_score[(int64_t)q * f.k + t] = 0.0;
     }
     return cntv;
+}
+
+static constexpr uint32_t NO_ROW = 0xFFFFFFFFu;
+
+// Stages up to kp rows (ids in s_rid[0, kp), NO_ROW = none) in shared memory with cp.async (16-byte, L2-cached, three
+// column chunks; coalesced -- 32 threads each walking their own row in global memory would serialise in the load unit,
+// one tag lookup per row per instruction) and runs the reference recurrences as independent sequential chains, chunk c
+// overlapping the loads of chunk c+1: thread j < kp: dot(query, row j); kp <= j < 2 kp: ||row j-kp||^2; j == 2 kp and
+// s_qq != NULL: ||query||^2.  Results -> s_dot / s_rr / *s_qq.  Block-wide; ends with a barrier.
+template <bool NEUMAIER, typename T, int THREADS>
+__device__ __forceinline__ void stage_and_chain(const T *__restrict__ rows, int ld, int dim, int kp, const uint32_t *s_rid,
+                                                unsigned char *srow, int pitch, const double *sq, double *s_dot, double *s_rr, double *s_qq)
+{
+    const int tid = threadIdx.x, j = tid;
+    const int gpr = ld * (int)sizeof(T) / 16;                 // 16-byte groups per row
+    const int c1 = gpr / 3, c2 = 2 * gpr / 3;                 // chunk boundaries (in groups)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int g_lo = c == 0 ? 0 : (c == 1 ? c1 : c2), g_hi = c == 0 ? c1 : (c == 1 ? c2 : gpr);
+        const int w = g_hi - g_lo;
+        for (int e = tid; e < kp * w; e += THREADS) {
+            const int r = e / w, g = g_lo + (e - r * w);
+            const uint32_t rid = s_rid[r];
+            if (rid != NO_ROW)
+                cp_async16(srow + (size_t)r * pitch + (size_t)g * 16,
+                           reinterpret_cast<const unsigned char *>(rows + (int64_t)rid * ld) + (size_t)g * 16);
+        }
+        cp_async_commit();
+    }
+    const int kind = j < kp ? 0 : (j < 2 * kp ? 1 : ((j == 2 * kp && s_qq != nullptr) ? 2 : 3));
+    const int cidx = kind == 0 ? j : (kind == 1 ? j - kp : 0);
+    const bool active = kind == 2 || (kind < 2 && s_rid[cidx] != NO_ROW);
+    const T *mine = reinterpret_cast<const T *>(srow + (size_t)cidx * pitch);
+    constexpr int EPG = 16 / (int)sizeof(T);                  // elements per 16-byte group
+    RefSum acc;
+    acc.init();
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (c == 0) cp_async_wait<2>();
+        else if (c == 1) cp_async_wait<1>();
+        else cp_async_wait<0>();
+        __syncthreads();
+        const int g_lo = c == 0 ? 0 : (c == 1 ? c1 : c2), g_hi = c == 0 ? c1 : (c == 1 ? c2 : gpr);
+        const int i_lo = g_lo * EPG, i_hi = min(g_hi * EPG, dim);
+        if (active) {
+            if (kind == 0)
+                ref_sum_range<NEUMAIER>(acc, i_lo, i_hi, [&](int i) { return __dmul_rn(sq[i], load_elem(mine, i)); });
+            else if (kind == 1)
+                ref_sum_range<NEUMAIER>(acc, i_lo, i_hi, [&](int i) { const double y = load_elem(mine, i); return __dmul_rn(y, y); });
+            else
+                ref_sum_range<NEUMAIER>(acc, i_lo, i_hi, [&](int i) { const double x = sq[i]; return __dmul_rn(x, x); });
+        }
+    }
+    if (active) {
+        const double r = acc.result<NEUMAIER>();
+        if (kind == 0) s_dot[cidx] = r;
+        else if (kind == 1) s_rr[cidx] = r;
+        else *s_qq = r;
+    }
+    __syncthreads();
 }
 
 // Where one query's candidate keys come from.
@@ -601,8 +670,11 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(SelectSrc
     uint32_t *lmax = reinterpret_cast<uint32_t *>(skeys + src.key_cap);            // [lists] (+pad)
     double *sq = reinterpret_cast<double *>(lmax + ((src.lists + 3) & ~3));        // [dim]
     const int pitch = ld * (int)sizeof(T) + 16;                                    // bytes, 16-B aligned rows
-    unsigned char *srow = reinterpret_cast<unsigned char *>(sq + ((dim + 1) & ~1)); // [kp][pitch], later the band scratch
+    unsigned char *srow = reinterpret_cast<unsigned char *>(sq + ((dim + 1) & ~1)); // [kp][pitch] staged rows
+    double *b_sc = reinterpret_cast<double *>(srow + (((size_t)kp * pitch + 15) & ~(size_t)15));  // [BAND_CAP] band scores
+    uint32_t *b_row = reinterpret_cast<uint32_t *>(b_sc + BAND_CAP);                           // [BAND_CAP] band rows
     __shared__ uint64_t s_top[64];
+    __shared__ uint32_t s_rid[64];
     __shared__ uint64_t surv[MERGE_SURV];
     __shared__ int hist[256];
     __shared__ int s_bin, s_need, s_m, s_nz, s_cnt, s_band, s_viol, s_out, s_total;
@@ -716,58 +788,13 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(SelectSrc
     }
     __syncthreads();
 
-    // ---------------- B. stage the candidate rows ----------------
+    // ---------------- B + C. stage the candidate rows, sequential reference chains ----------------
     const int j = tid;
     const uint64_t mykey = j < 64 ? s_top[j] : 0;
     const bool cand_valid = j < kp && mykey != 0;
-    const int gpr = ld * (int)sizeof(T) / 16;                 // 16-byte groups per row
-    const int c1 = gpr / 3, c2 = 2 * gpr / 3;                 // chunk boundaries (in groups)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const int g_lo = c == 0 ? 0 : (c == 1 ? c1 : c2), g_hi = c == 0 ? c1 : (c == 1 ? c2 : gpr);
-        const int w = g_hi - g_lo;
-        for (int e = tid; e < kp * w; e += SR_THREADS) {
-            const int r = e / w, g = g_lo + (e - r * w);
-            const uint64_t key = s_top[r];
-            if (key != 0)
-                cp_async16(srow + (size_t)r * pitch + (size_t)g * 16,
-                           reinterpret_cast<const unsigned char *>(rows + (int64_t)key_row(key) * ld) + (size_t)g * 16);
-        }
-        cp_async_commit();
-    }
-
-    // ---------------- C. sequential reference chains ----------------
-    const int kind = j < kp ? 0 : (j < 2 * kp ? 1 : (j == 2 * kp ? 2 : 3));
-    const int cidx = kind == 0 ? j : (kind == 1 ? j - kp : 0);
-    const bool active = kind == 2 || (kind < 2 && s_top[cidx] != 0);
-    const T *mine = reinterpret_cast<const T *>(srow + (size_t)cidx * pitch);
-    constexpr int EPG = 16 / (int)sizeof(T);                  // elements per 16-byte group
-    RefSum acc;
-    acc.init();
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        if (c == 0) cp_async_wait<2>();
-        else if (c == 1) cp_async_wait<1>();
-        else cp_async_wait<0>();
-        __syncthreads();
-        const int g_lo = c == 0 ? 0 : (c == 1 ? c1 : c2), g_hi = c == 0 ? c1 : (c == 1 ? c2 : gpr);
-        const int i_lo = g_lo * EPG, i_hi = min(g_hi * EPG, dim);
-        if (active) {
-            if (kind == 0)
-                ref_sum_range<NEUMAIER>(acc, i_lo, i_hi, [&](int i) { return __dmul_rn(sq[i], load_elem(mine, i)); });
-            else if (kind == 1)
-                ref_sum_range<NEUMAIER>(acc, i_lo, i_hi, [&](int i) { const double y = load_elem(mine, i); return __dmul_rn(y, y); });
-            else
-                ref_sum_range<NEUMAIER>(acc, i_lo, i_hi, [&](int i) { const double x = sq[i]; return __dmul_rn(x, x); });
-        }
-    }
-    if (active) {
-        const double r = acc.result<NEUMAIER>();
-        if (kind == 0) s_dot[cidx] = r;
-        else if (kind == 1) s_rr[cidx] = r;
-        else s_qq = r;
-    }
+    if (j < 64) s_rid[j] = cand_valid ? key_row(mykey) : NO_ROW;
     __syncthreads();
+    stage_and_chain<NEUMAIER, T, SR_THREADS>(rows, ld, dim, kp, s_rid, srow, pitch, sq, s_dot, s_rr, &s_qq);
 
     // ---------------- D. rank, emit, certify ----------------
     double sc = 0.0;
@@ -836,9 +863,7 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(SelectSrc
     if (tid == 0 && cum) { atomicAdd(cum, 1ull); if (s_viol) atomicAdd(cum + 4, 1ull); }
     if (bound_ok && src_complete && band <= BAND_CAP) {
         // ---------------- E. settle from the band ----------------
-        double *b_sc = reinterpret_cast<double *>(srow);
-        double *b_rr = b_sc + BAND_CAP;
-        uint32_t *b_row = reinterpret_cast<uint32_t *>(b_rr + BAND_CAP);
+        // the band's rows go through the same staging + chains as the candidates, kp rows at a time
         if (tid == 0) s_m = 0;
         __syncthreads();
         for (int e = tid; e < total; e += SR_THREADS) {
@@ -846,7 +871,18 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(SelectSrc
             if (k != 0 && key_score(k) >= thr) b_row[atomicAdd(&s_m, 1)] = key_row(k);
         }
         __syncthreads();
-        band_topk<NEUMAIER, T, SR_THREADS>(rows, ld, dim, sq, n1, band, b_sc, b_rr, b_row, &s_out, f, q);
+        for (int b0 = 0; b0 < band; b0 += kp) {
+            const int cnt = min(kp, band - b0);
+            if (tid < 64) s_rid[tid] = tid < cnt ? b_row[b0 + tid] : NO_ROW;
+            __syncthreads();
+            stage_and_chain<NEUMAIER, T, SR_THREADS>(rows, ld, dim, kp, s_rid, srow, pitch, sq, s_dot, s_rr, nullptr);
+            if (tid < cnt) {
+                const double n2 = __dsqrt_rn(s_rr[tid]);
+                b_sc[b0 + tid] = (n1 == 0.0 || n2 == 0.0) ? 0.0 : __ddiv_rn(s_dot[tid], __dmul_rn(n1, n2));
+            }
+            __syncthreads();
+        }
+        band_emit<SR_THREADS>(band, b_sc, b_row, &s_out, f, q);
         if (tid == 0) {
             flags[q] = 0;
             if (collect_thr) collect_thr[q] = INFINITY;
@@ -879,7 +915,7 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(SelectSrc
 // One CTA (512 threads) per query with flag 1.  The collect scan stored every row whose approximate
 // score reached (exact k-th candidate score - 2 eps): that set contains the reference's top-k (a row
 // outside it is more than eps below the k-th candidate).  All gathered rows are scored with the
-// reference recurrence (band_topk) and the best k by (score desc, row asc) are emitted; the query's flag is
+// reference recurrence (band_score_global + band_emit) and the best k by (score desc, row asc) are emitted; the query's flag is
 // cleared.  If the buffer overflowed the flag becomes 2 and the binary64 scan of every row takes over.
 static constexpr int CR_THREADS = 512;
 template <bool NEUMAIER, typename T>
@@ -912,7 +948,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) collect_rescore_kernel(const ui
         s_n1 = __dsqrt_rn(qq.result<NEUMAIER>());
     }
     __syncthreads();
-    band_topk<NEUMAIER, T, CR_THREADS>(rows, ld, dim, sq, s_n1, m, s_sc, s_rr, s_row, &s_out, f, q);
+    band_score_global<NEUMAIER, T, CR_THREADS>(rows, ld, dim, sq, s_n1, m, s_sc, s_rr, s_row);
+    band_emit<CR_THREADS>(m, s_sc, s_row, &s_out, f, q);
     if (tid == 0) {
         flags[q] = 0;
         atomicSub(uncertified_count, 1);
@@ -1338,9 +1375,7 @@ int k_rescore(const RescoreArgs &a, cudaStream_t st, const int *incomplete)
 static size_t select_rescore_smem(int key_cap, int lists, int kp, int dtype, int dim, int ld)
 {
     const int es = (int)dtype_size(dtype);
-    size_t rows_area = (size_t)kp * ((size_t)ld * es + 16);
-    const size_t band_area = (size_t)BAND_CAP * (8 + 8 + 4) + 16;
-    if (rows_area < band_area) rows_area = band_area;
+    const size_t rows_area = (((size_t)kp * ((size_t)ld * es + 16) + 15) & ~(size_t)15) + (size_t)BAND_CAP * (8 + 4) + 16;  // staged rows + band scratch
     return (size_t)key_cap * 8 + (size_t)((lists + 3) & ~3) * 4 + (size_t)((dim + 1) & ~1) * 8 + rows_area + 32;
 }
 // lists == 0: slab mode (tcgen05 scan); else list mode with lists x list_len keys per query

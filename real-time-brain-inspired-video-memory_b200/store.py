@@ -51,6 +51,14 @@ def _stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def device_row_limit(dim: int, dtype: str, device: int = 0) -> int:
+    """Rows of this shape the device's memory could hold at most: what a growable store reserves VIRTUAL addresses for
+    when the caller names no maximum (reserving costs no memory)."""
+    per_row = ((int(dim) + 7) & ~7) * {"f32": 4, "bf16": 2, "f64+bf16": 10}.get(dtype, 12) + 4
+    total = torch.cuda.get_device_properties(device).total_memory if torch.cuda.is_available() else 1 << 34
+    return max(1, min(total // per_row, (1 << 31) - 512))
+
+
 class _DeviceRange:
     """A library-owned device range as a __cuda_array_interface__ object (torch.as_tensor wraps it without a copy)."""
 
@@ -275,7 +283,10 @@ class EmbeddingStore:
         n = raw.shape[0]
         exact = "exact" in z.files and int(z["exact"]) == 1
         name = ("f64+bf16" if code == L.VM_BF16 else "f64") if exact else ("bf16" if code == L.VM_BF16 else "f32")
-        st = cls(dim, max(int(capacity or n), int(min_capacity), 1), name, device, max_capacity=max_capacity)
+        if max_capacity == "auto":       # growable, bounded by what the device could hold
+            max_capacity = device_row_limit(dim, name, device)
+        cap = max(int(capacity or n), int(min_capacity), 1)
+        st = cls(dim, cap, name, device, max_capacity=None if max_capacity is None else max(int(max_capacity), cap))
         if n:
             if code == L.VM_BF16 and not exact:
                 t = torch.from_numpy(raw.view(np.int16).copy()).view(torch.bfloat16)

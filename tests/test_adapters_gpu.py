@@ -156,9 +156,10 @@ def test_f1_hydrate_and_f3_sidecar_roundtrip(ad, tmp_path):
                                      row_ok=np.array([1 if r["embedding"] else 0 for r in kept], np.uint8))
     want = [[(kept[r]["chunk_id"], s) for r, s in lst] for lst in want]
     assert backend.store.topk(Q, k) == want
-    for dt in ("f32", "bf16"):
-        src = backend.store if dt == "f32" else ad.ResidentChunkStore("bf16")
-        if dt == "bf16":
+    assert backend.store.dtype == "f64" and backend.store.store.exact and backend.store.store.growable   # the adapters' default
+    for dt in ("f64", "bf16", "f32", "f64+bf16"):
+        src = backend.store if dt == "f64" else ad.ResidentChunkStore(dt)
+        if dt != "f64":
             src.upsert([(r["chunk_id"], r["embedding"]) for r in kept])
         p = str(tmp_path / f"chunks_{dt}")
         src.save(p)
