@@ -49,6 +49,19 @@ CONFIGS = {
 C4 = (1_000_000, 768, "bf16", 0.9, 4, 100)
 
 
+def _use_all_host_cores() -> int:
+    """torchrun pins OMP_NUM_THREADS=1 in every worker and an OpenMP runtime reads the variable only once, when it is
+    initialised -- so the CPU legs (rank 0 only) also set the thread count of the runtime that is already loaded."""
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+    except Exception:  # pragma: no cover
+        pass
+    return cores
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -256,7 +269,7 @@ def run_reference(args):
     if rank != 0:
         return
     # torchrun pins OMP_NUM_THREADS=1 in every worker; the reference arm is meant to use every host core
-    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    _use_all_host_cores()
     cfg = args.config if args.config in CONFIGS else ("c2" if args.gpus == 1 else "c3")
     cores = os.cpu_count() or 1
     rows_total, dim, dt, nq, k, _, _ = CONFIGS[cfg]
@@ -526,6 +539,10 @@ def bench_topk(ctx: Ctx, args, cfg: str, steps: int, warmup: int, variant: str =
     stats = store.last_stats
     launches = int(stats.scan_launches) * steps
     cert = store.counters(reset=True)
+    band_kept = band_spilled = None
+    if int(stats.scan_kernel) == 2 and int(stats.scan_variant) == 2:
+        bk, bs = store.band_keys()
+        band_kept, band_spilled = float(bk.mean()), float(bs.mean())
     # scan-kernel time: the same loop once more with VM_FLAG_TIMING -- every step then carries its own CUDA event pair
     # around the scan kernel on the launching stream (an event between two kernels rules out their programmatic
     # overlap, so the timed region above runs without it); the average over the last <= 64 steps is read back
@@ -609,6 +626,7 @@ def bench_topk(ctx: Ctx, args, cfg: str, steps: int, warmup: int, variant: str =
                               "certified_pct": 100.0 * (1.0 - cert["uncertified"] / n_q),
                               "band_settled": int(cert["band_settled"]), "collect_settled": int(cert["collect_settled"]),
                               "full_rescans": int(cert["full_rescans"]), "bound_violations": int(cert["bound_violations"]),
+                              "band_keys_per_query": band_kept, "spilled_keys_per_query": band_spilled,
                               "note": "rank 0's shard; counted on the device over the timed steps (VM_FLAG_ASYNC)"},
             "parity": parity,
             "clocks": clocks,
@@ -752,6 +770,7 @@ def bench_dedup(ctx: Ctx, args, steps: int, warmup: int, rows_override=None):
     sample = None
     if rank == 0 and not args.no_cpu_baseline:
         from oracle import oracle
+        _use_all_host_cores()
         ns = min(rows, 12288)
         E = x[:ns, :dim].float().cpu().numpy()
         t0 = time.perf_counter()
@@ -926,8 +945,7 @@ def run_ours(args):
                                        store_dtype=args.store_dtype))
         full = cfg in ("c2", "c3") and not args.rows and not args.only_main
         if rank == 0 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            os.environ["OMP_NUM_THREADS"] = str(cores)      # torchrun pins it to 1 in every worker
+            cores = _use_all_host_cores()                    # torchrun pins OMP_NUM_THREADS to 1 in every worker
             qps, ms, desc = cpu_reference_leg(cfg, 1, 1, args.cpu_sample_rows or 100000)
             line["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
             try:

@@ -191,6 +191,12 @@ typedef struct vm_store_counters {
 } vm_store_counters;
 int vm_store_read_counters(vm_store *s, vm_store_counters *out, int reset);
 
+/* Diagnostics of the last tcgen05 scan of this store: per query, how many keys the scan kept in the near-tie band
+ * (appended to the per-CTA slabs, including those that went on to the spill buffer) and how many were spilled --
+ * a measure of how tight the cooperative bounds were.  nq_cap = room in the two arrays (>= queries of that scan).
+ * Synchronises with the device. */
+int vm_store_band_keys(vm_store *s, int nq_cap, int64_t *kept_per_query, int64_t *spilled_per_query, int *nq_out);
+
 /* ---- top-k scorer ---------------------------------------------------------------------
  * Replaces the hot loop of PreLLMInjector._calculate_batch_similarities
  * (src/components/pre_llm_injector.py:356-370: every query x every stored row through

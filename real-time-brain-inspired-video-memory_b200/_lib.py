@@ -31,7 +31,7 @@ EXPORTS = [
     "vm_store_max_capacity", "vm_store_resident_bytes", "vm_store_rows_ptr", "vm_store_inv_norms_ptr", "vm_store_rows_exact_ptr", "vm_store_destroy", "vm_store_size", "vm_store_capacity", "vm_store_dim",
     "vm_store_ld", "vm_store_append", "vm_store_update", "vm_store_invalidate", "vm_store_set_size", "vm_store_clear",
     "vm_store_last_scan_ms",
-    "vm_store_avg_scan_ms", "vm_store_read_counters",
+    "vm_store_avg_scan_ms", "vm_store_read_counters", "vm_store_band_keys",
     "vm_topk", "vm_topk_sharded", "vm_merge_topk_lists", "vm_topk_packed_bytes", "vm_merge_topk_packed", "vm_merge_max_by_id", "vm_cosine_pairs", "vm_pairs_above", "vm_pairs_above_sharded",
     "vm_comm_unique_id", "vm_comm_init_rank", "vm_comm_destroy", "vm_comm_exchange_bytes", "vm_comm_attach_peer_buffers", "vm_comm_nranks", "vm_comm_rank", "vm_synth_fill",
 ]
@@ -102,6 +102,7 @@ def load() -> C.CDLL:
         "vm_store_last_scan_ms": (ci, [vp, P(C.c_float)]),
         "vm_store_avg_scan_ms": (ci, [vp, P(C.c_float), P(C.c_int)]),
         "vm_store_read_counters": (ci, [vp, P(StoreCounters), ci]),
+        "vm_store_band_keys": (ci, [vp, ci, P(i64), P(i64), P(ci)]),
         "vm_topk": (ci, [vp, vp, ci, ci, ci, ci, dbl, ci, ci, ci, vp, vp, vp, ci, P(TopkStats), vp]),
         "vm_topk_sharded": (ci, [vp, vp, i64, vp, ci, ci, ci, ci, dbl, ci, ci, ci, vp, vp, vp, ci, P(TopkStats), vp]),
         "vm_merge_topk_lists": (ci, [ci, vp, vp, vp, ci, ci, ci, vp, vp, vp, vp]),

@@ -8,6 +8,7 @@
 #include <string.h>
 #include <time.h>
 #include <new>
+#include <vector>
 
 namespace vm {
 
@@ -138,6 +139,7 @@ struct vm_store {
     int *extreme = nullptr;  // device counter: rows outside the fast scans' numeric range
     unsigned long long *cum = nullptr;  // device, [4]: lifetime certification counters (RescoreArgs::cum)
     int64_t n_batches = 0, n_queries = 0;  // host side of vm_store_read_counters
+    int last_band_ctas = 0, last_band_nq = 0;  // shape of the slab counters the last tcgen05 band scan left (vm_store_band_keys)
     Buf stage, stage_idx;
     Workspace ws;
     // VM_FLAG_TIMING: a ring of event pairs, one per timed call, so a whole timed loop can be read back afterwards
@@ -600,6 +602,29 @@ extern "C" int vm_store_avg_scan_ms(vm_store *s, float *ms, int *calls)
     return VM_OK;
 }
 
+// How many keys the last tcgen05 scan kept (a measure of how tight its bounds were): per query, keys appended to the
+// per-CTA slabs (incl. those that went on to the spill buffer) and keys spilled.  Synchronises with the device.
+extern "C" int vm_store_band_keys(vm_store *s, int nq_cap, int64_t *kept_per_query, int64_t *spilled_per_query, int *nq_out)
+{
+    VM_REQUIRE(s && kept_per_query && spilled_per_query, VM_ERR_BADARG, "NULL argument");
+    VM_REQUIRE(s->ws.ready && s->last_band_ctas > 0, VM_ERR_STATE, "no tcgen05 scan has run on this store yet");
+    const int ctas = s->last_band_ctas, nq = s->last_band_nq;
+    VM_REQUIRE(nq_cap >= nq, VM_ERR_BADARG, "room for %d queries needed", nq);
+    DeviceGuard g(s->device);
+    VM_CUDA_CHECK(cudaDeviceSynchronize());
+    std::vector<int> sc((size_t)ctas * nq), uc(nq);
+    VM_CUDA_CHECK(cudaMemcpy(sc.data(), s->ws.scnt.p, sc.size() * 4, cudaMemcpyDeviceToHost));
+    VM_CUDA_CHECK(cudaMemcpy(uc.data(), (int *)s->ws.seed.p + SEED_TAB_WORDS + 2 * MAXQ, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+    for (int q = 0; q < nq; ++q) {
+        int64_t k = 0;
+        for (int c = 0; c < ctas; ++c) k += sc[(size_t)c * nq + q];
+        kept_per_query[q] = k;
+        spilled_per_query[q] = uc[q];
+    }
+    if (nq_out) *nq_out = nq;
+    return VM_OK;
+}
+
 extern "C" int vm_store_read_counters(vm_store *s, vm_store_counters *out, int reset)
 {
     VM_REQUIRE(s && out, VM_ERR_BADARG, "NULL argument");
@@ -757,11 +782,12 @@ static int topk_batch(const TopkCall &c)
     const int split = (kernel == 2 && s->dtype == VM_BF16 && !(c.flags & VM_FLAG_NO_SPLIT) &&
                        (c.nq <= 48 || (c.flags & VM_FLAG_SPLIT)) && scan_tc_supported(s->dtype, s->dim, c.nq, kp, 1)) ? 1 : 0;
     // The kernels of one call are chained with programmatic dependent launch (common.cuh): each one's launch and
-    // prologue overlap its predecessor's drain.  Off while events bracket the scan (VM_FLAG_TIMING) or a graph is captured.
-#ifdef VIDMEM_GRAPH_PDL
-    const bool pdl = !(c.flags & VM_FLAG_TIMING);   // A/B build: programmatic edges inside the captured graph too
+    // prologue overlap its predecessor's drain -- also inside the captured graph of the host-buffer path (5 K-row store, 30
+    // queries: 74.4 -> 70.5 us per call; 1 M rows: no change).  Off while events bracket the scan (VM_FLAG_TIMING).
+#ifdef VIDMEM_NO_GRAPH_PDL
+    const bool pdl = !(c.flags & (VM_FLAG_TIMING | FLAG_INTERNAL_CAPTURE));   // A/B build: plain edges inside the captured graph
 #else
-    const bool pdl = !(c.flags & (VM_FLAG_TIMING | FLAG_INTERNAL_CAPTURE));
+    const bool pdl = !(c.flags & VM_FLAG_TIMING);   // also while a graph is captured: the launches become programmatic edges
 #endif
     int rc = k_normalize_queries(q_dev, c.q_dtype, c.nq, nq_pad, s->dim, s->ld, (float *)w.q_f32.p,
                                  (kernel == 2 && s->dtype == VM_BF16) ? w.q_bf16.p : nullptr,
@@ -794,6 +820,7 @@ static int topk_batch(const TopkCall &c)
     } else {
         int64_t tiles = (s->size + 127) / 128;
         a.ctas = (int)imin64(tiles, s->sm_count);
+        s->last_band_ctas = a.ctas; s->last_band_nq = c.nq;
         // small store: too few tiles per CTA for a threshold to form -> rank every row's key instead
         a.dump = tiles <= s->sm_count && tiles * SCAN_DUMP_TILE <= SCAN_DUMP_MAX_KEYS &&
                  (size_t)tiles * c.nq * SCAN_DUMP_TILE * 8 <= w.cand.bytes &&

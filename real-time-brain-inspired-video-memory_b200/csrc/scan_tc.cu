@@ -108,45 +108,37 @@ static TcLayout make_layout(int dtype, int ld, int nq, int split = 0)
     return L;
 }
 
-// k-th largest score (ordered bits) among the first n keys of one slab (global memory; a slot whose store has not
-// landed yet reads as 0 and is ignored): a lower bound on the shard's k-th best, because k rows of this CTA reach it.
-// One thread; rare (twice per slab at most).  k <= 16: one pass with the running top-k in registers.
-__device__ __noinline__ uint32_t own_kth_score(const uint64_t *slab, int n, int k)
+// k-th largest score (ordered bits, low 12 bits truncated: rounds down) among the first n <= SCAN_SLAB keys of one slab
+// (global memory; a slot whose store has not landed yet reads as 0 and is ignored): a lower bound on the shard's k-th
+// best, because k rows of this CTA reach it.  Warp-collective: one coalesced load, then a 20-step radix select over
+// warp reductions (~1 us; the single-thread insertion sort it replaces took ~10 us of dependent L2 loads, during which
+// the service warp adopted no published bounds).  Returns 0 when fewer than k keys are there.
+__device__ __forceinline__ uint32_t own_kth_score(const uint64_t *slab, int n, int k, int lane)
 {
-    if (k <= 16) {
-        uint32_t top[16];
+    constexpr int PER = SCAN_SLAB / 32;
+    uint32_t vals[PER];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) top[i] = 0u;   // descending
-        for (int j = 0; j < n; ++j) {
-            uint32_t h = (uint32_t)(__ldcg(slab + j) >> 32);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {            // insertion by compare-exchange down the array
-                const uint32_t hi = max(top[i], h);
-                h = min(top[i], h);
-                top[i] = hi;
-            }
-        }
-        uint32_t r = 0u;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) r = (i == k - 1) ? top[i] : r;
-        return r;
+    for (int t = 0; t < PER; ++t) {
+        const int i = lane + 32 * t;
+        vals[t] = i < n ? (uint32_t)(__ldcg(slab + i) >> 32) : 0u;
     }
-    uint32_t upper = 0xFFFFFFFFu;  // exclusive upper bound of the next pick
-    int picked = 0;
-    uint32_t cur = 0;
-    while (picked < k) {
-        uint32_t best = 0;
-        int mult = 0;
-        for (int j = 0; j < n; ++j) {
-            const uint32_t h = (uint32_t)(__ldcg(slab + j) >> 32);
-            if (h < upper) { if (h > best) { best = h; mult = 1; } else if (h == best) ++mult; }
-        }
-        if (mult == 0 || best == 0u) return 0u;
-        cur = best;
-        picked += mult;
-        upper = best;
+    uint32_t prefix = 0;
+    int need = k;
+    for (int bit = 31; bit >= 12; --bit) {
+        const uint32_t hi = bit == 31 ? 0u : (0xFFFFFFFFu << (bit + 1));
+        int cnt = 0;
+#pragma unroll
+        for (int t = 0; t < PER; ++t) cnt += ((vals[t] & hi) == prefix && ((vals[t] >> bit) & 1u)) ? 1 : 0;
+        const int tot = __reduce_add_sync(0xffffffffu, cnt);
+        if (tot >= need) prefix |= 1u << bit;
+        else need -= tot;
     }
-    return cur;
+    // fewer than k non-empty keys: the select runs out of candidates and ends on a prefix no key carries -> no bound
+    int ge = 0;
+#pragma unroll
+    for (int t = 0; t < PER; ++t) ge += (vals[t] != 0u && vals[t] >= prefix) ? 1 : 0;
+    ge = __reduce_add_sync(0xffffffffu, ge);
+    return (ge >= k && prefix != 0u) ? prefix : 0u;
 }
 
 template <bool TF32, bool DUMP, bool SPLIT>
@@ -471,7 +463,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int G = (int)gridDim.x;
             while (s_done[1] == 0 && s_done[0] < 4) __nanosleep(100);   // wait for the seed phase (it writes tauf)
             uint32_t pub0 = 0xFFFFFFFFu, pub1 = 0xFFFFFFFFu;            // running maxima last written to the table (lanes q, q+32)
-            uint32_t kth_done = 0;                                       // 2 bits per owned query (q, q+32): own k-th published at half / full slab
+            uint32_t kth_done = 0;                                       // 4 bits per query (q, q+32): highest slab level whose own k-th is published
             const uint64_t *my_slab = ub.slab + (size_t)blockIdx.x * nq * SCAN_SLAB;
             // the exit test is a warp vote: a lane that lags behind must not leave the loop while the others
             // are already inside the next round's warp reductions
@@ -494,17 +486,40 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (lane == 0 && sd > -INFINITY) atomicMax(gbound + q, f32_ordered(sd));
                     }
                 __syncwarp();
-                // 3. a slab that is half full / full: this CTA's own k-th best is a valid bound too (k of its rows reach it)
+                // 3. a slab that is half full / full: this CTA's own k-th best is a valid bound too (k of its rows reach it).
+                //    Served by the whole warp, at most KTH_PER_ROUND per round so that steps 1, 2 and 4 never starve
+                //    (on a store of tight clusters every cluster hit fills half a slab at once).
+#ifndef VIDMEM_AB_KTH_LEVELS
+#define VIDMEM_AB_KTH_LEVELS 2
+#endif
+#ifndef VIDMEM_AB_KTH_PER_ROUND
+#define VIDMEM_AB_KTH_PER_ROUND 1
+#endif
+                {
+                    constexpr int LV = VIDMEM_AB_KTH_LEVELS;   // levels: slab >> (LV - level) keys, level = 1 .. LV
+                    int served = 0;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int q = lane + 32 * h;
-                    if (q < nq) {
-                        const int have = *(volatile int *)(lcnt + q);
-                        const int level = have >= SCAN_SLAB ? 2 : (have >= SCAN_SLAB / 2 ? 1 : 0);
-                        const int done = (int)((kth_done >> (2 * h)) & 3u);
-                        if (level > done) {
-                            const uint32_t ok = own_kth_score(my_slab + (size_t)q * SCAN_SLAB, level == 2 ? SCAN_SLAB : SCAN_SLAB / 2, ub.ksel);
-                            if (ok != 0u) { atomicMax(gbound + q, ok); kth_done = (kth_done & ~(3u << (2 * h))) | ((uint32_t)level << (2 * h)); }
+                    for (int h = 0; h < 2; ++h) {
+                        const int q = lane + 32 * h;
+                        int level = 0;
+                        if (q < nq) {
+                            const int have = *(volatile int *)(lcnt + q);
+#pragma unroll
+                            for (int l = 1; l <= LV; ++l) level = have >= (SCAN_SLAB >> (LV - l)) ? l : level;
+                        }
+                        const int done = (int)((kth_done >> (4 * h)) & 15u);
+                        unsigned todo = __ballot_sync(0xffffffffu, level > done && (SCAN_SLAB >> (LV - level)) >= ub.ksel);
+                        while (todo && (VIDMEM_AB_KTH_PER_ROUND == 0 || served < VIDMEM_AB_KTH_PER_ROUND)) {
+                            const int src = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            ++served;
+                            const int lv = __shfl_sync(0xffffffffu, level, src);
+                            const int qq = src + 32 * h;
+                            const uint32_t ok = own_kth_score(my_slab + (size_t)qq * SCAN_SLAB, SCAN_SLAB >> (LV - lv), ub.ksel, lane);
+                            if (lane == src && ok != 0u) {
+                                atomicMax(gbound + qq, ok);
+                                kth_done = (kth_done & ~(15u << (4 * h))) | ((uint32_t)lv << (4 * h));
+                            }
                         }
                     }
                 }

@@ -242,6 +242,12 @@ class EmbeddingStore:
         L.check(self.lib.vm_store_read_counters(self._h, C.byref(c), 1 if reset else 0))
         return c.as_dict()
 
+    def band_keys(self):
+        """-> (kept [nq], spilled [nq]) int64 arrays: keys the last tcgen05 scan kept per query / spilled per query."""
+        kept, spilled, n = (C.c_int64 * 64)(), (C.c_int64 * 64)(), C.c_int(0)
+        L.check(self.lib.vm_store_band_keys(self._h, 64, kept, spilled, C.byref(n)))
+        return np.array(kept[:n.value], np.int64), np.array(spilled[:n.value], np.int64)
+
     def clear(self) -> None:
         L.check(self.lib.vm_store_clear(self._h))
 
