@@ -220,6 +220,14 @@ class ResidentChunkStore:
         self.upsert(items, meta=meta)
         return len(items)
 
+    def vectors(self, ids: Sequence[str]) -> np.ndarray:
+        """The resident embeddings of `ids` as float64 [len(ids), dim] (the values the exact steps score: the originals of
+        a binary64 store, the stored values otherwise); one device gather + one copy."""
+        import torch
+        rows = torch.as_tensor([self.row_of[c] for c in ids], dtype=torch.int64)
+        src = self.store.rows_exact if getattr(self.store, "exact", False) else self.store.rows
+        return src[rows.to(src.device), :self.dim].double().cpu().numpy()
+
     # -- queries ---------------------------------------------------------------------------------
     def topk(self, queries: Sequence[Any], k: int, min_score: float = -math.inf, score_mode: int = L.VM_SCORE_RAW,
              flags: int = 0):
@@ -344,6 +352,36 @@ class ChunkSimilarityBackend:
         rows, scores = o_idx[:m].cpu().numpy(), o_sc[:m].cpu().numpy()
         return [((self.store.ids[int(r)] if r >= 0 else rev[int(r)]), float(s)) for r, s in zip(rows, scores)]
 
+    # row f2: S1 and the cross-query merge in ONE device pass
+    def similarities_and_top_similar(self, chunk_embeddings: Sequence[Any], k: int, top_k2: int):
+        """-> (batch_similarities, top_similar_chunks): what _calculate_batch_similarities returns AND the merged seed list
+        of pre_llm_injector.py:235-249, computed without leaving the device in between -- the per-query top-k lists feed
+        `vm_merge_max_by_id` on the same stream, and both results come back after one synchronisation.  Falls back to
+        the two separate calls whenever a query needs the adapter's special cases (Exception, falsy or wrong-length
+        vectors) or the store is rank-routed."""
+        import torch
+        rs = self.store
+        queries = list(chunk_embeddings)
+        st = getattr(rs, "store", None)
+        plain = (st is not None and hasattr(st, "topk_device") and len(getattr(rs, "ids", ())) > 0 and len(queries) > 0 and
+                 all(not isinstance(q, Exception) and not _falsy_embedding(q) and len(q) == rs.dim for q in queries))
+        if not plain:
+            lists = rs.topk(queries, k)
+            return lists, self.merge_top_similar(lists, top_k2)
+        dev = st.device
+        q = torch.from_numpy(np.asarray(queries, dtype=np.float64)).to(dev)
+        idx, sc, cnt = st.topk_device(q, k, flags=L.VM_FLAG_ASYNC)
+        o_idx = torch.full((top_k2,), -1, dtype=torch.int64, device=dev)
+        o_sc = torch.zeros((top_k2,), dtype=torch.float64, device=dev)
+        o_cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+        L.check(L.load().vm_merge_max_by_id(dev.index, idx.data_ptr(), sc.data_ptr(), cnt.data_ptr(), len(queries), k, top_k2,
+                                            o_idx.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(),
+                                            torch.cuda.current_stream(dev).cuda_stream))
+        h_idx, h_sc, h_cnt, m_idx, m_sc, m_cnt = (t.cpu().numpy() for t in (idx, sc, cnt, o_idx, o_sc, o_cnt))   # first .cpu() synchronises
+        lists = [[(rs.ids[int(h_idx[i, j])], float(h_sc[i, j])) for j in range(int(h_cnt[i]))] for i in range(len(queries))]
+        merged = [(rs.ids[int(m_idx[j])], float(m_sc[j])) for j in range(int(m_cnt[0]))]
+        return lists, merged
+
     # S6 -- insert hook, same `text_chunks` list Neo4jHandler._create_chunks_with_embeddings receives
     def on_chunks_inserted(self, text_chunks: List[Dict[str, Any]]) -> None:
         self.store.upsert(((c["id"], c.get("embedding")) for c in text_chunks),
@@ -426,6 +464,29 @@ class VectorSearchBackend:
             scores = cosine_pairs(np.broadcast_to(q, S.shape).copy(), S, zero_rule=1, device=self.store.device)
         keep = [(i, float(sc)) for i, sc in enumerate(scores) if sc >= threshold]
         return keep if top_k is None else keep[:top_k]
+
+    async def rerank_prefilter(self, retriever, query: str, chunks: List[Dict], keep: int) -> List[Dict]:
+        """Row f4, opt-in (changes what the HTTP reranker sees, so it is OFF unless install_retriever is given
+        rerank_prefilter=N): of the chunks about to be sent to the reranker (retriever_hybrid.py:516-546) only the
+        `keep` most similar to the query by cosine of the RESIDENT embeddings go on, in their original order.  Chunks
+        without a resident embedding cannot be scored and are always kept.  Ties -> earlier chunk."""
+        if keep is None or len(chunks) <= keep:
+            return chunks
+        rs = self.store
+        known = [i for i, c in enumerate(chunks) if c.get("id") in getattr(rs, "row_of", {})
+                 and float(rs.store.inv_norms[rs.row_of[c["id"]]]) >= 0.0]
+        if not known or rs.dim is None:
+            return chunks
+        q = await retriever.neo4j_handler.embedder.aembed_query(query)
+        if _falsy_embedding(q) or len(q) != rs.dim:
+            return chunks
+        from .store import cosine_pairs
+        V = rs.vectors([chunks[i]["id"] for i in known])
+        sc = cosine_pairs(np.broadcast_to(np.asarray(q, np.float64), V.shape).copy(), V, zero_rule=1, device=rs.device)
+        room = max(int(keep) - (len(chunks) - len(known)), 0)
+        best = sorted(range(len(known)), key=lambda t: (-sc[t], known[t]))[:room]
+        chosen = {known[t] for t in best} | (set(range(len(chunks))) - set(known))
+        return [c for i, c in enumerate(chunks) if i in chosen]
 
     async def _post_compress_chunks(self, retriever, query: str, chunks: List[Dict]) -> List[Dict]:
         """S4 caller (:465-514): same splitter, same dict shape, same order and `[:top_k]` cut -- but the segment
@@ -515,10 +576,11 @@ def install_injector(injector, backend: Optional[ChunkSimilarityBackend] = None,
     return backend
 
 
-def install_retriever(retriever, store: ResidentChunkStore) -> VectorSearchBackend:
+def install_retriever(retriever, store: ResidentChunkStore, rerank_prefilter: Optional[int] = None) -> VectorSearchBackend:
     """Rebinds S3 (_vector_search_chunks), S4 (_cosine_similarity) and S4's caller (_post_compress_chunks) on a
     reference HybridRetriever instance.  The instance's own _vector_search_chunks is kept as the fallback for a
-    store that does not hold the whole graph (mirror mode)."""
+    store that does not hold the whole graph (mirror mode).  rerank_prefilter=N (opt-in, row f4): _rerank_chunks only
+    sends the N chunks closest to the query (cosine of the resident embeddings) to the HTTP reranker."""
     backend = VectorSearchBackend(store, fallback=getattr(retriever, "_vector_search_chunks", None))
 
     async def _vs(self, session, query):
@@ -530,6 +592,14 @@ def install_retriever(retriever, store: ResidentChunkStore) -> VectorSearchBacke
     retriever._vector_search_chunks = types.MethodType(_vs, retriever)
     retriever._post_compress_chunks = types.MethodType(_pc, retriever)
     retriever._cosine_similarity = backend._cosine_similarity      # static in the reference: called with (vec1, vec2)
+    inner_rerank = getattr(retriever, "_rerank_chunks", None)
+    if rerank_prefilter is not None and inner_rerank is not None:
+        async def _rr(self, query, chunks, raise_on_failure=False):
+            if getattr(self.config, "use_reranker", False) and chunks:      # the reference returns early otherwise (:518)
+                chunks = await backend.rerank_prefilter(self, query, chunks, rerank_prefilter)
+            return await inner_rerank(query, chunks, raise_on_failure)
+
+        retriever._rerank_chunks = types.MethodType(_rr, retriever)
     return backend
 
 

@@ -87,6 +87,12 @@ def test_s6_insert_hook_and_merge(ad):
     assert inj.fetches == 0                                          # resident mode never fetches
     merged = backend.merge_top_similar(got, k2)
     assert merged == [(ids[r], s) for r, s in oracle.merge_max_by_id(ref, k2)]
+    # f2: both steps in one device pass, and the fallback for queries that need the adapter's special cases
+    lists, seeds = backend.similarities_and_top_similar(_lists(Q), k, k2)
+    assert lists == got and seeds == merged
+    odd = _lists(Q) + [RuntimeError("embed failed"), []]
+    lists2, seeds2 = backend.similarities_and_top_similar(odd, k, k2)
+    assert lists2[:4] == got and lists2[4] == [] and seeds2 == backend.merge_top_similar(lists2, k2)
 
 
 def test_s3_vector_search_and_s4_filter(ad):
@@ -114,6 +120,53 @@ def test_s3_vector_search_and_s4_filter(ad):
     assert (3, thr) in kept
     a, b = [0.3, -0.2, 0.9, 0.4], [0.1, 0.7]
     assert backend._cosine_similarity(a, b) == oracle.cosine(a, b, "retriever")   # zip-truncated dot
+
+
+def test_f4_rerank_prefilter_is_opt_in(ad):
+    """install_retriever(..., rerank_prefilter=N): the reference's own _rerank_chunks receives only the N chunks closest
+    to the query by the resident embeddings (original order kept, unknown ids always kept); without the option, or with
+    the reranker disabled, nothing changes."""
+    d = 32
+    X = synth.synth_rows(71, 0, 40, d)
+    store = ad.ResidentChunkStore(initial_capacity=64)
+    store.upsert((f"c{i}", _lists(X[i:i + 1])[0]) for i in range(40))
+    q = X[5].copy(); q[::3] = -0.5
+
+    class Emb:
+        async def aembed_query(self, text):
+            return [float(v) for v in q]
+
+    def make(use):
+        seen = []
+
+        class Retr:
+            config = types.SimpleNamespace(top_k_chunks=4, use_reranker=use)
+            neo4j_handler = types.SimpleNamespace(embedder=Emb())
+
+            async def _rerank_chunks(self, query, chunks, raise_on_failure=False):
+                seen.append([c["id"] for c in chunks])
+                return list(reversed(chunks))
+
+            async def _vector_search_chunks(self, session, query):
+                return []
+        return Retr(), seen
+
+    chunks = [{"id": f"c{i}", "content": str(i)} for i in (30, 5, 17, 2, 9, 21)] + [{"id": "not-resident", "content": "x"}]
+    scores = {i: oracle.cosine(q, X[i], "retriever") for i in (30, 5, 17, 2, 9, 21)}
+    want = sorted(scores, key=lambda i: -scores[i])[:2]
+    retr, seen = make(True)
+    ad.install_retriever(retr, store, rerank_prefilter=3)
+    out = asyncio.run(retr._rerank_chunks("q", chunks))
+    assert seen == [[c["id"] for c in chunks if c["id"] == "not-resident" or int(c["id"][1:]) in want]] and len(seen[0]) == 3
+    assert [c["id"] for c in out] == list(reversed(seen[0]))
+    retr, seen = make(True)
+    ad.install_retriever(retr, store)                                # not asked for: the reference method is untouched
+    asyncio.run(retr._rerank_chunks("q", chunks))
+    assert seen == [[c["id"] for c in chunks]]
+    retr, seen = make(False)
+    ad.install_retriever(retr, store, rerank_prefilter=3)            # reranker disabled: chunks pass through unfiltered
+    asyncio.run(retr._rerank_chunks("q", chunks))
+    assert seen == [[c["id"] for c in chunks]]
 
 
 def test_s5_representative(ad):
