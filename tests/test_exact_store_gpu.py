@@ -169,3 +169,50 @@ def test_exact_store_sidecar_and_prefix_view(vm, dtype, tmp_path):
     v = st.prefix_view(1000)
     _check(*v.topk(Q, k), oracle.batch_similarities(Q, X[:1000], k, row_ok=ok[:1000]))
     v.close(); st.close(); st2.close()
+
+
+@pytest.mark.parametrize("dtype", EXACT)
+@pytest.mark.parametrize("n,d,nq,k", [(1, 8, 1, 1), (7, 24, 3, 10), (1000, 384, 5, 10), (4097, 768, 8, 3), (20000, 100, 2, 24),
+                                      (3000, 384, 17, 10), (30000, 384, 64, 40), (9473, 200, 33, 10)])
+def test_exact_store_every_path_vs_oracle(vm, dtype, n, d, nq, k):
+    """Shapes x paths (tcgen05 scan incl. dump mode / slabs / 64-candidate lists, CUDA-core scan, binary64 scan) x both
+    summation orders on float64 values; duplicates, a zero row, a query equal to a row."""
+    rng = np.random.default_rng(n * 31 + d)
+    X = rng.standard_normal((n, d)) * (1.0 + rng.random((n, 1)))
+    Q = rng.standard_normal((nq, d))
+    if n > 10:
+        X[3] = X[1]; X[n - 1] = X[1]; X[5] = 0.0
+        Q[0] = X[1]
+    st = vm.EmbeddingStore(d, n + 5, dtype)
+    st.append(X)
+    for sm, osm in ((vm.VM_SUM_NEUMAIER, oracle.SUM_NEUMAIER), (vm.VM_SUM_NAIVE, oracle.SUM_NAIVE)):
+        ref = oracle.batch_similarities(Q, X, k, sum_mode=osm)
+        for flags in (0, vm.VM_FLAG_FORCE_SIMT, vm.VM_FLAG_FORCE_EXACT):
+            if flags == vm.VM_FLAG_FORCE_SIMT and k > 24:
+                continue
+            idx, score, count = st.topk(Q, k, sum_mode=sm, flags=flags)
+            _check(idx, score, count, ref)
+    assert st.counters()["bound_violations"] == 0
+    st.close()
+
+
+@pytest.mark.parametrize("dtype", EXACT)
+def test_exact_store_mass_duplicates_take_the_fallbacks(vm, dtype):
+    """300 exact duplicates at the top (band settlement), 3 000 of them (beyond the band: collect pass) and a zero query
+    (every row ties at 0.0: binary64 scan of every row) -- each fallback reads the binary64 rows."""
+    d, n, k = 64, 20_000, 10
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((n, d))
+    X[100:400] = X[100]
+    X[5000:8000] = X[5000]
+    Q = np.stack([X[100], X[5000], rng.standard_normal(d), np.zeros(d)])
+    st = vm.EmbeddingStore(d, n, dtype)
+    st.append(X)
+    idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)
+    _check(idx, score, count, oracle.batch_similarities(Q, X, k))
+    assert list(idx[0]) == list(range(100, 110)) and list(idx[1]) == list(range(5000, 5010)) and list(idx[3]) == list(range(10))
+    c = st.counters()
+    assert c["uncertified"] >= 3 and c["band_settled"] >= 1 and c["bound_violations"] == 0
+    assert c["collect_settled"] + c["full_rescans"] >= 2
+    st.close()
+
