@@ -163,6 +163,24 @@ def _ncu_traffic(dt: str, rows_local: int):
     return None
 
 
+def _ncu_pairs_pipe():
+    """Tensor-pipe activity of pairs_tc2_kernel from the committed `ncu --set full` capture (profiles/*pairs*summary.json,
+    latest round first): {"pct", "rows", "file"} or None."""
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        names = sorted((n for n in os.listdir(pdir) if "pairs" in n and n.endswith("_summary.json")), reverse=True)
+    except OSError:
+        return None
+    for name in names:
+        try:
+            d = json.load(open(os.path.join(pdir, name)))
+            if d.get("tensor_pipe_active_pct") is not None:
+                return {"pct": float(d["tensor_pipe_active_pct"]), "rows": int(d.get("rows", 0)), "file": "profiles/" + name}
+        except Exception:
+            continue
+    return None
+
+
 class Ctx:
     """Process-wide state of one bench run (rank, device, communicator)."""
 
@@ -802,6 +820,7 @@ def bench_dedup(ctx: Ctx, args, steps: int, warmup: int, rows_override=None):
                "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
                             "traffic": None, "kernel": "pairs_tc2_kernel", "kernel_ms": ms, "peak_source": src,
                             "flops_counted": "2*D per unordered pair (upper triangle only), per GPU",
+                            "ncu_tensor_pipe_active_pct": _ncu_pairs_pipe(),
                             "frac_of_nominal_2250": tf / 2250.0},
                "parity": {"ok": bool(ok), "checked": "pair multiset (count + checksum) resident == e2e"
                                                      + (" == single-GPU pass" if world > 1 else "") + "; exact pair-set equality vs CPU oracle on a row sample",
@@ -961,6 +980,7 @@ def run_ours(args):
                        for sd in ("f64", "f64+bf16")}
             dd = note("dedup", bench_dedup(ctx, args, args.steps, args.warmup))
             stream = note("streaming", bench_streaming(ctx, args, args.steps))
+            stream_bf16 = note("streaming_bf16", bench_streaming(ctx, args, args.steps, "bf16"))
             if rank == 0:
                 line["clustered"] = {key: clustered[key] for key in ("value", "unit", "ms_per_step", "config", "roofline", "certification", "parity", "clocks")}
                 line["clustered"]["vs_iid"] = clustered["value"] / line["value"]
@@ -969,6 +989,7 @@ def run_ours(args):
                                               for sd, r in b64.items()}
                 line["dedup"] = dd
                 line["streaming"] = stream
+                line["streaming_bf16"] = {key: stream_bf16[key] for key in ("value", "unit", "ms_per_step", "config", "latency_ms", "growth", "roofline", "parity")}
             if world == 1 and cfg == "c2" and not args.no_scaling_baseline:
                 line["scaling_baseline"] = scaling_baseline(ctx)
     if rank == 0:

@@ -6,8 +6,8 @@
 // fp32 rows).  The N x N score matrix (4 TB at N = 1M) never exists: each 128 x 256 accumulator tile
 // is consumed straight out of TMEM by the epilogue, which applies the cached inverse norms, compares
 // against the threshold and appends the (rare) hits with one atomic each.  Only tiles that touch the
-// strict upper triangle are scheduled; tiles are rasterised in groups of 8 column blocks x all row
-// blocks so that the 2048-row column panel stays in L2 while the row panels stream.
+// strict upper triangle are scheduled; tiles are rasterised in groups of 8 (64 from 2^18 rows) column blocks x all
+// row blocks so that the group's column panel stays in L2 while the row panels stream.
 //
 // Persistent, warp-specialised (192 threads): warp 0 TMA producer (A 128-row box + B 256-row box per
 // 128-byte K block, 4 stages of 48 KB), warp 1 MMA issuer (M=128, N=256, 4 MMAs per stage, 2
@@ -23,7 +23,15 @@ using namespace tc;
 static constexpr int P_BM = 128, P_BN = 256;
 static constexpr int P_STAGES = 4, P_ACC = 2, P_THREADS = 192;
 static constexpr int P_A_BYTES = P_BM * 128, P_B_BYTES = P_BN * 128, P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
-static constexpr int P_GJ = 8;  // column blocks per raster group (2048 rows -> 3 MB bf16 panel at D=768)
+// Column blocks (of 256 rows) per raster group, chosen per call (PairsParams::gj_log2).  All CTAs work inside one group at
+// a time: its column panel stays in L2 while the row blocks stream, so a row block is re-read from DRAM once per GROUP.
+// 8 blocks (2 048 rows, 3 MB at D=768) were the round-1 choice; at 1 M rows that is 488 groups = 375 GB of DRAM reads
+// per pass, and the kernel runs under the power cap, where DRAM energy costs SM clock.  64 blocks (16 384 rows, 25 MB of
+// the 126 MB L2) cut the re-reads 8x: 1 M x 768 bf16 717 -> 619 ms (SM clock under the cap 1.01 -> 1.34 GHz); 128 blocks
+// 639 ms, 256 blocks (100 MB: no longer L2 resident) 735 ms.  Below 2^18 rows the narrow groups are kept (few groups
+// either way; measured equal within run-to-run noise).
+static constexpr int P_GJ_LOG2_SMALL = 3, P_GJ_LOG2_LARGE = 6;
+static constexpr int64_t P_GJ_LARGE_FROM_ROWS = 1 << 18;
 
 struct PairsParams {
     int64_t n;
@@ -36,29 +44,33 @@ struct PairsParams {
     long long st_cap;
     long long total_tiles;
     int part, nparts;
+    int gj_log2;              // log2(column blocks per raster group)
 };
 
 // Tile sequence of one CTA (pair): t = first, first + stride, ...  Tiles are numbered group by group;
-// group g holds GB*(g+1) row blocks x P_GJ column blocks (GB = 16 for 128-row blocks, 8 for 256-row
-// blocks), i.e. GB*P_GJ*(g+1) tiles.  The iterator keeps (group, offset in group) and advances with
+// group g holds GBU*J*(g+1) row blocks x J column blocks (J = 2^gj_log2 column blocks per group; GBU = 2 for 128-row
+// blocks, 1 for 256-row blocks), i.e. GBU*J*J*(g+1) tiles.  The iterator keeps (group, offset in group) and advances with
 // integer arithmetic only -- this runs on the single MMA-issuing thread between tiles.
-template <int GB>
+template <int GBU>   // row blocks per column block: 2 for 128-row blocks, 1 for 256-row blocks
 struct TileIter {
     long long t, stride, total;
     long long g, r;  // group and offset of t inside it
-    __device__ __forceinline__ void init(long long first, long long stride_, long long total_)
+    long long per;   // tiles of group g are per * (g + 1)
+    int lg;          // log2(column blocks per group)
+    __device__ __forceinline__ void init(long long first, long long stride_, long long total_, int gj_log2)
     {
-        t = first; stride = stride_; total = total_; g = 0; r = first;
+        t = first; stride = stride_; total = total_; g = 0; r = first; lg = gj_log2;
+        per = (long long)GBU << (2 * gj_log2);
         settle();
     }
     __device__ __forceinline__ void settle()
     {
-        while (r >= (long long)GB * P_GJ * (g + 1)) { r -= (long long)GB * P_GJ * (g + 1); ++g; }
+        while (r >= per * (g + 1)) { r -= per * (g + 1); ++g; }
     }
     __device__ __forceinline__ bool valid() const { return t < total; }
     __device__ __forceinline__ void next() { t += stride; r += stride; settle(); }
-    __device__ __forceinline__ int bi() const { return (int)(r >> 3); }
-    __device__ __forceinline__ int bj() const { return (int)(g * P_GJ + (r & 7)); }
+    __device__ __forceinline__ int bi() const { return (int)(r >> lg); }
+    __device__ __forceinline__ int bj() const { return (int)((g << lg) + (r & ((1 << lg) - 1))); }
 };
 
 template <bool TF32>
@@ -99,8 +111,8 @@ pairs_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            TileIter<16> ti;
-            for (ti.init((long long)blockIdx.x * p.nparts + p.part, (long long)gridDim.x * p.nparts, p.total_tiles); ti.valid(); ti.next()) {
+            TileIter<2> ti;
+            for (ti.init((long long)blockIdx.x * p.nparts + p.part, (long long)gridDim.x * p.nparts, p.total_tiles, p.gj_log2); ti.valid(); ti.next()) {
                 const int bi = ti.bi(), bj = ti.bj();
                 if (!valid_tile(bi, bj)) continue;
                 for (int kb = 0; kb < p.KB; ++kb) {
@@ -119,8 +131,8 @@ pairs_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             const uint32_t s0 = smem_u32(stages);
-            TileIter<16> ti;
-            for (ti.init((long long)blockIdx.x * p.nparts + p.part, (long long)gridDim.x * p.nparts, p.total_tiles); ti.valid(); ti.next()) {
+            TileIter<2> ti;
+            for (ti.init((long long)blockIdx.x * p.nparts + p.part, (long long)gridDim.x * p.nparts, p.total_tiles, p.gj_log2); ti.valid(); ti.next()) {
                 const int bi = ti.bi(), bj = ti.bj();
                 if (!valid_tile(bi, bj)) continue;
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -148,8 +160,8 @@ pairs_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int row_in_tile = quad * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
-        TileIter<16> ti;
-        for (ti.init((long long)blockIdx.x * p.nparts + p.part, (long long)gridDim.x * p.nparts, p.total_tiles); ti.valid(); ti.next()) {
+        TileIter<2> ti;
+        for (ti.init((long long)blockIdx.x * p.nparts + p.part, (long long)gridDim.x * p.nparts, p.total_tiles, p.gj_log2); ti.valid(); ti.next()) {
             const int bi = ti.bi(), bj = ti.bj();
             if (!valid_tile(bi, bj)) continue;
             const long long i = (long long)bi * P_BM + row_in_tile;
@@ -254,8 +266,8 @@ pairs_tc2_kernel(const __grid_constant__ CUtensorMap tmA, PairsParams p)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            TileIter<8> ti;
-            for (ti.init((long long)pair * p.nparts + p.part, (long long)npairs * p.nparts, p.total_tiles); ti.valid(); ti.next()) {
+            TileIter<1> ti;
+            for (ti.init((long long)pair * p.nparts + p.part, (long long)npairs * p.nparts, p.total_tiles, p.gj_log2); ti.valid(); ti.next()) {
                 const int bi = ti.bi(), bj = ti.bj();
                 if (!valid_tile(bi, bj)) continue;
                 for (int kb = 0; kb < p.KB; ++kb) {
@@ -274,8 +286,8 @@ pairs_tc2_kernel(const __grid_constant__ CUtensorMap tmA, PairsParams p)
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             const uint32_t s0 = smem_u32(stages);
-            TileIter<8> ti;
-            for (ti.init((long long)pair * p.nparts + p.part, (long long)npairs * p.nparts, p.total_tiles); ti.valid(); ti.next()) {
+            TileIter<1> ti;
+            for (ti.init((long long)pair * p.nparts + p.part, (long long)npairs * p.nparts, p.total_tiles, p.gj_log2); ti.valid(); ti.next()) {
                 const int bi = ti.bi(), bj = ti.bj();
                 if (!valid_tile(bi, bj)) continue;
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -303,8 +315,8 @@ pairs_tc2_kernel(const __grid_constant__ CUtensorMap tmA, PairsParams p)
         const int row_in_tile = quad * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
-        TileIter<8> ti;
-        for (ti.init((long long)pair * p.nparts + p.part, (long long)npairs * p.nparts, p.total_tiles); ti.valid(); ti.next()) {
+        TileIter<1> ti;
+        for (ti.init((long long)pair * p.nparts + p.part, (long long)npairs * p.nparts, p.total_tiles, p.gj_log2); ti.valid(); ti.next()) {
             const int bi = ti.bi(), bj = ti.bj();
             if (!valid_tile(bi, bj)) continue;
             const long long i = (long long)bi * 256 + rank * 128 + row_in_tile;
@@ -489,8 +501,10 @@ int k_pairs_above(int device, const void *x, int dtype, int64_t n, int dim, int 
     p.st_i = (int32_t *)w.st_i; p.st_j = (int32_t *)w.st_j; p.st_s = (float *)w.st_s;
     p.st_cnt = (unsigned long long *)w.cnt;
     p.st_cap = (long long)st_cap;
+    p.gj_log2 = n >= P_GJ_LARGE_FROM_ROWS ? P_GJ_LOG2_LARGE : P_GJ_LOG2_SMALL;
+    const long long P_GJ = 1ll << p.gj_log2;
     const long long groups = (p.nbj + P_GJ - 1) / P_GJ;
-    p.total_tiles = 64 * groups * (groups + 1);  // full groups; tiles outside the matrix are skipped in-kernel
+    p.total_tiles = P_GJ * P_GJ * groups * (groups + 1);  // full groups (2 P_GJ row blocks per group step); tiles outside the matrix are skipped in-kernel
     p.part = part; p.nparts = nparts;
 
     CUtensorMap tmA, tmB;
@@ -507,7 +521,7 @@ int k_pairs_above(int device, const void *x, int dtype, int64_t n, int dim, int 
     if (!one_cta) {
         // ---- CTA-pair kernel: 256 x 256 tiles ----
         const long long nb = (n + 255) / 256, groups = (nb + P_GJ - 1) / P_GJ;
-        p.total_tiles = 32 * groups * (groups + 1);
+        p.total_tiles = P_GJ * P_GJ * groups * (groups + 1) / 2;
         const size_t smem = (size_t)P2_STAGES * P2_STAGE_BYTES + P_ACC * P_BN * 4 + 8 * (2 * P2_STAGES + 2 * P_ACC) + 16 + 1024;
         const long long my_tiles = (p.total_tiles + nparts - 1) / nparts;
         long long pairs = sms / 2;
