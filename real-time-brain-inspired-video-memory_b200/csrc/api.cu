@@ -607,7 +607,7 @@ extern "C" int vm_store_avg_scan_ms(vm_store *s, float *ms, int *calls)
 extern "C" int vm_store_band_keys(vm_store *s, int nq_cap, int64_t *kept_per_query, int64_t *spilled_per_query, int *nq_out)
 {
     VM_REQUIRE(s && kept_per_query && spilled_per_query, VM_ERR_BADARG, "NULL argument");
-    VM_REQUIRE(s->ws.ready && s->last_band_ctas > 0, VM_ERR_STATE, "no tcgen05 scan has run on this store yet");
+    VM_REQUIRE(s->ws.ready && s->last_band_ctas > 0, VM_ERR_STATE, "the last top-k call of this store was not a band-keeping tcgen05 scan");
     const int ctas = s->last_band_ctas, nq = s->last_band_nq;
     VM_REQUIRE(nq_cap >= nq, VM_ERR_BADARG, "room for %d queries needed", nq);
     DeviceGuard g(s->device);
@@ -820,11 +820,12 @@ static int topk_batch(const TopkCall &c)
     } else {
         int64_t tiles = (s->size + 127) / 128;
         a.ctas = (int)imin64(tiles, s->sm_count);
-        s->last_band_ctas = a.ctas; s->last_band_nq = c.nq;
+
         // small store: too few tiles per CTA for a threshold to form -> rank every row's key instead
         a.dump = tiles <= s->sm_count && tiles * SCAN_DUMP_TILE <= SCAN_DUMP_MAX_KEYS &&
                  (size_t)tiles * c.nq * SCAN_DUMP_TILE * 8 <= w.cand.bytes &&
                  select_rescore_fits((int)tiles, SCAN_DUMP_TILE, kp, s->exact_dtype(), s->dim, s->ld);
+        s->last_band_ctas = a.dump ? 0 : a.ctas; s->last_band_nq = c.nq;   // dump mode keeps every row: no band counters
         rc = launch_scan_tc(a, s->dtype == VM_BF16 ? w.q_bf16.p : w.q_f32.p, (uint32_t *)w.seed.p, (int *)w.flags.p + c.nq + 1, nullptr, &sinfo);
         launches += 1;
     }

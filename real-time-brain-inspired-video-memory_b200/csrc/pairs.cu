@@ -16,6 +16,7 @@
 // pairs_finalize_kernel, so the emitted pair SET is exact for the stored values.
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <mutex>
 
 namespace vm {
 using namespace tc;
@@ -445,11 +446,28 @@ int k_row_inv_norms(const void *rows, int dtype, float *inv_norms, int64_t row0,
                     const double *exact = nullptr);
 
 namespace {
+// Scratch of one (device, stream): calls on different streams of a device -- from different host threads too -- never
+// share buffers; calls on the same stream reuse them in stream order.
 struct PairsWs {
     void *inv = nullptr, *st_i = nullptr, *st_j = nullptr, *st_s = nullptr, *cnt = nullptr;
     size_t inv_bytes = 0, st_entries = 0;
+    cudaStream_t stream = nullptr;
+    bool used = false;
 };
-PairsWs g_pws[16];
+constexpr int PWS_STREAMS = 8;
+PairsWs g_pws[16][PWS_STREAMS];
+std::mutex g_pws_mu;
+PairsWs *pairs_ws(int device, cudaStream_t st)
+{
+    std::lock_guard<std::mutex> lock(g_pws_mu);
+    PairsWs *free_slot = nullptr;
+    for (PairsWs &w : g_pws[device]) {
+        if (w.used && w.stream == st) return &w;
+        if (!w.used && !free_slot) free_slot = &w;
+    }
+    if (free_slot) { free_slot->used = true; free_slot->stream = st; }
+    return free_slot;
+}
 int ensure(void **p, size_t *have, size_t need)
 {
     if (need <= *have) return VM_OK;
@@ -471,7 +489,9 @@ int k_pairs_above(int device, const void *x, int dtype, int64_t n, int dim, int 
     VM_CUDA_CHECK(cudaMemsetAsync(out_count, 0, 8, st));
     if (n <= 1) return VM_OK;  // prune.py:73-74
     VM_REQUIRE(((uintptr_t)x & 127) == 0, VM_ERR_BADARG, "rows buffer must be 128-byte aligned");
-    PairsWs &w = g_pws[device];
+    PairsWs *wp = pairs_ws(device, st);
+    VM_REQUIRE(wp, VM_ERR_UNSUPPORTED, "all-pairs scorer: more than %d distinct streams in use on device %d", PWS_STREAMS, device);
+    PairsWs &w = *wp;
     int rc = ensure(&w.inv, &w.inv_bytes, (size_t)n * 4);
     if (rc != VM_OK) return rc;
     const size_t st_cap = (size_t)cap + ((size_t)cap / 8 > 65536 ? (size_t)cap / 8 : 65536);

@@ -77,3 +77,33 @@ def test_edge_semantics(dd):
     parts = [dd.pairs_above(x, 0.9, part=p, nparts=3) for p in range(3)]
     got = sorted(sum([list(zip(a.tolist(), b.tolist())) for a, b, _ in parts], []))
     assert got == list(zip(whole[0].tolist(), whole[1].tolist())) and len(got) > 0
+
+
+def test_two_streams_do_not_share_scratch(dd):
+    """Two calls enqueued back to back on different streams (different inputs, nothing synchronised in between): each
+    gets its own pair set -- the library keeps its scratch per (device, stream)."""
+    import ctypes as C
+    import torch
+    import vidmem_b200 as vm
+    lib = vm._lib.load()
+    dev = torch.device("cuda", 0)
+    cap = 1 << 16
+    jobs = []
+    for seed, n in ((11, 6000), (12, 9000)):
+        E = synth.synth_rows(seed, 0, n, 256, dup_period=7)
+        x = torch.from_numpy(E).to(dev).to(torch.bfloat16)
+        out = (torch.empty(cap, dtype=torch.int64, device=dev), torch.empty(cap, dtype=torch.int64, device=dev),
+               torch.empty(cap, dtype=torch.float32, device=dev), torch.zeros(1, dtype=torch.int64, device=dev))
+        jobs.append((E, x, out, torch.cuda.Stream(dev)))
+    torch.cuda.synchronize()
+    for _ in range(3):                                    # interleaved, asynchronous
+        for E, x, out, st in jobs:
+            vm._lib.check(lib.vm_pairs_above(0, x.data_ptr(), vm.VM_BF16, x.shape[0], x.shape[1], C.c_float(0.9), cap, out[0].data_ptr(),
+                                             out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), 0, 1, vm.VM_FLAG_ASYNC, st.cuda_stream))
+    torch.cuda.synchronize()
+    for E, x, out, st in jobs:
+        m = int(out[3].item())
+        got = sorted(zip(out[0][:m].tolist(), out[1][:m].tolist()))
+        oi, oj, _ = oracle.pairs_above(E, 0.9)
+        assert m > 50 and got == list(zip(oi.tolist(), oj.tolist()))
+
