@@ -107,3 +107,26 @@ def test_two_streams_do_not_share_scratch(dd):
         oi, oj, _ = oracle.pairs_above(E, 0.9)
         assert m > 50 and got == list(zip(oi.tolist(), oj.tolist()))
 
+
+@pytest.mark.parametrize("case", range(12))
+def test_random_pairs_near_the_threshold(dd, case):
+    """Seeded random stress: clusters whose internal cosine is drawn AROUND the threshold (the hard regime for the
+    epilogue's band and the binary64 re-decision), random sizes / dimensions / dtypes; the pair set must equal the
+    oracle's on the stored values."""
+    import torch
+    rng = np.random.default_rng(500 + case)
+    n = int(rng.integers(300, 14_000))
+    d = int(rng.choice([64, 96, 256, 384, 768]))
+    thr = float(rng.choice([0.8, 0.9, 0.95]))
+    per = int(rng.choice([2, 3, 8, 40]))
+    # cosine between cluster members ~ 1 / (1 + s^2): s chosen so that it straddles thr
+    s_mid = (1.0 / thr - 1.0) ** 0.5
+    s = s_mid * (1.0 + rng.uniform(-0.3, 0.3, size=(n // per + 1, 1)))
+    centres = rng.standard_normal((n // per + 1, d)) / d ** 0.5
+    E = (centres[np.arange(n) // per] + s[np.arange(n) // per] * rng.standard_normal((n, d)) / d ** 0.5 / 2 ** 0.5).astype(np.float32)
+    E[5] = 0.0
+    E[n - 1] = E[0]
+    dtype = torch.bfloat16 if case % 2 == 0 else torch.float32
+    found = _check(dd, E, thr, dtype)
+    assert found > 0
+
