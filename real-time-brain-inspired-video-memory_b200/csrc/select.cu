@@ -398,7 +398,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 static constexpr int SR_THREADS = 512;
-static constexpr int BAND_CAP = 1024;  // rows of one query's near-tie band the kernel rescores itself
+// Rows of one query's near-tie band the rescoring kernel settles itself: as many as shared memory leaves room for
+// (12 bytes each), between BAND_CAP_MIN and BAND_CAP_MAX.  Settling 2048 rows costs ~0.3 ms for the batch (64 staged
+// sub-batches per query, the queries in parallel) and no extra pass over the store; bands of up to 4096 rows are left
+// to the collect pass (a second streaming scan + its own rescoring), anything larger to the binary64 scan.
+static constexpr int BAND_CAP_MIN = 1024, BAND_CAP_MAX = 2048;
 
 // Exact scores of m gathered rows straight from global memory (block-wide; the collect pass, whose row sets do not fit
 // shared memory).  The rows sit in DRAM (the scan streams them through L2 with evict-first), so all their 128-byte lines
@@ -546,6 +550,7 @@ struct SelectSrc {
     int nq_pad, ksel;
     float band;
     int key_cap;           // keys one CTA stages in shared memory
+    int band_cap;          // band rows one CTA can settle (shared-memory room, see BAND_CAP_MIN / MAX)
 };
 
 // Slab mode: stages query q's keys in shared memory, filtered once more with the FINAL bound -- the k-th largest of the
@@ -651,9 +656,9 @@ __global__ void __launch_bounds__(SR_THREADS) slab_top_kernel(SelectSrc src, int
 //   D. rank, emit, certify: with s_k the k-th exact score, only rows whose approximate score reaches s_k - eps can
 //      still matter.  When the source is complete they are all in shared memory already: if they are all among the
 //      rescored kp the list is final, otherwise
-//   E. the whole band (<= BAND_CAP rows) is rescored with the reference recurrence right here and the exact top-k
+//   E. the whole band (<= band_cap rows) is rescored with the reference recurrence right here and the exact top-k
 //      of it is emitted -- no second scan.  Only an incomplete source (union-buffer overflow, CUDA-core lists) or a
-//      band beyond BAND_CAP flags the query for the collect pass / the binary64 scan of every row.
+//      band beyond band_cap flags the query for the collect pass / the binary64 scan of every row.
 // Every rescored candidate also audits the scan's error bound: |approximate - exact| > eps flags the query for the
 // binary64 scan (and is counted), so a wrong bound cannot silently produce a wrong list.
 template <bool NEUMAIER, typename T>
@@ -671,8 +676,8 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(SelectSrc
     double *sq = reinterpret_cast<double *>(lmax + ((src.lists + 3) & ~3));        // [dim]
     const int pitch = ld * (int)sizeof(T) + 16;                                    // bytes, 16-B aligned rows
     unsigned char *srow = reinterpret_cast<unsigned char *>(sq + ((dim + 1) & ~1)); // [kp][pitch] staged rows
-    double *b_sc = reinterpret_cast<double *>(srow + (((size_t)kp * pitch + 15) & ~(size_t)15));  // [BAND_CAP] band scores
-    uint32_t *b_row = reinterpret_cast<uint32_t *>(b_sc + BAND_CAP);                           // [BAND_CAP] band rows
+    double *b_sc = reinterpret_cast<double *>(srow + (((size_t)kp * pitch + 15) & ~(size_t)15));  // [band_cap] band scores
+    uint32_t *b_row = reinterpret_cast<uint32_t *>(b_sc + src.band_cap);                       // [band_cap] band rows
     __shared__ uint64_t s_top[64];
     __shared__ uint32_t s_rid[64];
     __shared__ uint64_t surv[MERGE_SURV];
@@ -861,7 +866,7 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(SelectSrc
         return;
     }
     if (tid == 0 && cum) { atomicAdd(cum, 1ull); if (s_viol) atomicAdd(cum + 4, 1ull); }
-    if (bound_ok && src_complete && band <= BAND_CAP) {
+    if (bound_ok && src_complete && band <= src.band_cap) {
         // ---------------- E. settle from the band ----------------
         // the band's rows go through the same staging + chains as the candidates, kp rows at a time
         if (tid == 0) s_m = 0;
@@ -1372,17 +1377,29 @@ int k_rescore(const RescoreArgs &a, cudaStream_t st, const int *incomplete)
 // Fused path when the candidate keys + kp whole rows fit in shared memory; otherwise the caller falls
 // back to k_merge_candidates + k_rescore.  Returns VM_ERR_UNSUPPORTED (without setting an error the
 // caller must report) when it does not apply.
-static size_t select_rescore_smem(int key_cap, int lists, int kp, int dtype, int dim, int ld)
+static constexpr size_t SR_SMEM_LIMIT = 180 * 1024;
+// everything but the band scratch
+static size_t select_rescore_base_smem(int key_cap, int lists, int kp, int dtype, int dim, int ld)
 {
     const int es = (int)dtype_size(dtype);
-    const size_t rows_area = (((size_t)kp * ((size_t)ld * es + 16) + 15) & ~(size_t)15) + (size_t)BAND_CAP * (8 + 4) + 16;  // staged rows + band scratch
+    const size_t rows_area = (((size_t)kp * ((size_t)ld * es + 16) + 15) & ~(size_t)15) + 16;  // staged rows
     return (size_t)key_cap * 8 + (size_t)((lists + 3) & ~3) * 4 + (size_t)((dim + 1) & ~1) * 8 + rows_area + 32;
+}
+// band rows that fit next to it (0: not even BAND_CAP_MIN)
+static int select_band_cap(int key_cap, int lists, int kp, int dtype, int dim, int ld)
+{
+    const size_t base = select_rescore_base_smem(key_cap, lists, kp, dtype, dim, ld);
+    if (base + (size_t)BAND_CAP_MIN * 12 > SR_SMEM_LIMIT) return 0;
+    size_t cap = (SR_SMEM_LIMIT - base) / 12;
+    cap &= ~(size_t)63;
+    if (cap > (size_t)BAND_CAP_MAX) cap = BAND_CAP_MAX;
+    return (int)cap;
 }
 // lists == 0: slab mode (tcgen05 scan); else list mode with lists x list_len keys per query
 bool select_rescore_fits(int lists, int list_len, int kp, int dtype, int dim, int ld)
 {
     const int key_cap = lists > 0 ? lists * list_len : SELECT_KEY_CAP;
-    return select_rescore_smem(key_cap, lists, kp, dtype, dim, ld) <= 180 * 1024 && kp <= 64 && 2 * kp + 1 <= SR_THREADS;
+    return select_band_cap(key_cap, lists, kp, dtype, dim, ld) >= BAND_CAP_MIN && kp <= 64 && 2 * kp + 1 <= SR_THREADS;
 }
 
 static SelectSrc make_src(const SelectArgs &sa)
@@ -1390,15 +1407,16 @@ static SelectSrc make_src(const SelectArgs &sa)
     const bool slab_mode = sa.slab != nullptr;
     const int lists = slab_mode ? 0 : sa.lists;
     return SelectSrc{sa.cand, lists, sa.list_len, sa.complete, sa.slab, sa.scnt, sa.ctas, sa.ubuf, sa.ucnt, sa.ucap, sa.seed_tab,
-                     sa.nq_pad, sa.ksel, sa.band, slab_mode ? SELECT_KEY_CAP : lists * sa.list_len};
+                     sa.nq_pad, sa.ksel, sa.band, slab_mode ? SELECT_KEY_CAP : lists * sa.list_len, 0};
 }
 
 int k_select_rescore(const SelectArgs &sa, const RescoreArgs &a, cudaStream_t st, bool pdl)
 {
-    const SelectSrc src = make_src(sa);
+    SelectSrc src = make_src(sa);
     VM_REQUIRE(src.slab == nullptr || src.ctas <= 256, VM_ERR_UNSUPPORTED, "select: %d scan CTAs exceed 256", src.ctas);
     if (!select_rescore_fits(src.lists, src.list_len, a.kp, a.dtype, a.dim, a.ld)) return VM_ERR_UNSUPPORTED;
-    const size_t smem = select_rescore_smem(src.key_cap, src.lists, a.kp, a.dtype, a.dim, a.ld);
+    src.band_cap = select_band_cap(src.key_cap, src.lists, a.kp, a.dtype, a.dim, a.ld);
+    const size_t smem = select_rescore_base_smem(src.key_cap, src.lists, a.kp, a.dtype, a.dim, a.ld) + (size_t)src.band_cap * 12;
 #define LAUNCH_SR(NEU, T)                                                                                              \
     do {                                                                                                               \
         static bool attr_set_dev[64] = {};                                                                             \

@@ -460,10 +460,20 @@ def test_near_duplicate_cluster_is_settled_from_the_band(vm, dtype):
     i4, s4, _ = st.topk_device(qd, k, sum_mode=vm.VM_SUM_NEUMAIER, flags=vm.VM_FLAG_ASYNC)
     torch.cuda.synchronize()
     assert np.array_equal(i4.cpu().numpy(), idx) and np.array_equal(s4.cpu().numpy(), score)
-    # a band of 1500 rows: beyond what the rescoring kernel takes itself (1024), within the collect pass (4096)
-    X1 = X.copy(); X1[30000:31200] = X1[5000:5001] + 0.0
+    # a band of 1500 rows is still settled by the rescoring kernel itself (it takes up to 2048)
+    X0 = X.copy(); X0[30000:31200] = X0[5000:5001] + 0.0
+    st0 = vm.EmbeddingStore(d, n, dtype); st0.append(X0)
+    ref0 = oracle.topk_blocked(Q[:1], X0, k, slack=2000)
+    with torch.cuda.stream(torch.cuda.Stream()):
+        i0, s0, _ = st0.topk(Q[:1], k, sum_mode=vm.VM_SUM_NEUMAIER)
+    c0 = st0.counters()
+    assert np.array_equal(i0, ref0[0]) and np.array_equal(s0, ref0[1])
+    assert c0["band_settled"] == 1 and c0["collect_settled"] == 0 and c0["full_rescans"] == 0
+    st0.close()
+    # a band of 2800 rows: beyond what the rescoring kernel takes itself (2048), within the collect pass (4096)
+    X1 = X.copy(); X1[30000:32500] = X1[5000:5001] + 0.0
     st1 = vm.EmbeddingStore(d, n, dtype); st1.append(X1)
-    ref1 = oracle.topk_blocked(Q[:1], X1, k, slack=2000)
+    ref1 = oracle.topk_blocked(Q[:1], X1, k, slack=3400)
     with torch.cuda.stream(torch.cuda.Stream()):
         i5, s5, _ = st1.topk(Q[:1], k, sum_mode=vm.VM_SUM_NEUMAIER)
     c1 = st1.counters()
