@@ -928,15 +928,21 @@ __global__ void __launch_bounds__(CR_THREADS, 1) collect_rescore_kernel(const ui
                                                                        const T *__restrict__ rows, int ld, int dim,
                                                                        const void *__restrict__ queries, int q_dtype, FinalizeArgs f,
                                                                        int32_t *__restrict__ flags, int32_t *__restrict__ uncertified_count,
-                                                                       int nq, unsigned long long *__restrict__ cum)
+                                                                       int nq, unsigned long long *__restrict__ cum, int stage_rows)
 {
+    // stage_rows > 0: the gathered rows take the rescoring kernel's staged route (stage_and_chain), stage_rows at a time;
+    // 0 (rows too wide for shared memory): they are scored straight from global memory
     extern __shared__ __align__(16) unsigned char cr_smem[];
     double *sq = reinterpret_cast<double *>(cr_smem);               // [dim]
     double *s_sc = sq + ((dim + 1) & ~1);                           // [cap]
-    double *s_rr = s_sc + cap;                                      // [cap]
-    uint32_t *s_row = reinterpret_cast<uint32_t *>(s_rr + cap);     // [cap]
+    double *s_rr = s_sc + cap;                                      // [cap] (global route only)
+    uint32_t *s_row = reinterpret_cast<uint32_t *>(s_sc + (stage_rows > 0 ? cap : 2 * cap));     // [cap]
+    const int pitch = ld * (int)sizeof(T) + 16;
+    unsigned char *srow = reinterpret_cast<unsigned char *>(s_row + ((cap + 3) & ~3));  // [stage_rows][pitch] (staged route only)
     __shared__ double s_n1;
     __shared__ int s_out;
+    __shared__ uint32_t s_rid[64];
+    __shared__ double s_dot[64], s_r2[64];
     const int q = blockIdx.x, tid = threadIdx.x;
     if (flags[nq] == 0 || flags[q] != 1) return;
     const int m = cnt[q];
@@ -953,7 +959,22 @@ __global__ void __launch_bounds__(CR_THREADS, 1) collect_rescore_kernel(const ui
         s_n1 = __dsqrt_rn(qq.result<NEUMAIER>());
     }
     __syncthreads();
-    band_score_global<NEUMAIER, T, CR_THREADS>(rows, ld, dim, sq, s_n1, m, s_sc, s_rr, s_row);
+    if (stage_rows > 0) {
+        const double n1 = s_n1;
+        for (int b0 = 0; b0 < m; b0 += stage_rows) {
+            const int c = min(stage_rows, m - b0);
+            if (tid < 64) s_rid[tid] = tid < c ? s_row[b0 + tid] : NO_ROW;
+            __syncthreads();
+            stage_and_chain<NEUMAIER, T, CR_THREADS>(rows, ld, dim, stage_rows, s_rid, srow, pitch, sq, s_dot, s_r2, nullptr);
+            if (tid < c) {
+                const double n2 = __dsqrt_rn(s_r2[tid]);
+                s_sc[b0 + tid] = (n1 == 0.0 || n2 == 0.0) ? 0.0 : __ddiv_rn(s_dot[tid], __dmul_rn(n1, n2));
+            }
+            __syncthreads();
+        }
+    } else {
+        band_score_global<NEUMAIER, T, CR_THREADS>(rows, ld, dim, sq, s_n1, m, s_sc, s_rr, s_row);
+    }
     band_emit<CR_THREADS>(m, s_sc, s_row, &s_out, f, q);
     if (tid == 0) {
         flags[q] = 0;
@@ -1451,7 +1472,11 @@ int k_slab_top(const SelectArgs &sa, int nq, int kp, uint64_t *merged, int *inco
 
 int k_collect_rescore(const uint64_t *buf, const int *cnt, int cap, const RescoreArgs &a, cudaStream_t st)
 {
-    const size_t smem = (size_t)((a.dim + 1) & ~1) * 8 + (size_t)cap * (8 + 8 + 4) + 32;
+    // staged route: scores + rows ids + 32 staged rows; global route (rows too wide): scores + norms + row ids
+    const size_t head = (size_t)((a.dim + 1) & ~1) * 8;
+    const size_t staged = head + (size_t)cap * 8 + (size_t)((cap + 3) & ~3) * 4 + (size_t)32 * ((size_t)a.ld * dtype_size(a.dtype) + 16) + 64;
+    const int stage_rows = staged <= 200 * 1024 ? 32 : 0;
+    const size_t smem = stage_rows ? staged : head + (size_t)cap * (8 + 8 + 4) + 32;
     VM_REQUIRE(smem <= 200 * 1024, VM_ERR_UNSUPPORTED, "collect pass: buffer of %d rows exceeds shared memory", cap);
 #define LAUNCH_CR(NEU, T)                                                                                               \
     do {                                                                                                                \
@@ -1463,7 +1488,7 @@ int k_collect_rescore(const uint64_t *buf, const int *cnt, int cap, const Rescor
             attr_set_dev[dev_idx_ & 63] = true;                                                                         \
         }                                                                                                               \
         collect_rescore_kernel<NEU, T><<<a.nq, CR_THREADS, smem, st>>>(buf, cnt, cap, (const T *)a.rows, a.ld, a.dim, a.queries, \
-                                                                       a.q_dtype, a.fin, a.flags, a.uncertified_count, a.nq, a.cum); \
+                                                                       a.q_dtype, a.fin, a.flags, a.uncertified_count, a.nq, a.cum, stage_rows); \
     } while (0)
     const bool neu = a.sum_mode == VM_SUM_NEUMAIER;
     if (a.dtype == VM_F32) { if (neu) LAUNCH_CR(true, float); else LAUNCH_CR(false, float); }
