@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(SelectSrc
                                                                    FinalizeArgs f, int32_t *__restrict__ flags,
                                                                    int32_t *__restrict__ uncertified_count,
                                                                    const int *__restrict__ extreme, float *__restrict__ collect_thr,
-                                                                   unsigned long long *__restrict__ cum)
+                                                                   unsigned long long *__restrict__ cum, const float *__restrict__ inv_norms)
 {
     extern __shared__ __align__(16) unsigned char sr_smem[];
     uint64_t *skeys = reinterpret_cast<uint64_t *>(sr_smem);                       // [key_cap]
@@ -805,6 +805,26 @@ __global__ void __launch_bounds__(SR_THREADS, 1) select_rescore_kernel(SelectSrc
     double sc = 0.0;
     const uint32_t row = cand_valid ? key_row(mykey) : 0;
     const double n1 = __dsqrt_rn(s_qq);
+    if (n1 == 0.0) {
+        // zero query (uniform: s_qq is shared): the reference scores 0.0 against every row (pre_llm_injector.py:385-386) and
+        // its stable sort keeps store order -> the first k scorable rows, no scan result needed
+        if (tid == 0) {
+            int c = 0;
+            const double outv = convert_score(0.0, f.score_mode);
+            if (outv > f.min_score)
+                for (int64_t r = 0; r < n_rows && c < f.k; ++r)
+                    if (__ldg(inv_norms + r) >= 0.0f) {
+                        f.out_idx[(int64_t)q * f.k + c] = r + f.row_offset;
+                        f.out_score[(int64_t)q * f.k + c] = outv;
+                        ++c;
+                    }
+            for (int t = c; t < f.k; ++t) { f.out_idx[(int64_t)q * f.k + t] = -1; f.out_score[(int64_t)q * f.k + t] = 0.0; }
+            f.out_count[q] = c;
+            flags[q] = 0;
+            if (collect_thr) collect_thr[q] = INFINITY;
+        }
+        return;
+    }
     if (cand_valid) {
         const double n2 = __dsqrt_rn(s_rr[j]);
         sc = (n1 == 0.0 || n2 == 0.0) ? 0.0 : __ddiv_rn(s_dot[j], __dmul_rn(n1, n2));
@@ -1449,7 +1469,7 @@ int k_select_rescore(const SelectArgs &sa, const RescoreArgs &a, cudaStream_t st
         }                                                                                                              \
         VM_CUDA_CHECK(launch_pdl(select_rescore_kernel<NEU, T>, dim3(a.nq), dim3(SR_THREADS), smem, st, pdl, src, a.nq, a.kp, \
                                  (const T *)a.rows, a.ld, a.dim, a.n_rows, a.queries, a.q_dtype, a.eps, a.fin, a.flags,      \
-                                 a.uncertified_count, a.extreme, a.collect_thr, a.cum));                                     \
+                                 a.uncertified_count, a.extreme, a.collect_thr, a.cum, a.inv_norms));                       \
     } while (0)
     const bool neu = a.sum_mode == VM_SUM_NEUMAIER;
     if (a.dtype == VM_F32) { if (neu) LAUNCH_SR(true, float); else LAUNCH_SR(false, float); }

@@ -100,7 +100,7 @@ def test_simt_vs_oracle(vm, dtype, n, d, nq, k):
 
 def test_many_duplicates_fall_back_to_exact(vm):
     # more exact ties at the top than the candidate list holds -> the whole tie band is rescored (300 duplicates) or,
-    # for the zero query (every row ties at 0.0), the binary64 scan of every row takes over
+    # the zero query (every row ties at 0.0) is answered from store order directly
     d, n, k = 64, 5000, 10
     rng = np.random.default_rng(5)
     X = rng.standard_normal((n, d)).astype(np.float32)
@@ -110,7 +110,7 @@ def test_many_duplicates_fall_back_to_exact(vm):
     st.append(X)
     idx, score, count = st.topk(Q, k, sum_mode=vm.VM_SUM_NEUMAIER)
     c = st.counters()
-    assert c["uncertified"] >= 2 and c["band_settled"] >= 1 and c["full_rescans"] >= 1 and c["bound_violations"] == 0
+    assert c["uncertified"] >= 1 and c["band_settled"] >= 1 and c["full_rescans"] == 0 and c["bound_violations"] == 0
     _check(idx, score, count, oracle.batch_similarities(Q, X, k), k)
     assert list(idx[0]) == list(range(100, 110))
     assert list(idx[2]) == list(range(10)) and (score[2] == 0.0).all()   # zero query: store order
