@@ -1075,90 +1075,155 @@ __device__ void exact_merge_query(const double *__restrict__ xlist_score, const 
     __syncthreads();
 }
 
+// 256 threads per CTA: thread t < 128 runs the dot chain of row tile*128+t, thread 128+t its ||row||^2 chain.  The tile's
+// rows are staged through shared memory in column chunks of 384 bytes per row (cp.async, coalesced, three buffers: the
+// next two chunks load while the chains run over one) -- a thread walking its own row in global memory would make every warp
+// instruction touch 32 different rows and serialise in the load unit (the first version of this kernel: 3.1 ms per
+// query-pass over 1 M x 384 fp32).
+static constexpr int XS_THREADS = 256;
+static constexpr int XS_CG = 24;                    // 16-byte groups per staged chunk
+static constexpr int XS_PITCH = XS_CG * 16 + 16;    // bytes; odd multiple of 16 -> conflict-free per-thread walks
+
 template <bool NEUMAIER, typename T>
-__global__ void __launch_bounds__(128) exact_scan_kernel(const T *__restrict__ rows, const float *__restrict__ inv_norms,
-                                                        int64_t n, int ld, int dim, const void *__restrict__ queries,
-                                                        int q_dtype, int nq, int32_t *__restrict__ flags, int k,
-                                                        double *__restrict__ xlist_score, uint32_t *__restrict__ xlist_row,
-                                                        int32_t *__restrict__ xlist_cnt, unsigned long long *__restrict__ cum,
-                                                        int *__restrict__ done_ctr, FinalizeArgs f, uint8_t *__restrict__ taken)
+__global__ void __launch_bounds__(XS_THREADS) exact_scan_kernel(const T *__restrict__ rows, const float *__restrict__ inv_norms,
+                                                               int64_t n, int ld, int dim, const void *__restrict__ queries,
+                                                               int q_dtype, int nq, int32_t *__restrict__ flags, int k,
+                                                               double *__restrict__ xlist_score, uint32_t *__restrict__ xlist_row,
+                                                               int32_t *__restrict__ xlist_cnt, unsigned long long *__restrict__ cum,
+                                                               int *__restrict__ done_ctr, FinalizeArgs f, uint8_t *__restrict__ taken)
 {
     pdl_launch_dependents();
     pdl_wait();
     // flags[nq] is the uncertified-query counter written by the rescoring kernel: nothing to do when 0
     if (flags && flags[nq] == 0) return;
     if (flags && cum && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(cum + 3, (unsigned long long)flags[nq]);
-    extern __shared__ double sq[];  // [dim] query as doubles
+    extern __shared__ __align__(16) unsigned char xs_smem[];
+    double *sq = reinterpret_cast<double *>(xs_smem);                                          // [dim] query as doubles
+    unsigned char *buf0 = reinterpret_cast<unsigned char *>(sq + ((dim + 1) & ~1));              // [3][128][XS_PITCH]
     __shared__ double l_score[XK], n_score[XK];
     __shared__ uint32_t l_row[XK], n_row[XK];
     __shared__ double c_score[128];
     __shared__ uint32_t c_row[128];
+    __shared__ double s_dotv[128], s_rrv[128];
     __shared__ int l_cnt, c_cnt;
     __shared__ double s_n1;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, rt = tid & 127;
+    const bool is_rr = tid >= 128;
+    const int gpr = ld * (int)sizeof(T) / 16;                   // 16-byte groups per row
+    const int nchunks = (gpr + XS_CG - 1) / XS_CG;
+    constexpr int EPG = 16 / (int)sizeof(T);                    // elements per group
     for (int q = 0; q < nq; ++q) {
         if (flags && flags[q] == 0) continue;  // uniform across the grid
         __syncthreads();
-        for (int i = tid; i < dim; i += 128) sq[i] = load_as_double(queries, q_dtype, (int64_t)q * dim + i);
+        for (int i = tid; i < dim; i += XS_THREADS) sq[i] = load_as_double(queries, q_dtype, (int64_t)q * dim + i);
         if (tid == 0) { l_cnt = 0; c_cnt = 0; }
         __syncthreads();
         if (tid == 0) {
             RefSum qq; qq.init();
-            for (int i = 0; i < dim; ++i) qq.add<NEUMAIER>(__dmul_rn(sq[i], sq[i]));
+            ref_sum_range<NEUMAIER>(qq, 0, dim, [&](int i) { return __dmul_rn(sq[i], sq[i]); });
             s_n1 = __dsqrt_rn(qq.result<NEUMAIER>());
         }
         __syncthreads();
         const double n1 = s_n1;
-        for (int64_t tile = blockIdx.x; tile * 128 < n; tile += gridDim.x) {
-            int64_t r = tile * 128 + tid;
-            bool live = r < n && inv_norms[r] >= 0.0f;
+        // linear pipeline over (tile, chunk) steps with three buffers: the loads of steps s+1 and s+2 are in flight while
+        // the chains run over step s, also across tile boundaries
+        const int64_t ntiles = (n + 127) / 128;
+        const int my_tiles = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+        const int total_steps = my_tiles > 0 ? my_tiles * nchunks : 0;
+        auto issue = [&](int st) {
+            if (st < total_steps) {
+                const int64_t tile = blockIdx.x + (int64_t)(st / nchunks) * gridDim.x;
+                const int c = st % nchunks;
+                unsigned char *buf = buf0 + (size_t)(st % 3) * 128 * XS_PITCH;
+                const int g0 = c * XS_CG, gw = min(XS_CG, gpr - g0);
+                for (int e = tid; e < 128 * gw; e += XS_THREADS) {
+                    const int rr_ = e / gw, g = e - rr_ * gw;
+                    const int64_t row = tile * 128 + rr_;
+                    if (row < n)
+                        cp_async16(buf + (size_t)rr_ * XS_PITCH + (size_t)g * 16,
+                                   reinterpret_cast<const unsigned char *>(rows + row * (int64_t)ld) + (size_t)(g0 + g) * 16);
+                }
+            }
+            cp_async_commit();  // always (an empty group keeps the wait arithmetic uniform)
+        };
+        issue(0);
+        issue(1);
+        RefSum acc;
+        acc.init();
+        for (int st = 0; st < total_steps; ++st) {
+            const int64_t tile = blockIdx.x + (int64_t)(st / nchunks) * gridDim.x;
+            const int c = st % nchunks;
+            const int64_t r = tile * 128 + rt;
+            const bool live = r < n && inv_norms[r] >= 0.0f;
+            issue(st + 2);
+            cp_async_wait<2>();   // everything but the two newest groups has landed: step st is complete
+            __syncthreads();
+            const unsigned char *cur = buf0 + (size_t)(st % 3) * 128 * XS_PITCH;
+            const int i_lo = c * XS_CG * EPG, i_hi = min((c + 1) * XS_CG * EPG, dim);
+            if (live && i_lo < i_hi) {
+                const T *mine = reinterpret_cast<const T *>(cur + (size_t)rt * XS_PITCH);
+                if (!is_rr)
+                    ref_sum_range<NEUMAIER>(acc, i_lo, i_hi, [&](int i) { return __dmul_rn(sq[i], load_elem(mine, i - i_lo)); });
+                else
+                    ref_sum_range<NEUMAIER>(acc, i_lo, i_hi, [&](int i) { const double y = load_elem(mine, i - i_lo); return __dmul_rn(y, y); });
+            }
+            if (c + 1 < nchunks) {
+                __syncthreads();  // all chains are done with this buffer before step st+3 is loaded into it
+                continue;
+            }
+            // ---- the tile is complete ----
+            if (live) { if (is_rr) s_rrv[rt] = acc.result<NEUMAIER>(); else s_dotv[rt] = acc.result<NEUMAIER>(); }
+            acc.init();
+            __syncthreads();      // also orders the buffer reuse
             double sc = 0.0;
-            if (live) sc = exact_cosine_sq<NEUMAIER, T>(sq, n1, rows + r * (int64_t)ld, dim);
             // candidate iff list not full or beats the current worst (k-th) entry
             bool hit = false;
-            if (live) {
-                int lc = l_cnt;
+            if (live && !is_rr) {
+                const double n2 = __dsqrt_rn(s_rrv[rt]);
+                sc = (n1 == 0.0 || n2 == 0.0) ? 0.0 : __ddiv_rn(s_dotv[rt], __dmul_rn(n1, n2));
+                const int lc = l_cnt;
                 hit = lc < k || better(sc, (uint32_t)r, l_score[lc - 1], l_row[lc - 1]);
             }
             if (hit) {
-                int p = atomicAdd(&c_cnt, 1);
+                const int p = atomicAdd(&c_cnt, 1);
                 c_score[p] = sc;
                 c_row[p] = (uint32_t)r;
             }
             // barrier + block-wide hit count in one step: every thread sees the same cc, so the
             // merge branch below is taken uniformly (a plain read of c_cnt could race with the
             // next tile's atomicAdd)
-            int cc = __syncthreads_count(hit ? 1 : 0);
-            int lc = l_cnt;
+            const int cc = __syncthreads_count(hit ? 1 : 0);
+            const int lc = l_cnt;
             if (cc > 0) {
                 // rank-merge list (lc) and candidates (cc): entry e in [0, lc+cc)
-                for (int e = tid; e < lc + cc; e += 128) {
-                    double se = e < lc ? l_score[e] : c_score[e - lc];
-                    uint32_t re = e < lc ? l_row[e] : c_row[e - lc];
+                for (int e = tid; e < lc + cc; e += XS_THREADS) {
+                    const double se = e < lc ? l_score[e] : c_score[e - lc];
+                    const uint32_t re = e < lc ? l_row[e] : c_row[e - lc];
                     int rank = 0;
                     for (int i = 0; i < lc; ++i) rank += better(l_score[i], l_row[i], se, re) ? 1 : 0;
                     for (int i = 0; i < cc; ++i) rank += better(c_score[i], c_row[i], se, re) ? 1 : 0;
                     if (rank < k) { n_score[rank] = se; n_row[rank] = re; }
                 }
                 __syncthreads();
-                int nl = min(k, lc + cc);
-                for (int e = tid; e < nl; e += 128) { l_score[e] = n_score[e]; l_row[e] = n_row[e]; }
+                const int nl = min(k, lc + cc);
+                for (int e = tid; e < nl; e += XS_THREADS) { l_score[e] = n_score[e]; l_row[e] = n_row[e]; }
                 if (tid == 0) { l_cnt = nl; c_cnt = 0; }
                 __syncthreads();
             }
         }
+        cp_async_wait<0>();
         __syncthreads();
-        int lc = l_cnt;
-        int64_t base = ((int64_t)blockIdx.x * nq + q) * k;
-        for (int e = tid; e < lc; e += 128) { xlist_score[base + e] = l_score[e]; xlist_row[base + e] = l_row[e]; }
+        const int lc = l_cnt;
+        const int64_t base = ((int64_t)blockIdx.x * nq + q) * k;
+        for (int e = tid; e < lc; e += XS_THREADS) { xlist_score[base + e] = l_score[e]; xlist_row[base + e] = l_row[e]; }
         if (tid == 0) xlist_cnt[(int64_t)blockIdx.x * nq + q] = lc;
     }
     if (done_ctr == nullptr) return;
     // conditional form: the last CTA to finish reduces the per-CTA lists of every flagged query
     __shared__ int s_last, s_out;
-    __shared__ double w_s[4];
-    __shared__ uint32_t w_r[4];
-    __shared__ int w_p[4];
+    __shared__ double w_s[XS_THREADS / 32];
+    __shared__ uint32_t w_r[XS_THREADS / 32];
+    __shared__ int w_p[XS_THREADS / 32];
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = atomicAdd(done_ctr, 1) == (int)gridDim.x - 1;
@@ -1167,7 +1232,7 @@ __global__ void __launch_bounds__(128) exact_scan_kernel(const T *__restrict__ r
     __threadfence();
     for (int q = 0; q < nq; ++q) {
         if (flags[q] == 0) continue;
-        exact_merge_query<128>(xlist_score, xlist_row, xlist_cnt, (int)gridDim.x, nq, k, q, f, taken, w_s, w_r, w_p, &s_out);
+        exact_merge_query<XS_THREADS>(xlist_score, xlist_row, xlist_cnt, (int)gridDim.x, nq, k, q, f, taken, w_s, w_r, w_p, &s_out);
         if (tid == 0) flags[q] = 0;
     }
     if (tid == 0) { *done_ctr = 0; flags[nq] = 0; }
@@ -1524,13 +1589,22 @@ int k_collect_rescore(const uint64_t *buf, const int *cnt, int cap, const Rescor
 // programmatically chained to the rescoring kernel.
 int k_exact(const ExactArgs &a, cudaStream_t st, bool pdl)
 {
-    size_t smem = (size_t)a.dim * sizeof(double);
-    VM_REQUIRE(smem <= 40 * 1024, VM_ERR_UNSUPPORTED, "exact scan: dim %d too large", a.dim);
+    VM_REQUIRE((size_t)a.dim * sizeof(double) <= 40 * 1024, VM_ERR_UNSUPPORTED, "exact scan: dim %d too large", a.dim);
+    const size_t smem = (size_t)((a.dim + 1) & ~1) * sizeof(double) + (size_t)3 * 128 * XS_PITCH + 16;  // query + three staged chunks
     const bool conditional = a.flags != nullptr && a.done_ctr != nullptr;
 #define LAUNCH_EX(NEU, T)                                                                                               \
-    VM_CUDA_CHECK(launch_pdl(exact_scan_kernel<NEU, T>, dim3(a.ctas), dim3(128), smem, st, pdl && conditional, (const T *)a.rows, \
-                             a.inv_norms, a.n, a.ld, a.dim, a.queries, a.q_dtype, a.nq, a.flags, a.k, a.xlist_score, a.xlist_row, \
-                             a.xlist_cnt, a.cum, conditional ? a.done_ctr : (int *)nullptr, a.fin, a.taken))
+    do {                                                                                                                \
+        static bool attr_set_dev[64] = {};                                                                              \
+        int dev_idx_ = 0;                                                                                               \
+        cudaGetDevice(&dev_idx_);                                                                                       \
+        if (!attr_set_dev[dev_idx_ & 63]) {                                                                             \
+            VM_CUDA_CHECK(cudaFuncSetAttribute(exact_scan_kernel<NEU, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+            attr_set_dev[dev_idx_ & 63] = true;                                                                         \
+        }                                                                                                               \
+        VM_CUDA_CHECK(launch_pdl(exact_scan_kernel<NEU, T>, dim3(a.ctas), dim3(XS_THREADS), smem, st, pdl && conditional, (const T *)a.rows, \
+                                 a.inv_norms, a.n, a.ld, a.dim, a.queries, a.q_dtype, a.nq, a.flags, a.k, a.xlist_score, a.xlist_row, \
+                                 a.xlist_cnt, a.cum, conditional ? a.done_ctr : (int *)nullptr, a.fin, a.taken));       \
+    } while (0)
     bool neu = a.sum_mode == VM_SUM_NEUMAIER;
     if (a.dtype == VM_F32) { if (neu) LAUNCH_EX(true, float); else LAUNCH_EX(false, float); }
     else if (a.dtype == VM_F64) { if (neu) LAUNCH_EX(true, double); else LAUNCH_EX(false, double); }
