@@ -473,6 +473,8 @@ class VectorSearchBackend:
         if keep is None or len(chunks) <= keep:
             return chunks
         rs = self.store
+        if getattr(rs, "store", None) is None or not hasattr(rs, "vectors"):     # empty, or a rank-routed store: nothing to score with
+            return chunks
         known = [i for i, c in enumerate(chunks) if c.get("id") in getattr(rs, "row_of", {})
                  and float(rs.store.inv_norms[rs.row_of[c["id"]]]) >= 0.0]
         if not known or rs.dim is None:
