@@ -1285,7 +1285,9 @@ extern "C" int vm_pairs_above_sharded(vm_comm *comm, void *x_dev, int dtype, int
         slot = mx;
     }
     if (slot == 0) { VM_CUDA_CHECK(cudaMemsetAsync(out_count_dev, 0, 8, st)); return VM_OK; }
-    const size_t per_rank = (size_t)slot * 20;  // [i slot*8 | j slot*8 | s slot*4]
+    // [i slot*8 | j slot*8 | s slot*4], padded to a multiple of 8 bytes: with an odd slot the next rank's int64 arrays
+    // would start on a 4-byte boundary (found when a new tile-to-rank dealing made the largest per-rank count odd)
+    const size_t per_rank = ((size_t)slot * 20 + 7) & ~(size_t)7;
     ENS(comm->pg_send, per_rank); ENS(comm->pg_recv, per_rank * G);
 #undef ENS
     char *sb = (char *)comm->pg_send.p;
