@@ -127,7 +127,7 @@ int vm_store_attach_exact(vm_store **out, int device, int dim, int shadow_dtype,
 /* GROWABLE store (the reference's store only ever grows, one SET c.embedding per new chunk,
  * neo4j_handler.py:221-253).  The library reserves a VIRTUAL address range for max_capacity rows and backs it with
  * physical HBM from its start as rows arrive (CUDA virtual memory management): vm_store_append grows the backed part on
- * demand (+25 % each time, capped at max_capacity), vm_store_reserve grows it explicitly.  Base addresses never change and
+ * demand (what the append needs + 256 MB of slack, capped at max_capacity), vm_store_reserve grows it explicitly.  Base addresses never change and
  * resident rows are never copied -- no second allocation, no device-to-device copy, HBM in use = the backed rows.
  * exact != 0: a binary64 store as vm_store_create_exact (dtype = the shadow type). */
 int vm_store_create_growable(vm_store **out, int device, int dim, int dtype, int exact, int64_t initial_capacity,

@@ -509,9 +509,13 @@ extern "C" int vm_store_append(vm_store *s, const void *rows, int src_dtype, int
     VM_REQUIRE(s, VM_ERR_BADARG, "store is NULL");
     VM_REQUIRE(n >= 0, VM_ERR_BADARG, "n < 0");
     if (s->ar_rows && s->size + n > s->capacity) {
-        // growable store: back more of the reserved range (+25 %, capped at the maximum: mapping costs time and HBM in
-        // proportion to the NEW rows only, so a small factor keeps the slack small); resident rows stay put
-        int64_t want = s->capacity + s->capacity / 4 > s->size + n ? s->capacity + s->capacity / 4 : s->size + n;
+        // growable store: back more of the reserved range -- what this append needs, plus 256 MB worth of rows of slack
+        // (capped at the maximum).  Mapping costs time in proportion to the NEW memory only (~4 ms per GB, and an
+        // occasional much slower call was seen with several processes mapping at once), so a bounded step keeps the
+        // worst insert latency of a streaming store at about a millisecond; resident rows stay put either way.
+        const int64_t row_bytes = (int64_t)s->ld * (int64_t)(dtype_size(s->dtype) + (s->rows_exact ? 8 : 0)) + 4;
+        const int64_t slack_rows = ((int64_t)256 << 20) / row_bytes + 1;
+        int64_t want = s->size + n + slack_rows;
         if (want > s->max_capacity) want = s->max_capacity;
         if (want >= s->size + n) {
             int rc = vm_store_reserve(s, want);
