@@ -510,9 +510,10 @@ extern "C" int vm_store_append(vm_store *s, const void *rows, int src_dtype, int
     VM_REQUIRE(n >= 0, VM_ERR_BADARG, "n < 0");
     if (s->ar_rows && s->size + n > s->capacity) {
         // growable store: back more of the reserved range -- what this append needs, plus 256 MB worth of rows of slack
-        // (capped at the maximum).  Mapping costs time in proportion to the NEW memory only (~4 ms per GB, and an
-        // occasional much slower call was seen with several processes mapping at once), so a bounded step keeps the
-        // worst insert latency of a streaming store at about a millisecond; resident rows stay put either way.
+        // (capped at the maximum).  Mapping costs time in proportion to the NEW memory only (0.26 ms per 256 MB measured;
+        // it can stall behind other users of the driver's resource-manager lock, e.g. a process polling NVML every few
+        // milliseconds), so a bounded step keeps the worst insert latency of a streaming store well under a millisecond;
+        // resident rows stay put either way.
         const int64_t row_bytes = (int64_t)s->ld * (int64_t)(dtype_size(s->dtype) + (s->rows_exact ? 8 : 0)) + 4;
         const int64_t slack_rows = ((int64_t)256 << 20) / row_bytes + 1;
         int64_t want = s->size + n + slack_rows;
