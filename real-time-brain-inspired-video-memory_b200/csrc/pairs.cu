@@ -15,6 +15,7 @@
 // Pairs whose fp32 score lies within eps of the threshold are re-decided in binary64 by
 // pairs_finalize_kernel, so the emitted pair SET is exact for the stored values.
 #include "tc_common.cuh"
+#include "raster.h"
 #include <stdlib.h>
 #include <mutex>
 
@@ -47,39 +48,6 @@ struct PairsParams {
     int part, nparts;
     int gj_log2;              // log2(column blocks per raster group)
     int groups;               // raster groups
-};
-
-// Tile sequence of one CTA (pair).  Tiles are numbered group by group; group g holds GBU*J*(g+1) row blocks x J column
-// blocks (J = 2^gj_log2 column blocks per group; GBU = 2 for 128-row blocks, 1 for 256-row blocks).  With several ranks
-// (part / nparts) a rank owns whole ROW BLOCKS of every group (bi % nparts == part), so it walks the same wide groups as
-// a single GPU would -- its column panel stays in its L2 and each of its row blocks is reused across all J columns
-// (dealing single tiles cyclically would leave every rank only J / nparts columns per group: measured at 8 GPUs,
-// 92 -> 105 ms per pass when J went 8 -> 64 that way).  Inside a rank the tiles go to the CTA pairs cyclically.
-// The iterator keeps (group, offset in the rank's part of it) and advances with integer arithmetic only -- it runs on
-// the single MMA-issuing thread between tiles.
-template <int GBU>
-struct TileIter {
-    long long u, stride, cur;  // offset inside the rank's tiles of group g; tiles the rank owns in group g
-    int g, groups, lg, part, nparts;
-    __device__ __forceinline__ long long local_tiles(int gg) const
-    {
-        const long long rows = ((long long)GBU << lg) * (gg + 1);               // row blocks of the group
-        return ((rows - part + nparts - 1) / nparts) << lg;                      // those with bi % nparts == part, x J columns
-    }
-    __device__ __forceinline__ void init(long long first, long long stride_, int groups_, int gj_log2, int part_, int nparts_)
-    {
-        u = first; stride = stride_; g = 0; groups = groups_; lg = gj_log2; part = part_; nparts = nparts_;
-        cur = local_tiles(0);
-        settle();
-    }
-    __device__ __forceinline__ void settle()
-    {
-        while (g < groups && u >= cur) { u -= cur; ++g; cur = local_tiles(g); }
-    }
-    __device__ __forceinline__ bool valid() const { return g < groups; }
-    __device__ __forceinline__ void next() { u += stride; settle(); }
-    __device__ __forceinline__ int bi() const { return (int)((u >> lg) * nparts + part); }
-    __device__ __forceinline__ int bj() const { return (int)(((long long)g << lg) + (u & ((1 << lg) - 1))); }
 };
 
 template <bool TF32>
