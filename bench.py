@@ -465,7 +465,7 @@ def parity_oracle_f64(store, q_host, k: int, n_queries: int, max_rows: int):
 # top-k scorer (C1 / C2 / C3, clustered variant)
 # ---------------------------------------------------------------------------------------------
 def bench_topk(ctx: Ctx, args, cfg: str, steps: int, warmup: int, variant: str = "iid", with_e2e: bool = True,
-               with_parity: bool = True, rows_override=None, store_dtype=None):
+               with_parity: bool = True, rows_override=None, store_dtype=None, cluster_rho=None):
     """store_dtype "f64" / "f64+bf16": the same workload on a BINARY64 store -- rows kept as float64 originals (here the
     synthetic values times (1 + 1e-9 g), g ~ N(0,1): not representable in fp32 / bf16), the scan streams their rounded
     fp32 / bf16 shadow, every exact step reads the originals; queries are float64 too."""
@@ -477,6 +477,7 @@ def bench_topk(ctx: Ctx, args, cfg: str, steps: int, warmup: int, variant: str =
     rows_total, dim, dt, nq, k, sseed, qseed = CONFIGS[cfg]
     if rows_override:
         rows_total = rows_override
+    rho = args.cluster_rho if cluster_rho is None else float(cluster_rho)
     row_lo = rows_total * rank // world
     row_hi = rows_total * (rank + 1) // world
     n_local = row_hi - row_lo
@@ -501,14 +502,14 @@ def bench_topk(ctx: Ctx, args, cfg: str, steps: int, warmup: int, variant: str =
             q_pinned = q_pinned.double() * (1.0 + 1e-9 * torch.randn(q_pinned.shape, generator=torch.Generator().manual_seed(qseed), dtype=torch.float64))
         q_pinned = q_pinned.pin_memory()
     else:
-        fill_clustered(store, n_local, dim, sseed, args.cluster_size, args.cluster_rho, row_lo)
+        fill_clustered(store, n_local, dim, sseed, args.cluster_size, rho, row_lo)
         store.set_size(n_local)
         torch.cuda.synchronize()
         # queries: perturbed members of random clusters (so the top-k sits inside a near-duplicate cluster)
         g = torch.Generator(device="cpu").manual_seed(qseed)
         ridx = torch.randint(0, max(n_local, 1), (nq,), generator=g)
         base = store.rows[ridx.to(dev), :dim].float()
-        q = base + (args.cluster_rho / dim ** 0.5) * torch.randn((nq, dim), generator=g).to(dev)
+        q = base + (rho / dim ** 0.5) * torch.randn((nq, dim), generator=g).to(dev)
         if world > 1:
             import torch.distributed as dist
             dist.broadcast(q, src=0)
@@ -626,7 +627,7 @@ def bench_topk(ctx: Ctx, args, cfg: str, steps: int, warmup: int, variant: str =
                                    f"{'row-sharded over %d GPUs + NCCL all-gather merge' % world if world > 1 else '1 GPU'}",
                        "variant": ("iid: counter-hash integers / 128 (SURVEY 8d)" if variant == "iid" else
                                    f"clustered: unit-norm Gaussian mixture, {args.cluster_size} near-duplicates per centre, "
-                                   f"noise rho={args.cluster_rho} (cosine between members ~{1 / (1 + args.cluster_rho ** 2):.3f}), non-representable values"),
+                                   f"noise rho={rho} (cosine between members ~{1 / (1 + rho ** 2):.4f}), non-representable values"),
                        "rows_per_gpu": n_local,
                        "l2_policy": ("inputs larger than L2 (%.0f MB store per GPU vs 126 MB L2)" % (n_local * dim * es / 1e6))
                        if not fits_l2 else
@@ -983,6 +984,10 @@ def run_ours(args):
         if full:
             clustered = note("clustered", bench_topk(ctx, args, cfg, min(args.steps, 20), 3, variant="clustered", with_e2e=False,
                                                      rows_override=None if world > 1 else None))
+            # tight clusters: every query's top-k lies inside ONE cluster of near-identical rows, more of them within the scan's
+            # error band than the candidate list holds -> every query is settled from the band (certification.band_settled)
+            tight = note("clustered_tight", bench_topk(ctx, args, cfg, min(args.steps, 20), 3, variant="clustered", with_e2e=False,
+                                                       cluster_rho=0.05))
             b64 = None
             if world == 1 and cfg == "c2":
                 b64 = {sd: note("binary64_" + sd, bench_topk(ctx, args, cfg, min(args.steps, 20), 3, with_e2e=True, store_dtype=sd))
@@ -993,6 +998,8 @@ def run_ours(args):
             if rank == 0:
                 line["clustered"] = {key: clustered[key] for key in ("value", "unit", "ms_per_step", "config", "roofline", "certification", "parity", "clocks")}
                 line["clustered"]["vs_iid"] = clustered["value"] / line["value"]
+                line["clustered_tight"] = {key: tight[key] for key in ("value", "unit", "ms_per_step", "config", "roofline", "certification", "parity", "clocks")}
+                line["clustered_tight"]["vs_iid"] = tight["value"] / line["value"]
                 if b64:
                     line["binary64_store"] = {sd: {key: r[key] for key in ("value", "unit", "ms_per_step", "config", "roofline", "certification", "parity", "e2e")}
                                               for sd, r in b64.items()}

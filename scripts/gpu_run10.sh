@@ -11,7 +11,7 @@ import json
 try:
     d=json.loads(open('gpurun_out/r2k/bench_n2.json').read().strip().splitlines()[-1])
     print('c3 n2', round(d['value']), d['ms_per_step'], d['parity'], 'e2e', d['e2e']['value'])
-    for k in ('clustered','dedup','streaming'):
+    for k in ("clustered","clustered_tight","dedup","streaming","streaming_bf16"):
         r=d.get(k) or {}
         print(k, r.get('value'), r.get('ms_per_step'), r.get('parity'))
     print('cpu_baseline', d.get('cpu_baseline'))
