@@ -804,6 +804,33 @@ def bench_dedup(ctx: Ctx, args, steps: int, warmup: int, rows_override=None):
         ok = ok and bool(same)
         sample = {"rows": int(ns), "oracle_pairs": int(len(ri)), "gpu_pairs": int(len(gi)), "set_equal": bool(same),
                   "cpu_pairs_per_s": (ns * (ns - 1) / 2) / dt_s}
+    # (c) rank 0, at the FULL size: the emitted list against the generator's definition -- every emitted pair really
+    #     exceeds the threshold (binary64 cosine of the regenerated rows), and every planted near-duplicate whose exact
+    #     cosine to its parent is clear of the threshold is in the list
+    planted_check = None
+    if rank == 0 and not args.no_cpu_baseline and hits <= cap:
+        from oracle import synth
+        m = int(cnt.item())
+        pi_, pj_ = oi[:m].cpu().numpy(), oj[:m].cpu().numpy()
+        A = synth.synth_rows_at(seed, pi_.astype(np.uint64), dim, dup).astype(np.float64)
+        B = synth.synth_rows_at(seed, pj_.astype(np.uint64), dim, dup).astype(np.float64)
+        ex = (A * B).sum(1) / np.sqrt((A * A).sum(1) * (B * B).sum(1)) if m else np.zeros(0)
+        all_above = bool((ex > thr).all() and (pi_ < pj_).all())
+        ids = np.arange(1, rows, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            hk = synth.splitmix64(np.array([np.uint64(seed) ^ np.uint64(0xD6E8FEB86659FD93)], dtype=np.uint64))[0]
+            hr = synth.splitmix64(hk + ids)
+            is_planted = hr % np.uint64(dup) == 0
+            planted = ids[is_planted]
+            parent = synth.splitmix64(hr[is_planted]) % planted
+        P = synth.synth_rows_at(seed, planted, dim, dup).astype(np.float64)
+        Pa = synth.synth_rows_at(seed, parent, dim, dup).astype(np.float64)
+        cs = (P * Pa).sum(1) / np.sqrt((P * P).sum(1) * (Pa * Pa).sum(1))
+        found = set(zip(pi_.tolist(), pj_.tolist()))
+        expect = {(int(min(a, b)), int(max(a, b))) for a, b, c in zip(planted, parent, cs) if c > thr + 1e-4}
+        planted_check = {"rows": int(rows), "emitted_pairs_all_above_threshold_in_binary64": all_above,
+                         "planted_pairs_clear_of_threshold": len(expect), "of_which_found": len(expect & found)}
+        ok = ok and all_above and expect <= found
     ok = ctx.all_true(bool(ok))
 
     rec = None
@@ -827,9 +854,10 @@ def bench_dedup(ctx: Ctx, args, steps: int, warmup: int, rows_override=None):
                             "flops_counted": "2*D per unordered pair (upper triangle only), per GPU",
                             "ncu_tensor_pipe_active_pct": _ncu_pairs_pipe(),
                             "frac_of_nominal_2250": tf / 2250.0},
-               "parity": {"ok": bool(ok), "checked": "pair multiset (count + checksum) resident == e2e"
+               "parity": {"ok": bool(ok), "checked": "full-size list vs the generator (every emitted pair above the threshold in binary64, every planted pair found); pair multiset (count + checksum) resident == e2e"
                                                      + (" == single-GPU pass" if world > 1 else "") + "; exact pair-set equality vs CPU oracle on a row sample",
-                          "pairs": hits, "checksum": hsum, "single_gpu_pairs": single_hits, "oracle_sample": sample},
+                          "pairs": hits, "checksum": hsum, "single_gpu_pairs": single_hits, "oracle_sample": sample,
+                          "full_size_structure": planted_check},
                "clocks": clocks}
         if sample:
             rec["cpu_baseline"] = {"value": sample["cpu_pairs_per_s"], "unit": "pairs/s", "cores": os.cpu_count() or 1, "kind": "port",
