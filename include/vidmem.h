@@ -86,13 +86,15 @@ typedef struct vm_comm vm_comm;   /* an NCCL communicator wrapper (one rank) */
 typedef struct vm_topk_stats {
     int32_t scan_kernel;      /* 0 = exact only, 1 = SIMT scan, 2 = tcgen05 scan */
     int32_t scan_launches;    /* kernels launched by the call (all kinds) */
-    int32_t uncertified;      /* queries the fast scan could not certify (settled by the collect pass or the exact scan) */
+    int32_t uncertified;      /* queries left for a fallback pass after the rescoring kernel (it settles near-tie bands itself):
+                                 settled by the collect pass or the binary64 scan of every row */
     int32_t candidates;       /* candidate list length per query (KP) */
     int32_t scan_ctas;
     int32_t scan_stages;      /* shared-memory pipeline depth of the tcgen05 scan (0 otherwise) */
     int32_t full_rescans;     /* of the uncertified queries, how many the collect pass could not settle and the
                                  binary64 scan of every row re-did (-1: not read back, e.g. graph replay) */
-    int32_t scan_variant;     /* tcgen05 scan: 0 = per-CTA lists, 1 = dump mode (small store), 2 = lists + threshold warp */
+    int32_t scan_variant;     /* tcgen05 scan: 1 = dump mode (small store: every row's key is ranked), 2 = band mode (lock-free
+                                 per-CTA slabs + spill buffer, cooperative bounds); 0 = not a tcgen05 scan */
 } vm_topk_stats;
 
 /* ---- library ----------------------------------------------------------------------- */
@@ -214,12 +216,14 @@ int vm_store_band_keys(vm_store *s, int nq_cap, int64_t *kept_per_query, int64_t
  *  out_mem    where the three outputs live
  *
  * How: a fast scan (the tcgen05/TMA tensor-core kernel; the CUDA-core kernel only for shapes it
- * does not fit) streams the store once and keeps, per query, a candidate list by approximate fp32
- * score; an exact binary64 pass rescores the candidates in the reference's summation order,
- * sorts them and CERTIFIES that no other row can reach the k-th score (approximation error
- * bound); uncertified queries (rare: more near-ties than the candidate list holds) get a second
- * scan that collects every row inside the error band, or, failing that, a binary64 scan of all
- * rows.  Results are therefore exact, not approximate. */
+ * does not fit) streams the store once and keeps, per query, EVERY row whose approximate fp32 score
+ * lies within the scan's error band of the k-th best (the complete near-tie band); an exact binary64
+ * pass rescores the best candidates in the reference's summation order, sorts them and CERTIFIES
+ * that no other row can reach the k-th score; when more near-ties exist than it rescored at first
+ * (near-duplicate chunks) it rescores the whole band in the same launch.  Only thousands of
+ * near-ties per query fall back to a second scan that collects the band, or a binary64 scan of all
+ * rows.  Results are therefore exact, not approximate; vm_store_read_counters reports how each
+ * query was settled. */
 int vm_topk(vm_store *s, const void *queries, int q_dtype, int q_mem, int nq, int k, double min_score,
             int score_mode, int sum_mode, int flags, int64_t *out_idx, double *out_score, int32_t *out_count,
             int out_mem, vm_topk_stats *stats, void *stream);
