@@ -19,6 +19,7 @@ results out, copies inside the timed region).  The same line carries, at every N
   dedup       config C4 (all-pairs, 1M x 768 bf16, threshold 0.9) on the same N GPUs: pairs/s, TFLOP/s per GPU
   streaming   config C5 (4096-row inserts interleaved with single-query top-10 over 10M x 384): p50/p99
   clustered   the main workload on a unit-norm Gaussian-mixture store with non-representable values
+  reference_size  (N = 1) config C1, the reference's own size: 5 000 x 384 store, 30 queries, L2 flushed before every step
   cpu_baseline  the oracle port on the box's host cores (bounded sample)
 `--impl reference` times the reference's CPU algorithm (oracle port, all host threads) on the same workload.
 """
@@ -1034,6 +1035,16 @@ def run_ours(args):
                 line["dedup"] = dd
                 line["streaming"] = stream
                 line["streaming_bf16"] = {key: stream_bf16[key] for key in ("value", "unit", "ms_per_step", "config", "latency_ms", "growth", "roofline", "parity")}
+            if world == 1 and cfg == "c2":
+                # config C1: the reference's OWN size (LIMIT 5000 store, 30 benchmark queries) -- latency-bound, L2 flushed per step
+                c1 = note("reference_size", bench_topk(ctx, args, "c1", min(args.steps, 100), 3))
+                if rank == 0:
+                    line["reference_size"] = {key: c1[key] for key in ("value", "unit", "ms_per_step", "steps", "config", "roofline", "certification",
+                                                                       "parity", "e2e", "clocks")}
+                    if not args.no_cpu_baseline:
+                        qps1, ms1, desc1 = cpu_reference_leg("c1", 3, 1, CONFIGS["c1"][0])
+                        line["reference_size"]["cpu_baseline"] = {"value": qps1, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                                                  "sample": desc1, "ms_per_step": ms1}
             if world == 1 and cfg == "c2" and not args.no_scaling_baseline:
                 line["scaling_baseline"] = scaling_baseline(ctx)
     if rank == 0:

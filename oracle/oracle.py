@@ -47,6 +47,10 @@ def lib() -> C.CDLL:
         L.vo_threshold_filter_ge.argtypes = [dp, dp, i64, i64, dbl, i64, cint, ip, dp]
         L.vo_pairs_above.restype = i64
         L.vo_pairs_above.argtypes = [fp, i64, i64, C.c_float, i64, ip, ip, fp]
+        L.vo_normalize_rows_f32.restype = None
+        L.vo_normalize_rows_f32.argtypes = [fp, i64, i64, fp]
+        L.vo_pairs_rescore.restype = None
+        L.vo_pairs_rescore.argtypes = [fp, i64, ip, ip, i64, fp]
         L.vo_representative.restype = i64
         L.vo_representative.argtypes = [fp, i64, i64, fp]
         L.vo_rescore_rows_f32.restype = None
@@ -148,6 +152,51 @@ def pairs_above(x, threshold: float, cap: Optional[int] = None):
     if total > cap:
         return pairs_above(x, threshold, cap=int(total))
     return oi[:total].copy(), oj[:total].copy(), os_[:total].copy()
+
+
+def pairs_above_streamed(x, threshold: float, block: int = 8192):
+    """The all-pairs restatement (vo_pairs_above, prune.py:67-79) for row counts where the O(N^2 D) scalar loop takes
+    hours (C4 at 262 144 rows and beyond).  A float32 BLAS product of the normalised rows pre-scores every block pair of
+    the upper triangle (|error| <= PRE_TOL = (d + 8) 2^-24 in cosine units, Cauchy-Schwarz on unit rows); every pair whose
+    pre-score exceeds threshold - 2 PRE_TOL is then decided by the oracle's own arithmetic (vo_pairs_rescore: binary64
+    accumulation of the float32-normalised rows, rounded once to float32, strict >).  A pair below that margin cannot
+    pass the oracle's comparison, so the returned set is the complete oracle pair set, in (i, j) order like pairs_above."""
+    xf = np.ascontiguousarray(x, np.float32)
+    n, d = xf.shape
+    if n <= 1:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float32)
+    L = lib()
+    xn = np.empty_like(xf)
+    L.vo_normalize_rows_f32(_ptr(xf, C.c_float), n, d, _ptr(xn, C.c_float))
+    thr32 = float(np.float32(threshold))
+    cut = np.float32(thr32 - 2.0 * (d + 8) * 2.0 ** -24 * 1.01)
+    ci, cj = [], []
+    buf = np.empty((min(block, n), min(block, n)), np.float32)  # one product buffer, reused (no page faults per block)
+    for b0 in range(0, n, block):
+        a = xn[b0:b0 + block]
+        for c0 in range(b0, n, block):
+            b = xn[c0:c0 + block]
+            s = buf.reshape(-1)[:a.shape[0] * b.shape[0]].reshape(a.shape[0], b.shape[0])
+            np.matmul(a, b.T, out=s)
+            if c0 == b0:
+                np.fill_diagonal(s, -2.0)                       # prune.py:77 fill_diagonal; i > j is dropped below
+            rows = np.flatnonzero(s.max(axis=1) > cut)          # few rows per block hold a candidate at all
+            if rows.size == 0:
+                continue
+            r, c = np.nonzero(s[rows] > cut)
+            gi, gj = rows[r] + b0, c + c0
+            keep = gi < gj
+            ci.append(gi[keep].astype(np.int64))
+            cj.append(gj[keep].astype(np.int64))
+    ci = np.concatenate(ci) if ci else np.zeros(0, np.int64)
+    cj = np.concatenate(cj) if cj else np.zeros(0, np.int64)
+    sc = np.empty(len(ci), np.float32)
+    if len(ci):
+        L.vo_pairs_rescore(_ptr(xn, C.c_float), d, _ptr(ci, C.c_int64), _ptr(cj, C.c_int64), len(ci), _ptr(sc, C.c_float))
+    hit = sc > np.float32(thr32)
+    ci, cj, sc = ci[hit], cj[hit], sc[hit]
+    order = np.lexsort((cj, ci))
+    return ci[order], cj[order], sc[order]
 
 
 def representative(x) -> Tuple[int, np.ndarray]:

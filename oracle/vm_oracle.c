@@ -290,6 +290,25 @@ int64_t vo_pairs_above(const float *x, int64_t n, int64_t d, float threshold, in
     return total;
 }
 
+/* Helpers of the streamed all-pairs tier (oracle.pairs_above_streamed): the SAME arithmetic as vo_pairs_above, applied
+ * to a candidate list instead of every pair.  vo_normalize_rows_f32 exposes the normalisation above;
+ * vo_pairs_rescore writes (float)sum_k (double)xn_i[k] * (double)xn_j[k] for each candidate (i, j). */
+void vo_normalize_rows_f32(const float *x, int64_t n, int64_t d, float *xn)
+{
+    normalize_rows_f32(x, n, d, xn);
+}
+
+void vo_pairs_rescore(const float *xn, int64_t d, const int64_t *ci, const int64_t *cj, int64_t m, float *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < m; ++p) {
+        const float *a = xn + ci[p] * d, *b = xn + cj[p] * d;
+        double acc = 0.0;
+        for (int64_t k = 0; k < d; ++k) acc += (double)a[k] * (double)b[k];
+        out[p] = (float)acc;
+    }
+}
+
 /* Graph._get_representative_relation: src/pipeline/prune.py:56-65
  * centroid = mean(E, axis=0) (float32); sims = cosine_similarity([centroid], E)[0];
  * argmax -> first maximal index.  Writes sims (float32) if out_sims != NULL. */

@@ -98,6 +98,27 @@ def test_prune_matches_reference(golden_dir):
         t = int(thr * 10)
         assert np.array_equal(i, g[f"pairs_i_{t}"]) and np.array_equal(j, g[f"pairs_j_{t}"])
         np.testing.assert_allclose(s, g[f"pairs_s_{t}"], rtol=1e-5)  # BLAS order unspecified -> tolerance
+        # the streamed tier (BLAS pre-scoring + the same decision arithmetic) is the same set, bit for bit
+        si, sj, ss = oracle.pairs_above_streamed(E, thr, block=64)
+        assert np.array_equal(si, i) and np.array_equal(sj, j) and np.array_equal(ss, s)
+
+
+def test_streamed_pair_tier_equals_the_scalar_tier():
+    """oracle.pairs_above_streamed (used where the O(N^2 D) loop takes hours) against oracle.pairs_above: ragged last
+    blocks, one block, zero rows, a threshold low enough for ~10^6 hits, thresholds at / around an attained score."""
+    for n, d, thr, dup, block in [(3000, 768, 0.9, 20, 1024), (5000, 96, 0.5, 7, 4096), (2049, 384, 0.05, 0, 512),
+                                  (1, 8, 0.5, 0, 8), (2, 8, -1.0, 0, 8), (700, 64, 0.3, 3, 8192)]:
+        E = oracle.synth_rows_c(44, 0, n, d, dup)
+        if n > 100:
+            E[17] = 0.0
+        a = oracle.pairs_above(E, thr)
+        b = oracle.pairs_above_streamed(E, thr, block=block)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)), (n, d, thr)
+    E = oracle.synth_rows_c(45, 0, 600, 128, 5)
+    _, _, s = oracle.pairs_above(E, 0.6)
+    for thr in (float(s[3]), float(np.nextafter(s[3], np.float32(0))), float(np.nextafter(s[3], np.float32(2)))):   # strict >
+        a, b = oracle.pairs_above(E, thr), oracle.pairs_above_streamed(E, thr, block=256)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
 
 
 def test_vector_search_semantics():
