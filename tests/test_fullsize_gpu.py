@@ -120,12 +120,13 @@ def test_c4_pair_set_equals_the_oracle_at_32k(vm):
     np.testing.assert_allclose(s, os_, rtol=2e-4, atol=1e-6)
 
 
-@pytest.mark.parametrize("n", [65_536] + ([262_144] if os.environ.get("VIDMEM_SLOW_TESTS") else []))
+@pytest.mark.parametrize("n", [65_536] if os.environ.get("VIDMEM_FAST_TESTS") else [262_144])
 def test_c4_pair_set_equals_the_streamed_oracle(vm, n):
-    """65 536 x 768 (always) and 262 144 x 768 (VIDMEM_SLOW_TESTS=1: 3.4e10 pairs, ~1.5 min of host sgemm on 16 cores; log
-    under profiles/) bf16 all-pairs at 0.9: the emitted pair SET equals the CPU oracle's streamed tier -- float32 BLAS
-    pre-scoring of every block pair, the oracle's own decision arithmetic for everything within the BLAS error bound of
-    the threshold (oracle.pairs_above_streamed, pinned to the scalar tier by tests/test_oracle_golden.py)."""
+    """262 144 x 768 bf16 all-pairs at 0.9 (3.4e10 pairs, the wide raster groups of the full-size run; ~50 s of host sgemm
+    on 16 cores -- VIDMEM_FAST_TESTS=1 runs 65 536 rows instead): the emitted pair SET equals the CPU oracle's streamed
+    tier -- float32 BLAS pre-scoring of every block pair, the oracle's own decision arithmetic for everything within the
+    BLAS error bound of the threshold (oracle.pairs_above_streamed, pinned to the scalar tier by
+    tests/test_oracle_golden.py).  Log of the first run: profiles/r2_pytest_c4_pairset_262k.txt."""
     import torch
     from vidmem_b200 import dedup
     d, thr, dup = 768, 0.9, 100
