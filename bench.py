@@ -263,6 +263,25 @@ def cpu_reference_leg(cfg_name: str, steps: int, warmup: int, sample_rows: int):
     return nq / full, per_step * 1e3, f"{nq} queries x {sample_rows} rows x {dim}: {what}"
 
 
+def cpu_interpreter_leg(cfg_name: str, n_queries: int):
+    """The reference's own execution model (SURVEY 8d "ref_python"): one interpreter thread, generator expressions over
+    Python floats (oracle/pyloop.py restates pre_llm_injector.py:346-388), on `n_queries` queries of the config against
+    the full store -- only sensible at C1's size (~60 us per pair).  Its lists must equal the C port's bit for bit."""
+    from oracle import oracle, pyloop, synth
+    rows_total, dim, _dt, nq, k, sseed, qseed = CONFIGS[cfg_name]
+    X = synth.synth_rows(sseed, 0, rows_total, dim)
+    Q = synth.synth_queries(qseed, nq, dim, sseed, rows_total)[:n_queries]
+    store = {i: [float(v) for v in X[i]] for i in range(rows_total)}
+    queries = [[float(v) for v in q] for q in Q]
+    t0 = time.perf_counter()
+    got = pyloop.batch_similarities(queries, store, k)
+    dt = time.perf_counter() - t0
+    mode = oracle.SUM_NEUMAIER if sys.version_info >= (3, 12) else oracle.SUM_NAIVE
+    same = got == oracle.batch_similarities(Q, X, k, sum_mode=mode)
+    return {"value": len(queries) / dt, "unit": UNIT, "cores": 1, "kind": "port (CPython loop)", "us_per_pair": dt / (len(queries) * rows_total) * 1e6,
+            "sample": f"{len(queries)} of {nq} queries x {rows_total} rows x {dim}, one interpreter thread", "equals_c_port": bool(same)}
+
+
 def cpu_blas_leg(cfg_name: str, sample_rows: int):
     """The reference's own vectorised idiom (src/pipeline/prune.py:62,76): sklearn cosine_similarity (BLAS
     sgemm over every host core, store re-normalised on every call) + argpartition/sort for the top-k, on the
@@ -1044,7 +1063,8 @@ def run_ours(args):
                     if not args.no_cpu_baseline:
                         qps1, ms1, desc1 = cpu_reference_leg("c1", 3, 1, CONFIGS["c1"][0])
                         line["reference_size"]["cpu_baseline"] = {"value": qps1, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                                                  "sample": desc1, "ms_per_step": ms1}
+                                                                  "sample": desc1, "ms_per_step": ms1,
+                                                                  "python_loop": cpu_interpreter_leg("c1", 3)}
             if world == 1 and cfg == "c2" and not args.no_scaling_baseline:
                 line["scaling_baseline"] = scaling_baseline(ctx)
     if rank == 0:

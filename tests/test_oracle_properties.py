@@ -8,7 +8,7 @@ import sys
 import numpy as np
 from hypothesis import given, settings, strategies as st
 
-from oracle import oracle
+from oracle import oracle, synth
 
 MODE = oracle.SUM_NEUMAIER if sys.version_info >= (3, 12) else oracle.SUM_NAIVE
 finite = st.floats(min_value=-1e6, max_value=1e6, allow_nan=False, allow_infinity=False, width=64)
@@ -80,3 +80,30 @@ def test_streamed_tier_equals_blocked_tier():
     assert [[r for r, _ in lst] for lst in ref] == b[0].tolist()
     assert [[s for _, s in lst] for lst in ref] == b[1].tolist()
 
+
+
+def test_interpreter_loop_equals_the_c_restatement():
+    """oracle/pyloop.py (what CPython computes, generator expressions and the interpreter's own sum()) against
+    vm_oracle.c: same rows, bit-identical scores -- incl. a zero row, a falsy row, a wrong-length row, duplicates and an
+    Exception query.  The C side uses the summation order of the running interpreter (Neumaier from 3.12 on)."""
+    import sys
+    from oracle import pyloop
+    mode = oracle.SUM_NEUMAIER if sys.version_info >= (3, 12) else oracle.SUM_NAIVE
+    X = synth.synth_rows(31, 0, 400, 96).astype(np.float64)
+    X *= 1.0 + 1e-9 * np.random.default_rng(3).standard_normal(X.shape)       # off the bf16 / fp32 grid
+    X[7] = 0.0
+    X[200] = X[20]
+    Q = synth.synth_queries(32, 5, 96, 31, 400).astype(np.float64)
+    store = {f"c{i}": [float(v) for v in X[i]] for i in range(len(X))}
+    store["c11"] = []                    # falsy: skipped (:363)
+    store["c12"] = store["c12"][:50]     # wrong length: scores 0.0 (:378-379)
+    row_ok = np.ones(len(X), np.uint8); row_ok[11] = 0
+    Xc = X.copy(); Xc[12] = 0.0          # a zero row scores 0.0 as well
+    queries = [[float(v) for v in q] for q in Q]
+    queries.insert(2, RuntimeError("embedding failed"))
+    got = pyloop.batch_similarities(queries, store, 7)
+    qok = np.ones(len(queries), np.uint8); qok[2] = 0
+    Qc = np.insert(Q, 2, 0.0, axis=0)
+    want = oracle.batch_similarities(Qc, Xc, 7, query_ok=qok, row_ok=row_ok, sum_mode=mode)
+    assert [[(int(c[1:]), s) for c, s in lst] for lst in got] == want
+    assert got[2] == []
