@@ -186,6 +186,26 @@ def _ncu_pairs_pipe():
     return None
 
 
+def _ncu_pairs_full_size(rows: int):
+    """The committed ncu pass of pairs_tc2_kernel at exactly `rows` rows (profiles/*pairs*summary.json): per-launch DRAM
+    traffic, tensor-pipe activity, SM clock under the profiler; None when no capture of this size exists."""
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        names = sorted((n for n in os.listdir(pdir) if "pairs" in n and n.endswith("_summary.json")), reverse=True)
+    except OSError:
+        return None
+    for name in names:
+        try:
+            d = json.load(open(os.path.join(pdir, name)))
+            if int(d.get("rows", -1)) == int(rows) and d.get("dram_bytes_read") is not None:
+                return {"traffic": float(d["dram_bytes_read"]) + float(d.get("dram_bytes_write") or 0.0),
+                        "tensor_pipe_active_pct": d.get("tensor_pipe_active_pct"), "tflops_under_ncu": d.get("tflops"),
+                        "sm_clock_ghz": d.get("sm_clock_ghz"), "l2_hit_rate_pct": d.get("l2_hit_rate_pct"), "file": "profiles/" + name}
+        except Exception:
+            continue
+    return None
+
+
 class Ctx:
     """Process-wide state of one bench run (rank, device, communicator)."""
 
@@ -711,7 +731,8 @@ def scaling_baseline(ctx: Ctx):
         ms3 = a0.elapsed_time(a1) / 10
         res = {"workload": f"c3: {r3}x{d3} {dt3} store on ONE GPU, {nq3}-query batch, top-{k3}",
                "value": nq3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3,
-               "hbm_frac": (r3 * d3 * 2 + r3 * 4) / (ms3 * 1e-3) / 1e9 / _peaks()[0]}
+               "hbm_frac": (r3 * d3 * 2 + r3 * 4) / (ms3 * 1e-3) / 1e9 / _peaks()[0],
+               "algorithmic_bytes": r3 * d3 * 2 + r3 * 4, "traffic": _ncu_traffic(dt3, r3)}
         s3.close()
         del s3
         torch.cuda.empty_cache()
@@ -858,6 +879,7 @@ def bench_dedup(ctx: Ctx, args, steps: int, warmup: int, rows_override=None):
         pairs = rows * (rows - 1) / 2
         peak, src = _tensor_peak()
         tf = pairs * 2 * dim / (ms * 1e-3) / 1e12 / world      # per GPU
+        full = _ncu_pairs_full_size(rows) if world == 1 else None   # the capture is of the single-GPU launch
         rec = {"metric": "dedup_unique_pairs_per_sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world,
                "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
                "scaling": "strong", "dtype": "bf16", "data": "synthetic",
@@ -870,9 +892,9 @@ def bench_dedup(ctx: Ctx, args, steps: int, warmup: int, rows_override=None):
                        "path": "pinned host rows -> H2D" + (" -> ncclBroadcast" if world > 1 else "") + " -> kernel -> pairs D2H"},
                "gpu_launches": 3 * steps + (1 * steps if world > 1 else 0),
                "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
-                            "traffic": None, "kernel": "pairs_tc2_kernel", "kernel_ms": ms, "peak_source": src,
+                            "traffic": full["traffic"] if full else None, "kernel": "pairs_tc2_kernel", "kernel_ms": ms, "peak_source": src,
                             "flops_counted": "2*D per unordered pair (upper triangle only), per GPU",
-                            "ncu_tensor_pipe_active_pct": _ncu_pairs_pipe(),
+                            "ncu_tensor_pipe_active_pct": _ncu_pairs_pipe(), "ncu_at_this_size": full,
                             "frac_of_nominal_2250": tf / 2250.0},
                "parity": {"ok": bool(ok), "checked": "full-size list vs the generator (every emitted pair above the threshold in binary64, every planted pair found); pair multiset (count + checksum) resident == e2e"
                                                      + (" == single-GPU pass" if world > 1 else "") + "; exact pair-set equality vs CPU oracle on a row sample",
@@ -990,7 +1012,8 @@ def bench_streaming(ctx: Ctx, args, rounds: int, dtype=None, rows_override=None)
                        "d2h_bytes_per_step": per_round_q * (k * 16 + 8)},
                "gpu_launches": int(st.last_stats.scan_launches) * len(q_lat) + 2 * len(i_lat),
                "roofline": {"bound": "hbm", "achieved": alg / (scan * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                            "frac": alg / (scan * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "scan_tc_kernel", "kernel_ms": scan,
+                            "frac": alg / (scan * 1e-3) / 1e9 / peak, "traffic": _ncu_traffic(dt, n0), "kernel": "scan_tc_kernel", "kernel_ms": scan,
+                            "traffic_note": "ncu pass at the store's starting size (%d rows); algorithmic_bytes is the size after the inserts" % n0,
                             "algorithmic_bytes": alg, "peak_source": src},
                "parity": {"ok": bool(ok), "checked": "a row of the last insert is its own exact top-1 (score 1.0, expected global row) on every rank"},
                "clocks": clocks}

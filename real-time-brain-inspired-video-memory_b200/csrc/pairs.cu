@@ -33,6 +33,16 @@ static constexpr int P_A_BYTES = P_BM * 128, P_B_BYTES = P_BN * 128, P_STAGE_BYT
 // 639 ms, 256 blocks (100 MB: no longer L2 resident) 735 ms.  Below 2^18 rows the narrow groups are kept (few groups
 // either way; measured equal within run-to-run noise).
 static constexpr int P_GJ_LOG2_SMALL = 3, P_GJ_LOG2_LARGE = 6;
+// L2 eviction priority of the streamed row blocks (A) and of the group's column panel (B); A/B builds override them.
+// Plain priority for both: with the pairs kept together (pairs_keep_pace) ordinary LRU already holds the panel and the
+// one or two live row blocks -- measured at 1 M x 768: 49 GB of DRAM reads per pass (the raster's minimum: 62 groups x
+// half the operand) against 100 GB with evict-first rows / evict-last panel, same run time.
+#ifndef VM_PAIRS_HINT_A
+#define VM_PAIRS_HINT_A L2_EVICT_NORMAL
+#endif
+#ifndef VM_PAIRS_HINT_B
+#define VM_PAIRS_HINT_B L2_EVICT_NORMAL
+#endif
 static constexpr int64_t P_GJ_LARGE_FROM_ROWS = 1 << 18;
 
 struct PairsParams {
@@ -48,6 +58,7 @@ struct PairsParams {
     int part, nparts;
     int gj_log2;              // log2(column blocks per raster group)
     int groups;               // raster groups
+    unsigned long long *prog; // tile-sequence steps issued by all CTA pairs of this launch (pace keeping, see pairs_keep_pace)
 };
 
 template <bool TF32>
@@ -206,6 +217,25 @@ pairs_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // =========================================================================================
 static constexpr int P2_STAGES = 6, P2_STAGE_BYTES = 2 * P_A_BYTES;
 
+// Pace keeping.  The tile sequence is dealt to the CTA pairs statically (pair p takes steps p, p + npairs, ...), and the L2
+// reuse of the raster rests on all pairs working on the SAME one or two row blocks of the current group: a row block is
+// fetched from DRAM once and then read by the 64 pairs that score it against the group's 64 column blocks.  Nothing kept
+// the pairs together, and over a 0.7 s launch (1 M rows: ~10^5 tiles per pair) they drift apart -- ncu at 1 M rows: L2 hit
+// rate 60 %, 2.1 TB of DRAM reads (1 400 x the operand; 96 % and 26 x at 262 144 rows), i.e. most row-block loads missed.
+// Every MMA thread now counts its sequence steps into one global counter, and a producer that is more than `window` steps
+// ahead of the launch-wide count waits for the others -- softly: after ~16 us it goes on regardless, so pairs that are not
+// resident yet (another kernel holding SMs) can never block the ones that are.
+__device__ __forceinline__ void pairs_keep_pace(const unsigned long long *prog, long long my_step, long long window)
+{
+    if (my_step <= window) return;
+    for (int spin = 0; spin < 64; ++spin) {
+        unsigned long long done;
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(done) : "l"(prog) : "memory");
+        if ((long long)done + window >= my_step) return;
+        __nanosleep(256);
+    }
+}
+
 template <bool TF32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 pairs_tc2_kernel(const __grid_constant__ CUtensorMap tmA, PairsParams p)
@@ -244,15 +274,18 @@ pairs_tc2_kernel(const __grid_constant__ CUtensorMap tmA, PairsParams p)
             int stage = 0;
             uint32_t phase = 0;
             TileIter<1> ti;
-            for (ti.init(pair, npairs, p.groups, p.gj_log2, p.part, p.nparts); ti.valid(); ti.next()) {
+            long long step = 0;                                  // sequence steps of this pair so far (valid or not)
+            const long long window = 4ll * npairs;
+            for (ti.init(pair, npairs, p.groups, p.gj_log2, p.part, p.nparts); ti.valid(); ti.next(), ++step) {
                 const int bi = ti.bi(), bj = ti.bj();
                 if (!valid_tile(bi, bj)) continue;
+                if (rank == 0) pairs_keep_pace(p.prog, step * npairs, window);   // the peer follows through the stage barriers
                 for (int kb = 0; kb < p.KB; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * P2_STAGE_BYTES);  // both CTAs' bytes
                     uint8_t *sa = stages + (size_t)stage * P2_STAGE_BYTES;
-                    tma_load_2d_2sm(&tmA, &full[stage], sa, kb * ELEMS, bi * 256 + (int)rank * 128, L2_EVICT_FIRST);
-                    tma_load_2d_2sm(&tmA, &full[stage], sa + P_A_BYTES, kb * ELEMS, bj * 256 + (int)rank * 128, L2_EVICT_LAST);
+                    tma_load_2d_2sm(&tmA, &full[stage], sa, kb * ELEMS, bi * 256 + (int)rank * 128, VM_PAIRS_HINT_A);
+                    tma_load_2d_2sm(&tmA, &full[stage], sa + P_A_BYTES, kb * ELEMS, bj * 256 + (int)rank * 128, VM_PAIRS_HINT_B);
                     if (++stage == P2_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -266,6 +299,7 @@ pairs_tc2_kernel(const __grid_constant__ CUtensorMap tmA, PairsParams p)
             TileIter<1> ti;
             for (ti.init(pair, npairs, p.groups, p.gj_log2, p.part, p.nparts); ti.valid(); ti.next()) {
                 const int bi = ti.bi(), bj = ti.bj();
+                atomicAdd(p.prog, 1ull);                         // one per sequence step, valid or not (pairs_keep_pace)
                 if (!valid_tile(bi, bj)) continue;
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -496,6 +530,7 @@ int k_pairs_above(int device, const void *x, int dtype, int64_t n, int dim, int 
     p.inv = (const float *)w.inv;
     p.st_i = (int32_t *)w.st_i; p.st_j = (int32_t *)w.st_j; p.st_s = (float *)w.st_s;
     p.st_cnt = (unsigned long long *)w.cnt;
+    p.prog = (unsigned long long *)w.cnt + 1;   // zeroed with the staging counter above
     p.st_cap = (long long)st_cap;
     p.gj_log2 = n >= P_GJ_LARGE_FROM_ROWS ? P_GJ_LOG2_LARGE : P_GJ_LOG2_SMALL;
     const long long P_GJ = 1ll << p.gj_log2;

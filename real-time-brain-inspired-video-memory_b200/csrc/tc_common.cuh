@@ -67,6 +67,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 }
 
 // L2 cache policies (same encodings CUTLASS uses for TMA::CacheHintSm90)
+static constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
 static constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
 static constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
 
