@@ -7,7 +7,8 @@
 // is consumed straight out of TMEM by the epilogue, which applies the cached inverse norms, compares
 // against the threshold and appends the (rare) hits with one atomic each.  Only tiles that touch the
 // strict upper triangle are scheduled; tiles are rasterised in groups of 8 (64 from 2^18 rows) column blocks x all
-// row blocks so that the group's column panel stays in L2 while the row panels stream.
+// row blocks so that the group's column panel stays in L2 while the row panels stream; the CTA pairs keep pace with each
+// other through a launch-wide step counter (pairs_keep_pace) so that a row block is fetched from DRAM once per group.
 //
 // Persistent, warp-specialised (192 threads): warp 0 TMA producer (A 128-row box + B 256-row box per
 // 128-byte K block, 4 stages of 48 KB), warp 1 MMA issuer (M=128, N=256, 4 MMAs per stage, 2
