@@ -107,3 +107,20 @@ def test_interpreter_loop_equals_the_c_restatement():
     want = oracle.batch_similarities(Qc, Xc, 7, query_ok=qok, row_ok=row_ok, sum_mode=mode)
     assert [[(int(c[1:]), s) for c, s in lst] for lst in got] == want
     assert got[2] == []
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(2, 220), st.sampled_from([8, 33, 96]), st.integers(0, 9), st.sampled_from([0.0, 0.35, 0.8, 0.9, 0.97]),
+       st.sampled_from([16, 64, 100, 4096]), st.integers(0, 2 ** 31 - 1))
+def test_streamed_pair_tier_property(n, d, dup, thr, block, seed):
+    """oracle.pairs_above_streamed == oracle.pairs_above for random shapes, duplicate densities, thresholds and block
+    sizes (ragged last blocks, a single block), with general float32 values, zero rows and exact duplicates mixed in."""
+    rng = np.random.default_rng(seed)
+    E = oracle.synth_rows_c(seed % 1000, 0, n, d, dup).astype(np.float32)
+    E *= (1.0 + 1e-3 * rng.standard_normal(E.shape)).astype(np.float32)      # off the 1/128 grid
+    if n > 4:
+        E[rng.integers(n)] = 0.0
+        E[rng.integers(n)] = E[rng.integers(n)]
+    a = oracle.pairs_above(E, thr)
+    b = oracle.pairs_above_streamed(E, thr, block=block)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
